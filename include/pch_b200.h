@@ -1,0 +1,114 @@
+/* pch_b200.h — C ABI of libpch_b200.so: the B200 (sm_100a) kernels behind pointcloudhookup's
+ * per-point LAS hot path.
+ *
+ * The reference (Daniel-Starr/pointcloudhookup) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the Python module surface imported by pyGUI_towers_test.py:16-26.  Each
+ * entry point below names the reference call (file:line, relative to the reference root) whose
+ * per-point arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is DEVICE memory owned by the caller, 16-byte
+ *     aligned; `const double* scales/offsets` are HOST pointers to 3 doubles (LAS header values).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing,
+ *     never synchronises; scratch comes from the caller via *_workspace_bytes().
+ *   - return 0 on success, <0 on error; pch_last_error() gives a thread-local message.
+ *   - raw LAS point data (`rec_dev`) starts at record 0 (file offset offset_to_point_data), record
+ *     i at byte i*rec_len, and must be readable up to the next multiple of 16 bytes past the end
+ *     (bulk-TMA tiles are fetched in whole 16-byte units).
+ */
+#ifndef PCH_B200_H
+#define PCH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCH_OK 0
+#define PCH_ERR_INVALID (-1)   /* bad argument */
+#define PCH_ERR_CUDA (-2)      /* CUDA runtime error (message has the call) */
+#define PCH_ERR_RANGE (-3)     /* voxel index range does not fit the packed 64-bit key */
+#define PCH_ERR_WORKSPACE (-4) /* workspace too small */
+
+typedef void* pch_stream_t;
+
+const char* pch_last_error(void);
+int pch_version(void);
+/* device-side error word raised by bounded spin loops (0 = fine); lives in caller workspace */
+
+/* ---------------------------------------------------------------- LAS attribute decode / encode */
+
+/* laspy.read(...); per chunk of `chunk_size` consecutive records, the int32 lattice extrema
+ * (ui/import_PC.py:45-48 slices las.points[start:end]; open3d takes the chunk's min bound,
+ * ui/import_PC.py:12).  minmax_dev: [n_chunks][6] = minX,minY,minZ,maxX,maxY,maxZ. */
+int pch_las_chunk_minmax(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t chunk_size,
+                         int32_t* minmax_dev, pch_stream_t stream);
+
+/* np.vstack((las.x, las.y, las.z)).T -> (n,3) float64, x = X*scale+offset
+ * (ui/import_PC.py:47-48; ui/extract.py:114-115,361-362). */
+int pch_las_decode_f64(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const double* scales,
+                       const double* offsets, double* xyz_dev, pch_stream_t stream);
+
+/* np.stack([las.x, las.y, las.z], axis=1).astype(np.float32) (utils/tower_extraction.py:60-62). */
+int pch_las_decode_f32(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const double* scales,
+                       const double* offsets, float* xyz_dev, pch_stream_t stream);
+
+/* `las.x = arr` (ui/import_PC.py:61-63; utils/tower_extraction.py:253-255):
+ * X = round_half_even((arr - offset)/scale) -> int32; (m,3) float64 -> (m,3) int32. */
+int pch_las_quantise(const double* xyz_dev, int64_t m, const double* scales, const double* offsets,
+                     int32_t* lattice_dev, pch_stream_t stream);
+
+/* LasData.write (ui/import_PC.py:65): zero records of `rec_len` bytes with X,Y,Z filled in, plus the
+ * lattice extrema for the header (minmax6_dev: minX,minY,minZ,maxX,maxY,maxZ). */
+int pch_las_encode(const int32_t* lattice_dev, int64_t m, int32_t rec_len, uint8_t* rec_out_dev,
+                   int32_t* minmax6_dev, pch_stream_t stream);
+
+/* ---------------------------------------------------------------- voxel-grid downsample */
+
+typedef struct pch_voxel_plan {
+    int32_t bits_x, bits_y, bits_z; /* bits per voxel-index axis (max over chunks)              */
+    int32_t bits_idx;               /* bits of the in-chunk point index packed below the key     */
+    int32_t key_bits;               /* bits_x + bits_y + bits_z                                   */
+    int32_t n_passes;               /* 8-bit radix passes the sort needs = ceil(key_bits / 8)     */
+    int32_t status;                 /* PCH_OK or PCH_ERR_RANGE                                    */
+    int32_t reserved;
+} pch_voxel_plan;
+
+/* open3d voxel_down_sample set-up (ui/import_PC.py:12): per chunk origin = min_bound - 0.5*voxel
+ * and the index range -> key layout.  origins_dev: [n_chunks][3] float64.  plan_dev: one struct. */
+int pch_voxel_plan_build(const int32_t* minmax_dev, int64_t n_chunks, int64_t chunk_size,
+                         const double* scales, const double* offsets, double voxel_size,
+                         double* origins_dev, pch_voxel_plan* plan_dev, pch_stream_t stream);
+
+/* idx = floor((p - origin)/voxel) per axis in float64 with a true divide (open3d, via
+ * ui/import_PC.py:8-13); key = ix|iy|iz|index-in-chunk packed per `plan` (a HOST copy). */
+int pch_voxel_keys(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t chunk_size,
+                   const double* scales, const double* offsets, double voxel_size,
+                   const double* origins_dev, const pch_voxel_plan* plan, uint64_t* keys_dev,
+                   pch_stream_t stream);
+
+/* Stable LSD radix sort of 64-bit keys on bits [bit_lo, bit_hi), independently inside consecutive
+ * segments of `seg_size` keys.  n_passes = ceil((bit_hi-bit_lo)/8); the result is left in
+ * keys_dev when n_passes is even, in tmp_dev when odd. */
+size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi);
+int pch_sort_u64_segmented(uint64_t* keys_dev, uint64_t* tmp_dev, int64_t n, int64_t seg_size,
+                           int32_t bit_lo, int32_t bit_hi, void* workspace_dev, size_t workspace_bytes,
+                           pch_stream_t stream);
+
+/* Per voxel (run of equal key>>bits_idx in a sorted chunk): running float64 sum in input order,
+ * mean = sum/count (open3d AccumulatedPoint, via ui/import_PC.py:12-13).  Any of the three outputs
+ * may be NULL:  mean_dev (m,3) f64 = process_chunk's return;  lattice_dev (m,3) int32 = the
+ * re-quantised values `las.x = final_points[:,0]` stores (ui/import_PC.py:61-63);  f32_dev (m,3) =
+ * astype(float32) of that file read back (utils/tower_extraction.py:60-62).
+ * chunk_counts_dev[n_chunks] and total_dev[1] (int64) receive the voxel counts. */
+size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size);
+int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_size, int32_t bits_idx,
+                     const uint8_t* rec_dev, int32_t rec_len, const double* scales, const double* offsets,
+                     double* mean_dev, int32_t* lattice_dev, float* f32_dev, int64_t* chunk_counts_dev,
+                     int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCH_B200_H */

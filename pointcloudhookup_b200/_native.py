@@ -1,0 +1,79 @@
+"""ctypes binding of libpch_b200.so (the C ABI declared in include/pch_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, this raises.
+ctypes releases the GIL for the duration of each call, so the reference GUI's worker threads
+(pyGUI_towers_test.py:385) stay responsive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpch_b200.so")
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class VoxelPlan(C.Structure):
+    _fields_ = [("bits_x", C.c_int32), ("bits_y", C.c_int32), ("bits_z", C.c_int32), ("bits_idx", C.c_int32),
+                ("key_bits", C.c_int32), ("n_passes", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f64 = C.c_double
+_sz = C.c_size_t
+_d3 = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); must list every symbol include/pch_b200.h declares
+SIGNATURES = {
+    "pch_last_error": (C.c_char_p, []),
+    "pch_version": (C.c_int, []),
+    "pch_las_chunk_minmax": (C.c_int, [_p, _i64, _i32, _i64, _p, _p]),
+    "pch_las_decode_f64": (C.c_int, [_p, _i64, _i32, _d3, _d3, _p, _p]),
+    "pch_las_decode_f32": (C.c_int, [_p, _i64, _i32, _d3, _d3, _p, _p]),
+    "pch_las_quantise": (C.c_int, [_p, _i64, _d3, _d3, _p, _p]),
+    "pch_las_encode": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "pch_voxel_plan_build": (C.c_int, [_p, _i64, _i64, _d3, _d3, _f64, _p, _p, _p]),
+    "pch_voxel_keys": (C.c_int, [_p, _i64, _i32, _i64, _d3, _d3, _f64, _p, C.POINTER(VoxelPlan), _p, _p]),
+    "pch_sort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "pch_sort_u64_segmented": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
+    "pch_voxel_reduce_workspace_bytes": (_sz, [_i64, _i64]),
+    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeError(
+                        f"{LIB_PATH} is not built (run `python -m pointcloudhookup_b200.build`); "
+                        "pointcloudhookup_b200 has no CPU fallback")
+                l = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().pch_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what or 'pch call'} failed ({rc}): {msg}")
+
+
+def d3(values) -> "C.Array":
+    return (C.c_double * 3)(*[float(v) for v in values])

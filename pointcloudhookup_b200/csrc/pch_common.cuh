@@ -1,0 +1,170 @@
+// pointcloudhookup_b200 — shared device/host helpers for the sm_100a kernels.
+// Everything here is header-inline so every .cu translation unit is self-contained (no -rdc).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <limits.h>
+#include "../../include/pch_b200.h"
+
+#define PCH_SM_COUNT_FALLBACK 148
+
+void pch_set_error(const char* fmt, ...);
+int pch_sm_count();
+
+#define PCH_CHECK_ARG(cond, ...)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            pch_set_error(__VA_ARGS__);                            \
+            return PCH_ERR_INVALID;                                \
+        }                                                          \
+    } while (0)
+
+#define PCH_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            pch_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return PCH_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define PCH_LAUNCH_CHECK() PCH_CUDA(cudaGetLastError())
+
+static inline int64_t pch_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t pch_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) — used to stream raw LAS record bytes and
+// geoid grid rows into shared memory with 16-byte-aligned bulk transfers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pch_smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void pch_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pch_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pch_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pch_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void pch_mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pch_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pch_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pch_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(pch_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void pch_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PCH_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PCH_DONE;\n"
+        "bra PCH_WAIT;\n"
+        "PCH_DONE:\n"
+        "}\n" ::"r"(pch_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoupled look-back (single-pass chained scan).  A status word carries flag + value in ONE
+// 64-bit store, so no fence is needed between value and flag.  Tiles take their id from an atomic
+// ticket, hence a tile only ever waits on tiles that already started: forward progress holds on
+// any grid size.  Spins are bounded; on overflow a device error flag is raised instead of hanging.
+// ---------------------------------------------------------------------------------------------
+#define PCH_FLAG_EMPTY 0ull
+#define PCH_FLAG_AGG 1ull
+#define PCH_FLAG_INCL 2ull
+#define PCH_SPIN_LIMIT (1u << 27)
+
+__device__ __forceinline__ uint64_t pch_ld_volatile_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pch_st_volatile_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t pch_ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pch_st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// 64-bit status: [63:62] flag, [61:0] value.  Called by ONE thread per tile.
+// `first` is the first tile of the scan domain (tile == first publishes inclusive directly).
+__device__ __forceinline__ uint64_t pch_lookback_u64(uint64_t* status, int64_t tile, int64_t first, uint64_t aggregate,
+                                                     int* err_flag) {
+    if (tile == first) {
+        pch_st_volatile_u64(&status[tile], (PCH_FLAG_INCL << 62) | aggregate);
+        return 0;
+    }
+    pch_st_volatile_u64(&status[tile], (PCH_FLAG_AGG << 62) | aggregate);
+    uint64_t excl = 0;
+    for (int64_t t = tile - 1; t >= first; --t) {
+        uint64_t w;
+        uint32_t spins = 0;
+        do {
+            w = pch_ld_volatile_u64(&status[t]);
+            if (++spins > PCH_SPIN_LIMIT) {
+                if (err_flag) atomicExch(err_flag, 1);
+                return excl;
+            }
+        } while ((w >> 62) == PCH_FLAG_EMPTY);
+        excl += w & ((1ull << 62) - 1);
+        if ((w >> 62) == PCH_FLAG_INCL) break;
+    }
+    pch_st_volatile_u64(&status[tile], (PCH_FLAG_INCL << 62) | (excl + aggregate));
+    return excl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// unaligned little-endian XYZ fetch from a raw LAS record (X,Y,Z int32 at byte 0,4,8)
+// ALIGN = guaranteed alignment of the record start in bytes (1, 2 or 4).
+// ---------------------------------------------------------------------------------------------
+template <int ALIGN>
+__device__ __forceinline__ void pch_load_xyz(const uint8_t* p, int& X, int& Y, int& Z) {
+    if (ALIGN >= 4) {
+        const int* q = reinterpret_cast<const int*>(p);
+        X = q[0]; Y = q[1]; Z = q[2];
+    } else if (ALIGN == 2) {
+        const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+        X = (int)((uint32_t)q[0] | ((uint32_t)q[1] << 16));
+        Y = (int)((uint32_t)q[2] | ((uint32_t)q[3] << 16));
+        Z = (int)((uint32_t)q[4] | ((uint32_t)q[5] << 16));
+    } else {
+        X = (int)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+        Y = (int)((uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24));
+        Z = (int)((uint32_t)p[8] | ((uint32_t)p[9] << 8) | ((uint32_t)p[10] << 16) | ((uint32_t)p[11] << 24));
+    }
+}
+
+// x = X*scale + offset exactly as numpy/laspy evaluate it: one rounded multiply, one rounded add
+// (never contracted into an FMA).
+__device__ __forceinline__ double pch_scaled(int X, double scale, double offset) {
+    return __dadd_rn(__dmul_rn((double)X, scale), offset);
+}
+
+__device__ __forceinline__ int pch_warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int pch_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// order-preserving float32 <-> uint32 (for radix select / atomic min on floats)
+__device__ __forceinline__ uint32_t pch_f32_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pch_ordered_to_f32(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}

@@ -1,0 +1,323 @@
+// Voxel-grid downsample = open3d PointCloud.voxel_down_sample as called by
+// ui/import_PC.py:8-13 (process_chunk) / ui/Sampling.py:10-18, on the raw LAS records of each
+// `chunk_size` slice (ui/import_PC.py:45-50):
+//   plan   : origin = chunk min bound - 0.5*voxel, index ranges -> packed key layout
+//   keys   : idx = floor((p - origin)/voxel) in float64 (true divide), key = ix|iy|iz|index-in-chunk
+//   (sort) : pch_sort_u64_segmented over the key bits, per chunk
+//   reduce : per run of equal voxel, float64 running sum in input order, mean = sum/count,
+//            optional re-quantisation (ui/import_PC.py:61-63) and float32 read-back
+//            (utils/tower_extraction.py:60-62) fused into the same pass.
+#include "pch_common.cuh"
+#include "pch_tiles.cuh"
+
+struct PchAffine3 {
+    double s[3], o[3];
+};
+
+__device__ __forceinline__ int bits_for(long long v) {  // bits needed to store values 0..v
+    int b = 0;
+    while (v > 0) { ++b; v >>= 1; }
+    return b;
+}
+
+__global__ void k_voxel_plan(const int32_t* __restrict__ mm, int64_t n_chunks, int64_t chunk_size, PchAffine3 a,
+                             double voxel, double* __restrict__ origins, pch_voxel_plan* __restrict__ plan) {
+    __shared__ long long s_max[3];
+    if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
+    __syncthreads();
+    const double half = __dmul_rn(voxel, 0.5);
+    for (int64_t c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+        for (int ax = 0; ax < 3; ++ax) {
+            double lo = pch_scaled(mm[c * 6 + ax], a.s[ax], a.o[ax]);
+            double hi = pch_scaled(mm[c * 6 + 3 + ax], a.s[ax], a.o[ax]);
+            if (hi < lo) { double t = lo; lo = hi; hi = t; }  // negative scale
+            double org = __dsub_rn(lo, half);
+            origins[c * 3 + ax] = org;
+            double ref = __ddiv_rn(__dsub_rn(hi, org), voxel);
+            long long im = (long long)floor(ref);
+            atomicMax(&s_max[ax], im);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pch_voxel_plan p;
+        p.bits_x = bits_for(s_max[0]);
+        p.bits_y = bits_for(s_max[1]);
+        p.bits_z = bits_for(s_max[2]);
+        p.bits_idx = bits_for(chunk_size - 1);
+        p.key_bits = p.bits_x + p.bits_y + p.bits_z;
+        p.n_passes = (p.key_bits + 7) / 8;
+        bool ok = (p.key_bits + p.bits_idx <= 64) && s_max[0] < 2147483647ll && s_max[1] < 2147483647ll &&
+                  s_max[2] < 2147483647ll;
+        p.status = ok ? PCH_OK : PCH_ERR_RANGE;
+        p.reserved = 0;
+        *plan = p;
+    }
+}
+
+static int make_affine3(const double* scales, const double* offsets, PchAffine3& a) {
+    PCH_CHECK_ARG(scales && offsets, "null scales/offsets");
+    for (int i = 0; i < 3; ++i) {
+        a.s[i] = scales[i];
+        a.o[i] = offsets[i];
+        PCH_CHECK_ARG(scales[i] != 0.0, "zero LAS scale");
+    }
+    return PCH_OK;
+}
+
+extern "C" int pch_voxel_plan_build(const int32_t* mm, int64_t n_chunks, int64_t chunk_size, const double* scales,
+                                    const double* offsets, double voxel, double* origins, pch_voxel_plan* plan,
+                                    pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n_chunks >= 1 && chunk_size >= 1, "n_chunks and chunk_size must be >= 1");
+    PCH_CHECK_ARG(voxel > 0.0, "voxel_size must be > 0 (open3d raises otherwise)");
+    PCH_CHECK_ARG(mm && origins && plan, "null pointer");
+    PchAffine3 a;
+    int rc = make_affine3(scales, offsets, a);
+    if (rc) return rc;
+    k_voxel_plan<<<1, 256, 0, st>>>(mm, n_chunks, chunk_size, a, voxel, origins, plan);
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct KeyLayout {
+    int sh_x, sh_y, sh_z;  // left shifts of ix, iy, iz
+};
+
+template <int ALIGN>
+__global__ void __launch_bounds__(PCH_TILE_THREADS, 2)
+k_voxel_keys(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine3 a, double voxel,
+             const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    pch_stream_tiles(rec, g, smem, [&](const PchTile& t) {
+        const double ox = origins[t.chunk * 3 + 0], oy = origins[t.chunk * 3 + 1], oz = origins[t.chunk * 3 + 2];
+        const int64_t chunk_start = t.chunk * g.chunk_size;
+        for (int r = threadIdx.x; r < t.count; r += PCH_TILE_THREADS) {
+            int X, Y, Z;
+            pch_load_xyz<ALIGN>(t.base + (size_t)r * g.rec_len, X, Y, Z);
+            double x = pch_scaled(X, a.s[0], a.o[0]);
+            double y = pch_scaled(Y, a.s[1], a.o[1]);
+            double z = pch_scaled(Z, a.s[2], a.o[2]);
+            // (p - origin) / voxel with a correctly rounded divide, then floor -> int (open3d)
+            uint64_t ix = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(x, ox), voxel));
+            uint64_t iy = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(y, oy), voxel));
+            uint64_t iz = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(z, oz), voxel));
+            uint64_t local = (uint64_t)(t.r0 + r - chunk_start);
+            keys[t.r0 + r] = (ix << kl.sh_x) | (iy << kl.sh_y) | (iz << kl.sh_z) | local;
+        }
+    });
+}
+
+extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, int64_t chunk_size, const double* scales,
+                              const double* offsets, double voxel, const double* origins, const pch_voxel_plan* plan,
+                              uint64_t* keys, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && rec_len >= 12 && rec_len <= 256, "bad n/rec_len");
+    PCH_CHECK_ARG(chunk_size > 0 && voxel > 0.0, "chunk_size and voxel_size must be > 0");
+    PCH_CHECK_ARG(plan != nullptr, "null plan");
+    if (plan->status != PCH_OK || plan->key_bits + plan->bits_idx > 64) {
+        pch_set_error("voxel index range needs %d+%d bits > 64: voxel_size too small for this chunk extent",
+                      plan->key_bits, plan->bits_idx);
+        return PCH_ERR_RANGE;
+    }
+    if (n == 0) return PCH_OK;
+    PCH_CHECK_ARG(rec && origins && keys, "null pointer");
+    PCH_CHECK_ARG((reinterpret_cast<uintptr_t>(rec) & 15) == 0, "record buffer must be 16-byte aligned");
+    PchAffine3 a;
+    int rc = make_affine3(scales, offsets, a);
+    if (rc) return rc;
+    PchTileGeom g = pch_tile_geom(n, rec_len, chunk_size);
+    KeyLayout kl;
+    kl.sh_z = plan->bits_idx;
+    kl.sh_y = kl.sh_z + plan->bits_z;
+    kl.sh_x = kl.sh_y + plan->bits_y;
+    size_t smem = pch_tile_smem_bytes(g);
+    int grid = pch_tile_grid(g, 2);
+    int al = pch_rec_align(rec_len);
+#define LAUNCH_KEYS(A)                                                                                       \
+    do {                                                                                                     \
+        PCH_CUDA(cudaFuncSetAttribute(k_voxel_keys<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, voxel, origins, kl, keys);          \
+    } while (0)
+    if (al == 4) LAUNCH_KEYS(4);
+    else if (al == 2) LAUNCH_KEYS(2);
+    else LAUNCH_KEYS(1);
+#undef LAUNCH_KEYS
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segmented in-order reduction
+// ------------------------------------------------------------------------------------------------
+#define VR_THREADS 256
+#define VR_ROWS 8
+#define VR_TILE (VR_THREADS * VR_ROWS)
+#define VR_WARPS (VR_THREADS / 32)
+
+struct ReduceGeom {
+    int64_t n, chunk_size, tiles_per_chunk, total_tiles;
+    int32_t bits_idx, rec_len;
+};
+
+extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size) {
+    if (n <= 0) return 256;
+    if (chunk_size <= 0 || chunk_size > n) chunk_size = n;
+    int64_t n_chunks = pch_ceil_div(n, chunk_size);
+    int64_t tiles = n_chunks * pch_ceil_div(chunk_size, VR_TILE);
+    return 256 + (size_t)tiles * 8;
+}
+
+template <int ALIGN>
+__global__ void __launch_bounds__(VR_THREADS)
+k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec, PchAffine3 a,
+               double* __restrict__ mean_out, int32_t* __restrict__ lat_out, float* __restrict__ f32_out,
+               unsigned long long* __restrict__ chunk_counts, long long* __restrict__ total_out,
+               uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
+    __shared__ uint64_t s_keys[VR_TILE + 1];  // [0] = key preceding the tile
+    __shared__ uint32_t s_wcount[VR_WARPS];
+    __shared__ uint64_t s_tile_off;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= g.total_tiles) return;
+    const int64_t chunk = tile / g.tiles_per_chunk;
+    const int64_t lt = tile - chunk * g.tiles_per_chunk;
+    const int64_t cstart = chunk * g.chunk_size;
+    int64_t cend = cstart + g.chunk_size;
+    if (cend > g.n) cend = g.n;
+    const int64_t start = cstart + lt * VR_TILE;
+    const int cnt = (int)min((int64_t)VR_TILE, cend - start);
+    const int bi = g.bits_idx;
+    const uint64_t idx_mask = bi >= 64 ? ~0ull : ((1ull << bi) - 1ull);
+
+    for (int i = tid; i < cnt; i += VR_THREADS) s_keys[i + 1] = keys[start + i];
+    if (tid == 0) s_keys[0] = lt > 0 ? keys[start - 1] : ~0ull;
+    __syncthreads();
+
+    // head flags in warp-blocked order: warp w owns [w*256, w*256+256), row j = 32 consecutive items
+    uint32_t row_rank[VR_ROWS];
+    uint32_t head_bits = 0;
+    uint32_t wtotal = 0;
+    const int wbase = warp * (32 * VR_ROWS);
+#pragma unroll
+    for (int j = 0; j < VR_ROWS; ++j) {
+        int i = wbase + j * 32 + lane;
+        bool head = false;
+        if (i < cnt) {
+            uint64_t k = s_keys[i + 1] >> bi;
+            head = (i == 0 && lt == 0) || (k != (s_keys[i] >> bi));
+        }
+        uint32_t b = __ballot_sync(0xffffffffu, head);
+        row_rank[j] = wtotal + __popc(b & ((1u << lane) - 1u));
+        wtotal += __popc(b);
+        if (head) head_bits |= 1u << j;
+    }
+    if (lane == 0) s_wcount[warp] = wtotal;
+    __syncthreads();
+    uint32_t wprefix = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < VR_WARPS; ++w) {
+        uint32_t c = s_wcount[w];
+        if (w < warp) wprefix += c;
+        tile_total += c;
+    }
+    if (tid == 0) {
+        s_tile_off = pch_lookback_u64(status, tile, 0, tile_total, err);
+        if (chunk_counts && tile_total) atomicAdd(&chunk_counts[chunk], (unsigned long long)tile_total);
+        if (tile == g.total_tiles - 1 && total_out) *total_out = (long long)(s_tile_off + tile_total);
+    }
+    __syncthreads();
+    const uint64_t tile_off = s_tile_off;
+
+#pragma unroll
+    for (int j = 0; j < VR_ROWS; ++j) {
+        if (!(head_bits & (1u << j))) continue;
+        const int i = wbase + j * 32 + lane;
+        const uint64_t m = tile_off + wprefix + row_rank[j];
+        const uint64_t vkey = s_keys[i + 1] >> bi;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        long long cntp = 0;
+        int64_t p = start + i;
+        uint64_t k = s_keys[i + 1];
+        while (true) {
+            const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
+            int X, Y, Z;
+            pch_load_xyz<ALIGN>(q, X, Y, Z);
+            sx = __dadd_rn(sx, pch_scaled(X, a.s[0], a.o[0]));
+            sy = __dadd_rn(sy, pch_scaled(Y, a.s[1], a.o[1]));
+            sz = __dadd_rn(sz, pch_scaled(Z, a.s[2], a.o[2]));
+            ++cntp;
+            ++p;
+            if (p >= cend) break;
+            int li = (int)(p - start);
+            k = li < cnt ? s_keys[li + 1] : keys[p];
+            if ((k >> bi) != vkey) break;
+        }
+        const double dn = (double)cntp;
+        const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
+        if (mean_out) {
+            mean_out[m * 3 + 0] = mx; mean_out[m * 3 + 1] = my; mean_out[m * 3 + 2] = mz;
+        }
+        if (lat_out || f32_out) {
+            int qx = __double2int_rn(__ddiv_rn(__dsub_rn(mx, a.o[0]), a.s[0]));
+            int qy = __double2int_rn(__ddiv_rn(__dsub_rn(my, a.o[1]), a.s[1]));
+            int qz = __double2int_rn(__ddiv_rn(__dsub_rn(mz, a.o[2]), a.s[2]));
+            if (lat_out) {
+                lat_out[m * 3 + 0] = qx; lat_out[m * 3 + 1] = qy; lat_out[m * 3 + 2] = qz;
+            }
+            if (f32_out) {
+                f32_out[m * 3 + 0] = (float)pch_scaled(qx, a.s[0], a.o[0]);
+                f32_out[m * 3 + 1] = (float)pch_scaled(qy, a.s[1], a.o[1]);
+                f32_out[m * 3 + 2] = (float)pch_scaled(qz, a.s[2], a.o[2]);
+            }
+        }
+    }
+}
+
+extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
+                                const uint8_t* rec, int32_t rec_len, const double* scales, const double* offsets,
+                                double* mean_out, int32_t* lat_out, float* f32_out, int64_t* chunk_counts,
+                                int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && chunk_size > 0, "bad n/chunk_size");
+    PCH_CHECK_ARG(rec_len >= 12 && rec_len <= 256, "bad record length");
+    PCH_CHECK_ARG(bits_idx >= 0 && bits_idx <= 63, "bad bits_idx");
+    PchAffine3 a;
+    int rc = make_affine3(scales, offsets, a);
+    if (rc) return rc;
+    if (chunk_size > n) chunk_size = n > 0 ? n : 1;
+    int64_t n_chunks = pch_ceil_div(n > 0 ? n : 1, chunk_size);
+    if (chunk_counts) PCH_CUDA(cudaMemsetAsync(chunk_counts, 0, sizeof(int64_t) * n_chunks, st));
+    if (total_out) PCH_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
+    if (n == 0) return PCH_OK;
+    PCH_CHECK_ARG(keys && rec && workspace, "null pointer");
+    ReduceGeom g;
+    g.n = n; g.chunk_size = chunk_size; g.bits_idx = bits_idx; g.rec_len = rec_len;
+    g.tiles_per_chunk = pch_ceil_div(chunk_size, VR_TILE);
+    int64_t last = n - (n_chunks - 1) * chunk_size;
+    g.total_tiles = (n_chunks - 1) * g.tiles_per_chunk + pch_ceil_div(last, VR_TILE);
+    size_t need = 256 + (size_t)g.total_tiles * 8;
+    if (workspace_bytes < need) {
+        pch_set_error("voxel_reduce workspace too small: %zu < %zu", workspace_bytes, need);
+        return PCH_ERR_WORKSPACE;
+    }
+    PCH_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    int* err = (int*)workspace;
+    uint32_t* counter = (uint32_t*)((uint8_t*)workspace + 64);
+    uint64_t* status = (uint64_t*)((uint8_t*)workspace + 256);
+    int al = pch_rec_align(rec_len);
+#define LAUNCH_RED(A)                                                                                          \
+    k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
+        keys, g, rec, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
+        status, counter, err)
+    if (al == 4) LAUNCH_RED(4);
+    else if (al == 2) LAUNCH_RED(2);
+    else LAUNCH_RED(1);
+#undef LAUNCH_RED
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}

@@ -1,0 +1,201 @@
+"""Device-side orchestration: torch supplies HBM buffers, pinned staging and the CUDA stream;
+every per-point operation is a kernel of libpch_b200.so called through the C ABI (_native).
+
+Nothing here computes on the CPU and nothing falls back: without a CUDA device or without the
+built library these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import VoxelPlan, check, d3
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _native.NativeError("no CUDA device: pointcloudhookup_b200 has no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _empty(n, dtype, device):
+    return torch.empty(int(n), dtype=dtype, device=device)
+
+
+@dataclasses.dataclass
+class DeviceLas:
+    """Raw LAS point records resident in HBM (record i at byte i*rec_len, buffer padded to 16 B)."""
+    rec: torch.Tensor           # uint8, >= align16(n*rec_len) bytes
+    n: int
+    rec_len: int
+    scales: np.ndarray
+    offsets: np.ndarray
+
+    @property
+    def device(self):
+        return self.rec.device
+
+
+def padded_bytes(n: int, rec_len: int) -> int:
+    return (n * rec_len + 15) // 16 * 16 + 16
+
+
+def upload_records(records, n: int, rec_len: int, scales, offsets, device=None,
+                   pinned: Optional[torch.Tensor] = None) -> DeviceLas:
+    """Host record bytes -> HBM.  `records` is a uint8 numpy array / memmap (or a pinned uint8
+    tensor); the copy goes through pinned memory so it is a real async DMA on the current stream."""
+    _require_cuda()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    nbytes = n * rec_len
+    dev = torch.empty(padded_bytes(n, rec_len), dtype=torch.uint8, device=device)
+    if nbytes:
+        if isinstance(records, torch.Tensor):
+            host = records.view(torch.uint8).reshape(-1)[:nbytes]
+            if not host.is_pinned():
+                host = host.pin_memory()
+        else:
+            if pinned is None or pinned.numel() < nbytes:
+                pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            host = pinned[:nbytes]
+            host.numpy()[:] = np.asarray(records).view(np.uint8).reshape(-1)[:nbytes]
+        dev[:nbytes].copy_(host, non_blocking=True)
+    dev[nbytes:].zero_()
+    return DeviceLas(dev, int(n), int(rec_len), np.asarray(scales, dtype=np.float64),
+                     np.asarray(offsets, dtype=np.float64))
+
+
+# ------------------------------------------------------------------------------------------------
+def decode_xyz(dl: DeviceLas, dtype=torch.float64) -> torch.Tensor:
+    """(n,3) float64 `np.vstack((las.x,las.y,las.z)).T` or float32 `.astype(np.float32)`."""
+    out = torch.empty((dl.n, 3), dtype=dtype, device=dl.device)
+    fn = _native.lib().pch_las_decode_f64 if dtype == torch.float64 else _native.lib().pch_las_decode_f32
+    check(fn(dl.rec.data_ptr(), dl.n, dl.rec_len, d3(dl.scales), d3(dl.offsets), out.data_ptr(), _stream()),
+          "pch_las_decode")
+    return out
+
+
+def quantise(xyz: torch.Tensor, scales, offsets) -> torch.Tensor:
+    assert xyz.dtype == torch.float64 and xyz.is_contiguous()
+    m = xyz.shape[0]
+    out = torch.empty((m, 3), dtype=torch.int32, device=xyz.device)
+    check(_native.lib().pch_las_quantise(xyz.data_ptr(), m, d3(scales), d3(offsets), out.data_ptr(), _stream()),
+          "pch_las_quantise")
+    return out
+
+
+def encode_records(lattice: torch.Tensor, rec_len: int):
+    """(m,3) int32 -> (uint8 records tensor, int32[6] lattice min/max)."""
+    assert lattice.dtype == torch.int32 and lattice.is_contiguous()
+    m = lattice.shape[0]
+    out = torch.empty(padded_bytes(m, rec_len), dtype=torch.uint8, device=lattice.device)
+    mm = torch.empty(6, dtype=torch.int32, device=lattice.device)
+    check(_native.lib().pch_las_encode(lattice.data_ptr(), m, rec_len, out.data_ptr(), mm.data_ptr(), _stream()),
+          "pch_las_encode")
+    return out[: m * rec_len], mm
+
+
+def chunk_minmax(dl: DeviceLas, chunk_size: int) -> torch.Tensor:
+    cs = max(1, min(int(chunk_size), max(dl.n, 1)))
+    n_chunks = max(1, -(-dl.n // cs))
+    mm = torch.empty((n_chunks, 6), dtype=torch.int32, device=dl.device)
+    check(_native.lib().pch_las_chunk_minmax(dl.rec.data_ptr(), dl.n, dl.rec_len, cs, mm.data_ptr(), _stream()),
+          "pch_las_chunk_minmax")
+    return mm
+
+
+def sort_u64_segmented(keys: torch.Tensor, seg_size: int, bit_lo: int, bit_hi: int,
+                       tmp: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns the tensor (keys or tmp) that holds the sorted result."""
+    assert keys.dtype == torch.int64 and keys.is_contiguous()
+    n = keys.numel()
+    if n == 0 or bit_hi <= bit_lo:
+        return keys
+    lib = _native.lib()
+    if tmp is None:
+        tmp = torch.empty_like(keys)
+    ws_bytes = lib.pch_sort_workspace_bytes(n, seg_size, bit_lo, bit_hi)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    check(lib.pch_sort_u64_segmented(keys.data_ptr(), tmp.data_ptr(), n, seg_size, bit_lo, bit_hi,
+                                     ws.data_ptr(), ws_bytes, _stream()), "pch_sort_u64_segmented")
+    n_passes = (bit_hi - bit_lo + 7) // 8
+    return tmp if n_passes % 2 else keys
+
+
+@dataclasses.dataclass
+class VoxelResult:
+    count: int                              # M
+    chunk_counts: torch.Tensor              # int64 [n_chunks]
+    mean: Optional[torch.Tensor] = None     # (M,3) float64, canonical (ix,iy,iz) order per chunk
+    lattice: Optional[torch.Tensor] = None  # (M,3) int32 re-quantised
+    f32: Optional[torch.Tensor] = None      # (M,3) float32 of the re-quantised values
+    plan: Optional[dict] = None
+    sorted_keys: Optional[torch.Tensor] = None
+
+
+def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
+                     want: Sequence[str] = ("mean",), keep_keys: bool = False) -> VoxelResult:
+    """open3d voxel_down_sample over consecutive chunk_size-point slices of the records
+    (ui/import_PC.py:45-60), entirely on the device."""
+    _require_cuda()
+    if voxel_size <= 0:
+        raise ValueError("voxel_size must be > 0")
+    lib = _native.lib()
+    dev = dl.device
+    n = dl.n
+    cs = max(1, min(int(chunk_size), max(n, 1)))
+    n_chunks = max(1, -(-n // cs))
+    if n == 0:
+        z = lambda dt: torch.zeros((0, 3), dtype=dt, device=dev)
+        return VoxelResult(0, torch.zeros(n_chunks, dtype=torch.int64, device=dev),
+                           z(torch.float64) if "mean" in want else None,
+                           z(torch.int32) if "lattice" in want else None,
+                           z(torch.float32) if "f32" in want else None)
+    st = _stream()
+    sc, of = d3(dl.scales), d3(dl.offsets)
+    mm = chunk_minmax(dl, cs)
+    origins = torch.empty((n_chunks, 3), dtype=torch.float64, device=dev)
+    plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
+    check(lib.pch_voxel_plan_build(mm.data_ptr(), n_chunks, cs, sc, of, float(voxel_size), origins.data_ptr(),
+                                   plan_dev.data_ptr(), st), "pch_voxel_plan_build")
+    ph = plan_dev.cpu().numpy()
+    plan = VoxelPlan(*[int(v) for v in ph])
+    if plan.status != 0:
+        raise ValueError(f"voxel_size is too small: index range needs {plan.key_bits}+{plan.bits_idx} bits (> 64)")
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    check(lib.pch_voxel_keys(dl.rec.data_ptr(), n, dl.rec_len, cs, sc, of, float(voxel_size), origins.data_ptr(),
+                             C.byref(plan), keys.data_ptr(), st), "pch_voxel_keys")
+    skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
+    # worst case every point is its own voxel; outputs are sized n and sliced after the count is known
+    mean = torch.empty((n, 3), dtype=torch.float64, device=dev) if "mean" in want else None
+    lat = torch.empty((n, 3), dtype=torch.int32, device=dev) if "lattice" in want else None
+    f32 = torch.empty((n, 3), dtype=torch.float32, device=dev) if "f32" in want else None
+    counts = torch.empty(n_chunks, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    ws_bytes = lib.pch_voxel_reduce_workspace_bytes(n, cs)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, dl.rec.data_ptr(), dl.rec_len, sc, of,
+                               _ptr(mean), _ptr(lat), _ptr(f32), counts.data_ptr(), total.data_ptr(),
+                               ws.data_ptr(), ws_bytes, st), "pch_voxel_reduce")
+    m = int(total.item())
+    err = int(ws[:4].view(torch.int32).item())
+    if err:
+        raise _native.NativeError("device look-back spin limit hit in voxel_reduce")
+    res = VoxelResult(m, counts,
+                      mean[:m] if mean is not None else None,
+                      lat[:m] if lat is not None else None,
+                      f32[:m] if f32 is not None else None,
+                      plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_},
+                      sorted_keys=skeys if keep_keys else None)
+    return res

@@ -108,6 +108,68 @@ int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_s
                      double* mean_dev, int32_t* lattice_dev, float* f32_dev, int64_t* chunk_counts_dev,
                      int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
+/* ---------------------------------------------------------------- tower extraction, stages A/B */
+
+/* centroid = np.mean(raw_points_f32, axis=0) (utils/tower_extraction.py:63): numpy's SEQUENTIAL
+ * float32 column sums (sums3_dev, float[3]) divided in float64 and cast to float32 (centroid3_dev). */
+int pch_f32_centroid(const float* xyz_dev, int64_t m, float* sums3_dev, float* centroid3_dev,
+                     pch_stream_t stream);
+
+/* points = raw_points - centroid (utils/tower_extraction.py:64), float32 subtract.  zs_dev (m) gets
+ * the shifted z column, shifted_dev (m,3) the whole shifted cloud; either may be NULL. */
+int pch_f32_shift(const float* xyz_dev, int64_t m, const float* centroid3_dev, float* zs_dev,
+                  float* shifted_dev, pch_stream_t stream);
+
+/* The two order statistics np.percentile(z_values, 25) interpolates between
+ * (utils/tower_extraction.py:82): out2_dev = {sorted[rank0], sorted[rank1]} exactly. */
+size_t pch_select_workspace_bytes(void);
+int pch_select_f32(const float* v_dev, int64_t n, int64_t rank0, int64_t rank1, float* out2_dev,
+                   void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+
+/* filtered_points = points[z_values > thr] (utils/tower_extraction.py:83-89), order preserving.
+ * keep[i] = zs_dev[i] > thr, or keep_mask_dev[i] != 0 when zs_dev is NULL.  out_xyz_dev (kept,3)
+ * receives xyz - centroid (float32; centroid3_dev may be NULL = no shift), out_src_dev the source
+ * index of every kept point, out_mask_dev (m) the keep flags; each may be NULL.  count_dev: int64. */
+size_t pch_compact_workspace_bytes(int64_t m);
+int pch_compact_points(const float* xyz_dev, const float* zs_dev, const uint8_t* keep_mask_dev, int64_t m,
+                       const float* centroid3_dev, float thr, float* out_xyz_dev, int32_t* out_src_dev,
+                       uint8_t* out_mask_dev, int64_t* count_dev, void* workspace_dev,
+                       size_t workspace_bytes, pch_stream_t stream);
+
+/* north_star extension (no reference code): ground = min z per XY cell, keep = z - ground > hag.
+ * cell index = floor((xy - min_xy)/cell) in float32; cell_min_dev: nx*ny uint32 scratch. */
+int pch_grid_min_ground(const float* xyz_dev, int64_t m, float min_x, float min_y, float cell, int32_t nx,
+                        int32_t ny, float hag, uint32_t* cell_min_dev, uint8_t* keep_dev,
+                        float* ground_z_dev, pch_stream_t stream);
+
+/* componentwise float32 min/max of an (m,3) cloud: out6_dev = minx,miny,minz,maxx,maxy,maxz. */
+int pch_f32_minmax(const float* xyz_dev, int64_t m, float* out6_dev, pch_stream_t stream);
+
+/* ---------------------------------------------------------------- tower extraction, stage C/D */
+
+typedef struct pch_cluster_stats {
+    int64_t count;   /* points carrying this label                                   */
+    float min[3];    /* axis-aligned bounds of the cluster (float32, exact)          */
+    float max[3];
+    double sum[3];   /* float64 coordinate sums (centroid = sum/count)               */
+} pch_cluster_stats;
+
+/* sklearn DBSCAN(eps, min_samples, algorithm='ball_tree') run independently on consecutive
+ * `chunk`-point slices of the (G,3) float32 candidates, labels offset per chunk
+ * (utils/tower_extraction.py:96-122).  Two calls because the radix-pass count depends on the data:
+ *   pch_dbscan_plan  -> bounds_dev [n_chunks*6] uint32 + plan_dev (copy it to the host)
+ *   pch_dbscan_run   -> labels_dev[G] int32 (identical to the reference's all_labels, -1 = noise),
+ *                       n_clusters_dev[1] int64, stats_dev[min(K,max_clusters)] per-label reduction
+ *                       (the bounding-box / centroid inputs of utils/tower_extraction.py:131-151 and
+ *                       of the AABB variant test/008.py:302-319). */
+int pch_dbscan_plan(const float* xyz_dev, int64_t G, int64_t chunk, double eps, uint32_t* bounds_dev,
+                    pch_voxel_plan* plan_dev, pch_stream_t stream);
+size_t pch_dbscan_workspace_bytes(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t max_clusters);
+int pch_dbscan_run(const float* xyz_dev, int64_t G, int64_t chunk, double eps, int32_t min_samples,
+                   const uint32_t* bounds_dev, const pch_voxel_plan* plan, int32_t* labels_dev,
+                   int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
+                   void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,24 @@ SIGNATURES = {
     "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
+class ClusterStats(C.Structure):
+    _fields_ = [("count", C.c_int64), ("min", C.c_float * 3), ("max", C.c_float * 3), ("sum", C.c_double * 3)]
+
+
+SIGNATURES.update({
+    "pch_f32_centroid": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "pch_f32_shift": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "pch_select_workspace_bytes": (_sz, []),
+    "pch_select_f32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "pch_compact_workspace_bytes": (_sz, [_i64]),
+    "pch_compact_points": (C.c_int, [_p, _p, _p, _i64, _p, C.c_float, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_grid_min_ground": (C.c_int, [_p, _i64, C.c_float, C.c_float, C.c_float, _i32, _i32, C.c_float, _p, _p, _p, _p]),
+    "pch_f32_minmax": (C.c_int, [_p, _i64, _p, _p]),
+    "pch_dbscan_plan": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
+    "pch_dbscan_workspace_bytes": (_sz, [_i64, _i64, C.POINTER(VoxelPlan), _i64]),
+    "pch_dbscan_run": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, C.POINTER(VoxelPlan), _p, _p, _p, _i64, _p, _sz, _p]),
+})
+
 _lib = None
 _lock = threading.Lock()
 

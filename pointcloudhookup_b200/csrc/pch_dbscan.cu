@@ -1,0 +1,792 @@
+// Chunked DBSCAN with scikit-learn's exact semantics (utils/tower_extraction.py:96-122):
+//   the filtered points are cut into consecutive 50 000-point chunks; every chunk is clustered
+//   independently with DBSCAN(eps, min_samples, algorithm='ball_tree'); labels are offset per chunk.
+// sklearn rules restated (probed against scikit-learn 1.9.0):
+//   * float32 input promoted to float64; neighbour iff ((dx*dx + dy*dy) + dz*dz) <= eps*eps
+//   * core iff #neighbours INCLUDING the point itself >= min_samples
+//   * cluster ids in order of each cluster's smallest core index; a border point takes the
+//     smallest id among clusters owning a core point within eps; everything else is -1
+//   * per chunk offset: labels += clusters found in all earlier chunks.
+// All chunks are processed in ONE batch of launches (a single chunk cannot fill a B200).
+//
+// Acceleration structure (exact, never changes the predicate): per chunk a grid of cell side
+// l = eps/sqrt(3)*(1-1e-7), so any two points of one cell are neighbours (a cell with >= min_samples
+// points is all-core and all core points of a cell share a cluster), and neighbours of a point lie
+// within +-2 cells per axis.  Clusters are a union-find over CELLS that hold a core point.
+#include "pch_common.cuh"
+
+struct DbPlan {
+    int32_t bits_x, bits_y, bits_z, bits_idx, key_bits, n_passes, status, reserved;
+};
+
+struct DbGeom {
+    int64_t G, chunk, n_chunks;
+    double cell, eps2;
+    int32_t min_pts;
+    int32_t sh_x, sh_y, sh_z, bits_idx;  // key layout
+    int32_t bits_x, bits_y, bits_z;
+};
+
+static unsigned db_grid(int64_t n, int threads, int per_sm = 8) {
+    int64_t b = pch_ceil_div(n > 0 ? n : 1, threads);
+    int64_t cap = (int64_t)pch_sm_count() * per_sm;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+// ---------------------------------------------------------------- D1: chunk bounds + plan
+__global__ void k_db_bounds_init(uint32_t* mm, int64_t n_chunks) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_chunks * 6) mm[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_db_bounds(const float* __restrict__ P, int64_t G, int64_t chunk, uint32_t* __restrict__ mm) {
+    // one block handles a 4096-point slab inside one chunk
+    const int64_t slabs_per_chunk = (chunk + 4095) / 4096;
+    const int64_t n_chunks = (G + chunk - 1) / chunk;
+    for (int64_t s = blockIdx.x; s < n_chunks * slabs_per_chunk; s += gridDim.x) {
+        int64_t c = s / slabs_per_chunk, ls = s - c * slabs_per_chunk;
+        int64_t lo = c * chunk + ls * 4096, hi = min(min(lo + 4096, (c + 1) * chunk), G);
+        uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0, 0, 0};
+        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                uint32_t u = pch_f32_to_ordered(P[i * 3 + a]);
+                mn[a] = min(mn[a], u);
+                mx[a] = max(mx[a], u);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            uint32_t lo_ = __reduce_min_sync(0xffffffffu, mn[a]);
+            uint32_t hi_ = __reduce_max_sync(0xffffffffu, mx[a]);
+            if ((threadIdx.x & 31) == 0 && lo < hi) {
+                atomicMin(&mm[c * 6 + a], lo_);
+                atomicMax(&mm[c * 6 + 3 + a], hi_);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int db_bits_for(long long v) {
+    int b = 0;
+    while (v > 0) { ++b; v >>= 1; }
+    return b;
+}
+
+__device__ __forceinline__ long long db_cell_of(float v, float mn, double cell) {
+    return (long long)floor(__ddiv_rn(__dsub_rn((double)v, (double)mn), cell));
+}
+
+__global__ void k_db_plan(const uint32_t* __restrict__ mm, int64_t n_chunks, int64_t chunk, double cell, DbPlan* plan) {
+    __shared__ long long s_max[3];
+    if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t c = threadIdx.x; c < n_chunks; c += blockDim.x)
+        for (int a = 0; a < 3; ++a) {
+            float lo = pch_ordered_to_f32(mm[c * 6 + a]), hi = pch_ordered_to_f32(mm[c * 6 + 3 + a]);
+            atomicMax(&s_max[a], db_cell_of(hi, lo, cell));
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        DbPlan p;
+        // +2 guard cells on the low side are not needed (indices are >= 0); neighbours beyond the
+        // max index simply do not exist
+        p.bits_x = db_bits_for(s_max[0]); p.bits_y = db_bits_for(s_max[1]); p.bits_z = db_bits_for(s_max[2]);
+        p.bits_idx = db_bits_for(chunk - 1);
+        p.key_bits = p.bits_x + p.bits_y + p.bits_z;
+        p.n_passes = (p.key_bits + 7) / 8;
+        p.status = (p.key_bits + p.bits_idx <= 62) ? PCH_OK : PCH_ERR_RANGE;
+        p.reserved = 0;
+        *plan = p;
+    }
+}
+
+// ---------------------------------------------------------------- D2: cell keys
+__global__ void k_db_keys(const float* __restrict__ P, DbGeom g, const uint32_t* __restrict__ mm, uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < g.G; i += stride) {
+        int64_t c = i / g.chunk;
+        float mnx = pch_ordered_to_f32(mm[c * 6 + 0]), mny = pch_ordered_to_f32(mm[c * 6 + 1]), mnz = pch_ordered_to_f32(mm[c * 6 + 2]);
+        uint64_t cx = (uint64_t)db_cell_of(P[i * 3 + 0], mnx, g.cell);
+        uint64_t cy = (uint64_t)db_cell_of(P[i * 3 + 1], mny, g.cell);
+        uint64_t cz = (uint64_t)db_cell_of(P[i * 3 + 2], mnz, g.cell);
+        keys[i] = (cx << g.sh_x) | (cy << g.sh_y) | (cz << g.sh_z) | (uint64_t)(i - c * g.chunk);
+    }
+}
+
+// ---------------------------------------------------------------- D2b: cells from sorted keys
+#define DC_THREADS 256
+#define DC_ROWS 8
+#define DC_TILE (DC_THREADS * DC_ROWS)
+
+struct DbCells {
+    float4* spts;            // [G] sorted points, w = bit pattern of the in-chunk original index
+    int32_t* pt_cell;        // [G] cell index of sorted position
+    int32_t* inv_pos;        // [G] original global index -> sorted position
+    int32_t* cell_start;     // [U+1]
+    uint64_t* cell_key;      // [U] key >> bits_idx
+    int32_t* chunk_cell0;    // [n_chunks+1] first cell of each chunk
+    long long* n_cells;      // [1]
+};
+
+__global__ void __launch_bounds__(DC_THREADS)
+k_db_cells(const uint64_t* __restrict__ keys, const float* __restrict__ P, DbGeom g, DbCells o, int64_t tiles_per_chunk,
+           int64_t total_tiles, uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
+    __shared__ uint64_t s_keys[DC_TILE + 1];
+    __shared__ uint32_t s_wcount[DC_THREADS / 32];
+    __shared__ uint64_t s_off;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= total_tiles) return;
+    const int64_t c = tile / tiles_per_chunk, lt = tile - c * tiles_per_chunk;
+    const int64_t cstart = c * g.chunk, cend = min(cstart + g.chunk, g.G);
+    const int64_t start = cstart + lt * DC_TILE;
+    const int cnt = (int)min((int64_t)DC_TILE, cend - start);
+    const int bi = g.bits_idx;
+    const uint64_t idx_mask = (1ull << bi) - 1ull;
+    for (int i = tid; i < cnt; i += DC_THREADS) s_keys[i + 1] = keys[start + i];
+    if (tid == 0) s_keys[0] = lt > 0 ? keys[start - 1] : ~0ull;
+    __syncthreads();
+    uint32_t incl[DC_ROWS];
+    uint32_t head_bits = 0, wtotal = 0;
+    const int wbase = warp * (32 * DC_ROWS);
+#pragma unroll
+    for (int j = 0; j < DC_ROWS; ++j) {
+        int i = wbase + j * 32 + lane;
+        bool head = false;
+        if (i < cnt) head = (i == 0 && lt == 0) || ((s_keys[i + 1] >> bi) != (s_keys[i] >> bi));
+        uint32_t b = __ballot_sync(0xffffffffu, head);
+        incl[j] = wtotal + __popc(b & ((2u << lane) - 1u));  // heads up to and including this item
+        wtotal += __popc(b);
+        if (head) head_bits |= 1u << j;
+    }
+    if (lane == 0) s_wcount[warp] = wtotal;
+    __syncthreads();
+    uint32_t wprefix = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < DC_THREADS / 32; ++w) {
+        uint32_t cc = s_wcount[w];
+        if (w < warp) wprefix += cc;
+        total += cc;
+    }
+    if (tid == 0) {
+        s_off = pch_lookback_u64(status, tile, 0, total, err);
+        if (tile == total_tiles - 1) {
+            *o.n_cells = (long long)(s_off + total);
+            o.cell_start[s_off + total] = (int32_t)g.G;
+            o.chunk_cell0[g.n_chunks] = (int32_t)(s_off + total);
+        }
+    }
+    __syncthreads();
+    const uint64_t off = s_off + wprefix;
+#pragma unroll
+    for (int j = 0; j < DC_ROWS; ++j) {
+        int i = wbase + j * 32 + lane;
+        if (i >= cnt) continue;
+        const int64_t pos = start + i;
+        const uint64_t k = s_keys[i + 1];
+        const int64_t cell = (int64_t)(off + incl[j]) - 1;  // cell that item i belongs to
+        // NOTE: an item before the first head of this tile belongs to the last cell of the
+        // previous tile: off+incl-1 is then exactly that cell (off counts cells before the tile).
+        const int64_t orig = cstart + (int64_t)(k & idx_mask);
+        o.pt_cell[pos] = (int32_t)cell;
+        o.inv_pos[orig] = (int32_t)pos;
+        float4 v;
+        v.x = P[orig * 3 + 0]; v.y = P[orig * 3 + 1]; v.z = P[orig * 3 + 2];
+        v.w = __int_as_float((int)(k & idx_mask));
+        o.spts[pos] = v;
+        if (head_bits & (1u << j)) {
+            o.cell_start[cell] = (int32_t)pos;
+            o.cell_key[cell] = k >> bi;
+            if (i == 0 && lt == 0) o.chunk_cell0[c] = (int32_t)cell;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- D2c: neighbour columns
+// For cell u and each of the 25 (ox,oy) in [-2,2]^2: first cell index and count (<=5) of the
+// existing cells with cz in [cz-2, cz+2] — one binary search per column.
+__global__ void k_db_nbr(DbGeom g, const uint64_t* __restrict__ cell_key, const int32_t* __restrict__ cell_start,
+                         const int32_t* __restrict__ chunk_cell0, const long long* __restrict__ U_dev,
+                         int32_t* __restrict__ nbr_first, uint8_t* __restrict__ nbr_cnt) {
+    const int64_t U = *U_dev;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int bxy = g.bits_y + g.bits_z;
+    const uint64_t mz = (1ull << g.bits_z) - 1ull, my = (1ull << g.bits_y) - 1ull;
+    for (; t < U * 25; t += stride) {
+        const int64_t u = t / 25;
+        const int col = (int)(t - u * 25);
+        const int ox = col / 5 - 2, oy = col % 5 - 2;
+        const uint64_t k = cell_key[u];
+        const long long cx = (long long)(k >> bxy), cy = (long long)((k >> g.bits_z) & my), cz = (long long)(k & mz);
+        const long long nx = cx + ox, ny = cy + oy;
+        int32_t first = 0;
+        int cntc = 0;
+        if (nx >= 0 && ny >= 0 && nx < (1ll << g.bits_x) && ny < (1ll << g.bits_y)) {
+            const int64_t c = cell_start[u] / g.chunk;
+            const long long z0 = cz - 2 < 0 ? 0 : cz - 2;
+            const long long z1 = cz + 2 > (long long)mz ? (long long)mz : cz + 2;
+            const uint64_t klo = ((uint64_t)nx << bxy) | ((uint64_t)ny << g.bits_z) | (uint64_t)z0;
+            const uint64_t khi = ((uint64_t)nx << bxy) | ((uint64_t)ny << g.bits_z) | (uint64_t)z1;
+            int32_t lo = chunk_cell0[c], hi = chunk_cell0[c + 1];
+            while (lo < hi) {
+                int32_t mid = (lo + hi) >> 1;
+                if (cell_key[mid] < klo) lo = mid + 1; else hi = mid;
+            }
+            first = lo;
+            const int32_t end = chunk_cell0[c + 1];
+            while (first + cntc < end && cell_key[first + cntc] <= khi) ++cntc;
+        }
+        nbr_first[t] = first;
+        nbr_cnt[t] = (uint8_t)cntc;
+    }
+}
+
+__device__ __forceinline__ double db_dist2(const float4& a, const float4& b) {
+    double dx = __dsub_rn((double)a.x, (double)b.x);
+    double dy = __dsub_rn((double)a.y, (double)b.y);
+    double dz = __dsub_rn((double)a.z, (double)b.z);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// ---------------------------------------------------------------- D3: core points
+__global__ void __launch_bounds__(256)
+k_db_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+          const int32_t* __restrict__ cell_start, const int32_t* __restrict__ nbr_first,
+          const uint8_t* __restrict__ nbr_cnt, uint8_t* __restrict__ core) {
+    int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; pos < g.G; pos += stride) {
+        const int32_t u = pt_cell[pos];
+        int count = cell_start[u + 1] - cell_start[u];  // every cell-mate (and the point itself) is a neighbour
+        if (count < g.min_pts) {
+            const float4 p = spts[pos];
+            for (int col = 0; col < 25 && count < g.min_pts; ++col) {
+                const int32_t f = nbr_first[(int64_t)u * 25 + col];
+                const int nc = nbr_cnt[(int64_t)u * 25 + col];
+                for (int k = 0; k < nc && count < g.min_pts; ++k) {
+                    const int32_t v = f + k;
+                    if (v == u) continue;
+                    const int32_t b = cell_start[v], e = cell_start[v + 1];
+                    for (int32_t q = b; q < e; ++q) {
+                        if (db_dist2(p, spts[q]) <= g.eps2) {
+                            if (++count >= g.min_pts) break;
+                        }
+                    }
+                }
+            }
+        }
+        core[pos] = count >= g.min_pts ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------- D4a: per-cell core summary
+// cell_info[u]: number of core points and their float32 AABB (for pruning cell-pair searches)
+struct __align__(16) DbCellInfo {
+    float mn[3];
+    int32_t n_core;
+    float mx[3];
+    int32_t parent;  // union-find parent (cell index); valid when n_core > 0
+};
+
+__global__ void __launch_bounds__(256)
+k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ spts, const int32_t* __restrict__ cell_start,
+              const uint8_t* __restrict__ core, DbCellInfo* __restrict__ info) {
+    const int64_t U = *U_dev;
+    // one warp per cell
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; w < U; w += nw) {
+        const int32_t b = cell_start[w], e = cell_start[w + 1];
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        int n = 0;
+        for (int32_t q = b + lane; q < e; q += 32) {
+            if (core[q]) {
+                float4 p = spts[q];
+                mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+                mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+                ++n;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+                mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+            }
+        }
+        if (lane == 0) {
+            DbCellInfo ci;
+            ci.mn[0] = mn[0]; ci.mn[1] = mn[1]; ci.mn[2] = mn[2];
+            ci.mx[0] = mx[0]; ci.mx[1] = mx[1]; ci.mx[2] = mx[2];
+            ci.n_core = n;
+            ci.parent = (int32_t)w;
+            info[w] = ci;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- D4b: union-find over core cells
+__device__ __forceinline__ int32_t uf_find(DbCellInfo* info, int32_t x) {
+    int32_t p = ((volatile DbCellInfo*)info)[x].parent;
+    while (p != x) {
+        int32_t gp = ((volatile DbCellInfo*)info)[p].parent;
+        if (gp != p) atomicCAS(&info[x].parent, p, gp);  // path halving (benign race)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(DbCellInfo* info, int32_t a, int32_t b) {
+    while (true) {
+        a = uf_find(info, a);
+        b = uf_find(info, b);
+        if (a == b) return;
+        if (a > b) { int32_t t = a; a = b; b = t; }      // smaller index becomes the root
+        if (atomicCAS(&info[b].parent, b, a) == b) return;
+    }
+}
+
+// conservative lower bound of the squared distance from point p to an AABB, in double
+__device__ __forceinline__ double db_box_dist2(const float4& p, const float* mn, const float* mx) {
+    double d = 0.0;
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double t = 0.0;
+        if (v[a] < mn[a]) t = (double)mn[a] - (double)v[a];
+        else if (v[a] > mx[a]) t = (double)v[a] - (double)mx[a];
+        d += t * t;
+    }
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restrict__ spts,
+           const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
+           const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt, DbCellInfo* __restrict__ info) {
+    const int64_t U = *U_dev;
+    // one warp per (cell A, neighbour column); only pairs with B > A are examined
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double slack = g.eps2 * (1.0 + 1e-12);  // pruning must never drop a true neighbour pair
+    for (; w < U * 25; w += nw) {
+        const int32_t A = (int32_t)(w / 25);
+        const int col = (int)(w - (int64_t)A * 25);
+        if (info[A].n_core == 0) continue;
+        const int32_t f = nbr_first[w];
+        const int nc = nbr_cnt[w];
+        for (int k = 0; k < nc; ++k) {
+            const int32_t B = f + k;
+            if (B <= A) continue;
+            if (info[B].n_core == 0) continue;
+            int same = 0;  // already joined? (work saving only; decided by lane 0 so the warp stays uniform)
+            if (lane == 0) same = uf_find(info, A) == uf_find(info, B);
+            same = __shfl_sync(0xffffffffu, same, 0);
+            if (same) continue;
+            float amn[3], amx[3], bmn[3], bmx[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                amn[a] = info[A].mn[a]; amx[a] = info[A].mx[a];
+                bmn[a] = info[B].mn[a]; bmx[a] = info[B].mx[a];
+            }
+            // box-box distance
+            double bb = 0.0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double t = 0.0;
+                if (amx[a] < bmn[a]) t = (double)bmn[a] - (double)amx[a];
+                else if (bmx[a] < amn[a]) t = (double)amn[a] - (double)bmx[a];
+                bb += t * t;
+            }
+            if (bb > slack) continue;
+            const int32_t ab = cell_start[A], ae = cell_start[A + 1];
+            const int32_t bbeg = cell_start[B], bend = cell_start[B + 1];
+            bool found = false;
+            for (int32_t a0 = ab; a0 < ae && !found; a0 += 32) {
+                const int32_t ai = a0 + lane;
+                float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool act = false;
+                if (ai < ae && core[ai]) {
+                    pa = spts[ai];
+                    act = db_box_dist2(pa, bmn, bmx) <= slack;
+                }
+                if (!__any_sync(0xffffffffu, act)) continue;
+                for (int32_t bi = bbeg; bi < bend; ++bi) {
+                    if (!core[bi]) continue;               // warp-uniform
+                    const float4 pb = spts[bi];
+                    if (db_box_dist2(pb, amn, amx) > slack) continue;  // warp-uniform
+                    bool hit = act && (db_dist2(pa, pb) <= g.eps2);
+                    if (__any_sync(0xffffffffu, hit)) { found = true; break; }
+                }
+            }
+            if (found && lane == 0) uf_union(info, A, B);
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void k_db_flatten(const long long* __restrict__ U_dev, DbCellInfo* __restrict__ info, int32_t* __restrict__ cell_root) {
+    const int64_t U = *U_dev;
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; u < U; u += stride) {
+        int32_t r = -1;
+        if (info[u].n_core > 0) {
+            r = (int32_t)u;
+            while (info[r].parent != r) r = info[r].parent;
+        }
+        cell_root[u] = r;
+    }
+}
+
+// ---------------------------------------------------------------- D5: cluster heads (min core index)
+__global__ void k_db_mincore(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+                             const uint8_t* __restrict__ core, const int32_t* __restrict__ cell_root,
+                             int32_t* __restrict__ root_min /*[U], init INT_MAX*/) {
+    int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; pos < g.G; pos += stride) {
+        if (!core[pos]) continue;
+        const int64_t c = pos / g.chunk;
+        const int32_t orig = (int32_t)(c * g.chunk) + __float_as_int(spts[pos].w);
+        atomicMin(&root_min[cell_root[pt_cell[pos]]], orig);
+    }
+}
+
+__global__ void k_db_heads(const long long* __restrict__ U_dev, const int32_t* __restrict__ cell_root,
+                           const int32_t* __restrict__ root_min, uint8_t* __restrict__ is_head /*[G], zeroed*/) {
+    const int64_t U = *U_dev;
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; u < U; u += stride)
+        if (cell_root[u] == (int32_t)u) is_head[root_min[u]] = 1;
+}
+
+// head_list[r] = original index of the r-th cluster head (ascending) -> cluster id r
+__global__ void k_db_cluster_ids(const long long* __restrict__ K_dev, const int32_t* __restrict__ head_list,
+                                 const int32_t* __restrict__ inv_pos, const int32_t* __restrict__ pt_cell,
+                                 const int32_t* __restrict__ cell_root, int32_t* __restrict__ root_label /*[U]*/) {
+    const int64_t K = *K_dev;
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; r < K; r += stride) root_label[cell_root[pt_cell[inv_pos[head_list[r]]]]] = (int32_t)r;
+}
+
+// ---------------------------------------------------------------- D6: labels (core + border + noise)
+__global__ void __launch_bounds__(256)
+k_db_labels(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+            const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
+            const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt,
+            const int32_t* __restrict__ cell_root, const int32_t* __restrict__ root_label,
+            int32_t* __restrict__ labels /*[G] original order*/) {
+    int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; pos < g.G; pos += stride) {
+        const int32_t u = pt_cell[pos];
+        const float4 p = spts[pos];
+        const int64_t c = pos / g.chunk;
+        const int64_t orig = c * g.chunk + __float_as_int(p.w);
+        int32_t lab;
+        if (core[pos]) {
+            lab = root_label[cell_root[u]];
+        } else {
+            int32_t best = INT_MAX;
+            for (int col = 0; col < 25; ++col) {
+                const int32_t f = nbr_first[(int64_t)u * 25 + col];
+                const int nc = nbr_cnt[(int64_t)u * 25 + col];
+                for (int k = 0; k < nc; ++k) {
+                    const int32_t v = f + k;
+                    const int32_t rt = cell_root[v];
+                    if (rt < 0) continue;                 // no core point in that cell
+                    const int32_t cl = root_label[rt];
+                    if (cl >= best) continue;
+                    const int32_t b = cell_start[v], e = cell_start[v + 1];
+                    for (int32_t q = b; q < e; ++q) {
+                        if (core[q] && db_dist2(p, spts[q]) <= g.eps2) { best = cl; break; }
+                    }
+                }
+            }
+            lab = best == INT_MAX ? -1 : best;
+        }
+        labels[orig] = lab;
+    }
+}
+
+// ---------------------------------------------------------------- D7: per-cluster reduction
+// acc[k]: count, float32 AABB (ordered-uint encoded while reducing), float64 coordinate sums
+struct DbClusterAcc {
+    unsigned long long count;
+    uint32_t mn[3], mx[3];
+    double sum[3];
+};
+
+__global__ void k_db_acc_init(int64_t cap, DbClusterAcc* acc) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < cap; k += stride) {
+        DbClusterAcc a;
+        a.count = 0;
+        for (int i = 0; i < 3; ++i) { a.mn[i] = 0xffffffffu; a.mx[i] = 0u; a.sum[i] = 0.0; }
+        acc[k] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ labels, int64_t G, int64_t cap,
+                    DbClusterAcc* __restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t Gpad = (G + 31) / 32 * 32;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // multiple of 32: whole warps stay together
+    for (; i < Gpad; i += stride) {
+        int32_t lab = -1;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < G) {
+            lab = labels[i];
+            if (lab >= cap) lab = -1;
+            if (lab >= 0) { x = P[i * 3 + 0]; y = P[i * 3 + 1]; z = P[i * 3 + 2]; }
+        }
+        const int32_t lab0 = __shfl_sync(0xffffffffu, lab, 0);
+        const bool uniform = __all_sync(0xffffffffu, lab == lab0);
+        uint32_t ux = pch_f32_to_ordered(x), uy = pch_f32_to_ordered(y), uz = pch_f32_to_ordered(z);
+        if (uniform) {
+            if (lab0 < 0) continue;  // warp-uniform
+            uint32_t mnx = __reduce_min_sync(0xffffffffu, ux), mny = __reduce_min_sync(0xffffffffu, uy),
+                     mnz = __reduce_min_sync(0xffffffffu, uz);
+            uint32_t mxx = __reduce_max_sync(0xffffffffu, ux), mxy = __reduce_max_sync(0xffffffffu, uy),
+                     mxz = __reduce_max_sync(0xffffffffu, uz);
+            double sx = x, sy = y, sz = z;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            }
+            if (lane == 0) {
+                DbClusterAcc* a = &acc[lab0];
+                atomicAdd(&a->count, 32ull);
+                atomicMin(&a->mn[0], mnx); atomicMin(&a->mn[1], mny); atomicMin(&a->mn[2], mnz);
+                atomicMax(&a->mx[0], mxx); atomicMax(&a->mx[1], mxy); atomicMax(&a->mx[2], mxz);
+                atomicAdd(&a->sum[0], sx); atomicAdd(&a->sum[1], sy); atomicAdd(&a->sum[2], sz);
+            }
+        } else if (lab >= 0) {
+            DbClusterAcc* a = &acc[lab];
+            atomicAdd(&a->count, 1ull);
+            atomicMin(&a->mn[0], ux); atomicMin(&a->mn[1], uy); atomicMin(&a->mn[2], uz);
+            atomicMax(&a->mx[0], ux); atomicMax(&a->mx[1], uy); atomicMax(&a->mx[2], uz);
+            atomicAdd(&a->sum[0], (double)x); atomicAdd(&a->sum[1], (double)y); atomicAdd(&a->sum[2], (double)z);
+        }
+    }
+}
+
+__global__ void k_db_acc_finish(int64_t cap, const long long* __restrict__ K_dev, const DbClusterAcc* __restrict__ acc,
+                                pch_cluster_stats* __restrict__ out) {
+    const int64_t K = min((int64_t)*K_dev, cap);
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < K; k += stride) {
+        pch_cluster_stats s;
+        s.count = (int64_t)acc[k].count;
+        for (int i = 0; i < 3; ++i) {
+            s.min[i] = pch_ordered_to_f32(acc[k].mn[i]);
+            s.max[i] = pch_ordered_to_f32(acc[k].mx[i]);
+            s.sum[i] = acc[k].sum[i];
+        }
+        out[k] = s;
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static double db_cell_side(double eps) { return eps / sqrt(3.0) * (1.0 - 1e-7); }
+
+extern "C" int pch_dbscan_plan(const float* P, int64_t G, int64_t chunk, double eps, uint32_t* bounds_dev,
+                               pch_voxel_plan* plan_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(G >= 1 && chunk >= 1, "G and chunk must be >= 1");
+    PCH_CHECK_ARG(eps > 0.0, "eps must be > 0");
+    PCH_CHECK_ARG(G < (1ll << 31), "more than 2^31-1 candidate points");
+    PCH_CHECK_ARG(P && bounds_dev && plan_dev, "null pointer");
+    if (chunk > G) chunk = G;
+    int64_t n_chunks = pch_ceil_div(G, chunk);
+    k_db_bounds_init<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>(bounds_dev, n_chunks);
+    PCH_LAUNCH_CHECK();
+    k_db_bounds<<<db_grid(G, 4096, 16), 256, 0, st>>>(P, G, chunk, bounds_dev);
+    PCH_LAUNCH_CHECK();
+    k_db_plan<<<1, 256, 0, st>>>(bounds_dev, n_chunks, chunk, db_cell_side(eps), (DbPlan*)plan_dev);
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+struct DbWs {
+    size_t total;
+    size_t keys, tmp, sortws, sortws_bytes, spts, pt_cell, inv_pos, cell_start, cell_key, chunk_cell0, scalars,
+        nbr_first, nbr_cnt, core, info, cell_root, root_min, root_label, is_head, head_list, scan_status, acc;
+};
+
+extern "C" size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi);
+extern "C" int pch_sort_u64_segmented(uint64_t* keys, uint64_t* tmp, int64_t n, int64_t seg_size, int32_t bit_lo,
+                                      int32_t bit_hi, void* workspace, size_t workspace_bytes, pch_stream_t stream);
+extern "C" size_t pch_compact_workspace_bytes(int64_t m);
+extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8_t* keep_mask, int64_t m,
+                                  const float* centroid3, float thr, float* out_xyz, int32_t* out_src,
+                                  uint8_t* out_mask, int64_t* count_dev, void* workspace, size_t workspace_bytes,
+                                  pch_stream_t stream);
+
+static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t max_clusters) {
+    DbWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += pch_align_up(bytes, 256); return o; };
+    int64_t n_chunks = pch_ceil_div(G, chunk);
+    int64_t tiles = n_chunks * pch_ceil_div(chunk, DC_TILE);
+    w.scalars = take(256);  // [0]=err int, [64]=tile counter, [128]=n_cells (i64), [136]=n_clusters (i64)
+    w.keys = take((size_t)G * 8);
+    w.tmp = take((size_t)G * 8);
+    w.sortws_bytes = pch_sort_workspace_bytes(G, chunk, plan->bits_idx, plan->bits_idx + plan->key_bits);
+    w.sortws = take(w.sortws_bytes);
+    w.spts = take((size_t)G * 16);
+    w.pt_cell = take((size_t)G * 4);
+    w.inv_pos = take((size_t)G * 4);
+    w.cell_start = take((size_t)(G + 1) * 4);
+    w.cell_key = take((size_t)G * 8);
+    w.chunk_cell0 = take((size_t)(n_chunks + 1) * 4);
+    w.nbr_first = take((size_t)G * 25 * 4);
+    w.nbr_cnt = take((size_t)G * 25);
+    w.core = take((size_t)G);
+    w.info = take((size_t)G * sizeof(DbCellInfo));
+    w.cell_root = take((size_t)G * 4);
+    w.root_min = take((size_t)G * 4);
+    w.root_label = take((size_t)G * 4);
+    w.is_head = take((size_t)G);
+    w.head_list = take((size_t)G * 4);
+    size_t sc = (size_t)tiles * 8 + 256;
+    size_t cw = pch_compact_workspace_bytes(G);
+    w.scan_status = take(sc > cw ? sc : cw);
+    w.acc = take((size_t)max_clusters * sizeof(DbClusterAcc));
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t pch_dbscan_workspace_bytes(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t max_clusters) {
+    if (G <= 0 || !plan) return 256;
+    if (chunk > G) chunk = G;
+    return db_ws(G, chunk, plan, max_clusters).total;
+}
+
+extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts,
+                              const uint32_t* bounds_dev, const pch_voxel_plan* plan, int32_t* labels_dev,
+                              int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
+                              void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(G >= 1 && chunk >= 1 && min_pts >= 1 && eps > 0.0, "bad G/chunk/min_samples/eps");
+    PCH_CHECK_ARG(G < (1ll << 31), "more than 2^31-1 candidate points");
+    PCH_CHECK_ARG(P && bounds_dev && plan && labels_dev && n_clusters_dev && workspace, "null pointer");
+    PCH_CHECK_ARG(max_clusters >= 1 && (stats_dev != nullptr), "stats buffer required");
+    if (plan->status != PCH_OK) {
+        pch_set_error("DBSCAN cell grid needs %d+%d key bits", plan->key_bits, plan->bits_idx);
+        return PCH_ERR_RANGE;
+    }
+    if (chunk > G) chunk = G;
+    DbWs w = db_ws(G, chunk, plan, max_clusters);
+    if (workspace_bytes < w.total) {
+        pch_set_error("dbscan workspace too small: %zu < %zu", workspace_bytes, w.total);
+        return PCH_ERR_WORKSPACE;
+    }
+    uint8_t* base = (uint8_t*)workspace;
+    int* err = (int*)(base + w.scalars);
+    uint32_t* counter = (uint32_t*)(base + w.scalars + 64);
+    long long* U_dev = (long long*)(base + w.scalars + 128);
+    uint64_t* keys = (uint64_t*)(base + w.keys);
+    uint64_t* tmp = (uint64_t*)(base + w.tmp);
+
+    DbGeom g;
+    g.G = G; g.chunk = chunk; g.n_chunks = pch_ceil_div(G, chunk);
+    g.cell = db_cell_side(eps);
+    g.eps2 = eps * eps;
+    g.min_pts = min_pts;
+    g.bits_idx = plan->bits_idx;
+    g.bits_x = plan->bits_x; g.bits_y = plan->bits_y; g.bits_z = plan->bits_z;
+    g.sh_z = plan->bits_idx; g.sh_y = g.sh_z + plan->bits_z; g.sh_x = g.sh_y + plan->bits_y;
+
+    PCH_CUDA(cudaMemsetAsync(base + w.scalars, 0, 256, st));
+    k_db_keys<<<db_grid(G, 256), 256, 0, st>>>(P, g, bounds_dev, keys);
+    PCH_LAUNCH_CHECK();
+    int rc = pch_sort_u64_segmented(keys, tmp, G, chunk, plan->bits_idx, plan->bits_idx + plan->key_bits,
+                                    base + w.sortws, w.sortws_bytes, stream);
+    if (rc) return rc;
+    const uint64_t* skeys = (plan->n_passes % 2) ? tmp : keys;
+
+    DbCells o;
+    o.spts = (float4*)(base + w.spts);
+    o.pt_cell = (int32_t*)(base + w.pt_cell);
+    o.inv_pos = (int32_t*)(base + w.inv_pos);
+    o.cell_start = (int32_t*)(base + w.cell_start);
+    o.cell_key = (uint64_t*)(base + w.cell_key);
+    o.chunk_cell0 = (int32_t*)(base + w.chunk_cell0);
+    o.n_cells = U_dev;
+    int64_t tiles_per_chunk = pch_ceil_div(chunk, DC_TILE);
+    int64_t last = G - (g.n_chunks - 1) * chunk;
+    int64_t total_tiles = (g.n_chunks - 1) * tiles_per_chunk + pch_ceil_div(last, DC_TILE);
+    uint64_t* status = (uint64_t*)(base + w.scan_status);
+    PCH_CUDA(cudaMemsetAsync(status, 0, (size_t)total_tiles * 8, st));
+    k_db_cells<<<(unsigned)total_tiles, DC_THREADS, 0, st>>>(skeys, P, g, o, tiles_per_chunk, total_tiles, status, counter, err);
+    PCH_LAUNCH_CHECK();
+
+    int32_t* nbr_first = (int32_t*)(base + w.nbr_first);
+    uint8_t* nbr_cnt = (uint8_t*)(base + w.nbr_cnt);
+    uint8_t* core = base + w.core;
+    DbCellInfo* info = (DbCellInfo*)(base + w.info);
+    int32_t* cell_root = (int32_t*)(base + w.cell_root);
+    int32_t* root_min = (int32_t*)(base + w.root_min);
+    int32_t* root_label = (int32_t*)(base + w.root_label);
+    uint8_t* is_head = base + w.is_head;
+    int32_t* head_list = (int32_t*)(base + w.head_list);
+    DbClusterAcc* acc = (DbClusterAcc*)(base + w.acc);
+
+    k_db_nbr<<<db_grid(G, 256), 256, 0, st>>>(g, o.cell_key, o.cell_start, o.chunk_cell0, U_dev, nbr_first, nbr_cnt);
+    PCH_LAUNCH_CHECK();
+    k_db_core<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt, core);
+    PCH_LAUNCH_CHECK();
+    k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info);
+    PCH_LAUNCH_CHECK();
+    k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first, nbr_cnt, info);
+    PCH_LAUNCH_CHECK();
+    k_db_flatten<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info, cell_root);
+    PCH_LAUNCH_CHECK();
+    PCH_CUDA(cudaMemsetAsync(root_min, 0x7f, (size_t)G * 4, st));
+    PCH_CUDA(cudaMemsetAsync(is_head, 0, (size_t)G, st));
+    k_db_mincore<<<db_grid(G, 256), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_min);
+    PCH_LAUNCH_CHECK();
+    k_db_heads<<<db_grid(G, 256), 256, 0, st>>>(U_dev, cell_root, root_min, is_head);
+    PCH_LAUNCH_CHECK();
+    // cluster ids = rank of each head in original order (exclusive scan of head flags, all chunks at once:
+    // this IS the reference's running `current_label` offset)
+    rc = pch_compact_points(P, nullptr, is_head, G, nullptr, 0.f, nullptr, head_list, nullptr, n_clusters_dev,
+                            base + w.scan_status, pch_compact_workspace_bytes(G), stream);
+    if (rc) return rc;
+    k_db_cluster_ids<<<db_grid(G, 256), 256, 0, st>>>((const long long*)n_clusters_dev, head_list, o.inv_pos, o.pt_cell,
+                                                      cell_root, root_label);
+    PCH_LAUNCH_CHECK();
+    k_db_labels<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first, nbr_cnt, cell_root,
+                                                     root_label, labels_dev);
+    PCH_LAUNCH_CHECK();
+    k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc);
+    PCH_LAUNCH_CHECK();
+    k_db_cluster_reduce<<<db_grid(G, 256), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc);
+    PCH_LAUNCH_CHECK();
+    k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev);
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}

@@ -199,3 +199,134 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
                       plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_},
                       sorted_keys=skeys if keep_keys else None)
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# tower extraction, device stages
+# ------------------------------------------------------------------------------------------------
+def f32_centroid(xyz: torch.Tensor):
+    """np.mean(raw_points_f32, axis=0) bit-exactly: (centroid float32[3], sequential sums float32[3])."""
+    assert xyz.dtype == torch.float32 and xyz.is_contiguous()
+    sums = torch.empty(3, dtype=torch.float32, device=xyz.device)
+    cen = torch.empty(3, dtype=torch.float32, device=xyz.device)
+    check(_native.lib().pch_f32_centroid(xyz.data_ptr(), xyz.shape[0], sums.data_ptr(), cen.data_ptr(), _stream()),
+          "pch_f32_centroid")
+    return cen, sums
+
+
+def f32_shift(xyz: torch.Tensor, centroid: torch.Tensor, want_z=True, want_xyz=False):
+    m = xyz.shape[0]
+    zs = torch.empty(m, dtype=torch.float32, device=xyz.device) if want_z else None
+    sh = torch.empty((m, 3), dtype=torch.float32, device=xyz.device) if want_xyz else None
+    check(_native.lib().pch_f32_shift(xyz.data_ptr(), m, centroid.data_ptr(), _ptr(zs), _ptr(sh), _stream()),
+          "pch_f32_shift")
+    return zs, sh
+
+
+def select_f32(v: torch.Tensor, rank0: int, rank1: int) -> torch.Tensor:
+    """Exact order statistics sorted(v)[rank0], sorted(v)[rank1] as a float32[2] device tensor."""
+    assert v.dtype == torch.float32 and v.is_contiguous()
+    lib = _native.lib()
+    wsb = lib.pch_select_workspace_bytes()
+    ws = torch.empty(wsb, dtype=torch.uint8, device=v.device)
+    out = torch.empty(2, dtype=torch.float32, device=v.device)
+    check(lib.pch_select_f32(v.data_ptr(), v.numel(), int(rank0), int(rank1), out.data_ptr(), ws.data_ptr(), wsb,
+                             _stream()), "pch_select_f32")
+    return out
+
+
+def compact_points(xyz: torch.Tensor, zs: Optional[torch.Tensor], thr: float,
+                   centroid: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None,
+                   want_src: bool = False, want_mask: bool = False):
+    """(filtered (G,3) float32 = xyz[keep] - centroid, G, src index or None, mask or None)."""
+    assert xyz.dtype == torch.float32 and xyz.is_contiguous()
+    lib = _native.lib()
+    m = xyz.shape[0]
+    dev = xyz.device
+    out = torch.empty((m, 3), dtype=torch.float32, device=dev)
+    src = torch.empty(m, dtype=torch.int32, device=dev) if want_src else None
+    mask = torch.empty(m, dtype=torch.uint8, device=dev) if want_mask else None
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    wsb = lib.pch_compact_workspace_bytes(m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(lib.pch_compact_points(xyz.data_ptr(), _ptr(zs), _ptr(keep_mask), m, _ptr(centroid), float(thr),
+                                 out.data_ptr(), _ptr(src), _ptr(mask), cnt.data_ptr(), ws.data_ptr(), wsb,
+                                 _stream()), "pch_compact_points")
+    g = int(cnt.item())
+    return out[:g], g, (src[:g] if src is not None else None), mask
+
+
+def f32_minmax(xyz: torch.Tensor) -> np.ndarray:
+    out = torch.empty(6, dtype=torch.float32, device=xyz.device)
+    check(_native.lib().pch_f32_minmax(xyz.data_ptr(), xyz.shape[0], out.data_ptr(), _stream()), "pch_f32_minmax")
+    return out.cpu().numpy()
+
+
+def grid_min_ground(xyz: torch.Tensor, cell: float = 2.0, hag: float = 3.0):
+    """north_star grid min-z ground model: (keep mask uint8 (m), ground_z float32 (m))."""
+    assert xyz.dtype == torch.float32 and xyz.is_contiguous()
+    m = xyz.shape[0]
+    dev = xyz.device
+    if m == 0:
+        return torch.zeros(0, dtype=torch.uint8, device=dev), torch.zeros(0, dtype=torch.float32, device=dev)
+    mm = f32_minmax(xyz)
+    c = np.float32(cell)
+    nx = int(np.floor((mm[3] - mm[0]) / c)) + 1
+    ny = int(np.floor((mm[4] - mm[1]) / c)) + 1
+    cell_min = torch.empty(nx * ny, dtype=torch.int32, device=dev)
+    keep = torch.empty(m, dtype=torch.uint8, device=dev)
+    gz = torch.empty(m, dtype=torch.float32, device=dev)
+    check(_native.lib().pch_grid_min_ground(xyz.data_ptr(), m, float(mm[0]), float(mm[1]), float(c), nx, ny,
+                                            float(np.float32(hag)), cell_min.data_ptr(), keep.data_ptr(),
+                                            gz.data_ptr(), _stream()), "pch_grid_min_ground")
+    return keep, gz
+
+
+@dataclasses.dataclass
+class DbscanResult:
+    labels: torch.Tensor          # int32 [G], the reference's all_labels
+    n_clusters: int
+    stats: np.ndarray             # structured host array [K]: count, min[3], max[3], sum[3]
+
+
+STATS_DTYPE = np.dtype([("count", "<i8"), ("min", "<f4", 3), ("max", "<f4", 3), ("sum", "<f8", 3)])
+assert STATS_DTYPE.itemsize == C.sizeof(_native.ClusterStats) == 56
+
+
+def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80, chunk: int = 50000) -> DbscanResult:
+    """Chunked sklearn-exact DBSCAN of the (G,3) float32 candidates (utils/tower_extraction.py:96-122)."""
+    _require_cuda()
+    assert points.dtype == torch.float32 and points.is_contiguous()
+    lib = _native.lib()
+    dev = points.device
+    G = points.shape[0]
+    if G == 0:
+        return DbscanResult(torch.zeros(0, dtype=torch.int32, device=dev), 0, np.zeros(0, dtype=STATS_DTYPE))
+    ch = max(1, min(int(chunk), G))
+    n_chunks = -(-G // ch)
+    st = _stream()
+    bounds = torch.empty(n_chunks * 6, dtype=torch.int32, device=dev)
+    plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
+    check(lib.pch_dbscan_plan(points.data_ptr(), G, ch, float(eps), bounds.data_ptr(), plan_dev.data_ptr(), st),
+          "pch_dbscan_plan")
+    plan = VoxelPlan(*[int(v) for v in plan_dev.cpu().numpy()])
+    if plan.status != 0:
+        raise ValueError("DBSCAN cell grid does not fit the packed key")
+    labels = torch.empty(G, dtype=torch.int32, device=dev)
+    nclu = torch.empty(1, dtype=torch.int64, device=dev)
+    cap = max(1024, G // 8)
+    while True:
+        stats = torch.empty(cap * STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        wsb = lib.pch_dbscan_workspace_bytes(G, ch, C.byref(plan), cap)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.pch_dbscan_run(points.data_ptr(), G, ch, float(eps), int(min_samples), bounds.data_ptr(),
+                                 C.byref(plan), labels.data_ptr(), nclu.data_ptr(), stats.data_ptr(), cap,
+                                 ws.data_ptr(), wsb, st), "pch_dbscan_run")
+        k = int(nclu.item())
+        if int(ws[:4].view(torch.int32).item()):
+            raise _native.NativeError("device look-back spin limit hit in dbscan")
+        if k <= cap:
+            break
+        cap = k
+    host = stats[: k * STATS_DTYPE.itemsize].cpu().numpy().view(STATS_DTYPE).copy()
+    return DbscanResult(labels, k, host)

@@ -1,0 +1,109 @@
+"""Host epilogue: minimum-volume oriented box of ONE cluster, the role trimesh plays in the reference
+(``trimesh.PointCloud(cluster_points).bounding_box_oriented``, utils/tower_extraction.py:137-139).
+
+This is O(#clusters) work on clusters that survived the device-side AABB pre-filter, exactly where
+the reference calls into trimesh/Qhull; scipy's ConvexHull is the same Qhull.  trimesh is absent and
+unpinned in the reference, so the algorithm is restated from its documented behaviour (SURVEY.md
+A.5): hull -> unique face normals (hemisphere-folded, spherical angles rounded to 1 decimal) ->
+for each, rotate normal to +Z, min-area edge-aligned rectangle of the projected hull -> smallest
+volume.  Extents stay in (rect long, rect short, along-normal) order unless ``ordered``.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.spatial import ConvexHull
+
+_TOL = np.finfo(np.float64).resolution * 100
+
+
+def _fold_to_hemisphere(normals: np.ndarray) -> np.ndarray:
+    n = np.array(normals, dtype=np.float64)
+    negative = n < -_TOL
+    zero = ~(negative | (n > _TOL))
+    sign = np.ones(len(n))
+    sign[negative[:, 2]] = -1.0
+    sign[zero[:, 2] & negative[:, 1]] = -1.0
+    sign[zero[:, 2] & zero[:, 1] & negative[:, 0]] = -1.0
+    return n * sign[:, None]
+
+
+def _to_plane_matrix(theta: float, phi: float) -> np.ndarray:
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+    spherical = np.array([[ct, -st, 0.0], [st, ct, 0.0], [0.0, 0.0, 1.0]]) @ \
+        np.array([[cp, 0.0, sp], [0.0, 1.0, 0.0], [-sp, 0.0, cp]])
+    out = np.eye(4)
+    out[:3, :3] = spherical.T
+    return out
+
+
+def _planar(theta: float, offset=(0.0, 0.0)) -> np.ndarray:
+    c, s = np.cos(theta), np.sin(theta)
+    t = np.eye(3)
+    t[0, :2] = [c, s]
+    t[1, :2] = [-s, c]
+    t[:2, 2] = offset
+    return t
+
+
+def min_area_rectangle(xy: np.ndarray):
+    hull = ConvexHull(xy, qhull_options="QbB")
+    seg = hull.points[hull.simplices]
+    verts = hull.points[hull.vertices]
+    edge = seg[:, 1] - seg[:, 0]
+    length = np.sqrt(np.dot(edge ** 2, [1, 1]))
+    keep = length > 1e-10
+    edge = edge[keep] / length[keep].reshape((-1, 1))
+    perp = np.fliplr(edge) * [-1.0, 1.0]
+    px = np.dot(edge, verts.T)
+    py = np.dot(perp, verts.T)
+    bounds = np.column_stack((px.min(axis=1), py.min(axis=1), px.max(axis=1), py.max(axis=1)))
+    extents = np.diff(bounds.reshape((-1, 2, 2)), axis=1).reshape((-1, 2))
+    best = np.prod(extents, axis=1).argmin()
+    rect = extents[best]
+    offset = -bounds[best][:2] - rect * 0.5
+    theta = np.arctan2(*edge[best][::-1])
+    t = _planar(theta, offset)
+    if rect[0] < rect[1]:
+        t = _planar(np.pi / 2) @ t
+        rect = np.roll(rect, 1)
+    return t, rect
+
+
+def oriented_bounds(points: np.ndarray, angle_digits: int = 1, ordered: bool = False):
+    pts = np.asarray(points, dtype=np.float64)
+    hull = ConvexHull(pts, qhull_options="QbB Pp Qt")
+    verts = pts[hull.vertices]
+    hemi = _fold_to_hemisphere(hull.equations[:, :3])
+    angles = np.column_stack((np.arctan2(hemi[:, 1], hemi[:, 0]), np.arccos(np.clip(hemi[:, 2], -1.0, 1.0))))
+    _, first = np.unique(np.round(angles * 10 ** angle_digits).astype(np.int64), axis=0, return_index=True)
+    best_volume, best = np.inf, None
+    for i in first:
+        to_plane = _to_plane_matrix(angles[i, 0], angles[i, 1])
+        proj = verts @ to_plane[:3, :3].T + to_plane[:3, 3]
+        thick = np.ptp(proj[:, 2])
+        rot2, rect = min_area_rectangle(proj[:, :2])
+        vol = np.prod(rect) * thick
+        if vol < best_volume:
+            best_volume = vol
+            ext = np.append(rect, thick)
+            rz = np.eye(4)
+            rz[:2, :2] = rot2[:2, :2]
+            best = (to_plane.copy(), rz)
+    to_origin = best[1] @ best[0]
+    moved = verts @ to_origin[:3, :3].T + to_origin[:3, 3]
+    to_origin[:3, 3] = -(moved.min(axis=0) + np.ptp(moved, axis=0) * 0.5)
+    if ordered:
+        order = ext.argsort()
+        ext = ext[order]
+        flip = np.eye(4)
+        flip[:3, :3] = -np.eye(3)[order]
+        flip[:3, :3] *= np.linalg.det(flip[:3, :3])
+        to_origin = flip @ to_origin
+    return to_origin, ext
+
+
+def bounding_box_oriented(points: np.ndarray, ordered: bool = False):
+    """(transform box->world 4x4, extents (3,)) — the ``obb.transform`` / ``obb.extents`` the
+    reference reads (utils/tower_extraction.py:139,151,165)."""
+    to_origin, ext = oriented_bounds(points, ordered=ordered)
+    return np.linalg.inv(to_origin), ext

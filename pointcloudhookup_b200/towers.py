@@ -1,0 +1,203 @@
+"""Tower extraction pipeline (utils/tower_extraction.py:57-218) on the device.
+
+Per-point work (float32 cast, centroid, shift, order statistics, height filter, chunked DBSCAN,
+per-cluster reduction) is CUDA (device.py -> libpch_b200.so).  What stays on the host is the
+reference's O(#clusters) control flow, reproduced literally: numpy's percentile index/lerp
+arithmetic on two scalars, ``set(all_labels) - {-1}`` iteration order, the size filter, the 30 m
+duplicate check, the north angle, and (box="obb") the trimesh-style oriented box of each cluster.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from . import device as dv
+
+DBSCAN_CHUNK = 50000  # utils/tower_extraction.py:96
+
+
+# ---------------------------------------------------------------------------------------------
+# numpy.percentile(float32 array, q) index / interpolation arithmetic, restated with the same
+# public numpy operations numpy 2.x executes (lib/_function_base_impl.py: percentile, _quantile,
+# _get_indexes, _get_gamma, _lerp) so dtype promotion and rounding are identical.
+# ---------------------------------------------------------------------------------------------
+def percentile_ranks_f32(n: int, q: float):
+    """(rank_prev, rank_next, gamma) of np.percentile(a_f32, q) for len(a) == n."""
+    qa = np.true_divide(q, np.float32(100), out=...)
+    vi = np.asanyarray((n - 1) * qa)
+    prev = np.asanyarray(np.floor(vi))
+    nxt = np.asanyarray(prev + 1)
+    if (vi >= n - 1).any():
+        prev[...] = -1
+        nxt[...] = -1
+    if (vi < 0).any():
+        prev[...] = 0
+        nxt[...] = 0
+    prev_i = prev.astype(np.intp)
+    next_i = nxt.astype(np.intp)
+    gamma = np.asanyarray(vi - prev_i)
+    gamma = np.asanyarray(gamma, dtype=vi.dtype)
+    return int(prev_i) % n, int(next_i) % n, gamma
+
+
+def percentile_lerp_f32(a: np.float32, b: np.float32, gamma):
+    a = np.asanyarray(a, dtype=np.float32)
+    b = np.asanyarray(b, dtype=np.float32)
+    t = gamma
+    diff = np.subtract(b, a)
+    lerp = np.asanyarray(np.add(a, diff * t))
+    np.subtract(b, diff * (1 - t), out=lerp, where=t >= 0.5, casting="unsafe", dtype=type(lerp.dtype))
+    return lerp[()]
+
+
+@dataclasses.dataclass
+class TowerStages:
+    """Device-resident intermediates of one extract_towers run (kept for parity tests)."""
+    raw: torch.Tensor               # (M,3) float32 raw_points
+    centroid: np.ndarray            # float32[3]
+    base: np.float32
+    offset_used: float
+    filtered: torch.Tensor          # (G,3) float32 = points[z > thr]
+    labels: torch.Tensor            # (G,) int32 all_labels
+    n_clusters: int
+    stats: np.ndarray               # per-label count / AABB / sums (host)
+    mask: Optional[torch.Tensor] = None
+
+
+def ground_filter_percentile(raw: torch.Tensor, pct: float = 25, offset: float = 3.0, min_keep: int = 1000,
+                             fallback_offset: float = 1.0, want_mask: bool = False):
+    """Stages A+B: centroid, shift, percentile threshold, compaction."""
+    m = raw.shape[0]
+    cen_dev, _ = dv.f32_centroid(raw)
+    zs, _ = dv.f32_shift(raw, cen_dev, want_z=True)
+    r0, r1, gamma = percentile_ranks_f32(m, pct)
+    two = dv.select_f32(zs, r0, r1).cpu().numpy()
+    base = percentile_lerp_f32(two[0], two[1], gamma)
+    thr = base + offset                      # np.float32 + python float -> float32 (NEP 50)
+    filtered, g, _, mask = dv.compact_points(raw, zs, float(thr), cen_dev, want_mask=want_mask)
+    used = offset
+    if g < min_keep:
+        thr = base + fallback_offset
+        filtered, g, _, mask = dv.compact_points(raw, zs, float(thr), cen_dev, want_mask=want_mask)
+        used = fallback_offset
+    return filtered, cen_dev, np.float32(base), used, mask
+
+
+def ground_filter_grid(raw: torch.Tensor, cell: float = 2.0, hag: float = 3.0, want_mask: bool = False):
+    """north_star grid min-z mode: keep points more than `hag` above their cell's lowest point."""
+    cen_dev, _ = dv.f32_centroid(raw)
+    _, shifted = dv.f32_shift(raw, cen_dev, want_z=False, want_xyz=True)
+    keep, _ = dv.grid_min_ground(shifted, cell, hag)
+    filtered, g, _, _ = dv.compact_points(shifted, None, 0.0, None, keep_mask=keep)
+    return filtered, cen_dev, np.float32("nan"), hag, (keep if want_mask else None)
+
+
+def run_stages(raw: torch.Tensor, eps: float = 8.0, min_points: int = 80, ground: str = "percentile",
+               want_mask: bool = False, **ground_kw) -> TowerStages:
+    if ground == "percentile":
+        filtered, cen_dev, base, used, mask = ground_filter_percentile(raw, want_mask=want_mask, **ground_kw)
+    elif ground == "grid":
+        filtered, cen_dev, base, used, mask = ground_filter_grid(raw, want_mask=want_mask, **ground_kw)
+    else:
+        raise ValueError(f"unknown ground mode {ground!r}")
+    db = dv.dbscan_chunked(filtered, eps, min_points, DBSCAN_CHUNK)
+    return TowerStages(raw, cen_dev.cpu().numpy(), base, used, filtered, db.labels, db.n_clusters, db.stats, mask)
+
+
+# ---------------------------------------------------------------------------------------------
+# host epilogue: O(#clusters)
+# ---------------------------------------------------------------------------------------------
+def north_angle_of(rotation: np.ndarray) -> float:
+    x_axis = rotation[:, 0]
+    h = np.array([x_axis[0], x_axis[1], 0])
+    if np.linalg.norm(h) > 1e-6:
+        h = h / np.linalg.norm(h)
+    else:
+        h = np.array([1, 0, 0])
+    a = np.degrees(np.arctan2(h[1], h[0]))
+    if a < 0:
+        a += 360
+    return (90 - a) % 360
+
+
+def label_iteration_order(n_clusters: int, present: np.ndarray) -> List[int]:
+    """Iteration order of ``set(all_labels) - {-1}`` (utils/tower_extraction.py:125,131): CPython
+    hash-table order of np.int32 keys.  Built literally from the labels that occur."""
+    s = set(np.asarray(present, dtype=np.int32)) - {-1}
+    return [int(v) for v in s]
+
+
+def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15.0, max_width=50.0, min_width=8,
+                  duplicate_threshold=30.0, box: str = "obb", log: Optional[Callable[[str], None]] = None,
+                  progress: Optional[Callable[[int], None]] = None, want_points: bool = True):
+    """Stages D+E.  Returns the reference's tower dict list (+ 'label')."""
+    from . import obb as _obb
+    centroid = stages.centroid
+    stats = stages.stats
+    K = stages.n_clusters
+    present = np.nonzero(stats["count"][:K] > 0)[0].astype(np.int32)
+    # every label 0..K-1 carries at least its head core point, so `present` is all of them; the
+    # set() is still built from the values to reproduce the reference's order
+    order = label_iteration_order(K, present)
+    towers, centres = [], []
+    labels_host = None
+    filtered_host = None
+    for li, label in enumerate(order):
+        try:
+            st = stats[label]
+            if box == "aabb":
+                mn, mx = st["min"], st["max"]
+                ext = (mx - mn).astype(np.float64)
+                ctr = ((mn + mx) / 2).astype(np.float64)
+                rot = np.eye(3)
+                height, width = ext[2], max(ext[0], ext[1])
+                if width <= 0:
+                    continue
+                cp = None
+            else:
+                # a box can only pass the size filter if the cluster's diameter allows it: the OBB's
+                # extents are bounded by the AABB diagonal.  Skip hopeless clusters without a hull.
+                diag = float(np.linalg.norm((st["max"] - st["min"]).astype(np.float64)))
+                if diag <= min_height:
+                    continue
+                if labels_host is None:
+                    labels_host = stages.labels.cpu().numpy()
+                    filtered_host = stages.filtered.cpu().numpy()
+                cp = filtered_host[labels_host == label]
+                tr, ext = _obb.bounding_box_oriented(cp, ordered=(box == "obb_ordered"))
+                ctr, rot = tr[:3, 3], tr[:3, :3]
+                height, width = ext[2], max(ext[0], ext[1])
+            aspect = height / width
+            if not (height > min_height and min_width < width < max_width and aspect > aspect_ratio_threshold):
+                continue
+            centre = ctr + centroid
+            dup = False
+            for c in centres:
+                d = np.linalg.norm(centre - c)
+                if d < duplicate_threshold:
+                    dup = True
+                    if log:
+                        log(f"⚠️ 跳过重复杆塔{label} (中心距: {d:.1f}m)")
+                    break
+            if dup:
+                continue
+            if cp is None and want_points:
+                if labels_host is None:
+                    labels_host = stages.labels.cpu().numpy()
+                    filtered_host = stages.filtered.cpu().numpy()
+                cp = filtered_host[labels_host == label]
+            towers.append({"label": int(label), "center": centre, "rotation": rot, "extent": ext,
+                           "height": height, "width": width, "north_angle": north_angle_of(rot), "points": cp})
+            centres.append(centre)
+            if log:
+                log(f"✅ 杆塔{label}: {height:.1f}m高 | {width:.1f}m宽 | 中心坐标{centre}")
+            if progress:
+                progress(75 + int(15 * (li + 1) / max(1, len(order))))
+        except Exception as e:  # the reference skips a failing cluster (utils/tower_extraction.py:213-215)
+            if log:
+                log(f"⚠️ 簇{label} 处理失败: {str(e)}")
+            continue
+    return towers

@@ -1,0 +1,131 @@
+"""GPU parity of the tower-extraction stages against the oracle (real numpy percentile, real
+scikit-learn DBSCAN): centroid, height filter, all_labels and the tower list, bit-exact for
+labels/masks/counts, 1e-4 m for float box outputs."""
+import numpy as np
+import pytest
+
+from conftest import make_las_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _downsampled_f32(n, towers, seed, terrain="flat", fractions=(0.80, 0.08, 0.07, 0.05), voxel=0.1, chunk=500000):
+    """Oracle-side: synthetic corridor -> voxel downsample -> LAS re-quantisation -> dict."""
+    from pointcloudhookup_b200 import synth
+    from oracle import las_io, voxel as ov
+    rec = synth.corridor_records(n, towers, terrain, seed, fractions)
+    las = make_las_dict(rec, synth.SCALES, synth.OFFSETS)
+    final, _ = ov.downsample_las_arrays(las, voxel, chunk)
+    sc, of = synth.SCALES, synth.OFFSETS
+    q = [las_io.quantise(final[:, i], sc[i], of[i]) for i in range(3)]
+    las2 = dict(las, X=q[0], Y=q[1], Z=q[2], n=len(q[0]))
+    return rec, las2
+
+
+def test_centroid_sequential_f32_bit_exact(cuda_device):
+    import torch
+    from pointcloudhookup_b200 import device as dv
+    rng = np.random.default_rng(7)
+    for m in (1, 7, 8, 9, 1000, 250001):
+        a = np.stack([437000 + rng.random(m) * 3000, 3.139e6 + rng.random(m) * 3000, 80 + rng.random(m) * 40],
+                     axis=1).astype(np.float32)
+        cen, sums = dv.f32_centroid(torch.from_numpy(a).to(cuda_device))
+        assert np.array_equal(cen.cpu().numpy(), np.mean(a, axis=0))
+        assert np.array_equal(sums.cpu().numpy(), np.add.reduce(a, axis=0))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 1001, 65537, 300000])
+def test_percentile_select_and_lerp(cuda_device, n):
+    import torch
+    from pointcloudhookup_b200 import device as dv, towers as tw
+    rng = np.random.default_rng(n)
+    z = (rng.normal(0, 5, n)).astype(np.float32)
+    if n > 10:
+        z[: n // 2] = z[0]  # ties
+    for q in (25, 10, 20, 50, 0, 100):
+        r0, r1, gamma = tw.percentile_ranks_f32(n, q)
+        two = dv.select_f32(torch.from_numpy(z).to(cuda_device), r0, r1).cpu().numpy()
+        srt = np.sort(z)
+        assert two[0] == srt[r0] and two[1] == srt[r1]
+        got = tw.percentile_lerp_f32(two[0], two[1], gamma)
+        exp = np.percentile(z, q)
+        assert got.dtype == exp.dtype == np.float32 and got == exp
+
+
+def _check_stages(stages, inter):
+    assert np.array_equal(stages.centroid, inter["centroid"])
+    assert stages.base == inter["base"] and stages.offset_used == inter["offset_used"]
+    assert np.array_equal(stages.filtered.cpu().numpy(), inter["filtered"])
+    got = stages.labels.cpu().numpy()
+    assert np.array_equal(got, inter["labels"]), f"{(got != inter['labels']).sum()} labels differ"
+    k = int(inter["labels"].max()) + 1 if inter["labels"].size else 0
+    assert stages.n_clusters == k
+    for lab in range(k):
+        pts = inter["filtered"][inter["labels"] == lab]
+        st = stages.stats[lab]
+        assert st["count"] == len(pts)
+        assert np.array_equal(st["min"], pts.min(0)) and np.array_equal(st["max"], pts.max(0))
+        assert np.allclose(st["sum"] / st["count"], pts.astype(np.float64).mean(0), atol=1e-6)
+
+
+@pytest.mark.parametrize("n,towers,seed,fractions", [
+    (300000, 2, 11, (0.80, 0.08, 0.07, 0.05)),          # conductors dense: towers chained by wires
+    (600000, 3, 12, (0.86, 0.085, 0.005, 0.05)),        # sparse conductors: isolated tower clusters
+    (1000000, 5, 1, (0.80, 0.08, 0.07, 0.05)),          # BASELINE config 0
+])
+def test_tower_stages_match_oracle(cuda_device, n, towers, seed, fractions):
+    import torch
+    from pointcloudhookup_b200 import towers as tw
+    from oracle import towers as ot
+    _, las2 = _downsampled_f32(n, towers, seed, fractions=fractions)
+    inter = {}
+    ref_aabb = ot.extract_towers_arrays(las2, box="aabb", intermediates=inter)
+    raw = torch.from_numpy(inter["raw"]).to(cuda_device)
+    stages = tw.run_stages(raw)
+    _check_stages(stages, inter)
+    got = tw.select_towers(stages, box="aabb")
+    assert [t["label"] for t in got] == [t["label"] for t in ref_aabb]
+    for a, b in zip(got, ref_aabb):
+        assert np.allclose(a["center"], b["center"], atol=1e-4) and np.allclose(a["extent"], b["extent"], atol=1e-4)
+        assert np.array_equal(a["points"], b["points"])
+    ref_obb = ot.extract_towers_arrays(las2, box="obb")
+    got_obb = tw.select_towers(stages, box="obb")
+    assert [t["label"] for t in got_obb] == [t["label"] for t in ref_obb]
+    for a, b in zip(got_obb, ref_obb):
+        assert np.allclose(a["center"], b["center"], atol=1e-4) and np.allclose(a["extent"], b["extent"], atol=1e-4)
+        assert abs(a["north_angle"] - b["north_angle"]) < 1e-6
+
+
+def test_dbscan_exact_eps_ties_and_borders(cuda_device):
+    """Lattice points exactly eps apart are neighbours (d <= eps), border points go to the
+    lowest-numbered cluster, labels are ordered by first core index; several ragged chunks."""
+    import torch
+    from sklearn.cluster import DBSCAN
+    from pointcloudhookup_b200 import device as dv
+    rng = np.random.default_rng(3)
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(3), indexing="ij"), -1).reshape(-1, 3)
+    pts = np.concatenate([g * 2.0, g * 2.0 + np.array([60.0, 0, 0]), rng.uniform(-5, 90, (400, 3))]).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    for eps, ms, chunk in ((2.0, 7, 1000000), (4.0, 30, 300), (2.0, 5, 257), (8.0, 80, 500)):
+        res = dv.dbscan_chunked(torch.from_numpy(pts).to(cuda_device), eps, ms, chunk)
+        exp = np.full(len(pts), -1, np.int32)
+        cur = 0
+        for s in range(0, len(pts), chunk):
+            lab = DBSCAN(eps=eps, min_samples=ms, algorithm="ball_tree").fit(pts[s:s + chunk]).labels_
+            lab[lab != -1] += cur
+            exp[s:s + chunk] = lab
+            cur = lab.max() + 1 if (lab != -1).any() else cur
+        assert np.array_equal(res.labels.cpu().numpy(), exp), (eps, ms, chunk)
+        assert res.n_clusters == cur
+
+
+def test_grid_min_ground_matches_self_oracle(cuda_device):
+    import torch
+    from pointcloudhookup_b200 import device as dv
+    from oracle import ground as og
+    rng = np.random.default_rng(9)
+    p = np.stack([rng.uniform(0, 300, 200000), rng.uniform(0, 60, 200000), rng.normal(50, 3, 200000)], 1).astype(np.float32)
+    keep, gz = dv.grid_min_ground(torch.from_numpy(p).to(cuda_device), 2.0, 3.0)
+    ek, egz = og.grid_min_keep_mask(p, 2.0, 3.0)
+    assert np.array_equal(gz.cpu().numpy(), egz)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), ek)

@@ -88,6 +88,17 @@ int pch_voxel_keys(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t c
                    const double* origins_dev, const pch_voxel_plan* plan, uint64_t* keys_dev,
                    pch_stream_t stream);
 
+/* The same two steps for an arbitrary (n,3) float64 point array — process_chunk(points_chunk,
+ * voxel_size) (ui/import_PC.py:8-13, ui/Sampling.py:10-18) is not restricted to LAS-lattice input.
+ * minmax_scratch_dev: [n_chunks*6] uint64.  Then sort, then pch_voxel_reduce with rec_dev = the
+ * float64 array, rec_len = 0, scales = offsets = NULL (only mean_dev is available). */
+int pch_voxel_plan_build_f64(const double* xyz_dev, int64_t n, int64_t chunk_size, double voxel_size,
+                             uint64_t* minmax_scratch_dev, double* origins_dev, pch_voxel_plan* plan_dev,
+                             pch_stream_t stream);
+int pch_voxel_keys_f64(const double* xyz_dev, int64_t n, int64_t chunk_size, double voxel_size,
+                       const double* origins_dev, const pch_voxel_plan* plan, uint64_t* keys_dev,
+                       pch_stream_t stream);
+
 /* Stable LSD radix sort of 64-bit keys on bits [bit_lo, bit_hi), independently inside consecutive
  * segments of `seg_size` keys.  n_passes = ceil((bit_hi-bit_lo)/8); the result is left in
  * keys_dev when n_passes is even, in tmp_dev when odd. */
@@ -169,6 +180,44 @@ int pch_dbscan_run(const float* xyz_dev, int64_t G, int64_t chunk, double eps, i
                    const uint32_t* bounds_dev, const pch_voxel_plan* plan, int32_t* labels_dev,
                    int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
                    void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+
+/* ---------------------------------------------------------------- geoid shift + CRS */
+
+typedef struct pch_geoid_grid {
+    double ll_lat, ll_lon;   /* lower-left node (degrees); rows run south -> north, cols west -> east */
+    double dlat, dlon;       /* node spacing (degrees)                                               */
+    int32_t rows, cols;
+    int32_t pitch;           /* floats per row in memory (>= cols, multiple of 4)                     */
+    int32_t is_global;       /* cols*dlon spans 360 degrees: east neighbour of the last column wraps  */
+} pch_geoid_grid;
+
+typedef struct pch_tm_params {
+    double rect_radius;      /* A = a/(1+n)(1+n^2/4+n^4/64+n^6/256)                                   */
+    double beta[6];          /* Krueger inverse series coefficients                                    */
+    double ecc;              /* first eccentricity e                                                   */
+    double lon0_deg, k0, fe, fn;
+} pch_tm_params;
+
+/* PROJ vgridshift forward: out_h = h + multiplier*N(lat,lon), N bilinear in float64 over float32
+ * nodes (utils/elevation_converter.py:29-31,48 with multiplier=+1; crs.py:25-35 with -1).
+ * lat/lon in degrees.  out_n_dev (nullable) receives N; NaN outside the grid / on nodata. */
+int pch_geoid_shift(const double* lat_dev, const double* lon_dev, const double* h_dev, int64_t n,
+                    const float* grid_dev, const pch_geoid_grid* grid, double multiplier,
+                    double* out_h_dev, double* out_n_dev, pch_stream_t stream);
+
+/* Transformer.from_crs("EPSG:4547","EPSG:4326",always_xy=True).transform(x, y)
+ * (utils/table_match_gim.py:72-75,232; test/005test.py:37,55): inverse Gauss-Krueger -> degrees. */
+int pch_gk_inverse(const double* x_dev, const double* y_dev, int64_t n, const pch_tm_params* tm,
+                   double* lon_dev, double* lat_dev, pch_stream_t stream);
+
+/* Fused per-point conversion of a whole LAS (test/005test.py:48-66 + utils/elevation_converter.py:48):
+ * decode -> (tm != NULL ? inverse GK : x,y already lon,lat) -> geoid shift; out_dev (n,3) float64 =
+ * lon, lat, h + multiplier*N.  win_* name the grid window staged in shared memory by bulk TMA
+ * (rows/cols 0 = read the grid from global memory); nodes outside the window are still read exactly. */
+int pch_las_geodetic(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const double* scales,
+                     const double* offsets, const pch_tm_params* tm, const float* grid_dev,
+                     const pch_geoid_grid* grid, int32_t win_row0, int32_t win_col0, int32_t win_rows,
+                     int32_t win_cols, double multiplier, double* out_dev, pch_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,7 @@ def geoid_height(grid, lat, lon):
     iy = np.floor(gy).astype(np.int64)
     fx = gx - ix
     fy = gy - iy
-    bad = (gy < 0) | (gy > rows - 1) | (~is_global & (gx > cols - 1))
+    bad = (gy < 0) | (gy > rows - 1) | ((not is_global) & (gx > cols - 1))
     iy = np.clip(iy, 0, rows - 1)
     ix = np.clip(ix, 0, cols - 1) if not is_global else ix % cols
     ix2 = ix + 1

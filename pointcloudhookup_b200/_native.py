@@ -41,6 +41,8 @@ SIGNATURES = {
     "pch_las_encode": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "pch_voxel_plan_build": (C.c_int, [_p, _i64, _i64, _d3, _d3, _f64, _p, _p, _p]),
     "pch_voxel_keys": (C.c_int, [_p, _i64, _i32, _i64, _d3, _d3, _f64, _p, C.POINTER(VoxelPlan), _p, _p]),
+    "pch_voxel_plan_build_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p, _p]),
+    "pch_voxel_keys_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, C.POINTER(VoxelPlan), _p, _p]),
     "pch_sort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "pch_sort_u64_segmented": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "pch_voxel_reduce_workspace_bytes": (_sz, [_i64, _i64]),
@@ -63,6 +65,23 @@ SIGNATURES.update({
     "pch_dbscan_plan": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
     "pch_dbscan_workspace_bytes": (_sz, [_i64, _i64, C.POINTER(VoxelPlan), _i64]),
     "pch_dbscan_run": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, C.POINTER(VoxelPlan), _p, _p, _p, _i64, _p, _sz, _p]),
+})
+
+class GeoidGrid(C.Structure):
+    _fields_ = [("ll_lat", C.c_double), ("ll_lon", C.c_double), ("dlat", C.c_double), ("dlon", C.c_double),
+                ("rows", C.c_int32), ("cols", C.c_int32), ("pitch", C.c_int32), ("is_global", C.c_int32)]
+
+
+class TmParams(C.Structure):
+    _fields_ = [("rect_radius", C.c_double), ("beta", C.c_double * 6), ("ecc", C.c_double),
+                ("lon0_deg", C.c_double), ("k0", C.c_double), ("fe", C.c_double), ("fn", C.c_double)]
+
+
+SIGNATURES.update({
+    "pch_geoid_shift": (C.c_int, [_p, _p, _p, _i64, _p, C.POINTER(GeoidGrid), _f64, _p, _p, _p]),
+    "pch_gk_inverse": (C.c_int, [_p, _p, _i64, C.POINTER(TmParams), _p, _p, _p]),
+    "pch_las_geodetic": (C.c_int, [_p, _i64, _i32, _d3, _d3, C.POINTER(TmParams), _p, C.POINTER(GeoidGrid),
+                                   _i32, _i32, _i32, _i32, _f64, _p, _p]),
 })
 
 _lib = None

@@ -56,6 +56,10 @@ __global__ void k_voxel_plan(const int32_t* __restrict__ mm, int64_t n_chunks, i
 }
 
 static int make_affine3(const double* scales, const double* offsets, PchAffine3& a) {
+    if (!scales && !offsets) {  // float64 point input: identity
+        for (int i = 0; i < 3; ++i) { a.s[i] = 1.0; a.o[i] = 0.0; }
+        return PCH_OK;
+    }
     PCH_CHECK_ARG(scales && offsets, "null scales/offsets");
     for (int i = 0; i < 3; ++i) {
         a.s[i] = scales[i];
@@ -169,6 +173,8 @@ extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size
     return 256 + (size_t)tiles * 8;
 }
 
+// ALIGN > 0: `rec` is a raw LAS byte stream (record alignment ALIGN); ALIGN == 0: `rec` is an
+// (n,3) float64 array (process_chunk's arbitrary point input).
 template <int ALIGN>
 __global__ void __launch_bounds__(VR_THREADS)
 k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec, PchAffine3 a,
@@ -244,12 +250,19 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         int64_t p = start + i;
         uint64_t k = s_keys[i + 1];
         while (true) {
-            const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
-            int X, Y, Z;
-            pch_load_xyz<ALIGN>(q, X, Y, Z);
-            sx = __dadd_rn(sx, pch_scaled(X, a.s[0], a.o[0]));
-            sy = __dadd_rn(sy, pch_scaled(Y, a.s[1], a.o[1]));
-            sz = __dadd_rn(sz, pch_scaled(Z, a.s[2], a.o[2]));
+            if (ALIGN > 0) {
+                const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
+                int X, Y, Z;
+                pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(q, X, Y, Z);
+                sx = __dadd_rn(sx, pch_scaled(X, a.s[0], a.o[0]));
+                sy = __dadd_rn(sy, pch_scaled(Y, a.s[1], a.o[1]));
+                sz = __dadd_rn(sz, pch_scaled(Z, a.s[2], a.o[2]));
+            } else {
+                const double* q = reinterpret_cast<const double*>(rec) + (size_t)(cstart + (int64_t)(k & idx_mask)) * 3;
+                sx = __dadd_rn(sx, q[0]);
+                sy = __dadd_rn(sy, q[1]);
+                sz = __dadd_rn(sz, q[2]);
+            }
             ++cntp;
             ++p;
             if (p >= cend) break;
@@ -284,8 +297,10 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
                                 int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(n >= 0 && chunk_size > 0, "bad n/chunk_size");
-    PCH_CHECK_ARG(rec_len >= 12 && rec_len <= 256, "bad record length");
+    PCH_CHECK_ARG(rec_len == 0 || (rec_len >= 12 && rec_len <= 256), "bad record length");
     PCH_CHECK_ARG(bits_idx >= 0 && bits_idx <= 63, "bad bits_idx");
+    PCH_CHECK_ARG(rec_len != 0 || (lat_out == nullptr && f32_out == nullptr),
+                  "float64 point input has no LAS lattice: only mean_dev is available");
     PchAffine3 a;
     int rc = make_affine3(scales, offsets, a);
     if (rc) return rc;
@@ -309,15 +324,145 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     int* err = (int*)workspace;
     uint32_t* counter = (uint32_t*)((uint8_t*)workspace + 64);
     uint64_t* status = (uint64_t*)((uint8_t*)workspace + 256);
-    int al = pch_rec_align(rec_len);
+    int al = rec_len == 0 ? 0 : pch_rec_align(rec_len);
 #define LAUNCH_RED(A)                                                                                          \
     k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
         keys, g, rec, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
         status, counter, err)
     if (al == 4) LAUNCH_RED(4);
     else if (al == 2) LAUNCH_RED(2);
-    else LAUNCH_RED(1);
+    else if (al == 1) LAUNCH_RED(1);
+    else LAUNCH_RED(0);
 #undef LAUNCH_RED
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// float64 point arrays: process_chunk(points_chunk, voxel_size) (ui/import_PC.py:8-13,
+// ui/Sampling.py:10-18) accepts ANY (n,3) array, not only LAS-lattice points.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_f64(unsigned long long u) {
+    return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u));
+}
+
+__global__ void k_f64_minmax_init(unsigned long long* mm, int64_t n_chunks) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_chunks * 6) mm[i] = ((i % 6) < 3) ? ~0ull : 0ull;
+}
+
+__global__ void __launch_bounds__(256)
+k_f64_chunk_minmax(const double* __restrict__ xyz, int64_t n, int64_t chunk, unsigned long long* __restrict__ mm) {
+    const int64_t slabs = (chunk + 4095) / 4096;
+    const int64_t n_chunks = (n + chunk - 1) / chunk;
+    for (int64_t s = blockIdx.x; s < n_chunks * slabs; s += gridDim.x) {
+        int64_t c = s / slabs, ls = s - c * slabs;
+        int64_t lo = c * chunk + ls * 4096, hi = min(min(lo + 4096, (c + 1) * chunk), n);
+        unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0, 0, 0};
+        for (int64_t i = lo + threadIdx.x; i < hi; i += 256)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                unsigned long long u = f64_to_ordered(xyz[i * 3 + a]);
+                mn[a] = min(mn[a], u);
+                mx[a] = max(mx[a], u);
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+                mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+            }
+            if ((threadIdx.x & 31) == 0 && lo < hi) {
+                atomicMin(&mm[c * 6 + a], mn[a]);
+                atomicMax(&mm[c * 6 + 3 + a], mx[a]);
+            }
+        }
+    }
+}
+
+__global__ void k_voxel_plan_f64(const unsigned long long* __restrict__ mm, int64_t n_chunks, int64_t chunk_size,
+                                 double voxel, double* __restrict__ origins, pch_voxel_plan* __restrict__ plan) {
+    __shared__ long long s_max[3];
+    if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
+    __syncthreads();
+    const double half = __dmul_rn(voxel, 0.5);
+    for (int64_t c = threadIdx.x; c < n_chunks; c += blockDim.x)
+        for (int ax = 0; ax < 3; ++ax) {
+            double lo = ordered_to_f64(mm[c * 6 + ax]), hi = ordered_to_f64(mm[c * 6 + 3 + ax]);
+            double org = __dsub_rn(lo, half);
+            origins[c * 3 + ax] = org;
+            atomicMax(&s_max[ax], (long long)floor(__ddiv_rn(__dsub_rn(hi, org), voxel)));
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pch_voxel_plan p;
+        p.bits_x = bits_for(s_max[0]); p.bits_y = bits_for(s_max[1]); p.bits_z = bits_for(s_max[2]);
+        p.bits_idx = bits_for(chunk_size - 1);
+        p.key_bits = p.bits_x + p.bits_y + p.bits_z;
+        p.n_passes = (p.key_bits + 7) / 8;
+        bool ok = (p.key_bits + p.bits_idx <= 64) && s_max[0] < 2147483647ll && s_max[1] < 2147483647ll &&
+                  s_max[2] < 2147483647ll;
+        p.status = ok ? PCH_OK : PCH_ERR_RANGE;
+        p.reserved = 0;
+        *plan = p;
+    }
+}
+
+__global__ void k_voxel_keys_f64(const double* __restrict__ xyz, int64_t n, int64_t chunk, double voxel,
+                                 const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t c = i / chunk;
+        uint64_t ix = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(xyz[i * 3 + 0], origins[c * 3 + 0]), voxel));
+        uint64_t iy = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(xyz[i * 3 + 1], origins[c * 3 + 1]), voxel));
+        uint64_t iz = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(xyz[i * 3 + 2], origins[c * 3 + 2]), voxel));
+        keys[i] = (ix << kl.sh_x) | (iy << kl.sh_y) | (iz << kl.sh_z) | (uint64_t)(i - c * chunk);
+    }
+}
+
+extern "C" int pch_voxel_plan_build_f64(const double* xyz, int64_t n, int64_t chunk_size, double voxel,
+                                        uint64_t* minmax_scratch, double* origins, pch_voxel_plan* plan,
+                                        pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 1 && chunk_size >= 1, "n and chunk_size must be >= 1");
+    PCH_CHECK_ARG(voxel > 0.0, "voxel_size must be > 0 (open3d raises otherwise)");
+    PCH_CHECK_ARG(xyz && minmax_scratch && origins && plan, "null pointer");
+    if (chunk_size > n) chunk_size = n;
+    int64_t n_chunks = pch_ceil_div(n, chunk_size);
+    k_f64_minmax_init<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>((unsigned long long*)minmax_scratch, n_chunks);
+    int64_t blocks = pch_ceil_div(n, 4096);
+    int64_t cap = (int64_t)pch_sm_count() * 16;
+    k_f64_chunk_minmax<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, (unsigned long long*)minmax_scratch);
+    k_voxel_plan_f64<<<1, 256, 0, st>>>((const unsigned long long*)minmax_scratch, n_chunks, chunk_size, voxel, origins, plan);
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_voxel_keys_f64(const double* xyz, int64_t n, int64_t chunk_size, double voxel, const double* origins,
+                                  const pch_voxel_plan* plan, uint64_t* keys, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && chunk_size > 0 && voxel > 0.0 && plan, "bad arguments");
+    if (plan->status != PCH_OK || plan->key_bits + plan->bits_idx > 64) {
+        pch_set_error("voxel index range needs %d+%d bits > 64: voxel_size too small", plan->key_bits, plan->bits_idx);
+        return PCH_ERR_RANGE;
+    }
+    if (n == 0) return PCH_OK;
+    PCH_CHECK_ARG(xyz && origins && keys, "null pointer");
+    if (chunk_size > n) chunk_size = n;
+    KeyLayout kl;
+    kl.sh_z = plan->bits_idx;
+    kl.sh_y = kl.sh_z + plan->bits_z;
+    kl.sh_x = kl.sh_y + plan->bits_y;
+    int64_t blocks = pch_ceil_div(n, 256);
+    int64_t cap = (int64_t)pch_sm_count() * 8;
+    k_voxel_keys_f64<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, voxel, origins, kl, keys);
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

@@ -330,3 +330,42 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
         cap = k
     host = stats[: k * STATS_DTYPE.itemsize].cpu().numpy().view(STATS_DTYPE).copy()
     return DbscanResult(labels, k, host)
+
+
+def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Optional[int] = None) -> VoxelResult:
+    """open3d voxel_down_sample of an arbitrary (n,3) float64 device array (process_chunk's input)."""
+    _require_cuda()
+    assert xyz.dtype == torch.float64 and xyz.is_contiguous() and xyz.dim() == 2 and xyz.shape[1] == 3
+    if voxel_size <= 0:
+        raise ValueError("voxel_size must be > 0")
+    lib = _native.lib()
+    dev = xyz.device
+    n = xyz.shape[0]
+    cs = max(1, min(int(chunk_size or n or 1), max(n, 1)))
+    n_chunks = max(1, -(-n // cs))
+    if n == 0:
+        return VoxelResult(0, torch.zeros(n_chunks, dtype=torch.int64, device=dev),
+                           torch.zeros((0, 3), dtype=torch.float64, device=dev))
+    st = _stream()
+    scratch = torch.empty(n_chunks * 6, dtype=torch.int64, device=dev)
+    origins = torch.empty((n_chunks, 3), dtype=torch.float64, device=dev)
+    plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
+    check(lib.pch_voxel_plan_build_f64(xyz.data_ptr(), n, cs, float(voxel_size), scratch.data_ptr(), origins.data_ptr(),
+                                       plan_dev.data_ptr(), st), "pch_voxel_plan_build_f64")
+    plan = VoxelPlan(*[int(v) for v in plan_dev.cpu().numpy()])
+    if plan.status != 0:
+        raise ValueError("voxel_size is too small.")
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    check(lib.pch_voxel_keys_f64(xyz.data_ptr(), n, cs, float(voxel_size), origins.data_ptr(), C.byref(plan),
+                                 keys.data_ptr(), st), "pch_voxel_keys_f64")
+    skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
+    mean = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    counts = torch.empty(n_chunks, dtype=torch.int64, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    wsb = lib.pch_voxel_reduce_workspace_bytes(n, cs)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, xyz.data_ptr(), 0, None, None,
+                               mean.data_ptr(), None, None, counts.data_ptr(), total.data_ptr(), ws.data_ptr(), wsb,
+                               st), "pch_voxel_reduce")
+    m = int(total.item())
+    return VoxelResult(m, counts, mean[:m], plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_})

@@ -1,0 +1,181 @@
+"""CPU: host-side logic (LAS container, numpy-percentile restatement, C ABI symbols, generator)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_las_header_roundtrip(tmp_path):
+    from pointcloudhookup_b200 import las, synth
+    from oracle import las_io
+    p = str(tmp_path / "a.las")
+    h = synth.write_corridor_las(p, 5000, 2, "flat", 3)
+    assert h.point_count == 5000 and h.record_length == 34 and h.point_format == 3 and h.version == (1, 2)
+    hdr, rec = las.read_raw(p)
+    assert rec.size == 5000 * 34
+    o = las_io.read_las(p)
+    r = synth.corridor_records(5000, 2, "flat", 3)
+    assert np.array_equal(o["X"], r["X"]) and np.array_equal(o["Z"], r["Z"])
+    assert np.allclose(hdr.mins, [o["X"].min() * 0.001 + 437000, o["Y"].min() * 0.001 + 3139000, o["Z"].min() * 0.001])
+    nh = las.new_header_like(hdr)
+    assert nh.record_length == 34 and nh.offset_to_point_data == 227 and nh.n_vlr == 0
+    las.write_raw(str(tmp_path / "b.las"), nh, rec, np.zeros(3), np.ones(3))
+    assert las.read_header(str(tmp_path / "b.las")).point_count == 5000
+
+
+def test_las_errors(tmp_path):
+    from pointcloudhookup_b200 import las
+    with pytest.raises(FileNotFoundError):
+        las.read_raw(str(tmp_path / "nope.las"))
+    bad = tmp_path / "bad.las"
+    bad.write_bytes(b"NOPE" + b"\0" * 400)
+    with pytest.raises(las.LasError):
+        las.read_raw(str(bad))
+    from pointcloudhookup_b200 import synth
+    p = str(tmp_path / "c.las")
+    synth.write_corridor_las(p, 100, 1, "flat", 1)
+    raw = bytearray(open(p, "rb").read())
+    raw[104] |= 0x80  # LAZ flag
+    (tmp_path / "laz.las").write_bytes(bytes(raw))
+    with pytest.raises(las.LasError):
+        las.read_raw(str(tmp_path / "laz.las"))
+    (tmp_path / "trunc.las").write_bytes(open(p, "rb").read()[:-10])
+    with pytest.raises(las.LasError):
+        las.read_raw(str(tmp_path / "trunc.las"))
+
+
+def test_las14_header(tmp_path):
+    from pointcloudhookup_b200 import las
+    h = las.LasHeader(version=(1, 4), point_format=6, record_length=30, header_size=375, offset_to_point_data=375,
+                      point_count=7, scales=np.array([0.01] * 3), offsets=np.zeros(3))
+    p = tmp_path / "v14.las"
+    p.write_bytes(las.header_bytes(h) + b"\0" * (7 * 30))
+    g = las.read_header(str(p))
+    assert g.point_count == 7 and g.version == (1, 4) and g.point_format == 6 and g.record_length == 30
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 100, 101, 1000, 4097, 99999, 2**24 + 3, 40_000_001])
+@pytest.mark.parametrize("q", [25, 10, 20, 50, 0, 100, 33.3])
+def test_percentile_restatement_matches_numpy(n, q):
+    """percentile_ranks_f32 + percentile_lerp_f32 == np.percentile for float32 input, including the
+    n > 2^24 regime where numpy's float32 virtual index loses integer precision."""
+    from pointcloudhookup_b200 import towers as tw
+    if n > 10**6:
+        z = np.arange(n, dtype=np.float32)   # sorted, distinct enough; value == index up to 2^24
+        z *= np.float32(0.37)
+    else:
+        z = np.random.default_rng(n).normal(0, 10, n).astype(np.float32)
+    r0, r1, gamma = tw.percentile_ranks_f32(n, q)
+    s = np.sort(z)
+    got = tw.percentile_lerp_f32(s[r0], s[r1], gamma)
+    exp = np.percentile(z, q)
+    assert got.dtype == np.float32 and got == exp
+    assert (got + 3.0).dtype == np.float32
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libpch_b200.so loads and exports every function include/pch_b200.h declares; the ctypes table
+    binds exactly that set (no compute call is made — there is no GPU here)."""
+    from pointcloudhookup_b200 import _native
+    header = open(os.path.join(ROOT, "include", "pch_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pch_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared but not exported"
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert _native.lib().pch_version() >= 100
+    assert ctypes.sizeof(_native.VoxelPlan) == 32 and ctypes.sizeof(_native.ClusterStats) == 56
+    assert ctypes.sizeof(_native.GeoidGrid) == 48 and ctypes.sizeof(_native.TmParams) == 96
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pointcloudhookup_b200 import _native, device as dv
+    with pytest.raises(_native.NativeError):
+        dv.upload_records(np.zeros(34, np.uint8), 1, 34, [1, 1, 1], [0, 0, 0])
+    from pointcloudhookup_b200.ui import import_PC
+    with pytest.raises(Exception):
+        import_PC.process_chunk(np.zeros((4, 3)), 0.1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pointcloudhookup_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_synth_tower_truth_and_order():
+    from pointcloudhookup_b200 import synth
+    r = synth.corridor_records(60000, 3, "hilly", 9)
+    gt = synth.tower_ground_truth(3, "hilly", 9)
+    assert gt.shape == (3, 5) and np.all((gt[:, 3] >= 25) & (gt[:, 3] <= 45))
+    tower = r[r["classification"] == 15]
+    assert 0.04 * 60000 < tower.size < 0.06 * 60000
+    # flight order: along-axis coordinate is non-decreasing inside every block
+    az = np.radians(synth.AZIMUTH_DEG)
+    e = r["X"] * 0.001 + 437000 - synth.ORIGIN_EN[0]
+    n = r["Y"] * 0.001 + 3139000 - synth.ORIGIN_EN[1]
+    s = e * np.sin(az) + n * np.cos(az)
+    assert np.all(np.diff(s[:20000]) > -1e-2)
+
+
+def test_dropin_surface_matches_reference_names():
+    import importlib
+    import inspect
+    import pointcloudhookup_b200 as pkg
+    want = {
+        "ui.import_PC": ["process_chunk", "run_voxel_downsampling"],
+        "ui.Sampling": ["process_chunk", "voxel_downsample_open3d"],
+        "ui.extract": ["create_bbox_using_kuangxuan_method", "create_bbox_lineset_from_bounds",
+                       "extract_and_visualize_towers_kuangxuan", "create_enhanced_tower_boxes_kuangxuan",
+                       "BBOX_PRESETS", "get_bbox_preset", "visualize_towers_with_point_cloud_kuangxuan",
+                       "extract_and_visualize_towers_original", "extract_and_visualize_towers"],
+        "ui.compress": ["GIMUtils", "utils", "GIMExtractor"],
+        "utils.tower_extraction": ["extract_towers", "_save_tower_las", "create_obb_geometries", "extract_towers_optimized"],
+        "utils.elevation_converter": ["ElevationConverter", "convert_elevation"],
+        "crs": ["ellipsoid_to_orthometric_egm96", "cgcs2000_gk114_to_wgs84"],
+    }
+    for mod, names in want.items():
+        m = importlib.import_module(f"{pkg.__name__}.{mod}")
+        for n in names:
+            assert hasattr(m, n), (mod, n)
+    from pointcloudhookup_b200.utils.tower_extraction import extract_towers
+    sig = inspect.signature(extract_towers)
+    assert list(sig.parameters)[:10] == ["input_las_path", "progress_callback", "log_callback", "eps", "min_points",
+                                          "aspect_ratio_threshold", "min_height", "max_width", "min_width",
+                                          "duplicate_threshold"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["eps"], d["min_points"], d["aspect_ratio_threshold"], d["min_height"], d["max_width"], d["min_width"],
+            d["duplicate_threshold"]) == (8.0, 80, 0.8, 15.0, 50.0, 8, 30.0)
+    from pointcloudhookup_b200.ui.import_PC import run_voxel_downsampling
+    d = {k: v.default for k, v in inspect.signature(run_voxel_downsampling).parameters.items()}
+    assert d["voxel_size"] == 0.1 and d["chunk_size"] == 1000000
+    with pytest.raises(FileNotFoundError):
+        run_voxel_downsampling("/nonexistent/in.las", "/tmp/x/out.las")
+
+
+def test_extract_box_geometry():
+    from pointcloudhookup_b200.ui import extract
+    lo, hi = extract.create_bbox_using_kuangxuan_method([10.0, 20.0, 30.0], 20.0, 17.0)
+    # test/kuangxuan.py:69-71: x in [cx - w, cx + w/0.6 (~1.67w)], y in [cy - w/2, cy + w], z in [cz - h, cz + 2h]
+    assert np.allclose(lo, [-10.0, 10.0, 13.0]) and np.allclose(hi, [10 + 33.4, 40.0, 64.0])
+    pts, col = extract.create_bbox_lineset_from_bounds(lo, hi)
+    assert pts.shape == (24, 3) and col == (1.0, 0.0, 0.0)
+    assert extract.get_bbox_preset("nope") == extract.get_bbox_preset("kuangxuan_original")
+    geo = extract.create_enhanced_tower_boxes_kuangxuan([{"center": np.array([0.0, 0, 0]), "extent": [10, 12, 30]}])
+    assert [g[0].shape for g in geo] == [(24, 3), (24, 3), (2, 3)]
+    from pointcloudhookup_b200.utils.tower_extraction import create_obb_geometries
+    g = create_obb_geometries([{"center": np.zeros(3), "extent": np.array([2.0, 4, 6]), "rotation": np.eye(3)}])
+    assert g[0].points.shape == (8, 3) and g[0].lines.shape == (12, 2)
+    assert np.allclose(np.ptp(g[0].points, axis=0), [2, 4, 6])

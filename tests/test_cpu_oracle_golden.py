@@ -1,0 +1,126 @@
+"""CPU: the oracle reproduces what the UNMODIFIED reference modules produced
+(tests/golden/reference_run.json, made by tests/golden/make_golden.py)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_run.json")))
+CASES = ["dense_wires", "towers", "hilly"]
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    return tmp_path_factory.mktemp("golden")
+
+
+def make_input(case, workdir):
+    from pointcloudhookup_b200 import synth
+    c = GOLD[case]["config"]
+    path = os.path.join(workdir, f"{case}.las")
+    if not os.path.exists(path):
+        synth.write_corridor_las(path, c["n"], c["towers"], c["terrain"], c["seed"], tuple(c["fractions"]))
+    return path, c
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_generator_is_deterministic(case, workdir):
+    path, _ = make_input(case, workdir)
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == GOLD[case]["input_sha256"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_voxel_matches_reference_run(case, workdir):
+    from oracle import las_io, voxel
+    path, c = make_input(case, workdir)
+    out = os.path.join(workdir, f"{case}_ds.las")
+    voxel.run_voxel_downsampling(path, out, c["voxel"], c["chunk"])
+    ds = las_io.read_las(out)
+    g = GOLD[case]["downsample"]
+    assert ds["n"] == g["count"]
+    assert digest(np.stack([ds["X"], ds["Y"], ds["Z"]], 1)) == g["xyz_sha256"]
+    pts = np.stack(las_io.scaled(las_io.read_las(path), 0, 5000), 1)
+    pc = voxel.voxel_down_sample(pts, c["voxel"])
+    assert pc.shape[0] == GOLD[case]["process_chunk"]["count"] and digest(pc) == GOLD[case]["process_chunk"]["sha256"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_towers_match_reference_run(case, workdir):
+    from oracle import towers, voxel
+    path, c = make_input(case, workdir)
+    out = os.path.join(workdir, f"{case}_ds.las")
+    if not os.path.exists(out):
+        voxel.run_voxel_downsampling(path, out, c["voxel"], c["chunk"])
+    inter = {}
+    from oracle import las_io
+    res = towers.extract_towers_arrays(las_io.read_las(out), box="obb", intermediates=inter)
+    g = GOLD[case]["towers"]
+    assert len(inter["labels"]) == g["n_filtered"] and digest(inter["labels"]) == g["labels_sha256"]
+    assert len(res) == g["count"]
+    for a, b in zip(res, g["list"]):
+        assert np.allclose(a["center"], b["center"], atol=1e-9)
+        assert np.allclose(a["extent"], b["extent"], atol=1e-9)
+        assert np.allclose(a["rotation"], b["rotation"], atol=1e-9)
+        assert abs(a["north_angle"] - b["north_angle"]) < 1e-9
+        assert digest(a["points"]) == b["points_sha256"]
+
+
+def test_oracle_elevation_matches_reference_run():
+    from oracle import geoid
+    e = GOLD["elevation"]
+    t = np.array(e["towers"])
+    assert np.array_equal(geoid.ellipsoid_to_orthometric(None, t[:, 0], t[:, 1], t[:, 2]), e["fallback"])
+    crop = geoid.read_gtx(os.path.join(HERE, "golden", "egm96_crop_20N35N_105E120E.gtx"))
+    got = geoid.ellipsoid_to_orthometric(crop, t[:, 0], t[:, 1], t[:, 2])
+    assert np.allclose(got, e["grid_egm96_plus1"], atol=1e-9)
+
+
+def test_oracle_crs_known_answers():
+    """EPSG:4547 -> 4326 pinned by the reference's own data: tower centres of its recorded run
+    (test/kuangxuan.py:29-33) vs the same towers as lat/lon (elevation_conversion.py:148-153)."""
+    from oracle import crs
+    en = [(437587.898, 3140691.58), (437787.178, 3140006.96), (437908.948, 3139606.82), (437676.583, 3140379.50)]
+    ll = [(28.379751, 113.363246), (28.373584, 113.365316), (28.369979, 113.366579), (28.376940, 113.364167)]
+    lon, lat = crs.gk_inverse([p[0] for p in en], [p[1] for p in en])
+    assert np.allclose(lat, [p[0] for p in ll], atol=6e-7) and np.allclose(lon, [p[1] for p in ll], atol=6e-7)
+
+
+def test_oracle_geoid_analytic_grid():
+    """On a grid sampled from N = 30 sin(lat) cos(lon) (the shipped npz), bilinear error is bounded by
+    h^2/8 * |f''| per axis."""
+    from oracle import geoid
+    lat = np.linspace(-90, 90, 721)
+    lon = np.linspace(-180, 179.75, 1440)
+    g = {"ll_lat": -90.0, "ll_lon": -180.0, "dlat": 0.25, "dlon": 0.25, "rows": 721, "cols": 1440,
+         "grid": (30 * np.sin(np.radians(lat))[:, None] * np.cos(np.radians(lon))[None, :]).astype(np.float32)}
+    rng = np.random.default_rng(0)
+    la, lo = rng.uniform(-89, 89, 2000), rng.uniform(-180, 180, 2000)
+    n = geoid.geoid_height(g, la, lo)
+    exact = 30 * np.sin(np.radians(la)) * np.cos(np.radians(lo))
+    bound = 2 * 30 * np.radians(0.25) ** 2 / 8 + 1e-5
+    assert np.abs(n - exact).max() < bound
+    # wrap across the seam and node hits
+    assert abs(float(geoid.geoid_height(g, 10.0, 179.9)) - 30 * np.sin(np.radians(10)) * np.cos(np.radians(179.9))) < bound
+    assert float(geoid.geoid_height(g, 0.25, 0.5)) == float(g["grid"][361, 722])
+    assert np.isnan(geoid.geoid_height(g, 91.0, 0.0))
+
+
+def test_oracle_obb_properties():
+    from oracle import obb
+    rng = np.random.default_rng(4)
+    box = rng.uniform(-1, 1, (4000, 3)) * np.array([10.0, 3.0, 20.0])
+    th = np.radians(33)
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    pts = box @ R.T + np.array([100.0, -50.0, 7.0])
+    tr, ext = obb.bounding_box_oriented(pts)
+    local = (pts - tr[:3, 3]) @ tr[:3, :3]
+    assert np.all(np.abs(local) <= ext / 2 + 1e-6)
+    assert np.prod(ext) <= np.prod(np.ptp(pts, axis=0)) + 1e-9
+    assert np.allclose(sorted(ext), [6, 20, 40], rtol=0.04)

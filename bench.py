@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — points/s of the per-point LAS hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload pipeline|voxel_geoid] [--points P]
+
+A "step" is one pass of the hot path over one synthetic corridor tile per GPU:
+  pipeline     (default; BASELINE.json configs[2]) 100 M-point hilly corridor, 50 towers per GPU:
+               decode -> voxel downsample (0.1 m, 500 k chunks) -> percentile ground filter ->
+               chunked DBSCAN -> per-cluster box/centroid reduction -> tower list (+ tower merge
+               across ranks).  This is the path north_star quotes its 5 Gpt/s target on.
+  voxel_geoid  (configs[1]) 20 M-point flat corridor: voxel downsample + per-point EPSG:4547->4326
+               and EGM96 geoid height conversion.
+`value` is whole-job input points/s with the records resident in HBM; `e2e` is the same metric through
+the host-buffer call (pinned host records -> H2D -> pipeline -> D2H of the results) every step.
+`--impl reference` times the CPU oracle (numpy + real scikit-learn, all host threads) on a bounded
+prefix of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "input points/s through the LAS hot path (decode->downsample->ground->tower)"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "voxel_geoid"])
+    ap.add_argument("--points", type=float, default=None, help="points per GPU")
+    ap.add_argument("--box", default="aabb", choices=["aabb", "obb"])
+    ap.add_argument("--ground", default="percentile", choices=["percentile", "grid"])
+    ap.add_argument("--ref-sample", type=float, default=None, help="points in the CPU sample (reference arm)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    if args.workload == "pipeline":
+        n = int(args.points or 100e6)
+        towers = max(2, round(n / 2e6))
+        return dict(workload="pipeline: 100M-pt hilly corridor tile, 50 towers, voxel 0.1 m chunk 500k -> pct25+3 m "
+                             "ground filter -> DBSCAN(8,80) on 50k chunks -> cluster reduce -> towers",
+                    n=n, towers=towers, terrain="hilly", seed=3, voxel=0.1, chunk=500000)
+    n = int(args.points or 20e6)
+    return dict(workload="voxel_geoid: 20M-pt flat corridor, voxel 0.1 m chunk 500k + per-point EPSG:4547->4326 + "
+                         "EGM96-style geoid height", n=n, towers=max(2, round(n / 2e6)), terrain="flat", seed=2,
+                voxel=0.1, chunk=500000)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_bytes_model(cfg, info):
+    """ALGORITHMIC bytes per launch for each kernel (DESIGN.md 'kernels'): every input read once,
+    every output written once.  n = input points, M = voxels, G = candidates, R = 34."""
+    n, M, G, R = cfg["n"], info.get("M", 0), info.get("G", 0), 34
+    return {
+        "k_chunk_minmax": n * R,
+        "k_voxel_keys": n * (R + 8),
+        "k_hist": None,          # mixed (voxel sort + DBSCAN sort): resolved from launches below
+        "k_pass": None,
+        "k_voxel_reduce": n * 8 + n * R + M * 12,
+        "k_seq_sum_serial": M * 12,
+        "k_shift": M * 12 + M * 4,
+        "k_sel_hist": M * 4,
+        "k_compact": M * 4 + G * 12 + G * 12,
+        "k_db_keys": G * 12 + G * 8,
+        "k_db_cells": G * 8 + G * 12 + G * (16 + 4 + 4),
+        "k_db_core": G * 16 + G,
+        "k_db_labels": G * 16 + G * 4,
+        "k_db_cluster_reduce": G * 16,
+        "k_las_geodetic": n * R + n * 24,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pointcloudhookup_b200 import _native, device as dv, dist as pdist, pipeline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload_config(args)
+    n = cfg["n"]
+    lib = _native.lib()
+
+    # ---- workload: one tile per rank, generated straight into pinned host memory
+    t0 = time.time()
+    pinned = torch.empty(n * 34, dtype=torch.uint8, pin_memory=True)
+    synth.corridor_records(n, cfg["towers"], cfg["terrain"], cfg["seed"] + rank,
+                           s_origin=pdist.tile_for_rank(rank, cfg["towers"]), out=pinned.numpy())
+    gen_s = time.time() - t0
+    grid = None
+    if args.workload == "voxel_geoid":
+        from pointcloudhookup_b200 import geo
+        lat = np.linspace(-90, 90, 721)
+        lon = -180 + 0.25 * np.arange(1440)
+        g = (30 * np.sin(np.radians(lat))[:, None] * np.cos(np.radians(lon))[None, :]).astype(np.float32)
+        grid = geo.upload_grid(geo.HostGrid(-90.0, -180.0, 0.25, 0.25, g), dev)
+
+    info = {}
+
+    def step(dl):
+        if args.workload == "pipeline":
+            res = pipeline.run_pipeline(dl, cfg["voxel"], cfg["chunk"], ground=args.ground, box=args.box)
+            info.update(M=res.n_voxels, G=res.n_candidates, K=res.n_clusters, towers=len(res.towers),
+                        voxel_passes=(res.voxel_plan or {}).get("n_passes", 0),
+                        db_passes=(res.db_plan or {}).get("n_passes", 0))
+            merged = pdist.merge_towers(res.towers) if world > 1 else res.towers
+            info["towers_merged"] = len(merged)
+            return res.n_clusters * 56 + 64
+        from pointcloudhookup_b200 import geo
+        v = dv.voxel_downsample(dl, cfg["voxel"], cfg["chunk"], want=("lattice",))
+        out = geo.las_to_geodetic(dl, grid, -1.0, geo.EPSG4547)
+        chk = out[:: max(1, n // 1024), 2].sum().item()   # force completion, tiny D2H
+        info.update(M=v.count, G=0, K=0, checksum=chk, voxel_passes=v.plan["n_passes"], db_passes=0)
+        return 8 + 64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dl = dv.upload_records(pinned, n, 34, synth.SCALES, synth.OFFSETS, dev)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step(dl)
+    barrier()
+
+    # ---- timed region 1: records resident in HBM; per-kernel CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.pch_profile_enable(1)
+    l0 = lib.pch_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dl)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = (lib.pch_launch_count() - l0) / args.steps
+    lib.pch_profile_enable(0)
+    import ctypes
+    cbuf = ctypes.create_string_buffer(65536)
+    lib.pch_profile_report(cbuf, 65536)
+    clocks = sampler.stop()
+    prof = {}
+    for line in cbuf.value.decode().splitlines():
+        nm, cnt, tot = line.split()
+        prof[nm] = (int(cnt), float(tot))
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n * world * args.steps / (ms_max / 1e3)
+
+    # ---- timed region 2: end to end through host buffers (H2D of the records + results D2H every step)
+    e2e = None
+    if not args.no_e2e:
+        del dl
+        torch.cuda.empty_cache()
+        barrier()
+        d2h = 0
+        e0.record()
+        for _ in range(args.steps):
+            dl2 = dv.upload_records(pinned, n, 34, synth.SCALES, synth.OFFSETS, dev)
+            d2h = step(dl2)
+            del dl2
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * args.steps / (float(t.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": n * 34, "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(t.item()) / args.steps}
+
+    # ---- roofline of the dominant kernel (from the live per-kernel events of timed region 1)
+    peak, peak_src = measured_peak()
+    model = kernel_bytes_model(cfg, info)
+    pv, pd = info.get("voxel_passes", 0), info.get("db_passes", 0)
+    if pv + pd:
+        keys_per_launch = (n * pv + info.get("G", 0) * pd) / (pv + pd)   # k_pass: voxel sort + DBSCAN cell sort
+        model["k_pass"] = 16 * keys_per_launch
+        model["k_hist"] = 8 * (n + info.get("G", 0)) / 2
+    total_kernel_ms = sum(v[1] for v in prof.values()) or 1.0
+    roof = None
+    if prof:
+        name, (cnt, tot) = max(prof.items(), key=lambda kv: kv[1][1])
+        per_launch_ms = tot / cnt
+        alg = model.get(name) or 0
+        achieved = alg / (per_launch_ms / 1e3) / 1e9
+        roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "launches_per_step": cnt / args.steps,
+                "ms_per_launch": per_launch_ms, "share_of_kernel_time": tot / total_kernel_ms}
+    kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                   "GBps": (model.get(k) / ((v[1] / v[0]) / 1e3) / 1e9) if model.get(k) else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (voxel means, distances) / f32 (tower stage) / int32 lattice",
+            "data": f"synthetic corridor LAS (PDRF 3, 34 B records), seed {cfg['seed']}+rank, generated in {gen_s:.1f}s",
+            "config": {"workload": cfg["workload"], "points_per_gpu": n, "voxel_size": cfg["voxel"],
+                       "chunk_size": cfg["chunk"], "ground": args.ground, "box": args.box,
+                       "parallelism": f"tile-per-gpu x{world}, tower merge by all_gather",
+                       "l2": "inputs (3.4 GB records per step) far exceed the 126 MB L2; no flush needed"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "stage_info": info, "kernels": kernels}
+    if rank == 0:
+        cpu = cpu_baseline(args, cfg, bounded=True)
+        line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def oracle_step(rec, cfg, args):
+    """One pass of the CPU oracle (numpy + real scikit-learn DBSCAN, n_jobs=-1) over `rec`."""
+    from oracle import las_io, towers as ot, voxel as ov
+    from pointcloudhookup_b200 import synth
+    las = {"scales": synth.SCALES, "offsets": synth.OFFSETS, "X": np.ascontiguousarray(rec["X"]),
+           "Y": np.ascontiguousarray(rec["Y"]), "Z": np.ascontiguousarray(rec["Z"]), "n": int(rec.size)}
+    final, _ = ov.downsample_las_arrays(las, cfg["voxel"], cfg["chunk"])
+    if args.workload == "pipeline":
+        q = [las_io.quantise(final[:, i], synth.SCALES[i], synth.OFFSETS[i]) for i in range(3)]
+        las2 = dict(las, X=q[0], Y=q[1], Z=q[2], n=len(q[0]))
+        return len(ot.extract_towers_arrays(las2, box="aabb" if args.box == "aabb" else "obb"))
+    from oracle import crs, geoid
+    x, y, z = las_io.scaled(las)
+    lon, lat = crs.gk_inverse(x, y)
+    lt = np.linspace(-90, 90, 721)
+    ln = -180 + 0.25 * np.arange(1440)
+    g = {"ll_lat": -90.0, "ll_lon": -180.0, "dlat": 0.25, "dlon": 0.25, "rows": 721, "cols": 1440,
+         "grid": (30 * np.sin(np.radians(lt))[:, None] * np.cos(np.radians(ln))[None, :]).astype(np.float32)}
+    return float(geoid.vgridshift(g, lon, lat, z, -1.0).sum())
+
+
+def cpu_baseline(args, cfg, bounded=True, steps=1, warmup=0):
+    from pointcloudhookup_b200 import synth
+    sample = int(args.ref_sample or (500_000 if args.workload == "pipeline" else 4_000_000))
+    sample = min(sample, cfg["n"])
+    towers = max(1, round(cfg["towers"] * sample / cfg["n"]))
+    rec = synth.corridor_records(sample, towers, cfg["terrain"], cfg["seed"])
+    for _ in range(warmup):
+        oracle_step(rec, cfg, args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(rec, cfg, args)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": sample / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first {sample} points ({towers} tower spans) of the same synthetic workload, "
+                      f"{dt:.1f} s per pass; numpy single-threaded + scikit-learn DBSCAN n_jobs=-1",
+            "seconds_per_pass": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload_config(args)
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup else 0
+    cpu = cpu_baseline(args, cfg, steps=steps, warmup=warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+            "ms_per_step": cpu["seconds_per_pass"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64/f32 (numpy)", "data": "synthetic corridor LAS, bounded sample",
+            "config": {"workload": cfg["workload"], "points_per_gpu": cfg["n"], "voxel_size": cfg["voxel"],
+                       "chunk_size": cfg["chunk"], "ground": args.ground, "box": args.box},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

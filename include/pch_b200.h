@@ -35,7 +35,13 @@ typedef void* pch_stream_t;
 
 const char* pch_last_error(void);
 int pch_version(void);
-/* device-side error word raised by bounded spin loops (0 = fine); lives in caller workspace */
+/* kernels launched by this library so far (process-wide; bench.py reports the per-step delta) */
+long long pch_launch_count(void);
+/* per-kernel device timing without a profiler: while enabled every launch is bracketed by CUDA
+ * events on its stream; pch_profile_report synchronises the device and writes one
+ * "kernel_name launches total_ms" line per kernel into buf, then clears the records. */
+void pch_profile_enable(int on);
+int pch_profile_report(char* buf, size_t cap);
 
 /* ---------------------------------------------------------------- LAS attribute decode / encode */
 

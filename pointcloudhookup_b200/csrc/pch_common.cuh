@@ -32,6 +32,18 @@ int pch_sm_count();
 
 #define PCH_LAUNCH_CHECK() PCH_CUDA(cudaGetLastError())
 
+// Every kernel launch goes through PCH_LAUNCH: it counts the launch (pch_launch_count) and, when
+// profiling is switched on (pch_profile_enable), brackets it with CUDA events on the launching
+// stream so bench.py can attribute device time per kernel without a profiler attached.
+void pch_prof_begin(cudaStream_t st, const char* name);
+void pch_prof_end(cudaStream_t st);
+#define PCH_LAUNCH(st, name, ...)       \
+    do {                                \
+        pch_prof_begin((st), (name));   \
+        __VA_ARGS__;                    \
+        pch_prof_end((st));             \
+    } while (0)
+
 static inline int64_t pch_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t pch_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -621,11 +621,11 @@ extern "C" int pch_dbscan_plan(const float* P, int64_t G, int64_t chunk, double 
     PCH_CHECK_ARG(P && bounds_dev && plan_dev, "null pointer");
     if (chunk > G) chunk = G;
     int64_t n_chunks = pch_ceil_div(G, chunk);
-    k_db_bounds_init<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>(bounds_dev, n_chunks);
+    PCH_LAUNCH(st, "k_db_bounds_init", k_db_bounds_init<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>(bounds_dev, n_chunks));
     PCH_LAUNCH_CHECK();
-    k_db_bounds<<<db_grid(G, 4096, 16), 256, 0, st>>>(P, G, chunk, bounds_dev);
+    PCH_LAUNCH(st, "k_db_bounds", k_db_bounds<<<db_grid(G, 4096, 16), 256, 0, st>>>(P, G, chunk, bounds_dev));
     PCH_LAUNCH_CHECK();
-    k_db_plan<<<1, 256, 0, st>>>(bounds_dev, n_chunks, chunk, db_cell_side(eps), (DbPlan*)plan_dev);
+    PCH_LAUNCH(st, "k_db_plan", k_db_plan<<<1, 256, 0, st>>>(bounds_dev, n_chunks, chunk, db_cell_side(eps), (DbPlan*)plan_dev));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -721,7 +721,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     g.sh_z = plan->bits_idx; g.sh_y = g.sh_z + plan->bits_z; g.sh_x = g.sh_y + plan->bits_y;
 
     PCH_CUDA(cudaMemsetAsync(base + w.scalars, 0, 256, st));
-    k_db_keys<<<db_grid(G, 256), 256, 0, st>>>(P, g, bounds_dev, keys);
+    PCH_LAUNCH(st, "k_db_keys", k_db_keys<<<db_grid(G, 256), 256, 0, st>>>(P, g, bounds_dev, keys));
     PCH_LAUNCH_CHECK();
     int rc = pch_sort_u64_segmented(keys, tmp, G, chunk, plan->bits_idx, plan->bits_idx + plan->key_bits,
                                     base + w.sortws, w.sortws_bytes, stream);
@@ -741,7 +741,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     int64_t total_tiles = (g.n_chunks - 1) * tiles_per_chunk + pch_ceil_div(last, DC_TILE);
     uint64_t* status = (uint64_t*)(base + w.scan_status);
     PCH_CUDA(cudaMemsetAsync(status, 0, (size_t)total_tiles * 8, st));
-    k_db_cells<<<(unsigned)total_tiles, DC_THREADS, 0, st>>>(skeys, P, g, o, tiles_per_chunk, total_tiles, status, counter, err);
+    PCH_LAUNCH(st, "k_db_cells", k_db_cells<<<(unsigned)total_tiles, DC_THREADS, 0, st>>>(skeys, P, g, o, tiles_per_chunk, total_tiles, status, counter, err));
     PCH_LAUNCH_CHECK();
 
     int32_t* nbr_first = (int32_t*)(base + w.nbr_first);
@@ -755,38 +755,38 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     int32_t* head_list = (int32_t*)(base + w.head_list);
     DbClusterAcc* acc = (DbClusterAcc*)(base + w.acc);
 
-    k_db_nbr<<<db_grid(G, 256), 256, 0, st>>>(g, o.cell_key, o.cell_start, o.chunk_cell0, U_dev, nbr_first, nbr_cnt);
+    PCH_LAUNCH(st, "k_db_nbr", k_db_nbr<<<db_grid(G, 256), 256, 0, st>>>(g, o.cell_key, o.cell_start, o.chunk_cell0, U_dev, nbr_first, nbr_cnt));
     PCH_LAUNCH_CHECK();
-    k_db_core<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt, core);
+    PCH_LAUNCH(st, "k_db_core", k_db_core<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt, core));
     PCH_LAUNCH_CHECK();
-    k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info);
+    PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info));
     PCH_LAUNCH_CHECK();
-    k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first, nbr_cnt, info);
+    PCH_LAUNCH(st, "k_db_union", k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first, nbr_cnt, info));
     PCH_LAUNCH_CHECK();
-    k_db_flatten<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info, cell_root);
+    PCH_LAUNCH(st, "k_db_flatten", k_db_flatten<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info, cell_root));
     PCH_LAUNCH_CHECK();
     PCH_CUDA(cudaMemsetAsync(root_min, 0x7f, (size_t)G * 4, st));
     PCH_CUDA(cudaMemsetAsync(is_head, 0, (size_t)G, st));
-    k_db_mincore<<<db_grid(G, 256), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_min);
+    PCH_LAUNCH(st, "k_db_mincore", k_db_mincore<<<db_grid(G, 256), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_min));
     PCH_LAUNCH_CHECK();
-    k_db_heads<<<db_grid(G, 256), 256, 0, st>>>(U_dev, cell_root, root_min, is_head);
+    PCH_LAUNCH(st, "k_db_heads", k_db_heads<<<db_grid(G, 256), 256, 0, st>>>(U_dev, cell_root, root_min, is_head));
     PCH_LAUNCH_CHECK();
     // cluster ids = rank of each head in original order (exclusive scan of head flags, all chunks at once:
     // this IS the reference's running `current_label` offset)
     rc = pch_compact_points(P, nullptr, is_head, G, nullptr, 0.f, nullptr, head_list, nullptr, n_clusters_dev,
                             base + w.scan_status, pch_compact_workspace_bytes(G), stream);
     if (rc) return rc;
-    k_db_cluster_ids<<<db_grid(G, 256), 256, 0, st>>>((const long long*)n_clusters_dev, head_list, o.inv_pos, o.pt_cell,
-                                                      cell_root, root_label);
+    PCH_LAUNCH(st, "k_db_cluster_ids", k_db_cluster_ids<<<db_grid(G, 256), 256, 0, st>>>((const long long*)n_clusters_dev, head_list, o.inv_pos, o.pt_cell,
+                                                      cell_root, root_label));
     PCH_LAUNCH_CHECK();
-    k_db_labels<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first, nbr_cnt, cell_root,
-                                                     root_label, labels_dev);
+    PCH_LAUNCH(st, "k_db_labels", k_db_labels<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first, nbr_cnt, cell_root,
+                                                     root_label, labels_dev));
     PCH_LAUNCH_CHECK();
-    k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc);
+    PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
     PCH_LAUNCH_CHECK();
-    k_db_cluster_reduce<<<db_grid(G, 256), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc);
+    PCH_LAUNCH(st, "k_db_cluster_reduce", k_db_cluster_reduce<<<db_grid(G, 256), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc));
     PCH_LAUNCH_CHECK();
-    k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev);
+    PCH_LAUNCH(st, "k_db_acc_finish", k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

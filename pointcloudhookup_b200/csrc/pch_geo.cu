@@ -137,7 +137,7 @@ extern "C" int pch_geoid_shift(const double* lat, const double* lon, const doubl
     if (rc) return rc;
     if (n == 0) return PCH_OK;
     PCH_CHECK_ARG(lat && lon && grid && (out_n || (h && out_h)), "null pointer");
-    k_geoid_shift<<<geo_grid(n, 256, 8), 256, 0, st>>>(lat, lon, h, n, grid, *g, multiplier, out_h, out_n);
+    PCH_LAUNCH(st, "k_geoid_shift", k_geoid_shift<<<geo_grid(n, 256, 8), 256, 0, st>>>(lat, lon, h, n, grid, *g, multiplier, out_h, out_n));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -149,7 +149,7 @@ extern "C" int pch_gk_inverse(const double* x, const double* y, int64_t n, const
     PCH_CHECK_ARG(p->rect_radius > 0.0 && p->k0 > 0.0, "bad projection constants");
     if (n == 0) return PCH_OK;
     PCH_CHECK_ARG(x && y && lon && lat, "null pointer");
-    k_gk_inverse<<<geo_grid(n, 128, 16), 128, 0, st>>>(x, y, n, *p, lon, lat);
+    PCH_LAUNCH(st, "k_gk_inverse", k_gk_inverse<<<geo_grid(n, 128, 16), 128, 0, st>>>(x, y, n, *p, lon, lat));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -247,7 +247,7 @@ extern "C" int pch_las_geodetic(const uint8_t* rec, int64_t n, int32_t rec_len, 
 #define LAUNCH_GEO(A, S)                                                                                         \
     do {                                                                                                         \
         PCH_CUDA(cudaFuncSetAttribute(k_las_geodetic<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_las_geodetic<A, S><<<grid_dim, PCH_TILE_THREADS, smem, st>>>(rec, tg, a, tmv, grid, *g, w, multiplier, use_crs, out); \
+        PCH_LAUNCH(st, "k_las_geodetic", k_las_geodetic<A, S><<<grid_dim, PCH_TILE_THREADS, smem, st>>>(rec, tg, a, tmv, grid, *g, w, multiplier, use_crs, out)); \
     } while (0)
     if (staged) {
         if (al == 4) LAUNCH_GEO(4, true); else if (al == 2) LAUNCH_GEO(2, true); else LAUNCH_GEO(1, true);

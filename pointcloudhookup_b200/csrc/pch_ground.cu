@@ -39,9 +39,9 @@ extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(m >= 1, "centroid of an empty cloud");
     PCH_CHECK_ARG(xyz && sums3 && centroid3, "null pointer");
-    k_seq_sum_serial<<<1, 32, 0, st>>>(xyz, m, sums3);
+    PCH_LAUNCH(st, "k_seq_sum_serial", k_seq_sum_serial<<<1, 32, 0, st>>>(xyz, m, sums3));
     PCH_LAUNCH_CHECK();
-    k_centroid_from_sums<<<1, 32, 0, st>>>(sums3, m, centroid3);
+    PCH_LAUNCH(st, "k_centroid_from_sums", k_centroid_from_sums<<<1, 32, 0, st>>>(sums3, m, centroid3));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -80,7 +80,7 @@ extern "C" int pch_f32_shift(const float* xyz, int64_t m, const float* centroid3
     PCH_CHECK_ARG(m >= 0, "m must be >= 0");
     if (m == 0) return PCH_OK;
     PCH_CHECK_ARG(xyz && centroid3 && (zs || shifted), "null pointer");
-    k_shift<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, centroid3, zs, shifted);
+    PCH_LAUNCH(st, "k_shift", k_shift<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, centroid3, zs, shifted));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -163,13 +163,13 @@ extern "C" int pch_select_f32(const float* v, int64_t n, int64_t rank0, int64_t 
         return PCH_ERR_WORKSPACE;
     }
     SelState* s = (SelState*)workspace;
-    k_sel_init<<<8, 256, 0, st>>>(s, rank0, rank1);
+    PCH_LAUNCH(st, "k_sel_init", k_sel_init<<<8, 256, 0, st>>>(s, rank0, rank1));
     PCH_LAUNCH_CHECK();
     unsigned grid = grid_for(n, 256 * 8, 8);
     for (int pass = 0; pass < 4; ++pass) {
-        k_sel_hist<<<grid, 256, 0, st>>>(v, n, s, pass);
+        PCH_LAUNCH(st, "k_sel_hist", k_sel_hist<<<grid, 256, 0, st>>>(v, n, s, pass));
         PCH_LAUNCH_CHECK();
-        k_sel_decide<<<1, 32, 0, st>>>(s, pass, out2);
+        PCH_LAUNCH(st, "k_sel_decide", k_sel_decide<<<1, 32, 0, st>>>(s, pass, out2));
         PCH_LAUNCH_CHECK();
     }
     return PCH_OK;
@@ -266,8 +266,8 @@ extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8
     uint32_t* counter = (uint32_t*)((uint8_t*)workspace + 64);
     uint64_t* status = (uint64_t*)((uint8_t*)workspace + 256);
     int64_t tiles = pch_ceil_div(m, CP_TILE);
-    k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src, out_mask,
-                                                      (long long*)count_dev, status, counter, err);
+    PCH_LAUNCH(st, "k_compact", k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src, out_mask,
+                                                      (long long*)count_dev, status, counter, err));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -317,9 +317,9 @@ extern "C" int pch_grid_min_ground(const float* xyz, int64_t m, float minx, floa
     int64_t n_cells = (int64_t)nx * ny;
     PCH_CUDA(cudaMemsetAsync(cell_min, 0xff, (size_t)n_cells * 4, st));
     unsigned grid = grid_for(m, 256, 8);
-    k_grid_min<<<grid, 256, 0, st>>>(xyz, m, minx, miny, cell, ny, n_cells, cell_min);
+    PCH_LAUNCH(st, "k_grid_min", k_grid_min<<<grid, 256, 0, st>>>(xyz, m, minx, miny, cell, ny, n_cells, cell_min));
     PCH_LAUNCH_CHECK();
-    k_grid_label<<<grid, 256, 0, st>>>(xyz, m, minx, miny, cell, ny, n_cells, cell_min, hag, keep, ground_z);
+    PCH_LAUNCH(st, "k_grid_label", k_grid_label<<<grid, 256, 0, st>>>(xyz, m, minx, miny, cell, ny, n_cells, cell_min, hag, keep, ground_z));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -359,9 +359,9 @@ __global__ void k_minmax_f32_fin(uint32_t* out6) {
 extern "C" int pch_f32_minmax(const float* xyz, int64_t m, float* out6, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(m >= 1 && xyz && out6, "bad arguments");
-    k_minmax_f32_init<<<1, 32, 0, st>>>((uint32_t*)out6);
-    k_minmax_f32<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, (uint32_t*)out6);
-    k_minmax_f32_fin<<<1, 32, 0, st>>>((uint32_t*)out6);
+    PCH_LAUNCH(st, "k_minmax_f32_init", k_minmax_f32_init<<<1, 32, 0, st>>>((uint32_t*)out6));
+    PCH_LAUNCH(st, "k_minmax_f32", k_minmax_f32<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, (uint32_t*)out6));
+    PCH_LAUNCH(st, "k_minmax_f32_fin", k_minmax_f32_fin<<<1, 32, 0, st>>>((uint32_t*)out6));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

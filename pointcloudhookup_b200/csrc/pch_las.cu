@@ -52,12 +52,12 @@ k_chunk_minmax(const uint8_t* __restrict__ rec, PchTileGeom g, int32_t* __restri
 }
 
 template <class K, class... Args>
-static int launch_tiles(K kernel, const PchTileGeom& g, int ctas_per_sm, cudaStream_t st, const uint8_t* rec,
-                        Args... args) {
+static int launch_tiles(const char* name, K kernel, const PchTileGeom& g, int ctas_per_sm, cudaStream_t st,
+                        const uint8_t* rec, Args... args) {
     size_t smem = pch_tile_smem_bytes(g);
     PCH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = pch_tile_grid(g, ctas_per_sm);
-    kernel<<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, args...);
+    PCH_LAUNCH(st, name, kernel<<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, args...));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -66,9 +66,9 @@ static int launch_tiles(K kernel, const PchTileGeom& g, int ctas_per_sm, cudaStr
     do {                                                                          \
         int a__ = pch_rec_align(rec_len);                                         \
         int rc__;                                                                 \
-        if (a__ == 4) rc__ = launch_tiles(KERNEL<4>, __VA_ARGS__);                \
-        else if (a__ == 2) rc__ = launch_tiles(KERNEL<2>, __VA_ARGS__);           \
-        else rc__ = launch_tiles(KERNEL<1>, __VA_ARGS__);                         \
+        if (a__ == 4) rc__ = launch_tiles(#KERNEL, KERNEL<4>, __VA_ARGS__);       \
+        else if (a__ == 2) rc__ = launch_tiles(#KERNEL, KERNEL<2>, __VA_ARGS__);  \
+        else rc__ = launch_tiles(#KERNEL, KERNEL<1>, __VA_ARGS__);                \
         if (rc__ != PCH_OK) return rc__;                                          \
     } while (0)
 
@@ -82,7 +82,7 @@ extern "C" int pch_las_chunk_minmax(const uint8_t* rec, int64_t n, int32_t rec_l
     if (n == 0) return PCH_OK;
     PchTileGeom g = pch_tile_geom(n, rec_len, chunk_size);
     int64_t n_chunks = pch_ceil_div(n, g.chunk_size);
-    k_init_minmax<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>(mm, n_chunks);
+    PCH_LAUNCH(st, "k_init_minmax", k_init_minmax<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>(mm, n_chunks));
     PCH_LAUNCH_CHECK();
     PCH_DISPATCH_ALIGN(rec_len, k_chunk_minmax, g, 2, st, rec, mm);
     return PCH_OK;
@@ -185,7 +185,7 @@ extern "C" int pch_las_quantise(const double* xyz, int64_t m, const double* scal
     int64_t blocks = pch_ceil_div(m * 3, 256);
     int64_t cap = (int64_t)pch_sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_quantise<<<(unsigned)blocks, 256, 0, st>>>(xyz, m, a, lattice);
+    PCH_LAUNCH(st, "k_quantise", k_quantise<<<(unsigned)blocks, 256, 0, st>>>(xyz, m, a, lattice));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -254,7 +254,7 @@ extern "C" int pch_las_encode(const int32_t* lattice, int64_t m, int32_t rec_len
     PCH_CHECK_ARG(m >= 0, "m must be >= 0");
     PCH_CHECK_ARG(rec_len >= 12 && rec_len <= 128, "record length %d outside [12, 128]", rec_len);
     if (mm6) {
-        k_init_minmax<<<1, 32, 0, st>>>(mm6, 1);
+        PCH_LAUNCH(st, "k_init_minmax", k_init_minmax<<<1, 32, 0, st>>>(mm6, 1));
         PCH_LAUNCH_CHECK();
     }
     if (m == 0) return PCH_OK;
@@ -265,7 +265,7 @@ extern "C" int pch_las_encode(const int32_t* lattice, int64_t m, int32_t rec_len
     int64_t tiles = pch_ceil_div(m, ENC_TILE);
     int64_t grid = (int64_t)pch_sm_count() * 2;
     if (grid > tiles) grid = tiles;
-    k_encode<<<(unsigned)grid, 256, smem, st>>>(lattice, m, rec_len, rec_out, mm6);
+    PCH_LAUNCH(st, "k_encode", k_encode<<<(unsigned)grid, 256, smem, st>>>(lattice, m, rec_len, rec_out, mm6));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

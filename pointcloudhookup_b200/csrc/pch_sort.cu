@@ -260,17 +260,17 @@ extern "C" int pch_sort_u64_segmented(uint64_t* keys, uint64_t* tmp, int64_t n, 
     PCH_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));
     int64_t hgrid = (int64_t)pch_sm_count() * 8;
     if (hgrid > g.total_tiles) hgrid = g.total_tiles;
-    k_hist<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys, g, w.hist);
+    PCH_LAUNCH(st, "k_hist", k_hist<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys, g, w.hist));
     PCH_LAUNCH_CHECK();
     int64_t rows = g.n_segs * g.n_passes;
-    k_scan<<<(unsigned)(rows < 4096 ? rows : 4096), 256, 0, st>>>(w.hist, rows);
+    PCH_LAUNCH(st, "k_scan", k_scan<<<(unsigned)(rows < 4096 ? rows : 4096), 256, 0, st>>>(w.hist, rows));
     PCH_LAUNCH_CHECK();
     uint64_t* src = keys;
     uint64_t* dst = tmp;
     for (int p = 0; p < g.n_passes; ++p) {
-        k_pass<<<(unsigned)g.total_tiles, RS_THREADS, 0, st>>>(src, dst, g, p, w.hist,
+        PCH_LAUNCH(st, "k_pass", k_pass<<<(unsigned)g.total_tiles, RS_THREADS, 0, st>>>(src, dst, g, p, w.hist,
                                                                w.status + (size_t)p * g.total_tiles * 256,
-                                                               w.counters + p, w.err);
+                                                               w.counters + p, w.err));
         PCH_LAUNCH_CHECK();
         uint64_t* t = src; src = dst; dst = t;
     }

@@ -79,7 +79,7 @@ extern "C" int pch_voxel_plan_build(const int32_t* mm, int64_t n_chunks, int64_t
     PchAffine3 a;
     int rc = make_affine3(scales, offsets, a);
     if (rc) return rc;
-    k_voxel_plan<<<1, 256, 0, st>>>(mm, n_chunks, chunk_size, a, voxel, origins, plan);
+    PCH_LAUNCH(st, "k_voxel_plan", k_voxel_plan<<<1, 256, 0, st>>>(mm, n_chunks, chunk_size, a, voxel, origins, plan));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -142,7 +142,7 @@ extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, in
 #define LAUNCH_KEYS(A)                                                                                       \
     do {                                                                                                     \
         PCH_CUDA(cudaFuncSetAttribute(k_voxel_keys<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, voxel, origins, kl, keys);          \
+        PCH_LAUNCH(st, "k_voxel_keys", k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, voxel, origins, kl, keys));          \
     } while (0)
     if (al == 4) LAUNCH_KEYS(4);
     else if (al == 2) LAUNCH_KEYS(2);
@@ -326,9 +326,9 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     uint64_t* status = (uint64_t*)((uint8_t*)workspace + 256);
     int al = rec_len == 0 ? 0 : pch_rec_align(rec_len);
 #define LAUNCH_RED(A)                                                                                          \
-    k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
+    PCH_LAUNCH(st, "k_voxel_reduce", k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
         keys, g, rec, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
-        status, counter, err)
+        status, counter, err))
     if (al == 4) LAUNCH_RED(4);
     else if (al == 2) LAUNCH_RED(2);
     else if (al == 1) LAUNCH_RED(1);
@@ -436,11 +436,11 @@ extern "C" int pch_voxel_plan_build_f64(const double* xyz, int64_t n, int64_t ch
     PCH_CHECK_ARG(xyz && minmax_scratch && origins && plan, "null pointer");
     if (chunk_size > n) chunk_size = n;
     int64_t n_chunks = pch_ceil_div(n, chunk_size);
-    k_f64_minmax_init<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>((unsigned long long*)minmax_scratch, n_chunks);
+    PCH_LAUNCH(st, "k_f64_minmax_init", k_f64_minmax_init<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>((unsigned long long*)minmax_scratch, n_chunks));
     int64_t blocks = pch_ceil_div(n, 4096);
     int64_t cap = (int64_t)pch_sm_count() * 16;
-    k_f64_chunk_minmax<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, (unsigned long long*)minmax_scratch);
-    k_voxel_plan_f64<<<1, 256, 0, st>>>((const unsigned long long*)minmax_scratch, n_chunks, chunk_size, voxel, origins, plan);
+    PCH_LAUNCH(st, "k_f64_chunk_minmax", k_f64_chunk_minmax<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, (unsigned long long*)minmax_scratch));
+    PCH_LAUNCH(st, "k_voxel_plan_f64", k_voxel_plan_f64<<<1, 256, 0, st>>>((const unsigned long long*)minmax_scratch, n_chunks, chunk_size, voxel, origins, plan));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -462,7 +462,7 @@ extern "C" int pch_voxel_keys_f64(const double* xyz, int64_t n, int64_t chunk_si
     kl.sh_x = kl.sh_y + plan->bits_y;
     int64_t blocks = pch_ceil_div(n, 256);
     int64_t cap = (int64_t)pch_sm_count() * 8;
-    k_voxel_keys_f64<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, voxel, origins, kl, keys);
+    PCH_LAUNCH(st, "k_voxel_keys_f64", k_voxel_keys_f64<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, voxel, origins, kl, keys));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

@@ -287,6 +287,7 @@ class DbscanResult:
     labels: torch.Tensor          # int32 [G], the reference's all_labels
     n_clusters: int
     stats: np.ndarray             # structured host array [K]: count, min[3], max[3], sum[3]
+    plan: Optional[dict] = None   # cell-grid key layout (bits per axis, radix passes)
 
 
 STATS_DTYPE = np.dtype([("count", "<i8"), ("min", "<f4", 3), ("max", "<f4", 3), ("sum", "<f8", 3)])
@@ -329,7 +330,7 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
             break
         cap = k
     host = stats[: k * STATS_DTYPE.itemsize].cpu().numpy().view(STATS_DTYPE).copy()
-    return DbscanResult(labels, k, host)
+    return DbscanResult(labels, k, host, {f: getattr(plan, f) for f, _ in VoxelPlan._fields_})
 
 
 def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Optional[int] = None) -> VoxelResult:

@@ -65,6 +65,7 @@ class TowerStages:
     n_clusters: int
     stats: np.ndarray               # per-label count / AABB / sums (host)
     mask: Optional[torch.Tensor] = None
+    db_plan: Optional[dict] = None
 
 
 def ground_filter_percentile(raw: torch.Tensor, pct: float = 25, offset: float = 3.0, min_keep: int = 1000,
@@ -104,7 +105,8 @@ def run_stages(raw: torch.Tensor, eps: float = 8.0, min_points: int = 80, ground
     else:
         raise ValueError(f"unknown ground mode {ground!r}")
     db = dv.dbscan_chunked(filtered, eps, min_points, DBSCAN_CHUNK)
-    return TowerStages(raw, cen_dev.cpu().numpy(), base, used, filtered, db.labels, db.n_clusters, db.stats, mask)
+    return TowerStages(raw, cen_dev.cpu().numpy(), base, used, filtered, db.labels, db.n_clusters, db.stats, mask,
+                       db.plan)
 
 
 # ---------------------------------------------------------------------------------------------

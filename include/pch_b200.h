@@ -128,8 +128,12 @@ int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_s
 /* ---------------------------------------------------------------- tower extraction, stages A/B */
 
 /* centroid = np.mean(raw_points_f32, axis=0) (utils/tower_extraction.py:63): numpy's SEQUENTIAL
- * float32 column sums (sums3_dev, float[3]) divided in float64 and cast to float32 (centroid3_dev). */
+ * float32 column sums (sums3_dev, float[3]) divided in float64 and cast to float32 (centroid3_dev).
+ * With a workspace the sums are evaluated in parallel, bit-identically (binade-local integer maps
+ * composed by scans; real float32 adds wherever a map would not be exact). */
+size_t pch_f32_centroid_workspace_bytes(int64_t m);
 int pch_f32_centroid(const float* xyz_dev, int64_t m, float* sums3_dev, float* centroid3_dev,
+                     void* workspace_dev /* NULL = serial reference kernel */, size_t workspace_bytes,
                      pch_stream_t stream);
 
 /* points = raw_points - centroid (utils/tower_extraction.py:64), float32 subtract.  zs_dev (m) gets

@@ -57,7 +57,8 @@ class ClusterStats(C.Structure):
 
 
 SIGNATURES.update({
-    "pch_f32_centroid": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "pch_f32_centroid_workspace_bytes": (_sz, [_i64]),
+    "pch_f32_centroid": (C.c_int, [_p, _i64, _p, _p, _p, _sz, _p]),
     "pch_f32_shift": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "pch_select_workspace_bytes": (_sz, []),
     "pch_select_f32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),

@@ -35,12 +35,291 @@ __global__ void k_centroid_from_sums(const float* __restrict__ sums, int64_t m, 
     if (c < 3) centroid[c] = (float)((double)sums[c] / (double)m);  // true_divide in f64, cast to f32
 }
 
-extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float* centroid3, pch_stream_t stream) {
+// v2: exact parallel evaluation of the same sequential float32 sums.
+//
+// While the running sum s stays inside one binade, s = m * 2^k with a 24-bit integer mantissa m, and
+// fl(s + a) adds an INTEGER to m: q + [r > h] + [r == h] * ((m + q) & 1), where a = q*2^k + r (r < 2^k,
+// h = 2^(k-1)) — round-to-nearest-even only looks at the parity of m.  So for a fixed k a run of
+// elements is a map  parity(m) -> increment of m, maps compose associatively, and:
+//   k_sum_prep   per tile of SQ_TILE elements: float64 sum / max / sign flags          (parallel)
+//   k_sum_window exclusive prefix of the tile sums -> predicted binade window per tile  (one CTA)
+//   k_sum_tables per tile and per k in its window: the composed map (D[parity 0], D[parity 1])
+//   k_sum_chain  one warp per column walks the tiles 32 at a time: a warp scan composes the maps,
+//                a ballot finds the first tile where the sum would leave the binade (or whose window
+//                misses k); that tile alone is summed with real float32 adds, then the walk resumes.
+// The result is bit-identical to the serial loop for ANY input: maps are only used where they are
+// provably exact (non-negative finite data, no binade crossing), everything else takes the real adds.
+#define SQ_TILE 2048
+#define SQ_THREADS 256
+#define SQ_EPT (SQ_TILE / SQ_THREADS)
+#define SQ_W 8
+#define SQ_SAT 0x7fffffffu
+
+struct SqTileInfo {
+    double sum;      // float64 sum of the tile (prediction only)
+    float maxv;
+    int32_t ok;      // all elements finite and >= 0
+};
+
+__global__ void __launch_bounds__(SQ_THREADS)
+k_sum_prep(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, SqTileInfo* __restrict__ info /*[3][n_tiles]*/) {
+    __shared__ double s_sum[3][SQ_THREADS / 32];
+    __shared__ float s_max[3][SQ_THREADS / 32];
+    __shared__ int s_ok[3][SQ_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t base = t * SQ_TILE;
+        double sum[3] = {0.0, 0.0, 0.0};
+        float mx[3] = {0.f, 0.f, 0.f};
+        int ok[3] = {1, 1, 1};
+        // the tile is 3*SQ_TILE contiguous floats; thread reads floats tid, tid+256, ... (coalesced)
+        for (int j = tid; j < 3 * SQ_TILE; j += SQ_THREADS) {
+            const int64_t e = base * 3 + j;
+            if (e < m * 3) {
+                const float v = xyz[e];
+                const int c = j % 3;
+                sum[c] += (double)v;
+                mx[c] = fmaxf(mx[c], v);
+                if (!(v >= 0.0f) || !(v < INFINITY)) ok[c] = 0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], o);
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+                ok[c] &= __shfl_xor_sync(0xffffffffu, ok[c], o);
+            }
+            if (lane == 0) { s_sum[c][warp] = sum[c]; s_max[c][warp] = mx[c]; s_ok[c][warp] = ok[c]; }
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double sm = 0.0; float mm = 0.f; int kk = 1;
+            for (int w = 0; w < SQ_THREADS / 32; ++w) { sm += s_sum[tid][w]; mm = fmaxf(mm, s_max[tid][w]); kk &= s_ok[tid][w]; }
+            SqTileInfo ti; ti.sum = sm; ti.maxv = mm; ti.ok = kk;
+            info[tid * n_tiles + t] = ti;
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA, 3 warps: per column exclusive float64 prefix of tile sums and column max -> klo[c][t]
+__global__ void k_sum_window(const SqTileInfo* __restrict__ info, int64_t n_tiles, int32_t* __restrict__ klo) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= 3) return;
+    const SqTileInfo* ti = info + c * n_tiles;
+    float amax = 0.f;
+    for (int64_t t = lane; t < n_tiles; t += 32) amax = fmaxf(amax, ti[t].maxv);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const int kcap = (amax > 0.f ? ilogbf(amax) : -126) + 2;
+    double carry = 0.0;
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += 32) {
+        const int64_t t = t0 + lane;
+        double v = t < n_tiles ? ti[t].sum : 0.0;
+        double x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        const double excl = carry + x - v;
+        if (t < n_tiles) {
+            int kc = excl > 0.0 ? (ilogb(excl) - 23) : -149;
+            if (kc > kcap) kc = kcap;
+            klo[c * n_tiles + t] = kc - SQ_W / 2;
+        }
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+}
+
+struct SqMap { uint32_t d0, d1; };
+
+__device__ __forceinline__ uint32_t sq_sat_add(uint32_t a, uint32_t b) {
+    uint32_t s = a + b;
+    return (a >= SQ_SAT || b >= SQ_SAT || s >= SQ_SAT || s < a) ? SQ_SAT : s;
+}
+// apply F first, then G
+__device__ __forceinline__ SqMap sq_compose(const SqMap& F, const SqMap& G) {
+    SqMap H;
+    H.d0 = sq_sat_add(F.d0, (F.d0 & 1u) ? G.d1 : G.d0);
+    H.d1 = sq_sat_add(F.d1, ((1u + F.d1) & 1u) ? G.d1 : G.d0);
+    return H;
+}
+
+// increment of the mantissa m (ulp 2^k) when adding the float with bit pattern `bits`, for parity p of m
+__device__ __forceinline__ void sq_elem(uint32_t bits, int k, uint32_t& q, uint32_t& gt, uint32_t& eq) {
+    int ea = (int)((bits >> 23) & 0xffu);
+    uint32_t ma = bits & 0x7fffffu;
+    if (ea == 0) ea = 1; else ma |= 0x800000u;
+    const int shift = k - (ea - 150);   // a = ma * 2^(ea-150)
+    gt = 0; eq = 0;
+    if (ma == 0) { q = 0; return; }
+    if (shift <= 0) {
+        q = (-shift >= 8) ? SQ_SAT : (ma << (-shift));
+    } else if (shift >= 26) {
+        q = 0;
+    } else {
+        q = shift >= 24 ? 0u : (ma >> shift);
+        const uint32_t r = shift >= 32 ? ma : (ma & ((1u << shift) - 1u));
+        const uint32_t h = 1u << (shift - 1);
+        gt = r > h;
+        eq = r == h;
+    }
+}
+
+__global__ void __launch_bounds__(SQ_THREADS)
+k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
+             const int32_t* __restrict__ klo, SqMap* __restrict__ table /*[3][n_tiles][SQ_W]*/) {
+    __shared__ float s_v[3 * SQ_TILE];
+    __shared__ SqMap s_w[SQ_THREADS / 32][SQ_W];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t base = t * SQ_TILE * 3;
+        for (int j = tid; j < 3 * SQ_TILE; j += SQ_THREADS) s_v[j] = (base + j < m * 3) ? xyz[base + j] : 0.0f;
+        __syncthreads();
+        for (int c = 0; c < 3; ++c) {
+            if (!info[c * n_tiles + t].ok) continue;  // block-uniform
+            const int k0 = klo[c * n_tiles + t];
+            SqMap mp[SQ_W];
+#pragma unroll
+            for (int w = 0; w < SQ_W; ++w) { mp[w].d0 = 0; mp[w].d1 = 0; }
+#pragma unroll
+            for (int e = 0; e < SQ_EPT; ++e) {
+                const uint32_t bits = __float_as_uint(s_v[(tid * SQ_EPT + e) * 3 + c]);
+#pragma unroll
+                for (int w = 0; w < SQ_W; ++w) {
+                    uint32_t q, gt, eq;
+                    sq_elem(bits, k0 + w, q, gt, eq);
+                    const uint32_t base_inc = sq_sat_add(q, gt);
+                    // parity of (m + D + q) decides a tie
+                    const uint32_t i0 = sq_sat_add(base_inc, eq & ((mp[w].d0 + q) & 1u));
+                    const uint32_t i1 = sq_sat_add(base_inc, eq & ((1u + mp[w].d1 + q) & 1u));
+                    mp[w].d0 = sq_sat_add(mp[w].d0, i0);
+                    mp[w].d1 = sq_sat_add(mp[w].d1, i1);
+                }
+            }
+            // ordered reduction across the block (lower thread = earlier elements)
+#pragma unroll
+            for (int w = 0; w < SQ_W; ++w) {
+                SqMap v = mp[w];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    SqMap nb;
+                    nb.d0 = __shfl_down_sync(0xffffffffu, v.d0, o);
+                    nb.d1 = __shfl_down_sync(0xffffffffu, v.d1, o);
+                    if (lane + o < 32 && (lane % (2 * o)) == 0) v = sq_compose(v, nb);
+                }
+                if (lane == 0) s_w[warp][w] = v;
+            }
+            __syncthreads();
+            if (tid < SQ_W) {
+                SqMap v = s_w[0][tid];
+                for (int ww = 1; ww < SQ_THREADS / 32; ++ww) v = sq_compose(v, s_w[ww][tid]);
+                table[((size_t)c * n_tiles + t) * SQ_W + tid] = v;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(96)
+k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
+            const int32_t* __restrict__ klo, const SqMap* __restrict__ table, float* __restrict__ sums,
+            int* __restrict__ stats /*[3][2]: tiles via maps, tiles via real adds*/) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= 3) return;
+    float s = 0.0f;
+    int64_t t = 0;
+    int n_map = 0, n_real = 0;
+    while (t < n_tiles) {
+        const uint32_t sb = __float_as_uint(s);
+        const int es = (int)((sb >> 23) & 0xffu);
+        int64_t advanced = 0;
+        if (es != 0 && es != 0xff && !(sb >> 31)) {
+            const int k = es - 150;
+            const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
+            const int64_t tt = t + lane;
+            SqMap F; F.d0 = SQ_SAT; F.d1 = SQ_SAT;
+            if (tt < n_tiles && info[c * n_tiles + tt].ok) {
+                const int idx = k - klo[c * n_tiles + tt];
+                if (idx >= 0 && idx < SQ_W) F = table[((size_t)c * n_tiles + tt) * SQ_W + idx];
+            }
+            // inclusive ordered scan of the maps across the 32 tiles
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                SqMap pv;
+                pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                if (lane >= o) F = sq_compose(pv, F);
+            }
+            const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
+            const bool ok = D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
+            const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+            const int L = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);   // leading tiles that stay in the binade
+            if (L > 0) {
+                const uint32_t Dl = __shfl_sync(0xffffffffu, D, L - 1);
+                s = __uint_as_float(((uint32_t)es << 23) | ((ms + Dl) & 0x7fffffu));
+                advanced = L;
+                n_map += L;
+            }
+        }
+        t += advanced;
+        if (advanced < 32 && t < n_tiles) {
+            // this tile leaves the binade / is outside its window / has negative data: real float32 adds
+            const int64_t lo = t * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
+            for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+                const int64_t i = i0 + lane;
+                const float v = i < hi ? xyz[i * 3 + c] : 0.0f;
+                const int cnt = (int)min((int64_t)32, hi - i0);
+                for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+            }
+            ++t;
+            ++n_real;
+        }
+    }
+    if (lane == 0) {
+        sums[c] = s;
+        if (stats) { stats[c * 2] = n_map; stats[c * 2 + 1] = n_real; }
+    }
+}
+
+extern "C" size_t pch_f32_centroid_workspace_bytes(int64_t m) {
+    int64_t nt = pch_ceil_div(m > 0 ? m : 1, SQ_TILE);
+    return 256 + pch_align_up((size_t)3 * nt * sizeof(SqTileInfo), 256) + pch_align_up((size_t)3 * nt * 4, 256) +
+           pch_align_up((size_t)3 * nt * SQ_W * sizeof(SqMap), 256);
+}
+
+extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float* centroid3, void* workspace,
+                                size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(m >= 1, "centroid of an empty cloud");
     PCH_CHECK_ARG(xyz && sums3 && centroid3, "null pointer");
-    PCH_LAUNCH(st, "k_seq_sum_serial", k_seq_sum_serial<<<1, 32, 0, st>>>(xyz, m, sums3));
-    PCH_LAUNCH_CHECK();
+    if (!workspace) {
+        PCH_LAUNCH(st, "k_seq_sum_serial", k_seq_sum_serial<<<1, 32, 0, st>>>(xyz, m, sums3));
+        PCH_LAUNCH_CHECK();
+    } else {
+        size_t need = pch_f32_centroid_workspace_bytes(m);
+        if (workspace_bytes < need) {
+            pch_set_error("centroid workspace too small: %zu < %zu", workspace_bytes, need);
+            return PCH_ERR_WORKSPACE;
+        }
+        int64_t nt = pch_ceil_div(m, SQ_TILE);
+        uint8_t* base = (uint8_t*)workspace;
+        int* stats = (int*)base;
+        size_t off = 256;
+        SqTileInfo* info = (SqTileInfo*)(base + off); off += pch_align_up((size_t)3 * nt * sizeof(SqTileInfo), 256);
+        int32_t* klo = (int32_t*)(base + off); off += pch_align_up((size_t)3 * nt * 4, 256);
+        SqMap* table = (SqMap*)(base + off);
+        unsigned grid = (unsigned)(nt < (int64_t)pch_sm_count() * 8 ? nt : (int64_t)pch_sm_count() * 8);
+        PCH_LAUNCH(st, "k_sum_prep", k_sum_prep<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info));
+        PCH_LAUNCH(st, "k_sum_window", k_sum_window<<<1, 96, 0, st>>>(info, nt, klo));
+        PCH_LAUNCH(st, "k_sum_tables", k_sum_tables<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info, klo, table));
+        PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<1, 96, 0, st>>>(xyz, m, nt, info, klo, table, sums3, stats));
+        PCH_LAUNCH_CHECK();
+    }
     PCH_LAUNCH(st, "k_centroid_from_sums", k_centroid_from_sums<<<1, 32, 0, st>>>(sums3, m, centroid3));
     PCH_LAUNCH_CHECK();
     return PCH_OK;

@@ -204,13 +204,22 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
 # ------------------------------------------------------------------------------------------------
 # tower extraction, device stages
 # ------------------------------------------------------------------------------------------------
-def f32_centroid(xyz: torch.Tensor):
-    """np.mean(raw_points_f32, axis=0) bit-exactly: (centroid float32[3], sequential sums float32[3])."""
+def f32_centroid(xyz: torch.Tensor, serial: bool = False, want_stats: bool = False):
+    """np.mean(raw_points_f32, axis=0) bit-exactly: (centroid float32[3], sequential sums float32[3]).
+    serial=True runs the one-thread-per-column reference kernel instead of the parallel evaluation."""
     assert xyz.dtype == torch.float32 and xyz.is_contiguous()
+    lib = _native.lib()
     sums = torch.empty(3, dtype=torch.float32, device=xyz.device)
     cen = torch.empty(3, dtype=torch.float32, device=xyz.device)
-    check(_native.lib().pch_f32_centroid(xyz.data_ptr(), xyz.shape[0], sums.data_ptr(), cen.data_ptr(), _stream()),
-          "pch_f32_centroid")
+    ws, wsb = None, 0
+    if not serial:
+        wsb = lib.pch_f32_centroid_workspace_bytes(xyz.shape[0])
+        ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+    check(lib.pch_f32_centroid(xyz.data_ptr(), xyz.shape[0], sums.data_ptr(), cen.data_ptr(), _ptr(ws), wsb,
+                               _stream()), "pch_f32_centroid")
+    if want_stats:
+        st = ws[:24].view(torch.int32).cpu().numpy().reshape(3, 2) if ws is not None else None
+        return cen, sums, st
     return cen, sums
 
 

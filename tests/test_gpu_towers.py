@@ -26,12 +26,49 @@ def test_centroid_sequential_f32_bit_exact(cuda_device):
     import torch
     from pointcloudhookup_b200 import device as dv
     rng = np.random.default_rng(7)
-    for m in (1, 7, 8, 9, 1000, 250001):
+    for m in (1, 7, 8, 9, 1000, 2047, 2048, 2049, 250001, 3_000_000):
         a = np.stack([437000 + rng.random(m) * 3000, 3.139e6 + rng.random(m) * 3000, 80 + rng.random(m) * 40],
                      axis=1).astype(np.float32)
-        cen, sums = dv.f32_centroid(torch.from_numpy(a).to(cuda_device))
-        assert np.array_equal(cen.cpu().numpy(), np.mean(a, axis=0))
-        assert np.array_equal(sums.cpu().numpy(), np.add.reduce(a, axis=0))
+        t = torch.from_numpy(a).to(cuda_device)
+        for serial in (True, False):
+            cen, sums = dv.f32_centroid(t, serial=serial)
+            assert np.array_equal(sums.cpu().numpy(), np.add.reduce(a, axis=0)), (m, serial)
+            assert np.array_equal(cen.cpu().numpy(), np.mean(a, axis=0)), (m, serial)
+
+
+def test_centroid_parallel_exact_on_adversarial_columns(cuda_device):
+    """The binade-map evaluation must equal numpy's sequential float32 sum for ties, huge dynamic range,
+    stagnation (sum stops growing), zeros, denormals, negative and mixed-sign data (real-add fallback)."""
+    import torch
+    from pointcloudhookup_b200 import device as dv
+    rng = np.random.default_rng(11)
+    m = 700_000
+    cols = {
+        "ties": rng.integers(0, 64, m) * 0.5,
+        "wide": 10 ** rng.uniform(-3, 6, m),
+        "tiny": rng.random(m) * 1e-3,
+        "const": np.full(m, 437500.0),
+        "zeros_mixed": np.where(rng.random(m) < 0.5, 0.0, rng.random(m) * 100),
+        "denormal": rng.random(m) * 1e-40,
+        "negative": -(3.139e6 + rng.random(m) * 3000),
+        "mixed_sign": rng.normal(0, 50, m),
+        "spike": np.where(np.arange(m) == 400_000, 3.0e12, rng.random(m) * 10),
+    }
+    names = list(cols)
+    for i in range(0, len(names), 3):
+        trio = names[i:i + 3]
+        a = np.stack([cols[k] for k in trio], axis=1).astype(np.float32)
+        cen, sums, st = dv.f32_centroid(torch.from_numpy(a).to(cuda_device), want_stats=True)
+        exp = np.add.reduce(a, axis=0)
+        assert np.array_equal(sums.cpu().numpy(), exp), (trio, sums.cpu().numpy(), exp, st)
+        assert np.array_equal(cen.cpu().numpy(), np.mean(a, axis=0)), trio
+    # stagnation regime: 30 M points, the float32 sum stops growing long before the end
+    big = 20_000_000
+    a = np.stack([437000 + rng.random(big) * 3000, 3.139e6 + rng.random(big) * 3000, 80 + rng.random(big) * 40],
+                 axis=1).astype(np.float32)
+    cen, sums, st = dv.f32_centroid(torch.from_numpy(a).to(cuda_device), want_stats=True)
+    assert np.array_equal(sums.cpu().numpy(), np.add.reduce(a, axis=0)), st
+    assert st[:, 1].max() < 200, st     # almost every tile went through the composed maps
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 10, 1001, 65537, 300000])

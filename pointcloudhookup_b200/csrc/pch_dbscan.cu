@@ -256,33 +256,62 @@ __device__ __forceinline__ double db_dist2(const float4& a, const float4& b) {
 }
 
 // ---------------------------------------------------------------- D3: core points
+// Phase 1 (thread per point): a point of a cell holding >= min_samples points is core at once (all
+// cell-mates are neighbours).  Every other point goes to a work list.  Phase 2 (one WARP per listed
+// point): the lanes stride over the points of the 25 neighbour columns — the cells of one column are
+// consecutive in the sorted order, so a column is ONE contiguous range — and count hits with ballots,
+// leaving as soon as min_samples is reached.
 __global__ void __launch_bounds__(256)
-k_db_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
-          const int32_t* __restrict__ cell_start, const int32_t* __restrict__ nbr_first,
-          const uint8_t* __restrict__ nbr_cnt, uint8_t* __restrict__ core) {
+k_db_core1(DbGeom g, const int32_t* __restrict__ pt_cell, const int32_t* __restrict__ cell_start,
+           uint8_t* __restrict__ core, int32_t* __restrict__ worklist, unsigned int* __restrict__ n_work) {
+    const int lane = threadIdx.x & 31;
+    const int64_t Gpad = (g.G + 31) / 32 * 32;
     int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; pos < g.G; pos += stride) {
+    for (; pos < Gpad; pos += stride) {
+        bool pending = false;
+        if (pos < g.G) {
+            const int32_t u = pt_cell[pos];
+            const bool dense = (cell_start[u + 1] - cell_start[u]) >= g.min_pts;
+            core[pos] = dense ? 1 : 0;
+            pending = !dense;
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, pending);
+        if (b) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(n_work, (unsigned int)__popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pending) worklist[base + __popc(b & ((1u << lane) - 1u))] = (int32_t)pos;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_db_core2(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+           const int32_t* __restrict__ cell_start, const int32_t* __restrict__ nbr_first,
+           const uint8_t* __restrict__ nbr_cnt, const int32_t* __restrict__ worklist,
+           const unsigned int* __restrict__ n_work, uint8_t* __restrict__ core) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n = *n_work;
+    for (; w < n; w += nw) {
+        const int32_t pos = worklist[w];
         const int32_t u = pt_cell[pos];
-        int count = cell_start[u + 1] - cell_start[u];  // every cell-mate (and the point itself) is a neighbour
-        if (count < g.min_pts) {
-            const float4 p = spts[pos];
-            for (int col = 0; col < 25 && count < g.min_pts; ++col) {
-                const int32_t f = nbr_first[(int64_t)u * 25 + col];
-                const int nc = nbr_cnt[(int64_t)u * 25 + col];
-                for (int k = 0; k < nc && count < g.min_pts; ++k) {
-                    const int32_t v = f + k;
-                    if (v == u) continue;
-                    const int32_t b = cell_start[v], e = cell_start[v + 1];
-                    for (int32_t q = b; q < e; ++q) {
-                        if (db_dist2(p, spts[q]) <= g.eps2) {
-                            if (++count >= g.min_pts) break;
-                        }
-                    }
-                }
+        const float4 p = spts[pos];
+        int count = 0;
+        for (int col = 0; col < 25 && count < g.min_pts; ++col) {
+            const int nc = nbr_cnt[(int64_t)u * 25 + col];
+            if (nc == 0) continue;
+            const int32_t f = nbr_first[(int64_t)u * 25 + col];
+            const int32_t b = cell_start[f], e = cell_start[f + nc];
+            for (int32_t q0 = b; q0 < e && count < g.min_pts; q0 += 32) {
+                const int32_t q = q0 + lane;
+                const bool hit = q < e && db_dist2(p, spts[q]) <= g.eps2;
+                count += __popc(__ballot_sync(0xffffffffu, hit));
             }
         }
-        core[pos] = count >= g.min_pts ? 1 : 0;
+        if (lane == 0 && count >= g.min_pts) core[pos] = 1;
     }
 }
 
@@ -373,8 +402,13 @@ __device__ __forceinline__ double db_box_dist2(const float4& p, const float* mn,
 __global__ void __launch_bounds__(256)
 k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restrict__ spts,
            const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
-           const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt, DbCellInfo* __restrict__ info) {
+           const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt, DbCellInfo* __restrict__ info,
+           const uint64_t* __restrict__ cell_key, int pass) {
+    // pass 0: only face/edge/corner-adjacent cells (|offset| <= 1): cheap hits that merge almost every
+    // dense region; pass 1: the remaining (distance-2) cells, most of which are then skipped by the
+    // "already in one set" test instead of being searched exhaustively.
     const int64_t U = *U_dev;
+    const uint64_t zmask = (1ull << g.bits_z) - 1ull;
     // one warp per (cell A, neighbour column); only pairs with B > A are examined
     const int lane = threadIdx.x & 31;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -384,12 +418,19 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
         const int32_t A = (int32_t)(w / 25);
         const int col = (int)(w - (int64_t)A * 25);
         if (info[A].n_core == 0) continue;
+        const int ox = col / 5 - 2, oy = col % 5 - 2;
+        const bool near_xy = ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1;
+        if (pass == 0 && !near_xy) continue;
+        const long long czA = (long long)(cell_key[A] & zmask);
         const int32_t f = nbr_first[w];
         const int nc = nbr_cnt[w];
         for (int k = 0; k < nc; ++k) {
             const int32_t B = f + k;
             if (B <= A) continue;
             if (info[B].n_core == 0) continue;
+            const long long dz = (long long)(cell_key[B] & zmask) - czA;
+            const bool near = near_xy && dz >= -1 && dz <= 1;
+            if ((pass == 0) != near) continue;
             int same = 0;  // already joined? (work saving only; decided by lane 0 so the warp stays uniform)
             if (lane == 0) same = uf_find(info, A) == uf_find(info, B);
             same = __shfl_sync(0xffffffffu, same, 0);
@@ -484,42 +525,58 @@ __global__ void k_db_cluster_ids(const long long* __restrict__ K_dev, const int3
 }
 
 // ---------------------------------------------------------------- D6: labels (core + border + noise)
+// core points take their cell's cluster id (thread per point); the non-core points (again the work
+// list of D3, minus those that turned out core) are searched by one warp each: smallest cluster id
+// among the core points within eps, else -1.
 __global__ void __launch_bounds__(256)
-k_db_labels(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
-            const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
-            const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt,
-            const int32_t* __restrict__ cell_root, const int32_t* __restrict__ root_label,
-            int32_t* __restrict__ labels /*[G] original order*/) {
+k_db_labels_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+                 const uint8_t* __restrict__ core, const int32_t* __restrict__ cell_root,
+                 const int32_t* __restrict__ root_label, int32_t* __restrict__ labels) {
     int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; pos < g.G; pos += stride) {
+        if (!core[pos]) continue;
+        const int64_t c = pos / g.chunk;
+        const int64_t orig = c * g.chunk + __float_as_int(spts[pos].w);
+        labels[orig] = root_label[cell_root[pt_cell[pos]]];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+                   const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
+                   const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt,
+                   const int32_t* __restrict__ cell_root, const int32_t* __restrict__ root_label,
+                   const int32_t* __restrict__ worklist, const unsigned int* __restrict__ n_work,
+                   int32_t* __restrict__ labels) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n = *n_work;
+    for (; w < n; w += nw) {
+        const int32_t pos = worklist[w];
+        if (core[pos]) continue;  // warp-uniform
         const int32_t u = pt_cell[pos];
         const float4 p = spts[pos];
-        const int64_t c = pos / g.chunk;
-        const int64_t orig = c * g.chunk + __float_as_int(p.w);
-        int32_t lab;
-        if (core[pos]) {
-            lab = root_label[cell_root[u]];
-        } else {
-            int32_t best = INT_MAX;
-            for (int col = 0; col < 25; ++col) {
-                const int32_t f = nbr_first[(int64_t)u * 25 + col];
-                const int nc = nbr_cnt[(int64_t)u * 25 + col];
-                for (int k = 0; k < nc; ++k) {
-                    const int32_t v = f + k;
-                    const int32_t rt = cell_root[v];
-                    if (rt < 0) continue;                 // no core point in that cell
-                    const int32_t cl = root_label[rt];
-                    if (cl >= best) continue;
-                    const int32_t b = cell_start[v], e = cell_start[v + 1];
-                    for (int32_t q = b; q < e; ++q) {
-                        if (core[q] && db_dist2(p, spts[q]) <= g.eps2) { best = cl; break; }
-                    }
+        int32_t best = INT_MAX;
+        for (int col = 0; col < 25; ++col) {
+            const int nc = nbr_cnt[(int64_t)u * 25 + col];
+            if (nc == 0) continue;
+            const int32_t f = nbr_first[(int64_t)u * 25 + col];
+            const int32_t b = cell_start[f], e = cell_start[f + nc];
+            for (int32_t q0 = b; q0 < e; q0 += 32) {
+                const int32_t q = q0 + lane;
+                if (q < e && core[q]) {
+                    const int32_t cl = root_label[cell_root[pt_cell[q]]];
+                    if (cl < best && db_dist2(p, spts[q]) <= g.eps2) best = cl;
                 }
             }
-            lab = best == INT_MAX ? -1 : best;
         }
-        labels[orig] = lab;
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0) {
+            const int64_t c = pos / g.chunk;
+            labels[c * g.chunk + __float_as_int(p.w)] = best == INT_MAX ? -1 : best;
+        }
     }
 }
 
@@ -633,7 +690,8 @@ extern "C" int pch_dbscan_plan(const float* P, int64_t G, int64_t chunk, double 
 struct DbWs {
     size_t total;
     size_t keys, tmp, sortws, sortws_bytes, spts, pt_cell, inv_pos, cell_start, cell_key, chunk_cell0, scalars,
-        nbr_first, nbr_cnt, core, info, cell_root, root_min, root_label, is_head, head_list, scan_status, acc;
+        nbr_first, nbr_cnt, core, info, cell_root, root_min, root_label, is_head, head_list, scan_status, acc,
+        worklist;
 };
 
 extern "C" size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi);
@@ -675,6 +733,7 @@ static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t 
     size_t cw = pch_compact_workspace_bytes(G);
     w.scan_status = take(sc > cw ? sc : cw);
     w.acc = take((size_t)max_clusters * sizeof(DbClusterAcc));
+    w.worklist = take((size_t)(G + 32) * 4);
     w.total = off;
     return w;
 }
@@ -708,6 +767,8 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     int* err = (int*)(base + w.scalars);
     uint32_t* counter = (uint32_t*)(base + w.scalars + 64);
     long long* U_dev = (long long*)(base + w.scalars + 128);
+    unsigned int* n_work = (unsigned int*)(base + w.scalars + 192);
+    int32_t* worklist = (int32_t*)(base + w.worklist);
     uint64_t* keys = (uint64_t*)(base + w.keys);
     uint64_t* tmp = (uint64_t*)(base + w.tmp);
 
@@ -757,12 +818,18 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
 
     PCH_LAUNCH(st, "k_db_nbr", k_db_nbr<<<db_grid(G, 256), 256, 0, st>>>(g, o.cell_key, o.cell_start, o.chunk_cell0, U_dev, nbr_first, nbr_cnt));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_core", k_db_core<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt, core));
+    PCH_LAUNCH(st, "k_db_core1", k_db_core1<<<db_grid(G, 256), 256, 0, st>>>(g, o.pt_cell, o.cell_start, core, worklist, n_work));
+    PCH_LAUNCH_CHECK();
+    PCH_LAUNCH(st, "k_db_core2", k_db_core2<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt,
+                                                                            worklist, n_work, core));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_union", k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first, nbr_cnt, info));
-    PCH_LAUNCH_CHECK();
+    for (int pass = 0; pass < 2; ++pass) {
+        PCH_LAUNCH(st, "k_db_union", k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first,
+                                                                                 nbr_cnt, info, o.cell_key, pass));
+        PCH_LAUNCH_CHECK();
+    }
     PCH_LAUNCH(st, "k_db_flatten", k_db_flatten<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info, cell_root));
     PCH_LAUNCH_CHECK();
     PCH_CUDA(cudaMemsetAsync(root_min, 0x7f, (size_t)G * 4, st));
@@ -779,8 +846,11 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH(st, "k_db_cluster_ids", k_db_cluster_ids<<<db_grid(G, 256), 256, 0, st>>>((const long long*)n_clusters_dev, head_list, o.inv_pos, o.pt_cell,
                                                       cell_root, root_label));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_labels", k_db_labels<<<db_grid(G, 256, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first, nbr_cnt, cell_root,
-                                                     root_label, labels_dev));
+    PCH_LAUNCH(st, "k_db_labels_core", k_db_labels_core<<<db_grid(G, 256), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_label, labels_dev));
+    PCH_LAUNCH_CHECK();
+    PCH_LAUNCH(st, "k_db_labels_border", k_db_labels_border<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first,
+                                                                                    nbr_cnt, cell_root, root_label, worklist, n_work,
+                                                                                    labels_dev));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
     PCH_LAUNCH_CHECK();

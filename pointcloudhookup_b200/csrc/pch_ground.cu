@@ -52,7 +52,7 @@ __global__ void k_centroid_from_sums(const float* __restrict__ sums, int64_t m, 
 #define SQ_TILE 2048
 #define SQ_THREADS 256
 #define SQ_EPT (SQ_TILE / SQ_THREADS)
-#define SQ_W 8
+#define SQ_W 4
 #define SQ_SAT 0x7fffffffu
 
 struct SqTileInfo {
@@ -61,6 +61,21 @@ struct SqTileInfo {
     int32_t ok;      // all elements finite and >= 0
 };
 
+// 8 consecutive points (24 floats, 96 bytes, 16-byte aligned) per thread; zero beyond m
+__device__ __forceinline__ void sq_load8(const float* __restrict__ xyz, int64_t p0, int64_t m, float v[24]) {
+    if (p0 + SQ_EPT <= m) {
+        const float4* q = reinterpret_cast<const float4*>(xyz + p0 * 3);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            float4 f = __ldg(q + i);
+            v[4 * i + 0] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) v[i] = (p0 * 3 + i < m * 3) ? xyz[p0 * 3 + i] : 0.0f;
+    }
+}
+
 __global__ void __launch_bounds__(SQ_THREADS)
 k_sum_prep(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, SqTileInfo* __restrict__ info /*[3][n_tiles]*/) {
     __shared__ double s_sum[3][SQ_THREADS / 32];
@@ -68,21 +83,20 @@ k_sum_prep(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, SqTileInfo
     __shared__ int s_ok[3][SQ_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t base = t * SQ_TILE;
+        float v[24];
+        sq_load8(xyz, t * SQ_TILE + (int64_t)tid * SQ_EPT, m, v);
         double sum[3] = {0.0, 0.0, 0.0};
         float mx[3] = {0.f, 0.f, 0.f};
         int ok[3] = {1, 1, 1};
-        // the tile is 3*SQ_TILE contiguous floats; thread reads floats tid, tid+256, ... (coalesced)
-        for (int j = tid; j < 3 * SQ_TILE; j += SQ_THREADS) {
-            const int64_t e = base * 3 + j;
-            if (e < m * 3) {
-                const float v = xyz[e];
-                const int c = j % 3;
-                sum[c] += (double)v;
-                mx[c] = fmaxf(mx[c], v);
-                if (!(v >= 0.0f) || !(v < INFINITY)) ok[c] = 0;
+#pragma unroll
+        for (int e = 0; e < SQ_EPT; ++e)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float x = v[e * 3 + c];
+                sum[c] += (double)x;
+                mx[c] = fmaxf(mx[c], x);
+                if (!(x >= 0.0f) || !(x < INFINITY)) ok[c] = 0;
             }
-        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -104,33 +118,51 @@ k_sum_prep(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, SqTileInfo
     }
 }
 
-// one CTA, 3 warps: per column exclusive float64 prefix of tile sums and column max -> klo[c][t]
-__global__ void k_sum_window(const SqTileInfo* __restrict__ info, int64_t n_tiles, int32_t* __restrict__ klo) {
-    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (c >= 3) return;
+// 3 CTAs (one per column) x 1024 threads: exclusive float64 prefix of the tile sums + column max ->
+// predicted binade window per tile: klo[c][t] .. klo[c][t] + SQ_W - 1
+__global__ void __launch_bounds__(1024) k_sum_window(const SqTileInfo* __restrict__ info, int64_t n_tiles, int32_t* __restrict__ klo) {
+    __shared__ double s_w[32];
+    __shared__ float s_m[32];
+    __shared__ double s_carry;
+    __shared__ int s_kcap;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SqTileInfo* ti = info + c * n_tiles;
     float amax = 0.f;
-    for (int64_t t = lane; t < n_tiles; t += 32) amax = fmaxf(amax, ti[t].maxv);
+    for (int64_t t = tid; t < n_tiles; t += 1024) amax = fmaxf(amax, ti[t].maxv);
 #pragma unroll
     for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    const int kcap = (amax > 0.f ? ilogbf(amax) : -126) + 2;
-    double carry = 0.0;
-    for (int64_t t0 = 0; t0 < n_tiles; t0 += 32) {
-        const int64_t t = t0 + lane;
-        double v = t < n_tiles ? ti[t].sum : 0.0;
+    if (lane == 0) s_m[warp] = amax;
+    if (tid == 0) s_carry = 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f;
+        for (int w = 0; w < 32; ++w) a = fmaxf(a, s_m[w]);
+        s_kcap = (a > 0.f ? ilogbf(a) : -126) + 2;
+    }
+    __syncthreads();
+    const int kcap = s_kcap;
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const int64_t t = t0 + tid;
+        const double v = t < n_tiles ? ti[t].sum : 0.0;
         double x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             double y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
         }
-        const double excl = carry + x - v;
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        double base = s_carry;
+        for (int w = 0; w < warp; ++w) base += s_w[w];
+        const double excl = base + x - v;
         if (t < n_tiles) {
             int kc = excl > 0.0 ? (ilogb(excl) - 23) : -149;
             if (kc > kcap) kc = kcap;
             klo[c * n_tiles + t] = kc - SQ_W / 2;
         }
-        carry += __shfl_sync(0xffffffffu, x, 31);
+        __syncthreads();
+        if (tid == 1023) s_carry = base + x;
+        __syncthreads();
     }
 }
 
@@ -148,7 +180,8 @@ __device__ __forceinline__ SqMap sq_compose(const SqMap& F, const SqMap& G) {
     return H;
 }
 
-// increment of the mantissa m (ulp 2^k) when adding the float with bit pattern `bits`, for parity p of m
+// increment of the mantissa m (ulp 2^k) when adding the float with bit pattern `bits`:
+// q + gt, plus 1 more on a tie (eq) when (m + q) is odd
 __device__ __forceinline__ void sq_elem(uint32_t bits, int k, uint32_t& q, uint32_t& gt, uint32_t& eq) {
     int ea = (int)((bits >> 23) & 0xffu);
     uint32_t ma = bits & 0x7fffffu;
@@ -162,67 +195,124 @@ __device__ __forceinline__ void sq_elem(uint32_t bits, int k, uint32_t& q, uint3
         q = 0;
     } else {
         q = shift >= 24 ? 0u : (ma >> shift);
-        const uint32_t r = shift >= 32 ? ma : (ma & ((1u << shift) - 1u));
+        const uint32_t r = ma & ((1u << shift) - 1u);
         const uint32_t h = 1u << (shift - 1);
         gt = r > h;
         eq = r == h;
     }
 }
 
+// Per tile, column and window slot: the composed map.  Fast path: when no element of the tile is an
+// exact tie for this k, the map does not depend on parity and is a plain sum (one block reduction);
+// otherwise the ordered composition is evaluated (rare: needs r == 2^(k-1) exactly).
 __global__ void __launch_bounds__(SQ_THREADS)
 k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
              const int32_t* __restrict__ klo, SqMap* __restrict__ table /*[3][n_tiles][SQ_W]*/) {
-    __shared__ float s_v[3 * SQ_TILE];
-    __shared__ SqMap s_w[SQ_THREADS / 32][SQ_W];
+    __shared__ unsigned long long s_sum[SQ_THREADS / 32][3 * SQ_W];
+    __shared__ uint32_t s_tie[SQ_THREADS / 32][3 * SQ_W];
+    __shared__ unsigned long long s_tot[3 * SQ_W];
+    __shared__ uint32_t s_ties[3 * SQ_W];
+    __shared__ SqMap s_cw[SQ_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t base = t * SQ_TILE * 3;
-        for (int j = tid; j < 3 * SQ_TILE; j += SQ_THREADS) s_v[j] = (base + j < m * 3) ? xyz[base + j] : 0.0f;
-        __syncthreads();
+        float v[24];
+        sq_load8(xyz, t * SQ_TILE + (int64_t)tid * SQ_EPT, m, v);
+        int k0[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) k0[c] = klo[c * n_tiles + t];
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
-            if (!info[c * n_tiles + t].ok) continue;  // block-uniform
-            const int k0 = klo[c * n_tiles + t];
-            SqMap mp[SQ_W];
-#pragma unroll
-            for (int w = 0; w < SQ_W; ++w) { mp[w].d0 = 0; mp[w].d1 = 0; }
-#pragma unroll
-            for (int e = 0; e < SQ_EPT; ++e) {
-                const uint32_t bits = __float_as_uint(s_v[(tid * SQ_EPT + e) * 3 + c]);
-#pragma unroll
-                for (int w = 0; w < SQ_W; ++w) {
-                    uint32_t q, gt, eq;
-                    sq_elem(bits, k0 + w, q, gt, eq);
-                    const uint32_t base_inc = sq_sat_add(q, gt);
-                    // parity of (m + D + q) decides a tie
-                    const uint32_t i0 = sq_sat_add(base_inc, eq & ((mp[w].d0 + q) & 1u));
-                    const uint32_t i1 = sq_sat_add(base_inc, eq & ((1u + mp[w].d1 + q) & 1u));
-                    mp[w].d0 = sq_sat_add(mp[w].d0, i0);
-                    mp[w].d1 = sq_sat_add(mp[w].d1, i1);
-                }
-            }
-            // ordered reduction across the block (lower thread = earlier elements)
 #pragma unroll
             for (int w = 0; w < SQ_W; ++w) {
-                SqMap v = mp[w];
+                unsigned long long acc = 0;
+                uint32_t ties = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    SqMap nb;
-                    nb.d0 = __shfl_down_sync(0xffffffffu, v.d0, o);
-                    nb.d1 = __shfl_down_sync(0xffffffffu, v.d1, o);
-                    if (lane + o < 32 && (lane % (2 * o)) == 0) v = sq_compose(v, nb);
+                for (int e = 0; e < SQ_EPT; ++e) {
+                    uint32_t q, gt, eq;
+                    sq_elem(__float_as_uint(v[e * 3 + c]), k0[c] + w, q, gt, eq);
+                    acc += (unsigned long long)q + gt;
+                    ties += eq;
                 }
-                if (lane == 0) s_w[warp][w] = v;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    ties += __shfl_xor_sync(0xffffffffu, ties, o);
+                }
+                if (lane == 0) { s_sum[warp][c * SQ_W + w] = acc; s_tie[warp][c * SQ_W + w] = ties; }
             }
+        }
+        __syncthreads();
+        if (tid < 3 * SQ_W) {
+            unsigned long long a = 0; uint32_t ti = 0;
+            for (int ww = 0; ww < SQ_THREADS / 32; ++ww) { a += s_sum[ww][tid]; ti += s_tie[ww][tid]; }
+            s_tot[tid] = a; s_ties[tid] = ti;
+            if (ti == 0) {
+                SqMap mp; mp.d0 = mp.d1 = a >= SQ_SAT ? SQ_SAT : (uint32_t)a;
+                const int c = tid / SQ_W, w = tid % SQ_W;
+                table[((size_t)c * n_tiles + t) * SQ_W + w] = mp;
+            }
+        }
+        __syncthreads();
+        // slow path for the (column, slot) pairs that contain exact ties: ordered composition
+#pragma unroll
+        for (int cw = 0; cw < 3 * SQ_W; ++cw) {
+            if (s_ties[cw] == 0) continue;  // block-uniform
+            const int c = cw / SQ_W, w = cw % SQ_W;   // compile-time after unrolling: v[] stays in registers
+            SqMap mp; mp.d0 = 0; mp.d1 = 0;
+#pragma unroll
+            for (int e = 0; e < SQ_EPT; ++e) {
+                uint32_t q, gt, eq;
+                sq_elem(__float_as_uint(v[e * 3 + c]), k0[c] + w, q, gt, eq);
+                const uint32_t base_inc = sq_sat_add(q, gt);
+                const uint32_t i0 = sq_sat_add(base_inc, eq & ((mp.d0 + q) & 1u));
+                const uint32_t i1 = sq_sat_add(base_inc, eq & ((1u + mp.d1 + q) & 1u));
+                mp.d0 = sq_sat_add(mp.d0, i0);
+                mp.d1 = sq_sat_add(mp.d1, i1);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                SqMap nb;
+                nb.d0 = __shfl_down_sync(0xffffffffu, mp.d0, o);
+                nb.d1 = __shfl_down_sync(0xffffffffu, mp.d1, o);
+                if (lane + o < 32 && (lane % (2 * o)) == 0) mp = sq_compose(mp, nb);
+            }
+            if (lane == 0) s_cw[warp] = mp;
             __syncthreads();
-            if (tid < SQ_W) {
-                SqMap v = s_w[0][tid];
-                for (int ww = 1; ww < SQ_THREADS / 32; ++ww) v = sq_compose(v, s_w[ww][tid]);
-                table[((size_t)c * n_tiles + t) * SQ_W + tid] = v;
+            if (tid == 0) {
+                SqMap r = s_cw[0];
+                for (int ww = 1; ww < SQ_THREADS / 32; ++ww) r = sq_compose(r, s_cw[ww]);
+                table[((size_t)c * n_tiles + t) * SQ_W + w] = r;
             }
             __syncthreads();
         }
-        __syncthreads();
     }
+}
+
+struct SqLane {   // what one lane needs to know about "its" tile
+    SqMap e[SQ_W];
+    int32_t klo;
+    int32_t ok;
+};
+
+__device__ __forceinline__ SqLane sq_fetch(int64_t tt, int64_t n_tiles, int c, const SqTileInfo* __restrict__ info,
+                                           const int32_t* __restrict__ klo, const SqMap* __restrict__ table) {
+    SqLane L;
+    L.ok = 0; L.klo = 0;
+#pragma unroll
+    for (int w = 0; w < SQ_W; ++w) { L.e[w].d0 = SQ_SAT; L.e[w].d1 = SQ_SAT; }
+    if (tt < n_tiles) {
+        L.ok = info[c * n_tiles + tt].ok;
+        L.klo = klo[c * n_tiles + tt];
+        if (L.ok) {
+            const uint4* p = reinterpret_cast<const uint4*>(table + ((size_t)c * n_tiles + tt) * SQ_W);
+#pragma unroll
+            for (int w = 0; w < SQ_W / 2; ++w) {
+                uint4 u = __ldg(p + w);
+                L.e[2 * w].d0 = u.x; L.e[2 * w].d1 = u.y; L.e[2 * w + 1].d0 = u.z; L.e[2 * w + 1].d1 = u.w;
+            }
+        }
+    }
+    return L;
 }
 
 __global__ void __launch_bounds__(96)
@@ -234,20 +324,21 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
     float s = 0.0f;
     int64_t t = 0;
     int n_map = 0, n_real = 0;
+    SqLane cur = sq_fetch(t + lane, n_tiles, c, info, klo, table);
     while (t < n_tiles) {
+        SqLane nxt = sq_fetch(t + 32 + lane, n_tiles, c, info, klo, table);  // prefetch: the common case advances 32
         const uint32_t sb = __float_as_uint(s);
         const int es = (int)((sb >> 23) & 0xffu);
-        int64_t advanced = 0;
+        int advanced = 0;
         if (es != 0 && es != 0xff && !(sb >> 31)) {
             const int k = es - 150;
             const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
-            const int64_t tt = t + lane;
             SqMap F; F.d0 = SQ_SAT; F.d1 = SQ_SAT;
-            if (tt < n_tiles && info[c * n_tiles + tt].ok) {
-                const int idx = k - klo[c * n_tiles + tt];
-                if (idx >= 0 && idx < SQ_W) F = table[((size_t)c * n_tiles + tt) * SQ_W + idx];
+            const int idx = k - cur.klo;
+            if (cur.ok) {
+#pragma unroll
+                for (int w = 0; w < SQ_W; ++w) if (idx == w) F = cur.e[w];
             }
-            // inclusive ordered scan of the maps across the 32 tiles
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 SqMap pv;
@@ -258,7 +349,7 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
             const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
             const bool ok = D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
             const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-            const int L = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);   // leading tiles that stay in the binade
+            const int L = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
             if (L > 0) {
                 const uint32_t Dl = __shfl_sync(0xffffffffu, D, L - 1);
                 s = __uint_as_float(((uint32_t)es << 23) | ((ms + Dl) & 0x7fffffu));
@@ -267,7 +358,11 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
             }
         }
         t += advanced;
-        if (advanced < 32 && t < n_tiles) {
+        if (advanced == 32) {
+            cur = nxt;
+            continue;
+        }
+        if (t < n_tiles) {
             // this tile leaves the binade / is outside its window / has negative data: real float32 adds
             const int64_t lo = t * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
             for (int64_t i0 = lo; i0 < hi; i0 += 32) {
@@ -279,6 +374,7 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
             ++t;
             ++n_real;
         }
+        cur = sq_fetch(t + lane, n_tiles, c, info, klo, table);
     }
     if (lane == 0) {
         sums[c] = s;
@@ -315,7 +411,7 @@ extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float
         SqMap* table = (SqMap*)(base + off);
         unsigned grid = (unsigned)(nt < (int64_t)pch_sm_count() * 8 ? nt : (int64_t)pch_sm_count() * 8);
         PCH_LAUNCH(st, "k_sum_prep", k_sum_prep<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info));
-        PCH_LAUNCH(st, "k_sum_window", k_sum_window<<<1, 96, 0, st>>>(info, nt, klo));
+        PCH_LAUNCH(st, "k_sum_window", k_sum_window<<<3, 1024, 0, st>>>(info, nt, klo));
         PCH_LAUNCH(st, "k_sum_tables", k_sum_tables<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info, klo, table));
         PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<1, 96, 0, st>>>(xyz, m, nt, info, klo, table, sums3, stats));
         PCH_LAUNCH_CHECK();

@@ -144,6 +144,16 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
     # every label 0..K-1 carries at least its head core point, so `present` is all of them; the
     # set() is still built from the values to reproduce the reference's order
     order = label_iteration_order(K, present)
+    if box == "aabb" and K:
+        # vectorised size filter (test/008.py:302-319 arithmetic in float32, like the reference's numpy):
+        # only labels that pass reach the python loop below, in the same set() order
+        ext_all = (stats["max"][:K] - stats["min"][:K]).astype(np.float64)
+        h_all = ext_all[:, 2]
+        w_all = np.maximum(ext_all[:, 0], ext_all[:, 1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ok = (w_all > 0) & (h_all > min_height) & (min_width < w_all) & (w_all < max_width) & \
+                 (h_all / w_all > aspect_ratio_threshold)
+        order = [l for l in order if ok[l]]
     towers, centres = [], []
     labels_host = None
     filtered_host = None

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--ground", default="percentile", choices=["percentile", "grid"])
     ap.add_argument("--ref-sample", type=float, default=None, help="points in the CPU sample (reference arm)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU sample (profiling runs)")
     return ap.parse_args()
 
 
@@ -290,8 +291,7 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "stage_info": info, "kernels": kernels}
     if rank == 0:
-        cpu = cpu_baseline(args, cfg, bounded=True)
-        line["cpu_baseline"] = cpu
+        line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline(args, cfg, bounded=True)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

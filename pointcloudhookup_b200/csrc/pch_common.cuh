@@ -152,10 +152,15 @@ __device__ __forceinline__ void pch_load_xyz(const uint8_t* p, int& X, int& Y, i
         const int* q = reinterpret_cast<const int*>(p);
         X = q[0]; Y = q[1]; Z = q[2];
     } else if (ALIGN == 2) {
-        const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
-        X = (int)((uint32_t)q[0] | ((uint32_t)q[1] << 16));
-        Y = (int)((uint32_t)q[2] | ((uint32_t)q[3] << 16));
-        Z = (int)((uint32_t)q[4] | ((uint32_t)q[5] << 16));
+        // 2-byte aligned record: four aligned 32-bit loads + funnel shifts instead of six 16-bit loads
+        // (the 4th word lies inside the same record: LAS records are >= 20 bytes)
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 2) * 8u;
+        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+        X = (int)__funnelshift_r(w0, w1, sh);
+        Y = (int)__funnelshift_r(w1, w2, sh);
+        Z = (int)__funnelshift_r(w2, w3, sh);
     } else {
         X = (int)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
         Y = (int)((uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24));

@@ -326,7 +326,8 @@ struct __align__(16) DbCellInfo {
 
 __global__ void __launch_bounds__(256)
 k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ spts, const int32_t* __restrict__ cell_start,
-              const uint8_t* __restrict__ core, DbCellInfo* __restrict__ info) {
+              const uint8_t* __restrict__ core, DbCellInfo* __restrict__ info, int64_t chunk,
+              int32_t* __restrict__ cell_mincore) {
     const int64_t U = *U_dev;
     // one warp per cell
     const int lane = threadIdx.x & 31;
@@ -336,9 +337,12 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
         const int32_t b = cell_start[w], e = cell_start[w + 1];
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         int n = 0;
+        int mincore = INT_MAX;
+        const int32_t chunk_base = (int32_t)((b / chunk) * chunk);
         for (int32_t q = b + lane; q < e; q += 32) {
             if (core[q]) {
                 float4 p = spts[q];
+                mincore = min(mincore, chunk_base + __float_as_int(p.w));
                 mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
                 mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
                 ++n;
@@ -347,6 +351,7 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             n += __shfl_xor_sync(0xffffffffu, n, o);
+            mincore = min(mincore, __shfl_xor_sync(0xffffffffu, mincore, o));
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
@@ -360,6 +365,7 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
             ci.n_core = n;
             ci.parent = (int32_t)w;
             info[w] = ci;
+            cell_mincore[w] = mincore;
         }
     }
 }
@@ -399,6 +405,7 @@ __device__ __forceinline__ double db_box_dist2(const float4& p, const float* mn,
     return d;
 }
 
+#define UN_CAP 256
 __global__ void __launch_bounds__(256)
 k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restrict__ spts,
            const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
@@ -410,7 +417,8 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
     const int64_t U = *U_dev;
     const uint64_t zmask = (1ull << g.bits_z) - 1ull;
     // one warp per (cell A, neighbour column); only pairs with B > A are examined
-    const int lane = threadIdx.x & 31;
+    __shared__ float3 s_la[256 / 32][UN_CAP];
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double slack = g.eps2 * (1.0 + 1e-12);  // pruning must never drop a true neighbour pair
@@ -454,22 +462,58 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
             const int32_t ab = cell_start[A], ae = cell_start[A + 1];
             const int32_t bbeg = cell_start[B], bend = cell_start[B + 1];
             bool found = false;
-            for (int32_t a0 = ab; a0 < ae && !found; a0 += 32) {
-                const int32_t ai = a0 + lane;
-                float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool act = false;
-                if (ai < ae && core[ai]) {
-                    pa = spts[ai];
-                    act = db_box_dist2(pa, bmn, bmx) <= slack;
+            // A is consumed in batches of up to UN_CAP candidates (core points of A within eps of B's
+            // core box), staged in shared memory; every batch is tested against the core points of B
+            // that are within eps of the batch's own bounding box.
+            float3* la = s_la[warp_in_block];
+            int32_t a0 = ab;
+            while (a0 < ae && !found) {
+                int n_la = 0;
+                float lmn[3] = {INFINITY, INFINITY, INFINITY}, lmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+                for (; a0 < ae && n_la <= UN_CAP - 32; a0 += 32) {
+                    const int32_t ai = a0 + lane;
+                    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bool act = false;
+                    if (ai < ae && core[ai]) {
+                        pa = spts[ai];
+                        act = db_box_dist2(pa, bmn, bmx) <= slack;
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        la[n_la + __popc(bal & ((1u << lane) - 1u))] = make_float3(pa.x, pa.y, pa.z);
+                        lmn[0] = fminf(lmn[0], pa.x); lmn[1] = fminf(lmn[1], pa.y); lmn[2] = fminf(lmn[2], pa.z);
+                        lmx[0] = fmaxf(lmx[0], pa.x); lmx[1] = fmaxf(lmx[1], pa.y); lmx[2] = fmaxf(lmx[2], pa.z);
+                    }
+                    n_la += __popc(bal);
                 }
-                if (!__any_sync(0xffffffffu, act)) continue;
-                for (int32_t bi = bbeg; bi < bend; ++bi) {
-                    if (!core[bi]) continue;               // warp-uniform
-                    const float4 pb = spts[bi];
-                    if (db_box_dist2(pb, amn, amx) > slack) continue;  // warp-uniform
-                    bool hit = act && (db_dist2(pa, pb) <= g.eps2);
-                    if (__any_sync(0xffffffffu, hit)) { found = true; break; }
+                if (n_la == 0) continue;
+#pragma unroll
+                for (int o = 16; o; o >>= 1)
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        lmn[ax] = fminf(lmn[ax], __shfl_xor_sync(0xffffffffu, lmn[ax], o));
+                        lmx[ax] = fmaxf(lmx[ax], __shfl_xor_sync(0xffffffffu, lmx[ax], o));
+                    }
+                __syncwarp();
+                for (int32_t b0 = bbeg; b0 < bend && !found; b0 += 32) {
+                    const int32_t bi = b0 + lane;
+                    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bool actb = false;
+                    if (bi < bend && core[bi]) {
+                        pb = spts[bi];
+                        actb = db_box_dist2(pb, lmn, lmx) <= slack;
+                    }
+                    if (!__any_sync(0xffffffffu, actb)) continue;
+                    bool hit = false;
+                    for (int j = 0; j < n_la; ++j) {
+                        const float3 q = la[j];   // broadcast read
+                        const float4 qa = make_float4(q.x, q.y, q.z, 0.f);
+                        hit = hit || (actb && db_dist2(qa, pb) <= g.eps2);
+                        if ((j & 15) == 15 && __any_sync(0xffffffffu, hit)) break;
+                    }
+                    if (__any_sync(0xffffffffu, hit)) found = true;
                 }
+                __syncwarp();
             }
             if (found && lane == 0) uf_union(info, A, B);
             __syncwarp();
@@ -492,16 +536,14 @@ __global__ void k_db_flatten(const long long* __restrict__ U_dev, DbCellInfo* __
 }
 
 // ---------------------------------------------------------------- D5: cluster heads (min core index)
-__global__ void k_db_mincore(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
-                             const uint8_t* __restrict__ core, const int32_t* __restrict__ cell_root,
-                             int32_t* __restrict__ root_min /*[U], init INT_MAX*/) {
-    int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void k_db_mincore(const long long* __restrict__ U_dev, const int32_t* __restrict__ cell_mincore,
+                             const int32_t* __restrict__ cell_root, int32_t* __restrict__ root_min /*[U], init large*/) {
+    const int64_t U = *U_dev;
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; pos < g.G; pos += stride) {
-        if (!core[pos]) continue;
-        const int64_t c = pos / g.chunk;
-        const int32_t orig = (int32_t)(c * g.chunk) + __float_as_int(spts[pos].w);
-        atomicMin(&root_min[cell_root[pt_cell[pos]]], orig);
+    for (; u < U; u += stride) {
+        const int32_t r = cell_root[u];
+        if (r >= 0) atomicMin(&root_min[r], cell_mincore[u]);
     }
 }
 
@@ -599,51 +641,101 @@ __global__ void k_db_acc_init(int64_t cap, DbClusterAcc* acc) {
     }
 }
 
+struct DbRun {
+    int32_t lab;
+    uint32_t cnt;
+    uint32_t mn[3], mx[3];
+    double sum[3];
+};
+
+__device__ __forceinline__ void db_flush(DbClusterAcc* __restrict__ acc, const DbRun& r) {
+    if (r.lab < 0 || r.cnt == 0) return;
+    DbClusterAcc* a = &acc[r.lab];
+    atomicAdd(&a->count, (unsigned long long)r.cnt);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        atomicMin(&a->mn[i], r.mn[i]);
+        atomicMax(&a->mx[i], r.mx[i]);
+        atomicAdd(&a->sum[i], r.sum[i]);
+    }
+}
+
+#define CR_PER_THREAD 16
+// Labels are spatially coherent (the candidates are in voxel-sorted order), so each thread folds a
+// run of CR_PER_THREAD consecutive points in registers, warps whose runs all carry one label merge
+// by shuffles, and a block whose warps agree merges in shared memory: one set of atomics per 4096
+// points instead of one per warp.
 __global__ void __launch_bounds__(256)
 k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ labels, int64_t G, int64_t cap,
                     DbClusterAcc* __restrict__ acc) {
-    const int lane = threadIdx.x & 31;
-    const int64_t Gpad = (G + 31) / 32 * 32;
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // multiple of 32: whole warps stay together
-    for (; i < Gpad; i += stride) {
-        int32_t lab = -1;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (i < G) {
-            lab = labels[i];
-            if (lab >= cap) lab = -1;
-            if (lab >= 0) { x = P[i * 3 + 0]; y = P[i * 3 + 1]; z = P[i * 3 + 2]; }
-        }
-        const int32_t lab0 = __shfl_sync(0xffffffffu, lab, 0);
-        const bool uniform = __all_sync(0xffffffffu, lab == lab0);
-        uint32_t ux = pch_f32_to_ordered(x), uy = pch_f32_to_ordered(y), uz = pch_f32_to_ordered(z);
-        if (uniform) {
-            if (lab0 < 0) continue;  // warp-uniform
-            uint32_t mnx = __reduce_min_sync(0xffffffffu, ux), mny = __reduce_min_sync(0xffffffffu, uy),
-                     mnz = __reduce_min_sync(0xffffffffu, uz);
-            uint32_t mxx = __reduce_max_sync(0xffffffffu, ux), mxy = __reduce_max_sync(0xffffffffu, uy),
-                     mxz = __reduce_max_sync(0xffffffffu, uz);
-            double sx = x, sy = y, sz = z;
+    __shared__ DbRun s_run[8];
+    __shared__ int s_uniform;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t per_block = 256 * CR_PER_THREAD;
+    const int64_t n_blocks = (G + per_block - 1) / per_block;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t i0 = blk * per_block + (int64_t)tid * CR_PER_THREAD;
+        DbRun r;
+        r.lab = -1; r.cnt = 0;
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
-                sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        for (int i = 0; i < 3; ++i) { r.mn[i] = 0xffffffffu; r.mx[i] = 0u; r.sum[i] = 0.0; }
+        for (int j = 0; j < CR_PER_THREAD; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= G) break;
+            int32_t lab = labels[i];
+            if (lab >= cap) lab = -1;
+            if (lab != r.lab) {
+                db_flush(acc, r);
+                r.lab = lab; r.cnt = 0;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { r.mn[a] = 0xffffffffu; r.mx[a] = 0u; r.sum[a] = 0.0; }
             }
-            if (lane == 0) {
-                DbClusterAcc* a = &acc[lab0];
-                atomicAdd(&a->count, 32ull);
-                atomicMin(&a->mn[0], mnx); atomicMin(&a->mn[1], mny); atomicMin(&a->mn[2], mnz);
-                atomicMax(&a->mx[0], mxx); atomicMax(&a->mx[1], mxy); atomicMax(&a->mx[2], mxz);
-                atomicAdd(&a->sum[0], sx); atomicAdd(&a->sum[1], sy); atomicAdd(&a->sum[2], sz);
+            if (lab >= 0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float v = P[i * 3 + a];
+                    const uint32_t u = pch_f32_to_ordered(v);
+                    r.mn[a] = min(r.mn[a], u);
+                    r.mx[a] = max(r.mx[a], u);
+                    r.sum[a] += (double)v;
+                }
+                ++r.cnt;
             }
-        } else if (lab >= 0) {
-            DbClusterAcc* a = &acc[lab];
-            atomicAdd(&a->count, 1ull);
-            atomicMin(&a->mn[0], ux); atomicMin(&a->mn[1], uy); atomicMin(&a->mn[2], uz);
-            atomicMax(&a->mx[0], ux); atomicMax(&a->mx[1], uy); atomicMax(&a->mx[2], uz);
-            atomicAdd(&a->sum[0], (double)x); atomicAdd(&a->sum[1], (double)y); atomicAdd(&a->sum[2], (double)z);
         }
+        // warp merge when every lane ended on the same label
+        const int32_t lab0 = __shfl_sync(0xffffffffu, r.lab, 0);
+        const bool wuni = __all_sync(0xffffffffu, r.lab == lab0);
+        if (wuni) {
+            r.cnt = __reduce_add_sync(0xffffffffu, r.cnt);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                r.mn[a] = __reduce_min_sync(0xffffffffu, r.mn[a]);
+                r.mx[a] = __reduce_max_sync(0xffffffffu, r.mx[a]);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) r.sum[a] += __shfl_xor_sync(0xffffffffu, r.sum[a], o);
+            }
+            if (lane == 0) s_run[warp] = r;
+        } else {
+            db_flush(acc, r);
+            if (lane == 0) { s_run[warp].lab = -2; s_run[warp].cnt = 0; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // fold consecutive warps that share a label, flush on change
+            DbRun t = s_run[0];
+            for (int w = 1; w < 8; ++w) {
+                const DbRun& n = s_run[w];
+                if (n.lab == t.lab && n.lab >= 0) {
+                    t.cnt += n.cnt;
+                    for (int a = 0; a < 3; ++a) { t.mn[a] = min(t.mn[a], n.mn[a]); t.mx[a] = max(t.mx[a], n.mx[a]); t.sum[a] += n.sum[a]; }
+                } else {
+                    db_flush(acc, t);
+                    t = n;
+                }
+            }
+            db_flush(acc, t);
+        }
+        __syncthreads();
     }
 }
 
@@ -691,7 +783,7 @@ struct DbWs {
     size_t total;
     size_t keys, tmp, sortws, sortws_bytes, spts, pt_cell, inv_pos, cell_start, cell_key, chunk_cell0, scalars,
         nbr_first, nbr_cnt, core, info, cell_root, root_min, root_label, is_head, head_list, scan_status, acc,
-        worklist;
+        worklist, cell_mincore;
 };
 
 extern "C" size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi);
@@ -734,6 +826,7 @@ static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t 
     w.scan_status = take(sc > cw ? sc : cw);
     w.acc = take((size_t)max_clusters * sizeof(DbClusterAcc));
     w.worklist = take((size_t)(G + 32) * 4);
+    w.cell_mincore = take((size_t)G * 4);
     w.total = off;
     return w;
 }
@@ -769,6 +862,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     long long* U_dev = (long long*)(base + w.scalars + 128);
     unsigned int* n_work = (unsigned int*)(base + w.scalars + 192);
     int32_t* worklist = (int32_t*)(base + w.worklist);
+    int32_t* cell_mincore = (int32_t*)(base + w.cell_mincore);
     uint64_t* keys = (uint64_t*)(base + w.keys);
     uint64_t* tmp = (uint64_t*)(base + w.tmp);
 
@@ -823,7 +917,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH(st, "k_db_core2", k_db_core2<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt,
                                                                             worklist, n_work, core));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info));
+    PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info, chunk, cell_mincore));
     PCH_LAUNCH_CHECK();
     for (int pass = 0; pass < 2; ++pass) {
         PCH_LAUNCH(st, "k_db_union", k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first,
@@ -834,7 +928,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH_CHECK();
     PCH_CUDA(cudaMemsetAsync(root_min, 0x7f, (size_t)G * 4, st));
     PCH_CUDA(cudaMemsetAsync(is_head, 0, (size_t)G, st));
-    PCH_LAUNCH(st, "k_db_mincore", k_db_mincore<<<db_grid(G, 256), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_min));
+    PCH_LAUNCH(st, "k_db_mincore", k_db_mincore<<<db_grid(G, 256), 256, 0, st>>>(U_dev, cell_mincore, cell_root, root_min));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_heads", k_db_heads<<<db_grid(G, 256), 256, 0, st>>>(U_dev, cell_root, root_min, is_head));
     PCH_LAUNCH_CHECK();
@@ -854,7 +948,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_cluster_reduce", k_db_cluster_reduce<<<db_grid(G, 256), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc));
+    PCH_LAUNCH(st, "k_db_cluster_reduce", k_db_cluster_reduce<<<db_grid(G, 256 * CR_PER_THREAD, 16), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_finish", k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev));
     PCH_LAUNCH_CHECK();

@@ -203,66 +203,68 @@ __device__ __forceinline__ void sq_elem(uint32_t bits, int k, uint32_t& q, uint3
 }
 
 // Per tile, column and window slot: the composed map.  Fast path: when no element of the tile is an
-// exact tie for this k, the map does not depend on parity and is a plain sum (one block reduction);
-// otherwise the ordered composition is evaluated (rare: needs r == 2^(k-1) exactly).
-__global__ void __launch_bounds__(SQ_THREADS)
+// exact tie for this k, the map does not depend on parity and is a plain (order-free) sum, so the
+// threads read the tile strided/coalesced and one block reduction finishes it; a (column, slot) that
+// does contain exact ties (r == 2^(k-1)) is re-evaluated as an ordered composition.
+__global__ void __launch_bounds__(SQ_THREADS, 4)
 k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
              const int32_t* __restrict__ klo, SqMap* __restrict__ table /*[3][n_tiles][SQ_W]*/) {
     __shared__ unsigned long long s_sum[SQ_THREADS / 32][3 * SQ_W];
     __shared__ uint32_t s_tie[SQ_THREADS / 32][3 * SQ_W];
-    __shared__ unsigned long long s_tot[3 * SQ_W];
     __shared__ uint32_t s_ties[3 * SQ_W];
     __shared__ SqMap s_cw[SQ_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        float v[24];
-        sq_load8(xyz, t * SQ_TILE + (int64_t)tid * SQ_EPT, m, v);
-        int k0[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) k0[c] = klo[c * n_tiles + t];
-#pragma unroll
+        const int64_t base = t * SQ_TILE;
         for (int c = 0; c < 3; ++c) {
+            const int k0 = klo[c * n_tiles + t];
+            unsigned long long acc[SQ_W];
+            uint32_t ties[SQ_W];
+#pragma unroll
+            for (int w = 0; w < SQ_W; ++w) { acc[w] = 0; ties[w] = 0; }
+#pragma unroll
+            for (int e = 0; e < SQ_EPT; ++e) {
+                const int64_t i = base + e * SQ_THREADS + tid;
+                const uint32_t bits = i < m ? __float_as_uint(__ldg(&xyz[i * 3 + c])) : 0u;
+#pragma unroll
+                for (int w = 0; w < SQ_W; ++w) {
+                    uint32_t q, gt, eq;
+                    sq_elem(bits, k0 + w, q, gt, eq);
+                    acc[w] += (unsigned long long)q + gt;
+                    ties[w] += eq;
+                }
+            }
 #pragma unroll
             for (int w = 0; w < SQ_W; ++w) {
-                unsigned long long acc = 0;
-                uint32_t ties = 0;
-#pragma unroll
-                for (int e = 0; e < SQ_EPT; ++e) {
-                    uint32_t q, gt, eq;
-                    sq_elem(__float_as_uint(v[e * 3 + c]), k0[c] + w, q, gt, eq);
-                    acc += (unsigned long long)q + gt;
-                    ties += eq;
-                }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
-                    acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    ties += __shfl_xor_sync(0xffffffffu, ties, o);
+                    acc[w] += __shfl_xor_sync(0xffffffffu, acc[w], o);
+                    ties[w] += __shfl_xor_sync(0xffffffffu, ties[w], o);
                 }
-                if (lane == 0) { s_sum[warp][c * SQ_W + w] = acc; s_tie[warp][c * SQ_W + w] = ties; }
+                if (lane == 0) { s_sum[warp][c * SQ_W + w] = acc[w]; s_tie[warp][c * SQ_W + w] = ties[w]; }
             }
         }
         __syncthreads();
         if (tid < 3 * SQ_W) {
             unsigned long long a = 0; uint32_t ti = 0;
             for (int ww = 0; ww < SQ_THREADS / 32; ++ww) { a += s_sum[ww][tid]; ti += s_tie[ww][tid]; }
-            s_tot[tid] = a; s_ties[tid] = ti;
+            s_ties[tid] = ti;
             if (ti == 0) {
                 SqMap mp; mp.d0 = mp.d1 = a >= SQ_SAT ? SQ_SAT : (uint32_t)a;
-                const int c = tid / SQ_W, w = tid % SQ_W;
-                table[((size_t)c * n_tiles + t) * SQ_W + w] = mp;
+                table[((size_t)(tid / SQ_W) * n_tiles + t) * SQ_W + (tid % SQ_W)] = mp;
             }
         }
         __syncthreads();
-        // slow path for the (column, slot) pairs that contain exact ties: ordered composition
-#pragma unroll
         for (int cw = 0; cw < 3 * SQ_W; ++cw) {
             if (s_ties[cw] == 0) continue;  // block-uniform
-            const int c = cw / SQ_W, w = cw % SQ_W;   // compile-time after unrolling: v[] stays in registers
+            const int c = cw / SQ_W, w = cw % SQ_W;
+            const int k = klo[c * n_tiles + t] + w;
             SqMap mp; mp.d0 = 0; mp.d1 = 0;
-#pragma unroll
-            for (int e = 0; e < SQ_EPT; ++e) {
+            for (int e = 0; e < SQ_EPT; ++e) {   // ordered: thread owns SQ_EPT consecutive elements
+                const int64_t i = base + (int64_t)tid * SQ_EPT + e;
+                const uint32_t bits = i < m ? __float_as_uint(__ldg(&xyz[i * 3 + c])) : 0u;
                 uint32_t q, gt, eq;
-                sq_elem(__float_as_uint(v[e * 3 + c]), k0[c] + w, q, gt, eq);
+                sq_elem(bits, k, q, gt, eq);
                 const uint32_t base_inc = sq_sat_add(q, gt);
                 const uint32_t i0 = sq_sat_add(base_inc, eq & ((mp.d0 + q) & 1u));
                 const uint32_t i1 = sq_sat_add(base_inc, eq & ((1u + mp.d1 + q) & 1u));
@@ -363,13 +365,58 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
             continue;
         }
         if (t < n_tiles) {
-            // this tile leaves the binade / is outside its window / has negative data: real float32 adds
+            // this tile leaves the binade / is outside its window / has negative data
             const int64_t lo = t * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
+            const bool tile_ok = info[c * n_tiles + t].ok != 0;
             for (int64_t i0 = lo; i0 < hi; i0 += 32) {
                 const int64_t i = i0 + lane;
                 const float v = i < hi ? xyz[i * 3 + c] : 0.0f;
                 const int cnt = (int)min((int64_t)32, hi - i0);
-                for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+                if (!tile_ok) {                       // negative / non-finite data: real float32 adds
+                    for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+                    continue;
+                }
+                // non-negative data: evaluate the 32 elements with on-the-fly maps for the current binade;
+                // only the element that actually crosses a binade boundary takes a real add
+                int start = 0;
+                while (start < cnt) {
+                    const uint32_t sb2 = __float_as_uint(s);
+                    const int es2 = (int)((sb2 >> 23) & 0xffu);
+                    int L = 0;
+                    if (es2 != 0 && es2 != 0xff) {
+                        const int k = es2 - 150;
+                        const uint32_t ms = (sb2 & 0x7fffffu) | 0x800000u;
+                        SqMap F; F.d0 = 0; F.d1 = 0;
+                        if (lane >= start && lane < cnt) {
+                            uint32_t q, gt, eq;
+                            sq_elem(__float_as_uint(v), k, q, gt, eq);
+                            const uint32_t b = sq_sat_add(q, gt);
+                            F.d0 = sq_sat_add(b, eq & (q & 1u));
+                            F.d1 = sq_sat_add(b, eq & ((1u + q) & 1u));
+                        }
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            SqMap pv;
+                            pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                            pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                            if (lane >= o) F = sq_compose(pv, F);
+                        }
+                        const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
+                        const bool ok = lane < cnt && D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
+                        uint32_t okmask = __ballot_sync(0xffffffffu, ok) | ((1u << start) - 1u);  // consumed lanes count as ok
+                        const int first_bad = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
+                        L = first_bad - start;   // elements start .. first_bad-1 stay inside the binade
+                        if (L > 0) {
+                            const uint32_t Dl = __shfl_sync(0xffffffffu, D, first_bad - 1);
+                            s = __uint_as_float(((uint32_t)es2 << 23) | ((ms + Dl) & 0x7fffffu));
+                            start = first_bad;
+                        }
+                    }
+                    if (start < cnt) {   // the element that crosses the binade (or s is still 0/denormal): one real add
+                        s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, start));
+                        ++start;
+                    }
+                }
             }
             ++t;
             ++n_real;

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(256) k_scan(uint32_t* __restrict__ hist, int64
 #define ST_INCL 0x80000000u
 #define ST_VAL 0x3fffffffu
 
-__global__ void __launch_bounds__(RS_THREADS, 3)
-k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, int pass,
+__global__ void __launch_bounds__(RS_THREADS, 4)
+k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, int pass, int shift, uint32_t dmask,
        const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
        int* __restrict__ err) {
     __shared__ uint64_t s_keys[RS_TILE];
@@ -143,9 +143,6 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int shift = g.bit_lo + 8 * pass;
-    const uint32_t dmask = (1u << g.pass_bits[pass]) - 1u;
-
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
     __syncthreads();
@@ -268,7 +265,7 @@ extern "C" int pch_sort_u64_segmented(uint64_t* keys, uint64_t* tmp, int64_t n, 
     uint64_t* src = keys;
     uint64_t* dst = tmp;
     for (int p = 0; p < g.n_passes; ++p) {
-        PCH_LAUNCH(st, "k_pass", k_pass<<<(unsigned)g.total_tiles, RS_THREADS, 0, st>>>(src, dst, g, p, w.hist,
+        PCH_LAUNCH(st, "k_pass", k_pass<<<(unsigned)g.total_tiles, RS_THREADS, 0, st>>>(src, dst, g, p, g.bit_lo + 8 * p, (1u << g.pass_bits[p]) - 1u, w.hist,
                                                                w.status + (size_t)p * g.total_tiles * 256,
                                                                w.counters + p, w.err));
         PCH_LAUNCH_CHECK();

@@ -305,10 +305,19 @@ k_db_core2(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict_
             if (nc == 0) continue;
             const int32_t f = nbr_first[(int64_t)u * 25 + col];
             const int32_t b = cell_start[f], e = cell_start[f + nc];
-            for (int32_t q0 = b; q0 < e && count < g.min_pts; q0 += 32) {
-                const int32_t q = q0 + lane;
-                const bool hit = q < e && db_dist2(p, spts[q]) <= g.eps2;
-                count += __popc(__ballot_sync(0xffffffffu, hit));
+            for (int32_t q0 = b; q0 < e && count < g.min_pts; q0 += 128) {
+                float4 c4[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int32_t q = q0 + r * 32 + lane;
+                    c4[r] = q < e ? spts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int32_t q = q0 + r * 32 + lane;
+                    const bool hit = q < e && db_dist2(p, c4[r]) <= g.eps2;
+                    count += __popc(__ballot_sync(0xffffffffu, hit));
+                }
             }
         }
         if (lane == 0 && count >= g.min_pts) core[pos] = 1;

@@ -290,140 +290,130 @@ k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const Sq
     }
 }
 
-struct SqLane {   // what one lane needs to know about "its" tile
-    SqMap e[SQ_W];
-    int32_t klo;
-    int32_t ok;
-};
+// One CTA per column.  All 256 threads stage the maps of SQ_BATCH tiles into shared memory (coalesced,
+// many loads in flight); warp 0 then walks the batch 32 tiles at a time with warp scans — no global
+// latency on the serial path.
+#define SQ_BATCH 1024
+#define SQ_CHAIN_THREADS 256
 
-__device__ __forceinline__ SqLane sq_fetch(int64_t tt, int64_t n_tiles, int c, const SqTileInfo* __restrict__ info,
-                                           const int32_t* __restrict__ klo, const SqMap* __restrict__ table) {
-    SqLane L;
-    L.ok = 0; L.klo = 0;
-#pragma unroll
-    for (int w = 0; w < SQ_W; ++w) { L.e[w].d0 = SQ_SAT; L.e[w].d1 = SQ_SAT; }
-    if (tt < n_tiles) {
-        L.ok = info[c * n_tiles + tt].ok;
-        L.klo = klo[c * n_tiles + tt];
-        if (L.ok) {
-            const uint4* p = reinterpret_cast<const uint4*>(table + ((size_t)c * n_tiles + tt) * SQ_W);
-#pragma unroll
-            for (int w = 0; w < SQ_W / 2; ++w) {
-                uint4 u = __ldg(p + w);
-                L.e[2 * w].d0 = u.x; L.e[2 * w].d1 = u.y; L.e[2 * w + 1].d0 = u.z; L.e[2 * w + 1].d1 = u.w;
-            }
-        }
-    }
-    return L;
-}
-
-__global__ void __launch_bounds__(96)
+__global__ void __launch_bounds__(SQ_CHAIN_THREADS)
 k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
             const int32_t* __restrict__ klo, const SqMap* __restrict__ table, float* __restrict__ sums,
             int* __restrict__ stats /*[3][2]: tiles via maps, tiles via real adds*/) {
-    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (c >= 3) return;
+    __shared__ SqMap s_tab[SQ_BATCH * SQ_W];
+    __shared__ int32_t s_klo[SQ_BATCH];
+    __shared__ uint8_t s_ok[SQ_BATCH];
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float s = 0.0f;
-    int64_t t = 0;
     int n_map = 0, n_real = 0;
-    SqLane cur = sq_fetch(t + lane, n_tiles, c, info, klo, table);
-    while (t < n_tiles) {
-        SqLane nxt = sq_fetch(t + 32 + lane, n_tiles, c, info, klo, table);  // prefetch: the common case advances 32
-        const uint32_t sb = __float_as_uint(s);
-        const int es = (int)((sb >> 23) & 0xffu);
-        int advanced = 0;
-        if (es != 0 && es != 0xff && !(sb >> 31)) {
-            const int k = es - 150;
-            const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
-            SqMap F; F.d0 = SQ_SAT; F.d1 = SQ_SAT;
-            const int idx = k - cur.klo;
-            if (cur.ok) {
-#pragma unroll
-                for (int w = 0; w < SQ_W; ++w) if (idx == w) F = cur.e[w];
-            }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                SqMap pv;
-                pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
-                pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
-                if (lane >= o) F = sq_compose(pv, F);
-            }
-            const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
-            const bool ok = D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
-            const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-            const int L = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
-            if (L > 0) {
-                const uint32_t Dl = __shfl_sync(0xffffffffu, D, L - 1);
-                s = __uint_as_float(((uint32_t)es << 23) | ((ms + Dl) & 0x7fffffu));
-                advanced = L;
-                n_map += L;
+    for (int64_t b0 = 0; b0 < n_tiles; b0 += SQ_BATCH) {
+        const int nb = (int)min((int64_t)SQ_BATCH, n_tiles - b0);
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(table + ((size_t)c * n_tiles + b0) * SQ_W);
+            uint4* dst = reinterpret_cast<uint4*>(s_tab);
+            for (int i = tid; i < nb * SQ_W / 2; i += SQ_CHAIN_THREADS) dst[i] = __ldg(src + i);
+            for (int i = tid; i < nb; i += SQ_CHAIN_THREADS) {
+                s_klo[i] = klo[c * n_tiles + b0 + i];
+                s_ok[i] = (uint8_t)(info[c * n_tiles + b0 + i].ok != 0);
             }
         }
-        t += advanced;
-        if (advanced == 32) {
-            cur = nxt;
-            continue;
-        }
-        if (t < n_tiles) {
-            // this tile leaves the binade / is outside its window / has negative data
-            const int64_t lo = t * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
-            const bool tile_ok = info[c * n_tiles + t].ok != 0;
-            for (int64_t i0 = lo; i0 < hi; i0 += 32) {
-                const int64_t i = i0 + lane;
-                const float v = i < hi ? xyz[i * 3 + c] : 0.0f;
-                const int cnt = (int)min((int64_t)32, hi - i0);
-                if (!tile_ok) {                       // negative / non-finite data: real float32 adds
-                    for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
-                    continue;
-                }
-                // non-negative data: evaluate the 32 elements with on-the-fly maps for the current binade;
-                // only the element that actually crosses a binade boundary takes a real add
-                int start = 0;
-                while (start < cnt) {
-                    const uint32_t sb2 = __float_as_uint(s);
-                    const int es2 = (int)((sb2 >> 23) & 0xffu);
-                    int L = 0;
-                    if (es2 != 0 && es2 != 0xff) {
-                        const int k = es2 - 150;
-                        const uint32_t ms = (sb2 & 0x7fffffu) | 0x800000u;
-                        SqMap F; F.d0 = 0; F.d1 = 0;
-                        if (lane >= start && lane < cnt) {
-                            uint32_t q, gt, eq;
-                            sq_elem(__float_as_uint(v), k, q, gt, eq);
-                            const uint32_t b = sq_sat_add(q, gt);
-                            F.d0 = sq_sat_add(b, eq & (q & 1u));
-                            F.d1 = sq_sat_add(b, eq & ((1u + q) & 1u));
-                        }
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            SqMap pv;
-                            pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
-                            pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
-                            if (lane >= o) F = sq_compose(pv, F);
-                        }
-                        const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
-                        const bool ok = lane < cnt && D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
-                        uint32_t okmask = __ballot_sync(0xffffffffu, ok) | ((1u << start) - 1u);  // consumed lanes count as ok
-                        const int first_bad = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
-                        L = first_bad - start;   // elements start .. first_bad-1 stay inside the binade
-                        if (L > 0) {
-                            const uint32_t Dl = __shfl_sync(0xffffffffu, D, first_bad - 1);
-                            s = __uint_as_float(((uint32_t)es2 << 23) | ((ms + Dl) & 0x7fffffu));
-                            start = first_bad;
-                        }
+        __syncthreads();
+        if (warp == 0) {
+            int t = 0;   // tile index inside the batch
+            while (t < nb) {
+                const uint32_t sb = __float_as_uint(s);
+                const int es = (int)((sb >> 23) & 0xffu);
+                int advanced = 0;
+                if (es != 0 && es != 0xff && !(sb >> 31)) {
+                    const int k = es - 150;
+                    const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
+                    SqMap F; F.d0 = SQ_SAT; F.d1 = SQ_SAT;
+                    const int tt = t + lane;
+                    if (tt < nb && s_ok[tt]) {
+                        const int idx = k - s_klo[tt];
+                        if (idx >= 0 && idx < SQ_W) F = s_tab[tt * SQ_W + idx];
                     }
-                    if (start < cnt) {   // the element that crosses the binade (or s is still 0/denormal): one real add
-                        s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, start));
-                        ++start;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        SqMap pv;
+                        pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                        pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                        if (lane >= o) F = sq_compose(pv, F);
+                    }
+                    const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
+                    const bool ok = D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
+                    const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+                    const int L = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
+                    if (L > 0) {
+                        const uint32_t Dl = __shfl_sync(0xffffffffu, D, L - 1);
+                        s = __uint_as_float(((uint32_t)es << 23) | ((ms + Dl) & 0x7fffffu));
+                        advanced = L;
+                        n_map += L;
                     }
                 }
+                t += advanced;
+                if (advanced == 32 || t >= nb) continue;
+                {
+                    // tile b0+t leaves the binade / is outside its window / has negative data
+                    const int64_t tg = b0 + t;
+                    const int64_t lo = tg * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
+                    const bool tile_ok = s_ok[t] != 0;
+                    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+                        const int64_t i = i0 + lane;
+                        const float v = i < hi ? xyz[i * 3 + c] : 0.0f;
+                        const int cnt = (int)min((int64_t)32, hi - i0);
+                        if (!tile_ok) {                       // negative / non-finite data: real float32 adds
+                            for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
+                            continue;
+                        }
+                        // non-negative data: on-the-fly maps for the current binade; only the element that
+                        // actually crosses a binade boundary takes a real add
+                        int start = 0;
+                        while (start < cnt) {
+                            const uint32_t sb2 = __float_as_uint(s);
+                            const int es2 = (int)((sb2 >> 23) & 0xffu);
+                            if (es2 != 0 && es2 != 0xff) {
+                                const int k = es2 - 150;
+                                const uint32_t ms = (sb2 & 0x7fffffu) | 0x800000u;
+                                SqMap F; F.d0 = 0; F.d1 = 0;
+                                if (lane >= start && lane < cnt) {
+                                    uint32_t q, gt, eq;
+                                    sq_elem(__float_as_uint(v), k, q, gt, eq);
+                                    const uint32_t bb = sq_sat_add(q, gt);
+                                    F.d0 = sq_sat_add(bb, eq & (q & 1u));
+                                    F.d1 = sq_sat_add(bb, eq & ((1u + q) & 1u));
+                                }
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) {
+                                    SqMap pv;
+                                    pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                                    pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                                    if (lane >= o) F = sq_compose(pv, F);
+                                }
+                                const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
+                                const bool ok = lane < cnt && D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
+                                const uint32_t okmask = __ballot_sync(0xffffffffu, ok) | ((1u << start) - 1u);
+                                const int first_bad = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
+                                if (first_bad > start) {
+                                    const uint32_t Dl = __shfl_sync(0xffffffffu, D, first_bad - 1);
+                                    s = __uint_as_float(((uint32_t)es2 << 23) | ((ms + Dl) & 0x7fffffu));
+                                    start = first_bad;
+                                }
+                            }
+                            if (start < cnt) {   // the element that crosses the binade (or s is still 0/denormal)
+                                s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, start));
+                                ++start;
+                            }
+                        }
+                    }
+                    ++t;
+                    ++n_real;
+                }
             }
-            ++t;
-            ++n_real;
         }
-        cur = sq_fetch(t + lane, n_tiles, c, info, klo, table);
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (tid == 0) {
         sums[c] = s;
         if (stats) { stats[c * 2] = n_map; stats[c * 2 + 1] = n_real; }
     }
@@ -460,7 +450,7 @@ extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float
         PCH_LAUNCH(st, "k_sum_prep", k_sum_prep<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info));
         PCH_LAUNCH(st, "k_sum_window", k_sum_window<<<3, 1024, 0, st>>>(info, nt, klo));
         PCH_LAUNCH(st, "k_sum_tables", k_sum_tables<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info, klo, table));
-        PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<1, 96, 0, st>>>(xyz, m, nt, info, klo, table, sums3, stats));
+        PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<3, SQ_CHAIN_THREADS, 0, st>>>(xyz, m, nt, info, klo, table, sums3, stats));
         PCH_LAUNCH_CHECK();
     }
     PCH_LAUNCH(st, "k_centroid_from_sums", k_centroid_from_sums<<<1, 32, 0, st>>>(sums3, m, centroid3));

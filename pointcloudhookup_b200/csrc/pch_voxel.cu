@@ -182,6 +182,7 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
                unsigned long long* __restrict__ chunk_counts, long long* __restrict__ total_out,
                uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
     __shared__ uint64_t s_keys[VR_TILE + 1];  // [0] = key preceding the tile
+    __shared__ int s_xyz[ALIGN > 0 ? VR_TILE : 1][3];  // lattice coordinates of the tile's points (LAS source)
     __shared__ uint32_t s_wcount[VR_WARPS];
     __shared__ uint64_t s_tile_off;
     __shared__ uint32_t s_tile;
@@ -200,7 +201,17 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     const int bi = g.bits_idx;
     const uint64_t idx_mask = bi >= 64 ? ~0ull : ((1ull << bi) - 1ull);
 
-    for (int i = tid; i < cnt; i += VR_THREADS) s_keys[i + 1] = keys[start + i];
+    for (int i = tid; i < cnt; i += VR_THREADS) {
+        const uint64_t k = keys[start + i];
+        s_keys[i + 1] = k;
+        if (ALIGN > 0) {
+            // every thread gathers the points of its own sorted slots: all loads of the tile are in
+            // flight at once, instead of being serialised inside the per-voxel loops below
+            int X, Y, Z;
+            pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len, X, Y, Z);
+            s_xyz[i][0] = X; s_xyz[i][1] = Y; s_xyz[i][2] = Z;
+        }
+    }
     if (tid == 0) s_keys[0] = lt > 0 ? keys[start - 1] : ~0ull;
     __syncthreads();
 
@@ -249,11 +260,16 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         long long cntp = 0;
         int64_t p = start + i;
         uint64_t k = s_keys[i + 1];
+        int li = i;
         while (true) {
             if (ALIGN > 0) {
-                const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
                 int X, Y, Z;
-                pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(q, X, Y, Z);
+                if (li < cnt) {
+                    X = s_xyz[li][0]; Y = s_xyz[li][1]; Z = s_xyz[li][2];
+                } else {   // the run continues past this tile
+                    const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
+                    pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(q, X, Y, Z);
+                }
                 sx = __dadd_rn(sx, pch_scaled(X, a.s[0], a.o[0]));
                 sy = __dadd_rn(sy, pch_scaled(Y, a.s[1], a.o[1]));
                 sz = __dadd_rn(sz, pch_scaled(Z, a.s[2], a.o[2]));
@@ -266,7 +282,7 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
             ++cntp;
             ++p;
             if (p >= cend) break;
-            int li = (int)(p - start);
+            li = (int)(p - start);
             k = li < cnt ? s_keys[li + 1] : keys[p];
             if ((k >> bi) != vkey) break;
         }

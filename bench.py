@@ -130,10 +130,10 @@ def kernel_bytes_model(cfg, info):
     n, M, G, R = cfg["n"], info.get("M", 0), info.get("G", 0), 34
     return {
         "k_chunk_minmax": n * R,
-        "k_voxel_keys": n * (R + 8),
+        "k_voxel_keys": n * (R + 8 + 16),
         "k_hist": None,          # mixed (voxel sort + DBSCAN sort): resolved from launches below
         "k_pass": None,
-        "k_voxel_reduce": n * 8 + n * R + M * 12,
+        "k_voxel_reduce": n * 8 + n * 16 + M * 12,
         "k_seq_sum_serial": M * 12,
         "k_shift": M * 12 + M * 4,
         "k_sel_hist": M * 4,

@@ -92,6 +92,7 @@ int pch_voxel_plan_build(const int32_t* minmax_dev, int64_t n_chunks, int64_t ch
 int pch_voxel_keys(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t chunk_size,
                    const double* scales, const double* offsets, double voxel_size,
                    const double* origins_dev, const pch_voxel_plan* plan, uint64_t* keys_dev,
+                   int32_t* xyz16_dev /* nullable: (n,4) int32 = X,Y,Z,0 copy for the reduce gathers */,
                    pch_stream_t stream);
 
 /* The same two steps for an arbitrary (n,3) float64 point array — process_chunk(points_chunk,
@@ -121,7 +122,9 @@ int pch_sort_u64_segmented(uint64_t* keys_dev, uint64_t* tmp_dev, int64_t n, int
  * chunk_counts_dev[n_chunks] and total_dev[1] (int64) receive the voxel counts. */
 size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size);
 int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_size, int32_t bits_idx,
-                     const uint8_t* rec_dev, int32_t rec_len, const double* scales, const double* offsets,
+                     const uint8_t* rec_dev, int32_t rec_len,
+                     const int32_t* xyz16_dev /* nullable: pch_voxel_keys' packed copy; gathers read it instead of rec_dev */,
+                     const double* scales, const double* offsets,
                      double* mean_dev, int32_t* lattice_dev, float* f32_dev, int64_t* chunk_counts_dev,
                      int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 

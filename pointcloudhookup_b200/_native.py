@@ -43,13 +43,13 @@ SIGNATURES = {
     "pch_las_quantise": (C.c_int, [_p, _i64, _d3, _d3, _p, _p]),
     "pch_las_encode": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "pch_voxel_plan_build": (C.c_int, [_p, _i64, _i64, _d3, _d3, _f64, _p, _p, _p]),
-    "pch_voxel_keys": (C.c_int, [_p, _i64, _i32, _i64, _d3, _d3, _f64, _p, C.POINTER(VoxelPlan), _p, _p]),
+    "pch_voxel_keys": (C.c_int, [_p, _i64, _i32, _i64, _d3, _d3, _f64, _p, C.POINTER(VoxelPlan), _p, _p, _p]),
     "pch_voxel_plan_build_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p, _p]),
     "pch_voxel_keys_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, C.POINTER(VoxelPlan), _p, _p]),
     "pch_sort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "pch_sort_u64_segmented": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "pch_voxel_reduce_workspace_bytes": (_sz, [_i64, _i64]),
-    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _p, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 class ClusterStats(C.Structure):

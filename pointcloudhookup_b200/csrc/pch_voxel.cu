@@ -92,7 +92,7 @@ struct KeyLayout {
 template <int ALIGN>
 __global__ void __launch_bounds__(PCH_TILE_THREADS, 2)
 k_voxel_keys(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine3 a, double voxel,
-             const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys) {
+             const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys, int4* __restrict__ xyz16) {
     extern __shared__ __align__(128) uint8_t smem[];
     pch_stream_tiles(rec, g, smem, [&](const PchTile& t) {
         const double ox = origins[t.chunk * 3 + 0], oy = origins[t.chunk * 3 + 1], oz = origins[t.chunk * 3 + 2];
@@ -109,13 +109,16 @@ k_voxel_keys(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine3 a, doubl
             uint64_t iz = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(z, oz), voxel));
             uint64_t local = (uint64_t)(t.r0 + r - chunk_start);
             keys[t.r0 + r] = (ix << kl.sh_x) | (iy << kl.sh_y) | (iz << kl.sh_z) | local;
+            // 16-byte aligned copy of the lattice coordinates: the reduce pass gathers ONE aligned
+            // vector per point instead of four loads from a 2-byte aligned 34-byte record
+            if (xyz16) xyz16[t.r0 + r] = make_int4(X, Y, Z, 0);
         }
     });
 }
 
 extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, int64_t chunk_size, const double* scales,
                               const double* offsets, double voxel, const double* origins, const pch_voxel_plan* plan,
-                              uint64_t* keys, pch_stream_t stream) {
+                              uint64_t* keys, int32_t* xyz16, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(n >= 0 && rec_len >= 12 && rec_len <= 256, "bad n/rec_len");
     PCH_CHECK_ARG(chunk_size > 0 && voxel > 0.0, "chunk_size and voxel_size must be > 0");
@@ -142,7 +145,7 @@ extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, in
 #define LAUNCH_KEYS(A)                                                                                       \
     do {                                                                                                     \
         PCH_CUDA(cudaFuncSetAttribute(k_voxel_keys<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        PCH_LAUNCH(st, "k_voxel_keys", k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, voxel, origins, kl, keys));          \
+        PCH_LAUNCH(st, "k_voxel_keys", k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, voxel, origins, kl, keys, (int4*)xyz16));          \
     } while (0)
     if (al == 4) LAUNCH_KEYS(4);
     else if (al == 2) LAUNCH_KEYS(2);
@@ -177,7 +180,8 @@ extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size
 // (n,3) float64 array (process_chunk's arbitrary point input).
 template <int ALIGN>
 __global__ void __launch_bounds__(VR_THREADS)
-k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec, PchAffine3 a,
+k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec,
+               const int4* __restrict__ xyz16, PchAffine3 a,
                double* __restrict__ mean_out, int32_t* __restrict__ lat_out, float* __restrict__ f32_out,
                unsigned long long* __restrict__ chunk_counts, long long* __restrict__ total_out,
                uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
@@ -201,15 +205,38 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     const int bi = g.bits_idx;
     const uint64_t idx_mask = bi >= 64 ? ~0ull : ((1ull << bi) - 1ull);
 
-    for (int i = tid; i < cnt; i += VR_THREADS) {
-        const uint64_t k = keys[start + i];
-        s_keys[i + 1] = k;
-        if (ALIGN > 0) {
-            // every thread gathers the points of its own sorted slots: all loads of the tile are in
-            // flight at once, instead of being serialised inside the per-voxel loops below
-            int X, Y, Z;
-            pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len, X, Y, Z);
-            s_xyz[i][0] = X; s_xyz[i][1] = Y; s_xyz[i][2] = Z;
+    {
+        // every thread gathers the points of its own sorted slots: first all key loads, then all
+        // point gathers, so the whole tile's loads are in flight at once instead of being serialised
+        // inside the per-voxel loops below
+        uint64_t kk[VR_ROWS];
+#pragma unroll
+        for (int j = 0; j < VR_ROWS; ++j) {
+            const int i = tid + j * VR_THREADS;
+            kk[j] = i < cnt ? keys[start + i] : 0ull;
+        }
+        int gx[VR_ROWS], gy[VR_ROWS], gz[VR_ROWS];
+#pragma unroll
+        for (int j = 0; j < VR_ROWS; ++j) {
+            const int i = tid + j * VR_THREADS;
+            gx[j] = gy[j] = gz[j] = 0;
+            if (ALIGN > 0 && i < cnt) {
+                const int64_t src = cstart + (int64_t)(kk[j] & idx_mask);
+                if (xyz16) {
+                    const int4 v = __ldg(xyz16 + src);
+                    gx[j] = v.x; gy[j] = v.y; gz[j] = v.z;
+                } else {
+                    pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(rec + (size_t)src * g.rec_len, gx[j], gy[j], gz[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < VR_ROWS; ++j) {
+            const int i = tid + j * VR_THREADS;
+            if (i < cnt) {
+                s_keys[i + 1] = kk[j];
+                if (ALIGN > 0) { s_xyz[i][0] = gx[j]; s_xyz[i][1] = gy[j]; s_xyz[i][2] = gz[j]; }
+            }
         }
     }
     if (tid == 0) s_keys[0] = lt > 0 ? keys[start - 1] : ~0ull;
@@ -266,7 +293,10 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
                 int X, Y, Z;
                 if (li < cnt) {
                     X = s_xyz[li][0]; Y = s_xyz[li][1]; Z = s_xyz[li][2];
-                } else {   // the run continues past this tile
+                } else if (xyz16) {   // the run continues past this tile
+                    const int4 v = __ldg(xyz16 + cstart + (int64_t)(k & idx_mask));
+                    X = v.x; Y = v.y; Z = v.z;
+                } else {
                     const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
                     pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(q, X, Y, Z);
                 }
@@ -308,7 +338,8 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
 }
 
 extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
-                                const uint8_t* rec, int32_t rec_len, const double* scales, const double* offsets,
+                                const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const double* scales,
+                                const double* offsets,
                                 double* mean_out, int32_t* lat_out, float* f32_out, int64_t* chunk_counts,
                                 int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -325,7 +356,8 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     if (chunk_counts) PCH_CUDA(cudaMemsetAsync(chunk_counts, 0, sizeof(int64_t) * n_chunks, st));
     if (total_out) PCH_CUDA(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
     if (n == 0) return PCH_OK;
-    PCH_CHECK_ARG(keys && rec && workspace, "null pointer");
+    PCH_CHECK_ARG(keys && (rec || (xyz16 && rec_len != 0)) && workspace, "null pointer");
+    PCH_CHECK_ARG(!xyz16 || (reinterpret_cast<uintptr_t>(xyz16) & 15) == 0, "xyz16 must be 16-byte aligned");
     ReduceGeom g;
     g.n = n; g.chunk_size = chunk_size; g.bits_idx = bits_idx; g.rec_len = rec_len;
     g.tiles_per_chunk = pch_ceil_div(chunk_size, VR_TILE);
@@ -343,7 +375,7 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     int al = rec_len == 0 ? 0 : pch_rec_align(rec_len);
 #define LAUNCH_RED(A)                                                                                          \
     PCH_LAUNCH(st, "k_voxel_reduce", k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
-        keys, g, rec, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
+        keys, g, rec, (const int4*)xyz16, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
         status, counter, err))
     if (al == 4) LAUNCH_RED(4);
     else if (al == 2) LAUNCH_RED(2);

@@ -174,8 +174,9 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     if plan.status != 0:
         raise ValueError(f"voxel_size is too small: index range needs {plan.key_bits}+{plan.bits_idx} bits (> 64)")
     keys = torch.empty(n, dtype=torch.int64, device=dev)
+    xyz16 = torch.empty((n, 4), dtype=torch.int32, device=dev)
     check(lib.pch_voxel_keys(dl.rec.data_ptr(), n, dl.rec_len, cs, sc, of, float(voxel_size), origins.data_ptr(),
-                             C.byref(plan), keys.data_ptr(), st), "pch_voxel_keys")
+                             C.byref(plan), keys.data_ptr(), xyz16.data_ptr(), st), "pch_voxel_keys")
     skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
     # worst case every point is its own voxel; outputs are sized n and sliced after the count is known
     mean = torch.empty((n, 3), dtype=torch.float64, device=dev) if "mean" in want else None
@@ -185,7 +186,8 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     total = torch.empty(1, dtype=torch.int64, device=dev)
     ws_bytes = lib.pch_voxel_reduce_workspace_bytes(n, cs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, dl.rec.data_ptr(), dl.rec_len, sc, of,
+    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, dl.rec.data_ptr(), dl.rec_len,
+                               xyz16.data_ptr(), sc, of,
                                _ptr(mean), _ptr(lat), _ptr(f32), counts.data_ptr(), total.data_ptr(),
                                ws.data_ptr(), ws_bytes, st), "pch_voxel_reduce")
     m = int(total.item())
@@ -374,7 +376,7 @@ def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Op
     total = torch.empty(1, dtype=torch.int64, device=dev)
     wsb = lib.pch_voxel_reduce_workspace_bytes(n, cs)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, xyz.data_ptr(), 0, None, None,
+    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, xyz.data_ptr(), 0, None, None, None,
                                mean.data_ptr(), None, None, counts.data_ptr(), total.data_ptr(), ws.data_ptr(), wsb,
                                st), "pch_voxel_reduce")
     m = int(total.item())

@@ -9,6 +9,7 @@ duplicate check, the north angle, and (box="obb") the trimesh-style oriented box
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Callable, List, Optional
 
 import numpy as np
@@ -72,7 +73,11 @@ def ground_filter_percentile(raw: torch.Tensor, pct: float = 25, offset: float =
                              fallback_offset: float = 1.0, want_mask: bool = False):
     """Stages A+B: centroid, shift, percentile threshold, compaction."""
     m = raw.shape[0]
-    cen_dev, _ = dv.f32_centroid(raw)
+    if os.environ.get("PCH_TRACE"):
+        cen_dev, _, st = dv.f32_centroid(raw, want_stats=True)
+        print(f"[pch] centroid tiles via maps / via real adds per column: {st.tolist()}", flush=True)
+    else:
+        cen_dev, _ = dv.f32_centroid(raw)
     zs, _ = dv.f32_shift(raw, cen_dev, want_z=True)
     r0, r1, gamma = percentile_ranks_f32(m, pct)
     two = dv.select_f32(zs, r0, r1).cpu().numpy()

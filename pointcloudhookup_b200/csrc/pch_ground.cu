@@ -290,6 +290,47 @@ k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const Sq
     }
 }
 
+// Level 2: 32 consecutive tiles (65 536 elements) whose windows start at the same binade are composed
+// into one "super" map per window slot, in parallel (one warp per super-tile).  The chain then walks
+// super-tiles and only descends to tile level where a super-tile cannot be applied.
+#define SQ_SUPER 32
+__global__ void __launch_bounds__(256)
+k_sum_super(int64_t n_tiles, int64_t n_super, const SqTileInfo* __restrict__ info, const int32_t* __restrict__ klo,
+            const SqMap* __restrict__ table, SqMap* __restrict__ stable /*[3][n_super][SQ_W]*/,
+            int32_t* __restrict__ sklo /*[3][n_super]; INT_MIN = unusable*/) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; w < 3 * n_super; w += nw) {
+        const int c = (int)(w / n_super);
+        const int64_t su = w - (int64_t)c * n_super;
+        const int64_t t = su * SQ_SUPER + lane;
+        const bool have = t < n_tiles;
+        const int k_me = have ? klo[c * n_tiles + t] : 0;
+        const int ok_me = have ? info[c * n_tiles + t].ok : 0;
+        const int k0 = __shfl_sync(0xffffffffu, k_me, 0);
+        // usable only when all 32 tiles exist, are non-negative and share one window
+        const bool uniform = __all_sync(0xffffffffu, have && ok_me && k_me == k0);
+        if (!uniform) {
+            if (lane == 0) sklo[c * n_super + su] = INT_MIN;
+            continue;
+        }
+#pragma unroll
+        for (int ww = 0; ww < SQ_W; ++ww) {
+            SqMap F = table[((size_t)c * n_tiles + t) * SQ_W + ww];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                SqMap pv;
+                pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                if (lane >= o) F = sq_compose(pv, F);
+            }
+            if (lane == 31) stable[((size_t)c * n_super + su) * SQ_W + ww] = F;
+        }
+        if (lane == 0) sklo[c * n_super + su] = k0;
+    }
+}
+
 // One CTA per column.  All 256 threads stage the maps of SQ_BATCH tiles into shared memory (coalesced,
 // many loads in flight); warp 0 then walks the batch 32 tiles at a time with warp scans — no global
 // latency on the serial path.
@@ -298,16 +339,23 @@ k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const Sq
 
 __global__ void __launch_bounds__(SQ_CHAIN_THREADS)
 k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
-            const int32_t* __restrict__ klo, const SqMap* __restrict__ table, float* __restrict__ sums,
+            const int32_t* __restrict__ klo, const SqMap* __restrict__ table, int64_t n_super,
+            const SqMap* __restrict__ stable, const int32_t* __restrict__ sklo, float* __restrict__ sums,
             int* __restrict__ stats /*[3][2]: tiles via maps, tiles via real adds*/) {
     __shared__ SqMap s_tab[SQ_BATCH * SQ_W];
     __shared__ int32_t s_klo[SQ_BATCH];
     __shared__ uint8_t s_ok[SQ_BATCH];
+    __shared__ SqMap s_stab[(SQ_BATCH / SQ_SUPER) * SQ_W];
+    __shared__ int32_t s_sklo[SQ_BATCH / SQ_SUPER];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float s = 0.0f;
     int n_map = 0, n_real = 0;
     for (int64_t b0 = 0; b0 < n_tiles; b0 += SQ_BATCH) {
         const int nb = (int)min((int64_t)SQ_BATCH, n_tiles - b0);
+        const int nsb = (int)min((int64_t)(SQ_BATCH / SQ_SUPER), n_super - b0 / SQ_SUPER);   // super-tiles in this batch
+        for (int i = tid; i < nsb * SQ_W; i += SQ_CHAIN_THREADS)
+            s_stab[i] = stable[((size_t)c * n_super + b0 / SQ_SUPER) * SQ_W + i];
+        for (int i = tid; i < nsb; i += SQ_CHAIN_THREADS) s_sklo[i] = sklo[c * n_super + b0 / SQ_SUPER + i];
         {
             const uint4* src = reinterpret_cast<const uint4*>(table + ((size_t)c * n_tiles + b0) * SQ_W);
             uint4* dst = reinterpret_cast<uint4*>(s_tab);
@@ -324,12 +372,43 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
                 const uint32_t sb = __float_as_uint(s);
                 const int es = (int)((sb >> 23) & 0xffu);
                 int advanced = 0;
+                // ---- level 2: whole super-tiles (only from a super-tile boundary)
+                if ((t % SQ_SUPER) == 0 && es != 0 && es != 0xff && !(sb >> 31)) {
+                    const int k = es - 150;
+                    const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
+                    const int su = t / SQ_SUPER + lane;
+                    SqMap F; F.d0 = SQ_SAT; F.d1 = SQ_SAT;
+                    if (su < nsb && s_sklo[su] != INT_MIN) {
+                        const int idx = k - s_sklo[su];
+                        if (idx >= 0 && idx < SQ_W) F = s_stab[su * SQ_W + idx];
+                    }
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        SqMap pv;
+                        pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                        pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                        if (lane >= o) F = sq_compose(pv, F);
+                    }
+                    const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
+                    const bool ok = D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
+                    const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+                    const int L = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
+                    if (L > 0) {
+                        const uint32_t Dl = __shfl_sync(0xffffffffu, D, L - 1);
+                        s = __uint_as_float(((uint32_t)es << 23) | ((ms + Dl) & 0x7fffffu));
+                        t += L * SQ_SUPER;
+                        n_map += L * SQ_SUPER;
+                        continue;
+                    }
+                }
+                // ---- level 1: the tiles up to the next super-tile boundary (so level 2 can resume there)
+                const int cap = min(nb, (t / SQ_SUPER + 1) * SQ_SUPER);
                 if (es != 0 && es != 0xff && !(sb >> 31)) {
                     const int k = es - 150;
                     const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
                     SqMap F; F.d0 = SQ_SAT; F.d1 = SQ_SAT;
                     const int tt = t + lane;
-                    if (tt < nb && s_ok[tt]) {
+                    if (tt < cap && s_ok[tt]) {
                         const int idx = k - s_klo[tt];
                         if (idx >= 0 && idx < SQ_W) F = s_tab[tt * SQ_W + idx];
                     }
@@ -352,7 +431,7 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
                     }
                 }
                 t += advanced;
-                if (advanced == 32 || t >= nb) continue;
+                if (t >= cap) continue;   // reached the boundary without a failing tile
                 {
                     // tile b0+t leaves the binade / is outside its window / has negative data
                     const int64_t tg = b0 + t;
@@ -421,8 +500,10 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
 
 extern "C" size_t pch_f32_centroid_workspace_bytes(int64_t m) {
     int64_t nt = pch_ceil_div(m > 0 ? m : 1, SQ_TILE);
+    int64_t ns = pch_ceil_div(nt, 32);
     return 256 + pch_align_up((size_t)3 * nt * sizeof(SqTileInfo), 256) + pch_align_up((size_t)3 * nt * 4, 256) +
-           pch_align_up((size_t)3 * nt * SQ_W * sizeof(SqMap), 256);
+           pch_align_up((size_t)3 * nt * SQ_W * sizeof(SqMap), 256) + pch_align_up((size_t)3 * ns * SQ_W * sizeof(SqMap), 256) +
+           pch_align_up((size_t)3 * ns * 4, 256);
 }
 
 extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float* centroid3, void* workspace,
@@ -445,12 +526,18 @@ extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float
         size_t off = 256;
         SqTileInfo* info = (SqTileInfo*)(base + off); off += pch_align_up((size_t)3 * nt * sizeof(SqTileInfo), 256);
         int32_t* klo = (int32_t*)(base + off); off += pch_align_up((size_t)3 * nt * 4, 256);
-        SqMap* table = (SqMap*)(base + off);
+        SqMap* table = (SqMap*)(base + off); off += pch_align_up((size_t)3 * nt * SQ_W * sizeof(SqMap), 256);
+        const int64_t ns = pch_ceil_div(nt, SQ_SUPER);
+        SqMap* stable = (SqMap*)(base + off); off += pch_align_up((size_t)3 * ns * SQ_W * sizeof(SqMap), 256);
+        int32_t* sklo = (int32_t*)(base + off);
         unsigned grid = (unsigned)(nt < (int64_t)pch_sm_count() * 8 ? nt : (int64_t)pch_sm_count() * 8);
         PCH_LAUNCH(st, "k_sum_prep", k_sum_prep<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info));
         PCH_LAUNCH(st, "k_sum_window", k_sum_window<<<3, 1024, 0, st>>>(info, nt, klo));
         PCH_LAUNCH(st, "k_sum_tables", k_sum_tables<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info, klo, table));
-        PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<3, SQ_CHAIN_THREADS, 0, st>>>(xyz, m, nt, info, klo, table, sums3, stats));
+        PCH_LAUNCH(st, "k_sum_super", k_sum_super<<<(unsigned)(pch_ceil_div(3 * ns, 8) < 1184 ? pch_ceil_div(3 * ns, 8) : 1184), 256, 0, st>>>(
+                                          nt, ns, info, klo, table, stable, sklo));
+        PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<3, SQ_CHAIN_THREADS, 0, st>>>(xyz, m, nt, info, klo, table, ns, stable, sklo,
+                                                                                 sums3, stats));
         PCH_LAUNCH_CHECK();
     }
     PCH_LAUNCH(st, "k_centroid_from_sums", k_centroid_from_sums<<<1, 32, 0, st>>>(sums3, m, centroid3));

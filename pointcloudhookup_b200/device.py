@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -335,6 +336,11 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
                                  C.byref(plan), labels.data_ptr(), nclu.data_ptr(), stats.data_ptr(), cap,
                                  ws.data_ptr(), wsb, st), "pch_dbscan_run")
         k = int(nclu.item())
+        if os.environ.get("PCH_TRACE"):
+            sc = ws[:256].cpu().numpy()
+            print(f"[pch] dbscan G={G} chunks={n_chunks} cells={int(sc[128:136].view(np.int64)[0])} "
+                  f"non-dense points={int(sc[192:196].view(np.uint32)[0])} clusters={k} plan={plan.bits_x},{plan.bits_y},{plan.bits_z}",
+                  flush=True)
         if int(ws[:4].view(torch.int32).item()):
             raise _native.NativeError("device look-back spin limit hit in dbscan")
         if k <= cap:

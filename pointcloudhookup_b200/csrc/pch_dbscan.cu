@@ -286,37 +286,83 @@ k_db_core1(DbGeom g, const int32_t* __restrict__ pt_cell, const int32_t* __restr
     }
 }
 
+// neighbour columns nearest first: a core point usually reaches min_samples in its own column
+__constant__ int c_db_order[25] = {12, 7, 11, 13, 17, 6, 8, 16, 18, 2, 10, 14, 22, 1, 3, 5, 9, 15, 19, 21, 23, 0, 4, 20, 24};
+
+// squared distance bounds from point p to the geometric box of cell (cx,cy,cz) of a chunk whose grid
+// origin is mn: lo = min distance, hi = distance to the farthest corner.  `pad` widens the box so the
+// rounding of floor((x-mn)/cell) can never put a point outside "its" box.
+__device__ __forceinline__ void db_cell_bounds(const float4& p, const float* mn, double cell, long long cx, long long cy,
+                                               long long cz, double& dmin2, double& dmax2) {
+    const double pad = 1e-6;
+    const double pv[3] = {(double)p.x, (double)p.y, (double)p.z};
+    const long long cc[3] = {cx, cy, cz};
+    dmin2 = 0.0; dmax2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double lo = (double)mn[a] + (double)cc[a] * cell - pad;
+        const double hi = (double)mn[a] + (double)(cc[a] + 1) * cell + pad;
+        double tmin = 0.0;
+        if (pv[a] < lo) tmin = lo - pv[a]; else if (pv[a] > hi) tmin = pv[a] - hi;
+        const double tmax = fmax(fabs(pv[a] - lo), fabs(hi - pv[a]));
+        dmin2 += tmin * tmin;
+        dmax2 += tmax * tmax;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_db_core2(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
            const int32_t* __restrict__ cell_start, const int32_t* __restrict__ nbr_first,
            const uint8_t* __restrict__ nbr_cnt, const int32_t* __restrict__ worklist,
-           const unsigned int* __restrict__ n_work, uint8_t* __restrict__ core) {
+           const unsigned int* __restrict__ n_work, uint8_t* __restrict__ core,
+           const uint64_t* __restrict__ cell_key, const uint32_t* __restrict__ bounds) {
     const int lane = threadIdx.x & 31;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n = *n_work;
+    const int bxy = g.bits_y + g.bits_z;
+    const uint64_t mz = (1ull << g.bits_z) - 1ull, my = (1ull << g.bits_y) - 1ull;
+    const double lim_lo = g.eps2 * (1.0 + 1e-9), lim_hi = g.eps2 * (1.0 - 1e-9);
     for (; w < n; w += nw) {
         const int32_t pos = worklist[w];
         const int32_t u = pt_cell[pos];
         const float4 p = spts[pos];
+        const int64_t ch = pos / g.chunk;
+        const float mn[3] = {pch_ordered_to_f32(bounds[ch * 6 + 0]), pch_ordered_to_f32(bounds[ch * 6 + 1]),
+                             pch_ordered_to_f32(bounds[ch * 6 + 2])};
         int count = 0;
-        for (int col = 0; col < 25 && count < g.min_pts; ++col) {
+        for (int oi = 0; oi < 25 && count < g.min_pts; ++oi) {
+            const int col = c_db_order[oi];
             const int nc = nbr_cnt[(int64_t)u * 25 + col];
             if (nc == 0) continue;
             const int32_t f = nbr_first[(int64_t)u * 25 + col];
-            const int32_t b = cell_start[f], e = cell_start[f + nc];
-            for (int32_t q0 = b; q0 < e && count < g.min_pts; q0 += 128) {
-                float4 c4[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int32_t q = q0 + r * 32 + lane;
-                    c4[r] = q < e ? spts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int kc = 0; kc < nc && count < g.min_pts; ++kc) {
+                const int32_t v = f + kc;
+                const int32_t b = cell_start[v], e = cell_start[v + 1];
+                if (v != u) {
+                    const uint64_t key = cell_key[v];
+                    double dmin2, dmax2;
+                    db_cell_bounds(p, mn, g.cell, (long long)(key >> bxy), (long long)((key >> g.bits_z) & my),
+                                   (long long)(key & mz), dmin2, dmax2);
+                    if (dmin2 > lim_lo) continue;                 // no point of this cell can be within eps
+                    if (dmax2 < lim_hi) { count += e - b; continue; }   // every point of this cell is within eps
+                } else {
+                    count += e - b;                               // own cell: all neighbours by construction
+                    continue;
                 }
+                for (int32_t q0 = b; q0 < e && count < g.min_pts; q0 += 128) {
+                    float4 c4[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int32_t q = q0 + r * 32 + lane;
-                    const bool hit = q < e && db_dist2(p, c4[r]) <= g.eps2;
-                    count += __popc(__ballot_sync(0xffffffffu, hit));
+                    for (int r = 0; r < 4; ++r) {
+                        const int32_t q = q0 + r * 32 + lane;
+                        c4[r] = q < e ? spts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int32_t q = q0 + r * 32 + lane;
+                        const bool hit = q < e && db_dist2(p, c4[r]) <= g.eps2;
+                        count += __popc(__ballot_sync(0xffffffffu, hit));
+                    }
                 }
             }
         }
@@ -924,7 +970,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH(st, "k_db_core1", k_db_core1<<<db_grid(G, 256), 256, 0, st>>>(g, o.pt_cell, o.cell_start, core, worklist, n_work));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_core2", k_db_core2<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt,
-                                                                            worklist, n_work, core));
+                                                                            worklist, n_work, core, o.cell_key, bounds_dev));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info, chunk, cell_mincore));
     PCH_LAUNCH_CHECK();

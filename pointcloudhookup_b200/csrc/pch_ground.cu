@@ -347,6 +347,7 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
     __shared__ uint8_t s_ok[SQ_BATCH];
     __shared__ SqMap s_stab[(SQ_BATCH / SQ_SUPER) * SQ_W];
     __shared__ int32_t s_sklo[SQ_BATCH / SQ_SUPER];
+    __shared__ float s_col[SQ_TILE];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float s = 0.0f;
     int n_map = 0, n_real = 0;
@@ -437,9 +438,15 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
                     const int64_t tg = b0 + t;
                     const int64_t lo = tg * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
                     const bool tile_ok = s_ok[t] != 0;
+#pragma unroll 16
+                    for (int j = 0; j < SQ_TILE / 32; ++j) {      // 64 independent loads per lane in flight
+                        const int64_t i = lo + j * 32 + lane;
+                        s_col[j * 32 + lane] = i < hi ? __ldg(&xyz[i * 3 + c]) : 0.0f;
+                    }
+                    __syncwarp();
                     for (int64_t i0 = lo; i0 < hi; i0 += 32) {
                         const int64_t i = i0 + lane;
-                        const float v = i < hi ? xyz[i * 3 + c] : 0.0f;
+                        const float v = i < hi ? s_col[(int)(i - lo)] : 0.0f;
                         const int cnt = (int)min((int64_t)32, hi - i0);
                         if (!tile_ok) {                       // negative / non-finite data: real float32 adds
                             for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));

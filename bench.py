@@ -272,8 +272,14 @@ def run_b200(args):
         per_launch_ms = tot / cnt
         alg = model.get(name) or 0
         achieved = alg / (per_launch_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic_100M.json")
+        if args.workload == "pipeline" and n == 100_000_000 and os.path.exists(tpath):
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+            # capture of this same configuration (profiles/r1_ncu_summary.md)
+            traffic = json.load(open(tpath)).get(name) or json.load(open(tpath)).get(name + "<2>")
         roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "launches_per_step": cnt / args.steps,
                 "ms_per_launch": per_launch_ms, "share_of_kernel_time": tot / total_kernel_ms}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,

@@ -180,7 +180,9 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
     }
     __syncthreads();
 
-    // ---- per digit (thread == digit): exclusive over warps, tile total, look-back, digit start
+    // ---- per digit (thread == digit): exclusive over warps, tile total; PUBLISH the aggregate now and
+    // do the look-back only after the shared-memory scatter, so predecessors have time to publish too
+    uint32_t my_sum;
     {
         const int d = tid;
         uint32_t sum = 0;
@@ -190,12 +192,27 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
             s_whist[w][d] = sum;
             sum += c;
         }
-        uint32_t* my = status + ((size_t)tile * 256 + d);
+        my_sum = sum;
+        pch_st_volatile_u32(status + ((size_t)tile * 256 + d), (tile == first_tile ? ST_INCL : ST_AGG) | sum);
+        s_dstart[d] = block_excl_scan_256(sum, s_scan);
+    }
+    __syncthreads();
+
+    // ---- scatter inside shared memory (runs of equal digit become contiguous)
+#pragma unroll
+    for (int j = 0; j < RS_KPT; ++j) {
+        int idx = wbase + j * 32 + lane;
+        if (idx < cnt) {
+            uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+            s_keys[s_dstart[d] + s_whist[warp][d] + rank[j]] = key[j];
+        }
+    }
+
+    // ---- look-back for digit `tid`
+    {
+        const int d = tid;
         uint32_t excl = 0;
-        if (tile == first_tile) {
-            pch_st_volatile_u32(my, ST_INCL | sum);
-        } else {
-            pch_st_volatile_u32(my, ST_AGG | sum);
+        if (tile != first_tile) {
             for (int64_t t = tile - 1; t >= first_tile; --t) {
                 const uint32_t* p = status + ((size_t)t * 256 + d);
                 uint32_t w, spins = 0;
@@ -209,22 +226,9 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
                 excl += w & ST_VAL;
                 if (w & ST_INCL) break;
             }
-            pch_st_volatile_u32(my, ST_INCL | ((excl + sum) & ST_VAL));
+            pch_st_volatile_u32(status + ((size_t)tile * 256 + d), ST_INCL | ((excl + my_sum) & ST_VAL));
         }
-        uint32_t dstart = block_excl_scan_256(sum, s_scan);
-        s_dstart[d] = dstart;
-        s_goff[d] = seg_start + (int64_t)hist[(seg * g.n_passes + pass) * 256 + d] + (int64_t)excl - (int64_t)dstart;
-    }
-    __syncthreads();
-
-    // ---- scatter inside shared memory, then stream out (runs of equal digit are contiguous)
-#pragma unroll
-    for (int j = 0; j < RS_KPT; ++j) {
-        int idx = wbase + j * 32 + lane;
-        if (idx < cnt) {
-            uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
-            s_keys[s_dstart[d] + s_whist[warp][d] + rank[j]] = key[j];
-        }
+        s_goff[d] = seg_start + (int64_t)hist[(seg * g.n_passes + pass) * 256 + d] + (int64_t)excl - (int64_t)s_dstart[d];
     }
     __syncthreads();
     for (int i = tid; i < cnt; i += RS_THREADS) {

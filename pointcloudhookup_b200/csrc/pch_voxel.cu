@@ -166,7 +166,6 @@ extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, in
 struct ReduceGeom {
     int64_t n, chunk_size, tiles_per_chunk, total_tiles;
     int32_t bits_idx, rec_len;
-    int32_t single_fast;  // 1 when |x|/scale stays far below 2^52 so a lone point re-quantises to itself
 };
 
 extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size) {
@@ -317,15 +316,6 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
             k = li < cnt ? s_keys[li + 1] : keys[p];
             if ((k >> bi) != vkey) break;
         }
-        if (ALIGN > 0 && cntp == 1 && g.single_fast) {
-            // single-point voxel: mean = the point itself, and rint((x - off)/scale) is its own lattice
-            // value (the float64 round trip is off by < 1e-6 lattice units, host-checked), so no divides
-            const int qx = s_xyz[i][0], qy = s_xyz[i][1], qz = s_xyz[i][2];
-            if (mean_out) { mean_out[m * 3 + 0] = sx; mean_out[m * 3 + 1] = sy; mean_out[m * 3 + 2] = sz; }
-            if (lat_out) { lat_out[m * 3 + 0] = qx; lat_out[m * 3 + 1] = qy; lat_out[m * 3 + 2] = qz; }
-            if (f32_out) { f32_out[m * 3 + 0] = (float)sx; f32_out[m * 3 + 1] = (float)sy; f32_out[m * 3 + 2] = (float)sz; }
-            continue;
-        }
         const double dn = (double)cntp;
         const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
         if (mean_out) {
@@ -370,12 +360,6 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     PCH_CHECK_ARG(!xyz16 || (reinterpret_cast<uintptr_t>(xyz16) & 15) == 0, "xyz16 must be 16-byte aligned");
     ReduceGeom g;
     g.n = n; g.chunk_size = chunk_size; g.bits_idx = bits_idx; g.rec_len = rec_len;
-    g.single_fast = 1;
-    for (int i = 0; i < 3; ++i) {
-        // worst |x| = |offset| + 2^31*|scale|; the round trip error is ~4 ulp(x)/scale lattice units
-        const double worst = (fabs(a.o[i]) + 2147483648.0 * fabs(a.s[i])) / fabs(a.s[i]);
-        if (!(worst < 1099511627776.0)) g.single_fast = 0;   // 2^40: error < 2^-10 lattice units
-    }
     g.tiles_per_chunk = pch_ceil_div(chunk_size, VR_TILE);
     int64_t last = n - (n_chunks - 1) * chunk_size;
     g.total_tiles = (n_chunks - 1) * g.tiles_per_chunk + pch_ceil_div(last, VR_TILE);

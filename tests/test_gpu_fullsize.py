@@ -1,0 +1,126 @@
+"""GPU, BASELINE.json sizes (20 M and 100 M points): size-independent properties, checked with torch
+library ops as the independent checker (sortedness, conservation / checksum of checksums, determinism,
+agreement of the parallel and the serial exact-sum kernels, per-label reductions)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=[20_000_000, 100_000_000], ids=["20M", "100M"])
+def corridor(request, cuda_device):
+    import torch
+    from pointcloudhookup_b200 import device as dv, synth
+    n = request.param
+    free, _ = torch.cuda.mem_get_info()
+    if free < n * 600:
+        pytest.skip("not enough free HBM for this size")
+    terrain = "hilly" if n >= 100_000_000 else "flat"
+    pinned = torch.empty(n * 34, dtype=torch.uint8, pin_memory=True)
+    synth.corridor_records(n, max(2, n // 2_000_000), terrain, 3, out=pinned.numpy())
+    dl = dv.upload_records(pinned, n, 34, synth.SCALES, synth.OFFSETS)
+    return n, dl
+
+
+def test_fullsize_voxel_properties(corridor):
+    import torch
+    from pointcloudhookup_b200 import device as dv
+    n, dl = corridor
+    chunk = 500_000
+    res = dv.voxel_downsample(dl, 0.1, chunk, want=("mean", "lattice", "f32"), keep_keys=True)
+    bi = res.plan["bits_idx"]
+    vox = (res.sorted_keys >> bi).view(-1, chunk)            # n is a multiple of the chunk size here
+    assert bool((vox[:, 1:] >= vox[:, :-1]).all())           # sorted inside every chunk
+    idx = (res.sorted_keys & ((1 << bi) - 1)).view(-1, chunk)
+    same = vox[:, 1:] == vox[:, :-1]
+    assert bool((idx[:, 1:][same] > idx[:, :-1][same]).all())  # stable: input order inside a voxel
+    assert bool((idx.sort(dim=1).values == torch.arange(chunk, device=idx.device)).all())  # a permutation per chunk
+    # number of voxels = number of distinct (chunk, voxel) pairs, per chunk too
+    cid = torch.arange(vox.shape[0], device=vox.device).unsqueeze(1).expand_as(vox)
+    uniq, counts = torch.unique_consecutive(torch.stack([cid.reshape(-1), vox.reshape(-1)]), dim=1, return_counts=True)
+    assert uniq.shape[1] == res.count == int(res.chunk_counts.sum())
+    assert torch.equal(torch.bincount(uniq[0], minlength=vox.shape[0]), res.chunk_counts)
+    # conservation ("checksum of checksums"): sum(mean * count) == sum of all points, per axis
+    pts = dv.decode_xyz(dl, torch.float64)
+    lhs = (res.mean * counts.unsqueeze(1).to(torch.float64)).sum(0)
+    rhs = pts.sum(0)
+    assert torch.allclose(lhs, rhs, rtol=1e-11, atol=0)
+    # every mean lies inside the bounding box of the cloud; lattice/f32 are the re-quantised means
+    assert bool((res.mean >= pts.min(0).values).all()) and bool((res.mean <= pts.max(0).values).all())
+    sc = torch.tensor(dl.scales, device=pts.device); of = torch.tensor(dl.offsets, device=pts.device)
+    assert torch.equal(res.lattice, torch.round((res.mean - of) / sc).to(torch.int32))
+    assert torch.equal(res.f32, (res.lattice.to(torch.float64) * sc + of).to(torch.float32))
+    # determinism
+    again = dv.voxel_downsample(dl, 0.1, chunk, want=("mean",))
+    assert torch.equal(again.mean, res.mean)
+
+
+def test_fullsize_tower_stage_properties(corridor):
+    import torch
+    from pointcloudhookup_b200 import device as dv, towers as tw
+    n, dl = corridor
+    raw = dv.voxel_downsample(dl, 0.1, 500_000, want=("f32",)).f32
+    m = raw.shape[0]
+    # exact sequential sum: parallel evaluation == serial kernel, bit for bit
+    cen_p, sum_p, st = dv.f32_centroid(raw, want_stats=True)
+    cen_s, sum_s = dv.f32_centroid(raw, serial=True)
+    assert torch.equal(sum_p, sum_s) and torch.equal(cen_p, cen_s)
+    assert int(st[:, 1].max()) < 64                          # only a handful of tiles needed real adds
+    # order statistics vs torch.kthvalue
+    zs, _ = dv.f32_shift(raw, cen_p, want_z=True)
+    assert torch.equal(zs, raw[:, 2] - cen_p[2])
+    r0, r1, _ = tw.percentile_ranks_f32(m, 25)
+    two = dv.select_f32(zs, r0, r1)
+    assert float(two[0]) == float(torch.kthvalue(zs, r0 + 1).values) and float(two[1]) == float(torch.kthvalue(zs, r1 + 1).values)
+    # compaction vs boolean indexing
+    thr = float(two[0]) + 3.0
+    filt, g, src, mask = dv.compact_points(raw, zs, thr, cen_p, want_src=True, want_mask=True)
+    keep = zs > thr
+    assert g == int(keep.sum()) and torch.equal(mask.bool(), keep)
+    assert torch.equal(filt, (raw - cen_p)[keep]) and torch.equal(src.long(), keep.nonzero().squeeze(1))
+    # DBSCAN invariants + per-label reductions
+    db = dv.dbscan_chunked(filt, 8.0, 80, 50_000)
+    lab = db.labels.long()
+    k = db.n_clusters
+    assert int(lab.min()) >= -1 and int(lab.max()) == k - 1
+    # labels are offset per 50 000-point chunk and ordered by first core index: label ids are non-decreasing
+    # over chunks, and every id 0..k-1 occurs
+    cnt = torch.bincount(lab[lab >= 0], minlength=k)
+    assert bool((cnt > 0).all())
+    chunk_of = torch.arange(g, device=lab.device) // 50_000
+    pos = lab >= 0
+    first_chunk = torch.full((k,), 1 << 40, device=lab.device, dtype=torch.long).scatter_reduce(0, lab[pos], chunk_of[pos], "amin")
+    last_chunk = torch.zeros(k, device=lab.device, dtype=torch.long).scatter_reduce(0, lab[pos], chunk_of[pos], "amax")
+    assert torch.equal(first_chunk, last_chunk)                         # no cluster spans two chunks
+    assert bool((first_chunk[1:] >= first_chunk[:-1]).all())            # ids grow with the chunk index
+    assert np.array_equal(db.stats["count"], cnt.cpu().numpy())
+    for a in range(3):
+        mn = torch.full((k,), float("inf"), device=lab.device).scatter_reduce(0, lab[pos], filt[pos, a], "amin")
+        mx = torch.full((k,), float("-inf"), device=lab.device).scatter_reduce(0, lab[pos], filt[pos, a], "amax")
+        assert np.array_equal(db.stats["min"][:, a], mn.cpu().numpy()) and np.array_equal(db.stats["max"][:, a], mx.cpu().numpy())
+        sm = torch.zeros(k, device=lab.device, dtype=torch.float64).scatter_add(0, lab[pos], filt[pos, a].double())
+        assert np.allclose(db.stats["sum"][:, a], sm.cpu().numpy(), rtol=1e-9, atol=1e-6)
+    again = dv.dbscan_chunked(filt, 8.0, 80, 50_000)
+    assert torch.equal(again.labels, db.labels)                         # deterministic despite atomics/union-find races
+
+
+def test_fullsize_geodetic_properties(corridor):
+    import torch
+    from pointcloudhookup_b200 import device as dv, geo
+    n, dl = corridor
+    lat = np.linspace(-90, 90, 721)
+    lon = -180 + 0.25 * np.arange(1440)
+    g = (30 * np.sin(np.radians(lat))[:, None] * np.cos(np.radians(lon))[None, :]).astype(np.float32)
+    dg = geo.upload_grid(geo.HostGrid(-90.0, -180.0, 0.25, 0.25, g))
+    out = geo.las_to_geodetic(dl, dg, -1.0, geo.EPSG4547)
+    out_g = geo.las_to_geodetic(dl, dg, -1.0, geo.EPSG4547, window=None)
+    assert torch.equal(out, out_g)                         # smem-staged window == global-memory grid reads
+    pts = dv.decode_xyz(dl, torch.float64)
+    n_h = pts[:, 2] - out[:, 2]                            # = N(lat, lon)
+    exact = 30 * torch.sin(torch.deg2rad(out[:, 1])) * torch.cos(torch.deg2rad(out[:, 0]))
+    assert float((n_h - exact).abs().max()) < 2e-3         # bilinear error bound on the analytic grid
+    plus = geo.las_to_geodetic(dl, dg, +1.0, geo.EPSG4547)
+    assert torch.allclose(plus[:, 2] + out[:, 2], 2 * pts[:, 2], rtol=0, atol=1e-9)   # multiplier symmetry
+    # corridor geometry: longitudes/latitudes fall in the expected window around 113.4E / 28.4N
+    assert 113.0 < float(out[:, 0].min()) and float(out[:, 0].max()) < 114.5
+    assert 28.0 < float(out[:, 1].min()) and float(out[:, 1].max()) < 30.5

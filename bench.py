@@ -263,6 +263,16 @@ def run_b200(args):
         e2e = {"value": n * world * args.steps / (float(t.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": n * 34, "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(t.item()) / args.steps}
+        # context: the bare pinned->HBM copy of one step's records (the PCIe floor under e2e)
+        buf = torch.empty(n * 34, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        e0.record()
+        buf.copy_(pinned, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e["h2d_copy_only_ms"] = e0.elapsed_time(e1)
+        e2e["h2d_copy_only_GBps"] = n * 34 / (e2e["h2d_copy_only_ms"] / 1e3) / 1e9
+        del buf
 
     # ---- roofline of the dominant kernel (from the live per-kernel events of timed region 1)
     peak, peak_src = measured_peak()

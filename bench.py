@@ -129,8 +129,8 @@ def kernel_bytes_model(cfg, info):
     every output written once.  n = input points, M = voxels, G = candidates, R = 34."""
     n, M, G, R = cfg["n"], info.get("M", 0), info.get("G", 0), 34
     return {
-        "k_chunk_minmax": n * R,
-        "k_voxel_keys": n * (R + 8 + 16),
+        "k_chunk_minmax": n * (R + 16),
+        "k_voxel_keys16": n * (16 + 8),
         "k_hist": None,          # mixed (voxel sort + DBSCAN sort): resolved from launches below
         "k_pass": None,
         "k_voxel_reduce": n * 8 + n * 16 + M * 12,

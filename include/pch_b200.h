@@ -49,7 +49,9 @@ int pch_profile_report(char* buf, size_t cap);
  * (ui/import_PC.py:45-48 slices las.points[start:end]; open3d takes the chunk's min bound,
  * ui/import_PC.py:12).  minmax_dev: [n_chunks][6] = minX,minY,minZ,maxX,maxY,maxZ. */
 int pch_las_chunk_minmax(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t chunk_size,
-                         int32_t* minmax_dev, pch_stream_t stream);
+                         int32_t* minmax_dev,
+                         int32_t* xyz16_dev /* nullable: also emit the (n,4) int32 X,Y,Z,0 copy in this pass */,
+                         pch_stream_t stream);
 
 /* np.vstack((las.x, las.y, las.z)).T -> (n,3) float64, x = X*scale+offset
  * (ui/import_PC.py:47-48; ui/extract.py:114-115,361-362). */
@@ -94,6 +96,12 @@ int pch_voxel_keys(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t c
                    const double* origins_dev, const pch_voxel_plan* plan, uint64_t* keys_dev,
                    int32_t* xyz16_dev /* nullable: (n,4) int32 = X,Y,Z,0 copy for the reduce gathers */,
                    pch_stream_t stream);
+
+/* pch_voxel_keys from the packed lattice copy written by pch_las_chunk_minmax (no second pass over
+ * the raw records). */
+int pch_voxel_keys_xyz16(const int32_t* xyz16_dev, int64_t n, int64_t chunk_size, const double* scales,
+                         const double* offsets, double voxel_size, const double* origins_dev,
+                         const pch_voxel_plan* plan, uint64_t* keys_dev, pch_stream_t stream);
 
 /* The same two steps for an arbitrary (n,3) float64 point array — process_chunk(points_chunk,
  * voxel_size) (ui/import_PC.py:8-13, ui/Sampling.py:10-18) is not restricted to LAS-lattice input.

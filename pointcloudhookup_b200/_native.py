@@ -37,7 +37,8 @@ SIGNATURES = {
     "pch_launch_count": (C.c_longlong, []),
     "pch_profile_enable": (None, [C.c_int]),
     "pch_profile_report": (C.c_int, [C.c_char_p, _sz]),
-    "pch_las_chunk_minmax": (C.c_int, [_p, _i64, _i32, _i64, _p, _p]),
+    "pch_las_chunk_minmax": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _p]),
+    "pch_voxel_keys_xyz16": (C.c_int, [_p, _i64, _i64, _d3, _d3, _f64, _p, C.POINTER(VoxelPlan), _p, _p]),
     "pch_las_decode_f64": (C.c_int, [_p, _i64, _i32, _d3, _d3, _p, _p]),
     "pch_las_decode_f32": (C.c_int, [_p, _i64, _i32, _d3, _d3, _p, _p]),
     "pch_las_quantise": (C.c_int, [_p, _i64, _d3, _d3, _p, _p]),

@@ -576,6 +576,25 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
     }
 }
 
+// between the two union passes: point every cell straight at its root so the "already joined" test of
+// the second pass is two loads instead of two pointer chases
+__global__ void k_db_compress(const long long* __restrict__ U_dev, DbCellInfo* __restrict__ info) {
+    const int64_t U = *U_dev;
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; u < U; u += stride) {
+        if (info[u].n_core <= 0) continue;
+        int32_t r = (int32_t)u;
+        while (true) {
+            const int32_t p = ((volatile DbCellInfo*)info)[r].parent;
+            if (p == r) break;
+            r = p;
+        }
+        // only ever replaces a parent by an ancestor: safe against concurrent readers in this kernel
+        info[u].parent = r;
+    }
+}
+
 __global__ void k_db_flatten(const long long* __restrict__ U_dev, DbCellInfo* __restrict__ info, int32_t* __restrict__ cell_root) {
     const int64_t U = *U_dev;
     int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -703,6 +722,12 @@ struct DbRun {
     double sum[3];
 };
 
+__device__ __forceinline__ void db_run_reset(DbRun& r, int32_t lab) {
+    r.lab = lab; r.cnt = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { r.mn[a] = 0xffffffffu; r.mx[a] = 0u; r.sum[a] = 0.0; }
+}
+
 __device__ __forceinline__ void db_flush(DbClusterAcc* __restrict__ acc, const DbRun& r) {
     if (r.lab < 0 || r.cnt == 0) return;
     DbClusterAcc* a = &acc[r.lab];
@@ -715,82 +740,64 @@ __device__ __forceinline__ void db_flush(DbClusterAcc* __restrict__ acc, const D
     }
 }
 
-#define CR_PER_THREAD 16
-// Labels are spatially coherent (the candidates are in voxel-sorted order), so each thread folds a
-// run of CR_PER_THREAD consecutive points in registers, warps whose runs all carry one label merge
-// by shuffles, and a block whose warps agree merges in shared memory: one set of atomics per 4096
-// points instead of one per warp.
+#define CR_ROWS 32
+// Labels are spatially coherent (the candidates are in voxel-sorted order).  A warp reads rows of 32
+// consecutive points (coalesced); a row whose 32 labels agree is reduced with shuffles into the warp's
+// running accumulator (held redundantly by all lanes), which is flushed with one set of atomics only
+// when the label changes; mixed rows fall back to per-point atomics.
 __global__ void __launch_bounds__(256)
 k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ labels, int64_t G, int64_t cap,
                     DbClusterAcc* __restrict__ acc) {
-    __shared__ DbRun s_run[8];
-    __shared__ int s_uniform;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t per_block = 256 * CR_PER_THREAD;
-    const int64_t n_blocks = (G + per_block - 1) / per_block;
-    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t i0 = blk * per_block + (int64_t)tid * CR_PER_THREAD;
-        DbRun r;
-        r.lab = -1; r.cnt = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { r.mn[i] = 0xffffffffu; r.mx[i] = 0u; r.sum[i] = 0.0; }
-        for (int j = 0; j < CR_PER_THREAD; ++j) {
-            const int64_t i = i0 + j;
-            if (i >= G) break;
-            int32_t lab = labels[i];
-            if (lab >= cap) lab = -1;
-            if (lab != r.lab) {
-                db_flush(acc, r);
-                r.lab = lab; r.cnt = 0;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) { r.mn[a] = 0xffffffffu; r.mx[a] = 0u; r.sum[a] = 0.0; }
+    const int lane = threadIdx.x & 31;
+    const int64_t n_rows = (G + 31) / 32;
+    const int64_t n_groups = (n_rows + CR_ROWS - 1) / CR_ROWS;
+    int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t ngw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; grp < n_groups; grp += ngw) {
+        DbRun run;
+        db_run_reset(run, -1);
+        for (int j = 0; j < CR_ROWS; ++j) {
+            const int64_t i = (grp * CR_ROWS + j) * 32 + lane;
+            if ((grp * CR_ROWS + j) >= n_rows) break;   // warp-uniform
+            int32_t lab = -1;
+            float v[3] = {0.f, 0.f, 0.f};
+            if (i < G) {
+                lab = labels[i];
+                if (lab >= cap) lab = -1;
+                if (lab >= 0) { v[0] = P[i * 3 + 0]; v[1] = P[i * 3 + 1]; v[2] = P[i * 3 + 2]; }
             }
-            if (lab >= 0) {
+            const int32_t lab0 = __shfl_sync(0xffffffffu, lab, 0);
+            const bool uniform = __all_sync(0xffffffffu, lab == lab0);
+            if (uniform) {
+                if (lab0 < 0) continue;
+                if (lab0 != run.lab) {
+                    if (lane == 0) db_flush(acc, run);
+                    db_run_reset(run, lab0);
+                }
+                run.cnt += 32;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    const float v = P[i * 3 + a];
-                    const uint32_t u = pch_f32_to_ordered(v);
-                    r.mn[a] = min(r.mn[a], u);
-                    r.mx[a] = max(r.mx[a], u);
-                    r.sum[a] += (double)v;
+                    const uint32_t u = pch_f32_to_ordered(v[a]);
+                    run.mn[a] = min(run.mn[a], __reduce_min_sync(0xffffffffu, u));
+                    run.mx[a] = max(run.mx[a], __reduce_max_sync(0xffffffffu, u));
+                    double s = (double)v[a];
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    run.sum[a] += s;
                 }
-                ++r.cnt;
-            }
-        }
-        // warp merge when every lane ended on the same label
-        const int32_t lab0 = __shfl_sync(0xffffffffu, r.lab, 0);
-        const bool wuni = __all_sync(0xffffffffu, r.lab == lab0);
-        if (wuni) {
-            r.cnt = __reduce_add_sync(0xffffffffu, r.cnt);
+            } else if (lab >= 0) {
+                DbClusterAcc* a = &acc[lab];
+                atomicAdd(&a->count, 1ull);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                r.mn[a] = __reduce_min_sync(0xffffffffu, r.mn[a]);
-                r.mx[a] = __reduce_max_sync(0xffffffffu, r.mx[a]);
-#pragma unroll
-                for (int o = 16; o; o >>= 1) r.sum[a] += __shfl_xor_sync(0xffffffffu, r.sum[a], o);
-            }
-            if (lane == 0) s_run[warp] = r;
-        } else {
-            db_flush(acc, r);
-            if (lane == 0) { s_run[warp].lab = -2; s_run[warp].cnt = 0; }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // fold consecutive warps that share a label, flush on change
-            DbRun t = s_run[0];
-            for (int w = 1; w < 8; ++w) {
-                const DbRun& n = s_run[w];
-                if (n.lab == t.lab && n.lab >= 0) {
-                    t.cnt += n.cnt;
-                    for (int a = 0; a < 3; ++a) { t.mn[a] = min(t.mn[a], n.mn[a]); t.mx[a] = max(t.mx[a], n.mx[a]); t.sum[a] += n.sum[a]; }
-                } else {
-                    db_flush(acc, t);
-                    t = n;
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t u = pch_f32_to_ordered(v[k]);
+                    atomicMin(&a->mn[k], u);
+                    atomicMax(&a->mx[k], u);
+                    atomicAdd(&a->sum[k], (double)v[k]);
                 }
             }
-            db_flush(acc, t);
         }
-        __syncthreads();
+        if (lane == 0) db_flush(acc, run);
     }
 }
 
@@ -978,6 +985,10 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
         PCH_LAUNCH(st, "k_db_union", k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first,
                                                                                  nbr_cnt, info, o.cell_key, pass));
         PCH_LAUNCH_CHECK();
+        if (pass == 0) {
+            PCH_LAUNCH(st, "k_db_compress", k_db_compress<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info));
+            PCH_LAUNCH_CHECK();
+        }
     }
     PCH_LAUNCH(st, "k_db_flatten", k_db_flatten<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info, cell_root));
     PCH_LAUNCH_CHECK();
@@ -1003,7 +1014,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_cluster_reduce", k_db_cluster_reduce<<<db_grid(G, 256 * CR_PER_THREAD, 16), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc));
+    PCH_LAUNCH(st, "k_db_cluster_reduce", k_db_cluster_reduce<<<db_grid(G, 8 * 32 * CR_ROWS, 16), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_finish", k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev));
     PCH_LAUNCH_CHECK();

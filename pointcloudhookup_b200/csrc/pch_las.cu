@@ -22,7 +22,7 @@ __global__ void k_init_minmax(int32_t* mm, int64_t n_chunks) {
 
 template <int ALIGN>
 __global__ void __launch_bounds__(PCH_TILE_THREADS, 2)
-k_chunk_minmax(const uint8_t* __restrict__ rec, PchTileGeom g, int32_t* __restrict__ mm) {
+k_chunk_minmax(const uint8_t* __restrict__ rec, PchTileGeom g, int32_t* __restrict__ mm, int4* __restrict__ xyz16) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int s_part[PCH_TILE_THREADS / 32][6];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -33,6 +33,9 @@ k_chunk_minmax(const uint8_t* __restrict__ rec, PchTileGeom g, int32_t* __restri
             pch_load_xyz<ALIGN>(t.base + (size_t)r * g.rec_len, X, Y, Z);
             mnx = min(mnx, X); mny = min(mny, Y); mnz = min(mnz, Z);
             mxx = max(mxx, X); mxy = max(mxy, Y); mxz = max(mxz, Z);
+            // optional 16-byte aligned copy of the lattice coordinates: every later pass (keys, reduce
+            // gathers) reads this instead of the 2-byte aligned AoS records
+            if (xyz16) xyz16[t.r0 + r] = make_int4(X, Y, Z, 0);
         }
         mnx = pch_warp_min(mnx); mny = pch_warp_min(mny); mnz = pch_warp_min(mnz);
         mxx = pch_warp_max(mxx); mxy = pch_warp_max(mxy); mxz = pch_warp_max(mxz);
@@ -73,7 +76,7 @@ static int launch_tiles(const char* name, K kernel, const PchTileGeom& g, int ct
     } while (0)
 
 extern "C" int pch_las_chunk_minmax(const uint8_t* rec, int64_t n, int32_t rec_len, int64_t chunk_size,
-                                    int32_t* mm, pch_stream_t stream) {
+                                    int32_t* mm, int32_t* xyz16, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_rec_args(rec, n, rec_len);
     if (rc) return rc;
@@ -84,7 +87,8 @@ extern "C" int pch_las_chunk_minmax(const uint8_t* rec, int64_t n, int32_t rec_l
     int64_t n_chunks = pch_ceil_div(n, g.chunk_size);
     PCH_LAUNCH(st, "k_init_minmax", k_init_minmax<<<(unsigned)pch_ceil_div(n_chunks * 6, 256), 256, 0, st>>>(mm, n_chunks));
     PCH_LAUNCH_CHECK();
-    PCH_DISPATCH_ALIGN(rec_len, k_chunk_minmax, g, 2, st, rec, mm);
+    PCH_CHECK_ARG((reinterpret_cast<uintptr_t>(xyz16) & 15) == 0, "xyz16 must be 16-byte aligned");
+    PCH_DISPATCH_ALIGN(rec_len, k_chunk_minmax, g, 2, st, rec, mm, (int4*)xyz16);
     return PCH_OK;
 }
 

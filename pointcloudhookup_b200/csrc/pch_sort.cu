@@ -9,8 +9,8 @@
 // cell grid (utils/tower_extraction.py:107-112).
 #include "pch_common.cuh"
 
-#define RS_THREADS 256
-#define RS_KPT 16
+#define RS_THREADS 512
+#define RS_KPT 8
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 8
@@ -103,7 +103,8 @@ k_hist(const uint64_t* __restrict__ keys, SortGeom g, uint32_t* __restrict__ his
     }
 }
 
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*8*/) {
+// exclusive scan of one value per thread over the whole block (threads beyond the 256 digits pass 0)
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*blockDim/32*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t x = v;
 #pragma unroll
@@ -132,19 +133,19 @@ __global__ void __launch_bounds__(256) k_scan(uint32_t* __restrict__ hist, int64
 #define ST_INCL 0x80000000u
 #define ST_VAL 0x3fffffffu
 
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, int pass, int shift, uint32_t dmask,
        const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
        int* __restrict__ err) {
     __shared__ uint64_t s_keys[RS_TILE];
-    __shared__ uint32_t s_whist[RS_WARPS][256];
+    __shared__ uint16_t s_whist[RS_WARPS][256];   // a warp ranks 32*RS_KPT = 256 keys: counts fit 16 bits
     __shared__ uint32_t s_dstart[256];
     __shared__ int64_t s_goff[256];
-    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_scan[RS_THREADS / 32];
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
-    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * 256 / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&s_whist[0][0])[i] = 0;
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= g.total_tiles) return;
@@ -172,7 +173,7 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
         uint32_t old = 0;
         if (lane == leader && d < 256u) {
             old = s_whist[warp][d];
-            s_whist[warp][d] = old + __popc(peers);
+            s_whist[warp][d] = (uint16_t)(old + __popc(peers));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[j] = (uint16_t)(old + before);
@@ -182,19 +183,22 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
 
     // ---- per digit (thread == digit): exclusive over warps, tile total; PUBLISH the aggregate now and
     // do the look-back only after the shared-memory scatter, so predecessors have time to publish too
-    uint32_t my_sum;
-    {
+    uint32_t my_sum = 0;
+    if (tid < 256) {
         const int d = tid;
         uint32_t sum = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             uint32_t c = s_whist[w][d];
-            s_whist[w][d] = sum;
+            s_whist[w][d] = (uint16_t)sum;
             sum += c;
         }
         my_sum = sum;
         pch_st_volatile_u32(status + ((size_t)tile * 256 + d), (tile == first_tile ? ST_INCL : ST_AGG) | sum);
-        s_dstart[d] = block_excl_scan_256(sum, s_scan);
+    }
+    {
+        const uint32_t ds = block_excl_scan_256(my_sum, s_scan);
+        if (tid < 256) s_dstart[tid] = ds;
     }
     __syncthreads();
 
@@ -209,7 +213,7 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
     }
 
     // ---- look-back for digit `tid`
-    {
+    if (tid < 256) {
         const int d = tid;
         uint32_t excl = 0;
         if (tile != first_tile) {

@@ -155,6 +155,54 @@ extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, in
     return PCH_OK;
 }
 
+// keys from the packed lattice copy (plain coalesced 16-byte loads; no second pass over the records)
+__global__ void __launch_bounds__(256)
+k_voxel_keys16(const int4* __restrict__ xyz16, int64_t n, int64_t chunk, PchAffine3 a, double voxel,
+               const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int4 v = __ldg(xyz16 + i);
+        const int64_t c = i / chunk;
+        const double x = pch_scaled(v.x, a.s[0], a.o[0]);
+        const double y = pch_scaled(v.y, a.s[1], a.o[1]);
+        const double z = pch_scaled(v.z, a.s[2], a.o[2]);
+        const uint64_t ix = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(x, origins[c * 3 + 0]), voxel));
+        const uint64_t iy = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(y, origins[c * 3 + 1]), voxel));
+        const uint64_t iz = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(z, origins[c * 3 + 2]), voxel));
+        keys[i] = (ix << kl.sh_x) | (iy << kl.sh_y) | (iz << kl.sh_z) | (uint64_t)(i - c * chunk);
+    }
+}
+
+extern "C" int pch_voxel_keys_xyz16(const int32_t* xyz16, int64_t n, int64_t chunk_size, const double* scales,
+                                    const double* offsets, double voxel, const double* origins,
+                                    const pch_voxel_plan* plan, uint64_t* keys, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && chunk_size > 0 && voxel > 0.0 && plan, "bad arguments");
+    if (plan->status != PCH_OK || plan->key_bits + plan->bits_idx > 64) {
+        pch_set_error("voxel index range needs %d+%d bits > 64: voxel_size too small for this chunk extent",
+                      plan->key_bits, plan->bits_idx);
+        return PCH_ERR_RANGE;
+    }
+    if (n == 0) return PCH_OK;
+    PCH_CHECK_ARG(xyz16 && origins && keys, "null pointer");
+    PCH_CHECK_ARG((reinterpret_cast<uintptr_t>(xyz16) & 15) == 0, "xyz16 must be 16-byte aligned");
+    PchAffine3 a;
+    int rc = make_affine3(scales, offsets, a);
+    if (rc) return rc;
+    if (chunk_size > n) chunk_size = n;
+    KeyLayout kl;
+    kl.sh_z = plan->bits_idx;
+    kl.sh_y = kl.sh_z + plan->bits_z;
+    kl.sh_x = kl.sh_y + plan->bits_y;
+    int64_t blocks = pch_ceil_div(n, 256);
+    int64_t cap = (int64_t)pch_sm_count() * 16;
+    PCH_LAUNCH(st, "k_voxel_keys16", k_voxel_keys16<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+                                         (const int4*)xyz16, n, chunk_size, a, voxel, origins, kl, keys));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // segmented in-order reduction
 // ------------------------------------------------------------------------------------------------

@@ -107,12 +107,12 @@ def encode_records(lattice: torch.Tensor, rec_len: int):
     return out[: m * rec_len], mm
 
 
-def chunk_minmax(dl: DeviceLas, chunk_size: int) -> torch.Tensor:
+def chunk_minmax(dl: DeviceLas, chunk_size: int, xyz16: Optional[torch.Tensor] = None) -> torch.Tensor:
     cs = max(1, min(int(chunk_size), max(dl.n, 1)))
     n_chunks = max(1, -(-dl.n // cs))
     mm = torch.empty((n_chunks, 6), dtype=torch.int32, device=dl.device)
-    check(_native.lib().pch_las_chunk_minmax(dl.rec.data_ptr(), dl.n, dl.rec_len, cs, mm.data_ptr(), _stream()),
-          "pch_las_chunk_minmax")
+    check(_native.lib().pch_las_chunk_minmax(dl.rec.data_ptr(), dl.n, dl.rec_len, cs, mm.data_ptr(), _ptr(xyz16),
+                                             _stream()), "pch_las_chunk_minmax")
     return mm
 
 
@@ -165,7 +165,8 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
                            z(torch.float32) if "f32" in want else None)
     st = _stream()
     sc, of = d3(dl.scales), d3(dl.offsets)
-    mm = chunk_minmax(dl, cs)
+    xyz16 = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    mm = chunk_minmax(dl, cs, xyz16)
     origins = torch.empty((n_chunks, 3), dtype=torch.float64, device=dev)
     plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
     check(lib.pch_voxel_plan_build(mm.data_ptr(), n_chunks, cs, sc, of, float(voxel_size), origins.data_ptr(),
@@ -175,9 +176,8 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     if plan.status != 0:
         raise ValueError(f"voxel_size is too small: index range needs {plan.key_bits}+{plan.bits_idx} bits (> 64)")
     keys = torch.empty(n, dtype=torch.int64, device=dev)
-    xyz16 = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    check(lib.pch_voxel_keys(dl.rec.data_ptr(), n, dl.rec_len, cs, sc, of, float(voxel_size), origins.data_ptr(),
-                             C.byref(plan), keys.data_ptr(), xyz16.data_ptr(), st), "pch_voxel_keys")
+    check(lib.pch_voxel_keys_xyz16(xyz16.data_ptr(), n, cs, sc, of, float(voxel_size), origins.data_ptr(),
+                                   C.byref(plan), keys.data_ptr(), st), "pch_voxel_keys_xyz16")
     skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
     # worst case every point is its own voxel; outputs are sized n and sliced after the count is known
     mean = torch.empty((n, 3), dtype=torch.float64, device=dev) if "mean" in want else None
@@ -327,7 +327,7 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
         raise ValueError("DBSCAN cell grid does not fit the packed key")
     labels = torch.empty(G, dtype=torch.int32, device=dev)
     nclu = torch.empty(1, dtype=torch.int64, device=dev)
-    cap = max(1024, G // 8)
+    cap = max(4096, G // 256)
     while True:
         stats = torch.empty(cap * STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         wsb = lib.pch_dbscan_workspace_bytes(G, ch, C.byref(plan), cap)

@@ -240,21 +240,25 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         del dl
-        torch.cuda.empty_cache()
         barrier()
         d2h = 0
-        e0.record()
-        for _ in range(args.steps):
+
+        def e2e_step():
             if args.workload == "pipeline":
                 # public host-buffer entry: sliced H2D on a copy stream overlapped with the voxel stage
                 res = pipeline.run_pipeline_from_host(pinned, n, 34, synth.SCALES, synth.OFFSETS, cfg["voxel"],
                                                       cfg["chunk"], ground=args.ground, box=args.box)
-                merged = pdist.merge_towers(res.towers) if world > 1 else res.towers
-                d2h = res.n_clusters * 56 + 64
-            else:
-                dl2 = dv.upload_records(pinned, n, 34, synth.SCALES, synth.OFFSETS, dev)
-                d2h = step(dl2)
-                del dl2
+                if world > 1:
+                    pdist.merge_towers(res.towers)
+                return res.n_clusters * 56 + 64
+            dl2 = dv.upload_records(pinned, n, 34, synth.SCALES, synth.OFFSETS, dev)
+            return step(dl2)
+
+        e2e_step()          # one untimed pass: allocator and pinned-page warm-up for this code path
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            d2h = e2e_step()
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -740,7 +740,21 @@ __device__ __forceinline__ void db_flush(DbClusterAcc* __restrict__ acc, const D
     }
 }
 
-#define CR_ROWS 32
+// merge the 32 lane-local partial runs (same label in every lane) and flush once
+__device__ __forceinline__ void db_warp_flush(DbClusterAcc* __restrict__ acc, DbRun& r, int lane) {
+    if (r.lab < 0) return;   // warp-uniform: the run label is shared by all lanes
+    r.cnt = __reduce_add_sync(0xffffffffu, r.cnt);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        r.mn[a] = __reduce_min_sync(0xffffffffu, r.mn[a]);
+        r.mx[a] = __reduce_max_sync(0xffffffffu, r.mx[a]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) r.sum[a] += __shfl_xor_sync(0xffffffffu, r.sum[a], o);
+    }
+    if (lane == 0) db_flush(acc, r);
+}
+
+#define CR_ROWS 64
 // Labels are spatially coherent (the candidates are in voxel-sorted order).  A warp reads rows of 32
 // consecutive points (coalesced); a row whose 32 labels agree is reduced with shuffles into the warp's
 // running accumulator (held redundantly by all lanes), which is flushed with one set of atomics only
@@ -771,19 +785,17 @@ k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ lab
             if (uniform) {
                 if (lab0 < 0) continue;
                 if (lab0 != run.lab) {
-                    if (lane == 0) db_flush(acc, run);
+                    db_warp_flush(acc, run, lane);
                     db_run_reset(run, lab0);
                 }
-                run.cnt += 32;
+                // lane-local accumulation; lanes are merged only when the run ends
+                run.cnt += 1;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     const uint32_t u = pch_f32_to_ordered(v[a]);
-                    run.mn[a] = min(run.mn[a], __reduce_min_sync(0xffffffffu, u));
-                    run.mx[a] = max(run.mx[a], __reduce_max_sync(0xffffffffu, u));
-                    double s = (double)v[a];
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    run.sum[a] += s;
+                    run.mn[a] = min(run.mn[a], u);
+                    run.mx[a] = max(run.mx[a], u);
+                    run.sum[a] += (double)v[a];
                 }
             } else if (lab >= 0) {
                 DbClusterAcc* a = &acc[lab];
@@ -797,7 +809,7 @@ k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ lab
                 }
             }
         }
-        if (lane == 0) db_flush(acc, run);
+        db_warp_flush(acc, run, lane);
     }
 }
 

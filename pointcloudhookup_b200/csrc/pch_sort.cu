@@ -9,8 +9,8 @@
 // cell grid (utils/tower_extraction.py:107-112).
 #include "pch_common.cuh"
 
-#define RS_THREADS 512
-#define RS_KPT 8
+#define RS_THREADS 256
+#define RS_KPT 16
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 8
@@ -133,12 +133,12 @@ __global__ void __launch_bounds__(256) k_scan(uint32_t* __restrict__ hist, int64
 #define ST_INCL 0x80000000u
 #define ST_VAL 0x3fffffffu
 
-__global__ void __launch_bounds__(RS_THREADS, 3)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, int pass, int shift, uint32_t dmask,
        const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
        int* __restrict__ err) {
     __shared__ uint64_t s_keys[RS_TILE];
-    __shared__ uint16_t s_whist[RS_WARPS][256];   // a warp ranks 32*RS_KPT = 256 keys: counts fit 16 bits
+    __shared__ uint16_t s_whist[RS_WARPS][256];   // a warp ranks 32*RS_KPT = 512 keys: counts fit 16 bits
     __shared__ uint32_t s_dstart[256];
     __shared__ int64_t s_goff[256];
     __shared__ uint32_t s_scan[RS_THREADS / 32];

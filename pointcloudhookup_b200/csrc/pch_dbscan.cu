@@ -780,15 +780,16 @@ k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ lab
                 if (lab >= cap) lab = -1;
                 if (lab >= 0) { v[0] = P[i * 3 + 0]; v[1] = P[i * 3 + 1]; v[2] = P[i * 3 + 2]; }
             }
-            const int32_t lab0 = __shfl_sync(0xffffffffu, lab, 0);
-            const bool uniform = __all_sync(0xffffffffu, lab == lab0);
-            if (uniform) {
-                if (lab0 < 0) continue;
-                if (lab0 != run.lab) {
-                    db_warp_flush(acc, run, lane);
-                    db_run_reset(run, lab0);
-                }
-                // lane-local accumulation; lanes are merged only when the run ends
+            // noise (-1) lanes simply do not contribute; the row's first labelled lane proposes the run label
+            const uint32_t valid = __ballot_sync(0xffffffffu, lab >= 0);
+            if (valid == 0) continue;
+            const int32_t cand = __shfl_sync(0xffffffffu, lab, __ffs(valid) - 1);
+            if (run.lab < 0) db_run_reset(run, cand);
+            if (!__any_sync(0xffffffffu, lab == run.lab)) {   // the current run ended before this row
+                db_warp_flush(acc, run, lane);
+                db_run_reset(run, cand);
+            }
+            if (lab == run.lab) {                             // lane-local accumulation, merged when the run ends
                 run.cnt += 1;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
@@ -797,7 +798,7 @@ k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ lab
                     run.mx[a] = max(run.mx[a], u);
                     run.sum[a] += (double)v[a];
                 }
-            } else if (lab >= 0) {
+            } else if (lab >= 0) {                            // a second label inside the row: rare, direct atomics
                 DbClusterAcc* a = &acc[lab];
                 atomicAdd(&a->count, 1ull);
 #pragma unroll

@@ -382,8 +382,11 @@ struct __align__(16) DbCellInfo {
 __global__ void __launch_bounds__(256)
 k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ spts, const int32_t* __restrict__ cell_start,
               const uint8_t* __restrict__ core, DbCellInfo* __restrict__ info, int64_t chunk,
-              int32_t* __restrict__ cell_mincore) {
+              int32_t* __restrict__ cell_mincore, DbGeom g, const uint64_t* __restrict__ cell_key,
+              const uint32_t* __restrict__ bounds, unsigned long long* __restrict__ cell_mask) {
     const int64_t U = *U_dev;
+    const int bxy = g.bits_y + g.bits_z;
+    const uint64_t mzk = (1ull << g.bits_z) - 1ull, myk = (1ull << g.bits_y) - 1ull;
     // one warp per cell
     const int lane = threadIdx.x & 31;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -393,10 +396,23 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         int n = 0;
         int mincore = INT_MAX;
-        const int32_t chunk_base = (int32_t)((b / chunk) * chunk);
+        const int64_t ch = b / chunk;
+        const int32_t chunk_base = (int32_t)(ch * chunk);
+        // 4x4x4 occupancy of the cell by its core points (sub-cell side = cell/4): lets the union pass
+        // decide most cell pairs with integer geometry instead of point searches
+        const uint64_t key = cell_key[w];
+        const double lo3[3] = {(double)pch_ordered_to_f32(bounds[ch * 6 + 0]) + (double)(long long)(key >> bxy) * g.cell,
+                               (double)pch_ordered_to_f32(bounds[ch * 6 + 1]) + (double)(long long)((key >> g.bits_z) & myk) * g.cell,
+                               (double)pch_ordered_to_f32(bounds[ch * 6 + 2]) + (double)(long long)(key & mzk) * g.cell};
+        const double inv_h = 4.0 / g.cell;
+        unsigned long long mask = 0ull;
         for (int32_t q = b + lane; q < e; q += 32) {
             if (core[q]) {
                 float4 p = spts[q];
+                int sx = (int)floor(((double)p.x - lo3[0]) * inv_h), sy = (int)floor(((double)p.y - lo3[1]) * inv_h),
+                    sz = (int)floor(((double)p.z - lo3[2]) * inv_h);
+                sx = min(max(sx, 0), 3); sy = min(max(sy, 0), 3); sz = min(max(sz, 0), 3);
+                mask |= 1ull << (sx * 16 + sy * 4 + sz);
                 mincore = min(mincore, chunk_base + __float_as_int(p.w));
                 mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
                 mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
@@ -407,6 +423,7 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
         for (int o = 16; o; o >>= 1) {
             n += __shfl_xor_sync(0xffffffffu, n, o);
             mincore = min(mincore, __shfl_xor_sync(0xffffffffu, mincore, o));
+            mask |= __shfl_xor_sync(0xffffffffu, mask, o);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
@@ -421,6 +438,7 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
             ci.parent = (int32_t)w;
             info[w] = ci;
             cell_mincore[w] = mincore;
+            cell_mask[w] = mask;
         }
     }
 }
@@ -465,7 +483,7 @@ __global__ void __launch_bounds__(256)
 k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restrict__ spts,
            const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
            const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt, DbCellInfo* __restrict__ info,
-           const uint64_t* __restrict__ cell_key, int pass) {
+           const uint64_t* __restrict__ cell_key, int pass, const unsigned long long* __restrict__ cell_mask) {
     // pass 0: only face/edge/corner-adjacent cells (|offset| <= 1): cheap hits that merge almost every
     // dense region; pass 1: the remaining (distance-2) cells, most of which are then skipped by the
     // "already in one set" test instead of being searched exhaustively.
@@ -485,6 +503,7 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
         const bool near_xy = ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1;
         if (pass == 0 && !near_xy) continue;
         const long long czA = (long long)(cell_key[A] & zmask);
+        const unsigned long long mA = cell_mask[A];
         const int32_t f = nbr_first[w];
         const int nc = nbr_cnt[w];
         for (int k = 0; k < nc; ++k) {
@@ -498,6 +517,39 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
             if (lane == 0) same = uf_find(info, A) == uf_find(info, B);
             same = __shfl_sync(0xffffffffu, same, 0);
             if (same) continue;
+            {
+                // Sub-cell geometry (exact, integer): a pair of occupied sub-cells whose FARTHEST corners are
+                // within eps proves a core-core neighbour pair (certain hit); if even the NEAREST corners of
+                // every occupied pair are beyond eps there is none (certain miss).  Units: sub-cell side
+                // h = cell/4 = eps/(4*sqrt(3))*(1-1e-7), (eps/h)^2 = 48.00001; the integer thresholds 47 / 49
+                // leave room for the 1e-6 m slack of the cell assignment.
+                const unsigned long long mB = cell_mask[B];
+                const int d0x = ox * 4, d0y = oy * 4, d0z = (int)dz * 4;
+                bool hit = false, maybe = false;
+                for (unsigned long long rest = mB; rest && !hit; rest &= rest - 1) {
+                    const int b = __ffsll((long long)rest) - 1;
+                    const int bx = b >> 4, by = (b >> 2) & 3, bz = b & 3;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int a = lane + 32 * half;
+                        if ((mA >> a) & 1ull) {
+                            const int dx = abs(d0x + bx - (a >> 4)), dy = abs(d0y + by - ((a >> 2) & 3)), dzz = abs(d0z + bz - (a & 3));
+                            const int smax = (dx + 1) * (dx + 1) + (dy + 1) * (dy + 1) + (dzz + 1) * (dzz + 1);
+                            const int mx_ = max(dx - 1, 0), my_ = max(dy - 1, 0), mz_ = max(dzz - 1, 0);
+                            const int smin = mx_ * mx_ + my_ * my_ + mz_ * mz_;
+                            hit = hit || smax <= 47;
+                            maybe = maybe || smin < 49;
+                        }
+                    }
+                    hit = __any_sync(0xffffffffu, hit);
+                }
+                if (hit) {
+                    if (lane == 0) uf_union(info, A, B);
+                    __syncwarp();
+                    continue;
+                }
+                if (!__any_sync(0xffffffffu, maybe)) continue;   // certain miss
+            }
             float amn[3], amx[3], bmn[3], bmx[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -858,7 +910,7 @@ struct DbWs {
     size_t total;
     size_t keys, tmp, sortws, sortws_bytes, spts, pt_cell, inv_pos, cell_start, cell_key, chunk_cell0, scalars,
         nbr_first, nbr_cnt, core, info, cell_root, root_min, root_label, is_head, head_list, scan_status, acc,
-        worklist, cell_mincore;
+        worklist, cell_mincore, cell_mask;
 };
 
 extern "C" size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi);
@@ -902,6 +954,7 @@ static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t 
     w.acc = take((size_t)max_clusters * sizeof(DbClusterAcc));
     w.worklist = take((size_t)(G + 32) * 4);
     w.cell_mincore = take((size_t)G * 4);
+    w.cell_mask = take((size_t)G * 8);
     w.total = off;
     return w;
 }
@@ -938,6 +991,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     unsigned int* n_work = (unsigned int*)(base + w.scalars + 192);
     int32_t* worklist = (int32_t*)(base + w.worklist);
     int32_t* cell_mincore = (int32_t*)(base + w.cell_mincore);
+    unsigned long long* cell_mask = (unsigned long long*)(base + w.cell_mask);
     uint64_t* keys = (uint64_t*)(base + w.keys);
     uint64_t* tmp = (uint64_t*)(base + w.tmp);
 
@@ -992,11 +1046,11 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH(st, "k_db_core2", k_db_core2<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, nbr_first, nbr_cnt,
                                                                             worklist, n_work, core, o.cell_key, bounds_dev));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info, chunk, cell_mincore));
+    PCH_LAUNCH(st, "k_db_cellinfo", k_db_cellinfo<<<db_grid(G, 256 / 32 * 8), 256, 0, st>>>(U_dev, o.spts, o.cell_start, core, info, chunk, cell_mincore, g, o.cell_key, bounds_dev, cell_mask));
     PCH_LAUNCH_CHECK();
     for (int pass = 0; pass < 2; ++pass) {
         PCH_LAUNCH(st, "k_db_union", k_db_union<<<db_grid(G, 64, 16), 256, 0, st>>>(g, U_dev, o.spts, o.cell_start, core, nbr_first,
-                                                                                 nbr_cnt, info, o.cell_key, pass));
+                                                                                 nbr_cnt, info, o.cell_key, pass, cell_mask));
         PCH_LAUNCH_CHECK();
         if (pass == 0) {
             PCH_LAUNCH(st, "k_db_compress", k_db_compress<<<db_grid(G, 256), 256, 0, st>>>(U_dev, info));

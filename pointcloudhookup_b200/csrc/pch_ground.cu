@@ -181,24 +181,24 @@ __device__ __forceinline__ SqMap sq_compose(const SqMap& F, const SqMap& G) {
 }
 
 // increment of the mantissa m (ulp 2^k) when adding the float with bit pattern `bits`:
-// q + gt, plus 1 more on a tie (eq) when (m + q) is odd
+// q + gt, plus 1 more on a tie (eq) when (m + q) is odd.
+// a = ma * 2^(ea-150);  a / 2^k = ma * 2^-shift.  With t = (ma << 32) >> shift (64-bit), q is the high
+// word and the low word is the fraction in units of 2^-32: > 0x80000000 rounds up, == is the tie.
+// (shift <= 32 loses no bits; for shift > 32 the value is < 2^-8 of an ulp, so q = gt = eq = 0.)
 __device__ __forceinline__ void sq_elem(uint32_t bits, int k, uint32_t& q, uint32_t& gt, uint32_t& eq) {
     int ea = (int)((bits >> 23) & 0xffu);
     uint32_t ma = bits & 0x7fffffu;
     if (ea == 0) ea = 1; else ma |= 0x800000u;
-    const int shift = k - (ea - 150);   // a = ma * 2^(ea-150)
-    gt = 0; eq = 0;
-    if (ma == 0) { q = 0; return; }
-    if (shift <= 0) {
-        q = (-shift >= 8) ? SQ_SAT : (ma << (-shift));
-    } else if (shift >= 26) {
-        q = 0;
+    const int shift = k - (ea - 150);
+    if (shift >= 0) {
+        const unsigned long long t = shift < 64 ? (((unsigned long long)ma << 32) >> shift) : 0ull;
+        q = (uint32_t)(t >> 32);
+        const uint32_t f = (uint32_t)t;
+        gt = f > 0x80000000u;
+        eq = f == 0x80000000u;
     } else {
-        q = shift >= 24 ? 0u : (ma >> shift);
-        const uint32_t r = ma & ((1u << shift) - 1u);
-        const uint32_t h = 1u << (shift - 1);
-        gt = r > h;
-        eq = r == h;
+        gt = 0; eq = 0;
+        q = ma == 0 ? 0u : ((-shift >= 8) ? SQ_SAT : (ma << (-shift)));
     }
 }
 

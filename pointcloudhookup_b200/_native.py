@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpch_b200.so")
+LIB_PATH = os.environ.get("PCH_LIB_PATH") or os.path.join(_HERE, "libpch_b200.so")   # override: tuning variants only
 
 
 class NativeError(RuntimeError):

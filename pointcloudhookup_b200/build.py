@@ -25,6 +25,23 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Compile a tuning variant (extra -D flags) into csrc/variants/<name>/ and libpch_b200_<name>.so."""
+    vdir = os.path.join(CSRC, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in sources():
+        o = os.path.join(vdir, src[:-3] + ".o")
+        r = subprocess.run([NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o],
+                           capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(r.stderr)
+        objs.append(o)
+    lib = os.path.join(HERE, f"libpch_b200_{name}.so")
+    subprocess.run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], check=True)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "pch_b200.h"))

@@ -45,12 +45,27 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 static thread_local cudaEvent_t g_pending_e0 = nullptr;
 static thread_local const char* g_pending_name = nullptr;
+static std::vector<cudaEvent_t> g_pool;   // recycled events: creating one per launch costs more than the record
+
+static cudaEvent_t prof_get_event() {
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (!g_pool.empty()) {
+            cudaEvent_t e = g_pool.back();
+            g_pool.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    return e;
+}
 
 void pch_prof_begin(cudaStream_t st, const char* name) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
-    cudaEvent_t e0;
-    if (cudaEventCreate(&e0) != cudaSuccess) return;
+    cudaEvent_t e0 = prof_get_event();
+    if (!e0) return;
     cudaEventRecord(e0, st);
     g_pending_e0 = e0;
     g_pending_name = name;
@@ -58,20 +73,30 @@ void pch_prof_begin(cudaStream_t st, const char* name) {
 
 void pch_prof_end(cudaStream_t st) {
     if (!g_pending_e0) return;
-    cudaEvent_t e1;
-    if (cudaEventCreate(&e1) == cudaSuccess) {
+    cudaEvent_t e1 = prof_get_event();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (e1) {
         cudaEventRecord(e1, st);
-        std::lock_guard<std::mutex> lk(g_prof_mu);
         g_prof.push_back({g_pending_name, g_pending_e0, e1});
     } else {
-        cudaEventDestroy(g_pending_e0);
+        g_pool.push_back(g_pending_e0);
     }
     g_pending_e0 = nullptr;
 }
 
 extern "C" long long pch_launch_count(void) { return g_launches.load(); }
 
-extern "C" void pch_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+extern "C" void pch_profile_enable(int on) {
+    if (on) {   // pre-create a pool so the timed region only pays for cudaEventRecord
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        while (g_pool.size() < 2048) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) break;
+            g_pool.push_back(e);
+        }
+    }
+    g_prof_on.store(on ? 1 : 0);
+}
 
 // Synchronises, then writes "name launches total_ms\n" lines into buf (and clears the records).
 extern "C" int pch_profile_report(char* buf, size_t cap) {
@@ -90,8 +115,8 @@ extern "C" int pch_profile_report(char* buf, size_t cap) {
                 a.first += 1;
                 a.second += ms;
             }
-            cudaEventDestroy(r.e0);
-            cudaEventDestroy(r.e1);
+            g_pool.push_back(r.e0);
+            g_pool.push_back(r.e1);
         }
         g_prof.clear();
     }

@@ -10,7 +10,12 @@
 #include "pch_common.cuh"
 
 #define RS_THREADS 256
+#ifndef RS_KPT
 #define RS_KPT 16
+#endif
+#ifndef RS_MINB
+#define RS_MINB 4
+#endif
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 8
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(256) k_scan(uint32_t* __restrict__ hist, int64
 #define ST_INCL 0x80000000u
 #define ST_VAL 0x3fffffffu
 
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB)
 k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, int pass, int shift, uint32_t dmask,
        const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
        int* __restrict__ err) {

@@ -207,7 +207,9 @@ extern "C" int pch_voxel_keys_xyz16(const int32_t* xyz16, int64_t n, int64_t chu
 // segmented in-order reduction
 // ------------------------------------------------------------------------------------------------
 #define VR_THREADS 256
+#ifndef VR_ROWS
 #define VR_ROWS 8
+#endif
 #define VR_TILE (VR_THREADS * VR_ROWS)
 #define VR_WARPS (VR_THREADS / 32)
 

@@ -1,0 +1,18 @@
+"""Time the voxel stage with different library builds (PCH_LIB_PATH set by the caller)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, ctypes
+from pointcloudhookup_b200 import synth, device as dv, _native
+n = 50_000_000
+pinned = torch.empty(n * 34, dtype=torch.uint8, pin_memory=True)
+synth.corridor_records(n, 25, "hilly", 3, out=pinned.numpy())
+dl = dv.upload_records(pinned, n, 34, synth.SCALES, synth.OFFSETS)
+lib = _native.lib()
+for _ in range(2): dv.voxel_downsample(dl, 0.1, 500000, want=("f32",))
+lib.pch_profile_enable(1)
+for _ in range(3): dv.voxel_downsample(dl, 0.1, 500000, want=("f32",))
+buf = ctypes.create_string_buffer(65536); lib.pch_profile_report(buf, 65536)
+out = {}
+for line in buf.value.decode().splitlines():
+    nm, c, t = line.split(); out[nm] = float(t) / 3
+print(os.environ.get("PCH_LIB_PATH", "default").split("_")[-1], {k: round(v, 3) for k, v in sorted(out.items(), key=lambda kv: -kv[1])[:5]})

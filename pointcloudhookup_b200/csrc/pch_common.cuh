@@ -97,6 +97,7 @@ __device__ __forceinline__ void pch_mbar_wait(uint64_t* bar, uint32_t parity) {
 #define PCH_FLAG_AGG 1ull
 #define PCH_FLAG_INCL 2ull
 #define PCH_SPIN_LIMIT (1u << 27)
+#define PCH_LB_WIN 8
 
 __device__ __forceinline__ uint64_t pch_ld_volatile_u64(const uint64_t* p) {
     uint64_t v;
@@ -125,18 +126,31 @@ __device__ __forceinline__ uint64_t pch_lookback_u64(uint64_t* status, int64_t t
     }
     pch_st_volatile_u64(&status[tile], (PCH_FLAG_AGG << 62) | aggregate);
     uint64_t excl = 0;
-    for (int64_t t = tile - 1; t >= first; --t) {
-        uint64_t w;
-        uint32_t spins = 0;
-        do {
-            w = pch_ld_volatile_u64(&status[t]);
-            if (++spins > PCH_SPIN_LIMIT) {
-                if (err_flag) atomicExch(err_flag, 1);
-                return excl;
+    // windowed walk: PCH_LB_WIN predecessors are fetched with independent loads, then consumed in order
+    int64_t t = tile - 1;
+    bool done = false;
+    while (!done) {
+        uint64_t w[PCH_LB_WIN];
+#pragma unroll
+        for (int j = 0; j < PCH_LB_WIN; ++j) {
+            const int64_t tt = t - j;
+            w[j] = tt >= first ? pch_ld_volatile_u64(&status[tt]) : (PCH_FLAG_INCL << 62);
+        }
+#pragma unroll
+        for (int j = 0; j < PCH_LB_WIN; ++j) {
+            if (done) break;
+            uint32_t spins = 0;
+            while ((w[j] >> 62) == PCH_FLAG_EMPTY) {
+                w[j] = pch_ld_volatile_u64(&status[t - j]);
+                if (++spins > PCH_SPIN_LIMIT) {
+                    if (err_flag) atomicExch(err_flag, 1);
+                    return excl;
+                }
             }
-        } while ((w >> 62) == PCH_FLAG_EMPTY);
-        excl += w & ((1ull << 62) - 1);
-        if ((w >> 62) == PCH_FLAG_INCL) break;
+            excl += w[j] & ((1ull << 62) - 1);
+            if ((w[j] >> 62) == PCH_FLAG_INCL) done = true;
+        }
+        t -= PCH_LB_WIN;
     }
     pch_st_volatile_u64(&status[tile], (PCH_FLAG_INCL << 62) | (excl + aggregate));
     return excl;

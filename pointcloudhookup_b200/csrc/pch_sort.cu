@@ -19,6 +19,7 @@
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 8
+#define LB_WIN 8
 
 struct SortGeom {
     int64_t n, seg_size, tiles_per_seg, total_tiles, n_segs;
@@ -222,18 +223,33 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
         const int d = tid;
         uint32_t excl = 0;
         if (tile != first_tile) {
-            for (int64_t t = tile - 1; t >= first_tile; --t) {
-                const uint32_t* p = status + ((size_t)t * 256 + d);
-                uint32_t w, spins = 0;
-                do {
-                    w = pch_ld_volatile_u32(p);
-                    if (++spins > PCH_SPIN_LIMIT) {
-                        atomicExch(err, 1);
-                        w = ST_INCL;
+            // Walk back over the predecessors LB_WIN at a time: the window's status words are fetched
+            // with independent loads (one L2 latency per window instead of one per tile), then consumed
+            // in order; a word that is not published yet is re-polled.
+            int64_t t = tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t w[LB_WIN];
+#pragma unroll
+                for (int j = 0; j < LB_WIN; ++j) {
+                    const int64_t tt = t - j;
+                    w[j] = tt >= first_tile ? pch_ld_volatile_u32(status + ((size_t)tt * 256 + d)) : ST_INCL;
+                }
+#pragma unroll
+                for (int j = 0; j < LB_WIN; ++j) {
+                    if (done) break;
+                    uint32_t spins = 0;
+                    while ((w[j] & (ST_AGG | ST_INCL)) == 0) {
+                        w[j] = pch_ld_volatile_u32(status + ((size_t)(t - j) * 256 + d));
+                        if (++spins > PCH_SPIN_LIMIT) {
+                            atomicExch(err, 1);
+                            w[j] = ST_INCL;
+                        }
                     }
-                } while ((w & (ST_AGG | ST_INCL)) == 0);
-                excl += w & ST_VAL;
-                if (w & ST_INCL) break;
+                    excl += w[j] & ST_VAL;
+                    if (w[j] & ST_INCL) done = true;
+                }
+                t -= LB_WIN;
             }
             pch_st_volatile_u32(status + ((size_t)tile * 256 + d), ST_INCL | ((excl + my_sum) & ST_VAL));
         }

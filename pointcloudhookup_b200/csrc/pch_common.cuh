@@ -97,7 +97,7 @@ __device__ __forceinline__ void pch_mbar_wait(uint64_t* bar, uint32_t parity) {
 #define PCH_FLAG_AGG 1ull
 #define PCH_FLAG_INCL 2ull
 #define PCH_SPIN_LIMIT (1u << 27)
-#define PCH_LB_WIN 32
+#define PCH_LB_WIN 8
 
 __device__ __forceinline__ uint64_t pch_ld_volatile_u64(const uint64_t* p) {
     uint64_t v;

@@ -19,7 +19,7 @@
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASSES 8
-#define LB_WIN 32
+#define LB_WIN 8
 
 struct SortGeom {
     int64_t n, seg_size, tiles_per_seg, total_tiles, n_segs;

@@ -240,6 +240,13 @@ int pch_las_geodetic(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const d
                      const pch_geoid_grid* grid, int32_t win_row0, int32_t win_col0, int32_t win_rows,
                      int32_t win_cols, double multiplier, double* out_dev, pch_stream_t stream);
 
+/* ---------------------------------------------------------------- tower-level match */
+
+/* haversine(lat1, lon1, lat2, lon2) in metres with R = 6371 km (utils/table_match_gim.py:17-34) for
+ * every pair of match_towers' double loop (:168-192): out_dev[i*n2 + j], degrees in. */
+int pch_haversine_matrix(const double* lat1_dev, const double* lon1_dev, int64_t n1, const double* lat2_dev,
+                         const double* lon2_dev, int64_t n2, double* out_dev, pch_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

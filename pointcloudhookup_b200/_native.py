@@ -84,6 +84,7 @@ class TmParams(C.Structure):
 
 SIGNATURES.update({
     "pch_geoid_shift": (C.c_int, [_p, _p, _p, _i64, _p, C.POINTER(GeoidGrid), _f64, _p, _p, _p]),
+    "pch_haversine_matrix": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _p, _p]),
     "pch_gk_inverse": (C.c_int, [_p, _p, _i64, C.POINTER(TmParams), _p, _p, _p]),
     "pch_las_geodetic": (C.c_int, [_p, _i64, _i32, _d3, _d3, C.POINTER(TmParams), _p, C.POINTER(GeoidGrid),
                                    _i32, _i32, _i32, _i32, _f64, _p, _p]),

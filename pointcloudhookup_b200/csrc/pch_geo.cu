@@ -258,3 +258,37 @@ extern "C" int pch_las_geodetic(const uint8_t* rec, int64_t n, int32_t rec_len, 
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// tower-level matching: great-circle distance matrix between GIM towers and the
+// converted point-cloud towers — utils/table_match_gim.py:17-34 (haversine, R = 6371 km) evaluated
+// for every (i, j) of match_towers' double loop (:168-192).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_haversine_matrix(const double* __restrict__ lat1, const double* __restrict__ lon1, int64_t n1,
+                                   const double* __restrict__ lat2, const double* __restrict__ lon2, int64_t n2,
+                                   double* __restrict__ out) {
+    const double d2r = 0.017453292519943295;   // math.radians
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; t < n1 * n2; t += stride) {
+        const int64_t i = t / n2, j = t - i * n2;
+        const double la1 = lat1[i] * d2r, lo1 = lon1[i] * d2r, la2 = lat2[j] * d2r, lo2 = lon2[j] * d2r;
+        const double dlat = la2 - la1, dlon = lo2 - lo1;
+        const double s1 = sin(dlat / 2), s2 = sin(dlon / 2);
+        const double a = s1 * s1 + cos(la1) * cos(la2) * s2 * s2;
+        const double c = 2 * atan2(sqrt(a), sqrt(1 - a));
+        out[t] = 6371.0 * c * 1000;
+    }
+}
+
+extern "C" int pch_haversine_matrix(const double* lat1, const double* lon1, int64_t n1, const double* lat2,
+                                    const double* lon2, int64_t n2, double* out, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n1 >= 0 && n2 >= 0, "negative size");
+    if (n1 == 0 || n2 == 0) return PCH_OK;
+    PCH_CHECK_ARG(lat1 && lon1 && lat2 && lon2 && out, "null pointer");
+    PCH_LAUNCH(st, "k_haversine_matrix", k_haversine_matrix<<<geo_grid(n1 * n2, 128, 8), 128, 0, st>>>(lat1, lon1, n1, lat2, lon2, n2, out));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}

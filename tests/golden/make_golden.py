@@ -271,6 +271,46 @@ def run_elevation():
     return out
 
 
+def run_match():
+    """utils/table_match_gim.py::match_towers (unmodified) — PyQt5 is GUI-only there and is stubbed; pyproj's
+    Transformer.from_crs is served by the oracle's inverse Gauss-Krueger."""
+    import importlib
+    from oracle import crs as o_crs
+    for name in ("PyQt5", "PyQt5.QtWidgets", "PyQt5.QtCore", "PyQt5.QtGui"):
+        m = types.ModuleType(name)
+        m.__getattr__ = lambda attr: type(attr, (), {})      # any Qt class name resolves to a dummy class
+        sys.modules[name] = m
+    install_shims(None)
+
+    class _T:
+        def transform(self, x, y):
+            lon, lat = o_crs.gk_inverse(x, y)
+            return (float(lon), float(lat)) if np.ndim(x) == 0 else (lon, lat)
+    sys.modules["pyproj"].Transformer.from_crs = staticmethod(lambda *a, **k: _T())
+    # the module does `from utils.elevation_converter import ElevationConverter`
+    utils_pkg = types.ModuleType("utils")
+    utils_pkg.__path__ = [os.path.join(REF, "utils")]
+    sys.modules["utils"] = utils_pkg
+    tm = load_ref("utils/table_match_gim.py", "ref_table_match_gim")
+    # point-cloud towers: the reference's own recorded run (test/kuangxuan.py:29-33)
+    pc = [{"center": np.array([437587.898, 3140691.58, 131.45735]), "height": 17.4, "north_angle": 12.0},
+          {"center": np.array([437787.178, 3140006.96, 87.7722064]), "height": 29.8, "north_angle": 15.5},
+          {"center": np.array([437908.948, 3139606.82, 80.0563301]), "height": 21.8, "north_angle": 16.1},
+          {"center": np.array([437676.583, 3140379.50, 82.5588932]), "height": 21.0, "north_angle": 14.9}]
+    # GIM towers: lat/lng/h in the layout of test/data1.py, placed 0-70 m away from the cloud towers
+    gim = [{"lat": 28.379751, "lng": 113.363246, "h": 106.0, "r": 10.0, "properties": {"杆塔编号": "P142"}},
+           {"lat": 28.376940 + 3.0e-4, "lng": 113.364167, "h": 57.9, "r": 11.0, "properties": {"杆塔编号": "P143"}},
+           {"lat": 28.373584, "lng": 113.365316 + 7.5e-4, "h": 62.0, "r": 12.0, "properties": {"杆塔编号": "P144"}},
+           {"lat": 28.369979, "lng": 113.366579, "h": 300.0, "r": 13.0, "properties": {"杆塔编号": "P145"}},
+           {"lat": 28.40, "lng": 113.40, "h": 50.0, "r": 0.0, "properties": {"杆塔编号": "far"}}]
+    matched, conv = tm.match_towers(gim, pc, tm.Transformer.from_crs("EPSG:4547", "EPSG:4326", always_xy=True))
+    hav = [[tm.haversine(g["lat"], g["lng"], c["converted_center"][1], c["converted_center"][0]) for c in conv] for g in gim]
+    return {"pc": [{"center": t["center"].tolist(), "height": t["height"], "north_angle": t["north_angle"]} for t in pc],
+            "gim": gim, "matched": [list(m) for m in matched],
+            "converted": [{k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in c.items()} for c in conv],
+            "haversine": hav}
+
+
 def main():
     install_shims(None)
     result = {"generator": "tests/golden/make_golden.py", "numpy": np.__version__}
@@ -281,6 +321,7 @@ def main():
             print("case", name, flush=True)
             result[name] = run_case(name, cfg, wd)
     result["elevation"] = run_elevation()
+    result["match"] = run_match()
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_run.json"), "w") as f:
         json.dump(result, f, indent=1)
     print(json.dumps({k: (v if not isinstance(v, dict) else list(v.keys())) for k, v in result.items()}, indent=1))

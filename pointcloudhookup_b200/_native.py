@@ -50,7 +50,9 @@ SIGNATURES = {
     "pch_sort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "pch_sort_u64_segmented": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "pch_voxel_reduce_workspace_bytes": (_sz, [_i64, _i64]),
-    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _p, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _p, _p, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_voxel_index3_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
+    "pch_voxel_wide_words": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p]),
 }
 
 class ClusterStats(C.Structure):

@@ -231,7 +231,8 @@ extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size
 template <int ALIGN>
 __global__ void __launch_bounds__(VR_THREADS)
 k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec,
-               const int4* __restrict__ xyz16, PchAffine3 a,
+               const int4* __restrict__ xyz16, const int32_t* __restrict__ vidx /* (n,3) or NULL: wide keys */,
+               PchAffine3 a,
                double* __restrict__ mean_out, int32_t* __restrict__ lat_out, float* __restrict__ f32_out,
                unsigned long long* __restrict__ chunk_counts, long long* __restrict__ total_out,
                uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
@@ -303,7 +304,16 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         bool head = false;
         if (i < cnt) {
             uint64_t k = s_keys[i + 1] >> bi;
-            head = (i == 0 && lt == 0) || (k != (s_keys[i] >> bi));
+            if (vidx) {   // wide keys: the word only carries one axis; compare the full (ix,iy,iz) triples
+                head = (i == 0 && lt == 0);
+                if (!head) {
+                    const int32_t* va = vidx + (cstart + (int64_t)(s_keys[i + 1] & idx_mask)) * 3;
+                    const int32_t* vb = vidx + (cstart + (int64_t)(s_keys[i] & idx_mask)) * 3;
+                    head = va[0] != vb[0] || va[1] != vb[1] || va[2] != vb[2];
+                }
+            } else {
+                head = (i == 0 && lt == 0) || (k != (s_keys[i] >> bi));
+            }
         }
         uint32_t b = __ballot_sync(0xffffffffu, head);
         row_rank[j] = wtotal + __popc(b & ((1u << lane) - 1u));
@@ -333,6 +343,7 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         const int i = wbase + j * 32 + lane;
         const uint64_t m = tile_off + wprefix + row_rank[j];
         const uint64_t vkey = s_keys[i + 1] >> bi;
+        const int32_t* vhead = vidx ? vidx + (cstart + (int64_t)(s_keys[i + 1] & idx_mask)) * 3 : nullptr;
         double sx = 0.0, sy = 0.0, sz = 0.0;
         long long cntp = 0;
         int64_t p = start + i;
@@ -364,7 +375,10 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
             if (p >= cend) break;
             li = (int)(p - start);
             k = li < cnt ? s_keys[li + 1] : keys[p];
-            if ((k >> bi) != vkey) break;
+            if (vidx) {
+                const int32_t* vn = vidx + (cstart + (int64_t)(k & idx_mask)) * 3;
+                if (vn[0] != vhead[0] || vn[1] != vhead[1] || vn[2] != vhead[2]) break;
+            } else if ((k >> bi) != vkey) break;
         }
         const double dn = (double)cntp;
         const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
@@ -388,8 +402,8 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
 }
 
 extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
-                                const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const double* scales,
-                                const double* offsets,
+                                const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const int32_t* vidx,
+                                const double* scales, const double* offsets,
                                 double* mean_out, int32_t* lat_out, float* f32_out, int64_t* chunk_counts,
                                 int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -425,7 +439,7 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     int al = rec_len == 0 ? 0 : pch_rec_align(rec_len);
 #define LAUNCH_RED(A)                                                                                          \
     PCH_LAUNCH(st, "k_voxel_reduce", k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
-        keys, g, rec, (const int4*)xyz16, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
+        keys, g, rec, (const int4*)xyz16, vidx, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
         status, counter, err))
     if (al == 4) LAUNCH_RED(4);
     else if (al == 2) LAUNCH_RED(2);
@@ -561,6 +575,63 @@ extern "C" int pch_voxel_keys_f64(const double* xyz, int64_t n, int64_t chunk_si
     int64_t blocks = pch_ceil_div(n, 256);
     int64_t cap = (int64_t)pch_sm_count() * 8;
     PCH_LAUNCH(st, "k_voxel_keys_f64", k_voxel_keys_f64<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, voxel, origins, kl, keys));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// wide keys: when bits(ix)+bits(iy)+bits(iz)+bits(index) > 64 the voxel index does not fit one sort
+// word.  The triples are stored once; the chunk is then sorted by three stable rounds (z, y, x), each
+// round sorting words  axis_index << bits_idx | index  built in the order of the previous round (LSD
+// over axes), and the reduce pass compares triples instead of word prefixes.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_voxel_index3(const double* __restrict__ xyz, int64_t n, int64_t chunk, double voxel,
+                               const double* __restrict__ origins, int32_t* __restrict__ vidx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t c = i / chunk;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            vidx[i * 3 + a] = (int32_t)(long long)floor(__ddiv_rn(__dsub_rn(xyz[i * 3 + a], origins[c * 3 + a]), voxel));
+    }
+}
+
+__global__ void k_wide_words(const uint64_t* __restrict__ prev /* NULL = identity order */, const int32_t* __restrict__ vidx,
+                             int64_t n, int64_t chunk, int bits_idx, int axis, uint64_t* __restrict__ out) {
+    const uint64_t idx_mask = (1ull << bits_idx) - 1ull;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t c = i / chunk;
+        const uint64_t idx = prev ? (prev[i] & idx_mask) : (uint64_t)(i - c * chunk);
+        out[i] = ((uint64_t)(uint32_t)vidx[(c * chunk + (int64_t)idx) * 3 + axis] << bits_idx) | idx;
+    }
+}
+
+extern "C" int pch_voxel_index3_f64(const double* xyz, int64_t n, int64_t chunk_size, double voxel, const double* origins,
+                                    int32_t* vidx, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && chunk_size > 0 && voxel > 0.0, "bad arguments");
+    if (n == 0) return PCH_OK;
+    PCH_CHECK_ARG(xyz && origins && vidx, "null pointer");
+    if (chunk_size > n) chunk_size = n;
+    int64_t blocks = pch_ceil_div(n, 256), cap = (int64_t)pch_sm_count() * 8;
+    PCH_LAUNCH(st, "k_voxel_index3", k_voxel_index3<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(xyz, n, chunk_size, voxel, origins, vidx));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_voxel_wide_words(const uint64_t* prev, const int32_t* vidx, int64_t n, int64_t chunk_size, int32_t bits_idx,
+                                    int32_t axis, uint64_t* out, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && chunk_size > 0 && bits_idx >= 0 && bits_idx <= 32 && axis >= 0 && axis < 3, "bad arguments");
+    if (n == 0) return PCH_OK;
+    PCH_CHECK_ARG(vidx && out, "null pointer");
+    if (chunk_size > n) chunk_size = n;
+    int64_t blocks = pch_ceil_div(n, 256), cap = (int64_t)pch_sm_count() * 8;
+    PCH_LAUNCH(st, "k_wide_words", k_wide_words<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(prev, vidx, n, chunk_size, bits_idx, axis, out));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

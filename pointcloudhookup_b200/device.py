@@ -174,7 +174,19 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     ph = plan_dev.cpu().numpy()
     plan = VoxelPlan(*[int(v) for v in ph])
     if plan.status != 0:
-        raise ValueError(f"voxel_size is too small: index range needs {plan.key_bits}+{plan.bits_idx} bits (> 64)")
+        # index range does not fit one sort word: decode to float64 and take the wide-key path
+        del xyz16
+        pts = decode_xyz(dl, torch.float64)
+        w = voxel_downsample_points(pts, voxel_size, cs)
+        lat = quantise(w.mean, dl.scales, dl.offsets) if ("lattice" in want or "f32" in want) else None
+        f32 = None
+        if "f32" in want:
+            # astype(float32) of the re-quantised values: encode the lattice into minimal records and run the
+            # ordinary float32 decode kernel over them
+            recs, _ = encode_records(lat, 20)
+            f32 = decode_xyz(DeviceLas(recs, w.count, 20, dl.scales, dl.offsets), torch.float32)
+        return VoxelResult(w.count, w.chunk_counts, w.mean if "mean" in want else None,
+                           lat if "lattice" in want else None, f32, plan=w.plan)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     check(lib.pch_voxel_keys_xyz16(xyz16.data_ptr(), n, cs, sc, of, float(voxel_size), origins.data_ptr(),
                                    C.byref(plan), keys.data_ptr(), st), "pch_voxel_keys_xyz16")
@@ -188,7 +200,7 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     ws_bytes = lib.pch_voxel_reduce_workspace_bytes(n, cs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, dl.rec.data_ptr(), dl.rec_len,
-                               xyz16.data_ptr(), sc, of,
+                               xyz16.data_ptr(), None, sc, of,
                                _ptr(mean), _ptr(lat), _ptr(f32), counts.data_ptr(), total.data_ptr(),
                                ws.data_ptr(), ws_bytes, st), "pch_voxel_reduce")
     m = int(total.item())
@@ -371,18 +383,31 @@ def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Op
     check(lib.pch_voxel_plan_build_f64(xyz.data_ptr(), n, cs, float(voxel_size), scratch.data_ptr(), origins.data_ptr(),
                                        plan_dev.data_ptr(), st), "pch_voxel_plan_build_f64")
     plan = VoxelPlan(*[int(v) for v in plan_dev.cpu().numpy()])
+    if max(plan.bits_x, plan.bits_y, plan.bits_z) > 31:
+        raise ValueError("voxel_size is too small.")          # open3d: index does not fit an int
+    vidx = None
     if plan.status != 0:
-        raise ValueError("voxel_size is too small.")
-    keys = torch.empty(n, dtype=torch.int64, device=dev)
-    check(lib.pch_voxel_keys_f64(xyz.data_ptr(), n, cs, float(voxel_size), origins.data_ptr(), C.byref(plan),
-                                 keys.data_ptr(), st), "pch_voxel_keys_f64")
-    skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
+        # wide keys: three stable sort rounds (z, y, x) over  axis_index << bits_idx | index  words
+        vidx = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        check(lib.pch_voxel_index3_f64(xyz.data_ptr(), n, cs, float(voxel_size), origins.data_ptr(), vidx.data_ptr(), st),
+              "pch_voxel_index3_f64")
+        skeys = None
+        for axis, bits in ((2, plan.bits_z), (1, plan.bits_y), (0, plan.bits_x)):
+            words = torch.empty(n, dtype=torch.int64, device=dev)
+            check(lib.pch_voxel_wide_words(_ptr(skeys), vidx.data_ptr(), n, cs, plan.bits_idx, axis, words.data_ptr(), st),
+                  "pch_voxel_wide_words")
+            skeys = sort_u64_segmented(words, cs, plan.bits_idx, plan.bits_idx + max(bits, 1))
+    else:
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        check(lib.pch_voxel_keys_f64(xyz.data_ptr(), n, cs, float(voxel_size), origins.data_ptr(), C.byref(plan),
+                                     keys.data_ptr(), st), "pch_voxel_keys_f64")
+        skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
     mean = torch.empty((n, 3), dtype=torch.float64, device=dev)
     counts = torch.empty(n_chunks, dtype=torch.int64, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
     wsb = lib.pch_voxel_reduce_workspace_bytes(n, cs)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, xyz.data_ptr(), 0, None, None, None,
+    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, xyz.data_ptr(), 0, None, _ptr(vidx), None, None,
                                mean.data_ptr(), None, None, counts.data_ptr(), total.data_ptr(), ws.data_ptr(), wsb,
                                st), "pch_voxel_reduce")
     m = int(total.item())

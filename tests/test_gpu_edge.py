@@ -88,11 +88,37 @@ def test_process_chunk_matches_oracle_on_arbitrary_floats(cuda_device):
         pts[: n // 4] = np.round(pts[: n // 4], 1)        # exact voxel-boundary / duplicate values
         got = import_PC.process_chunk(pts, v)
         assert np.array_equal(got, ov.voxel_down_sample(pts, v)), (n, v)
-    # documented limit: voxel index bits + point-index bits must fit one 64-bit sort word
-    with pytest.raises(ValueError):
-        import_PC.process_chunk(pts, 1e-3)
+    # index range wider than one 64-bit sort word (18+18+18 voxel bits + 17 index bits): wide-key path
+    got = import_PC.process_chunk(pts, 1e-3)
+    assert np.array_equal(got, ov.voxel_down_sample(pts, 1e-3))
     got32 = import_PC.process_chunk(pts.astype(np.float32), 0.5)   # astype(float64) of float32 input
     assert np.array_equal(got32, ov.voxel_down_sample(pts.astype(np.float32).astype(np.float64), 0.5))
+
+
+def test_wide_keys_through_las_path(cuda_device):
+    """A LAS chunk whose extent/voxel ratio needs more than 64 key bits takes the wide-key fallback and still
+    reproduces the oracle (means, re-quantised lattice, float32 read-back, per-chunk counts)."""
+    from pointcloudhookup_b200 import device as dv
+    from oracle import las_io, voxel as ov
+    from conftest import make_las_dict
+    rng = np.random.default_rng(12)
+    n = 60000
+    rec = np.zeros(n, dtype=np.dtype([("X", "<i4"), ("Y", "<i4"), ("Z", "<i4"), ("pad", "u1", 22)]))
+    for k in "XYZ":
+        rec[k] = rng.integers(-2**30, 2**30, n)
+    rec["X"][: n // 3] = rec["X"][0] + rng.integers(0, 3, n // 3)     # some points share voxels
+    rec["Y"][: n // 3] = rec["Y"][0]
+    rec["Z"][: n // 3] = rec["Z"][0]
+    sc, of = np.array([0.001, 0.001, 0.001]), np.array([0.0, 0.0, 0.0])
+    dl = dv.upload_records(rec.view(np.uint8), n, 34, sc, of)
+    res = dv.voxel_downsample(dl, 0.01, 25000, want=("mean", "lattice", "f32"))   # 2^31 mm / 10 mm -> 28 bits per axis
+    las = make_las_dict(rec, sc, of)
+    ref, cnt = ov.downsample_las_arrays(las, 0.01, 25000)
+    assert res.count == len(ref) and np.array_equal(res.chunk_counts.cpu().numpy(), cnt)
+    assert np.array_equal(res.mean.cpu().numpy(), ref)
+    lat = np.stack([las_io.quantise(ref[:, i], sc[i], of[i]) for i in range(3)], 1)
+    assert np.array_equal(res.lattice.cpu().numpy(), lat)
+    assert np.array_equal(res.f32.cpu().numpy(), (lat.astype(np.float64) * sc + of).astype(np.float32))
 
 
 def test_negative_scale_and_offsets(cuda_device):
@@ -119,7 +145,7 @@ def test_errors(cuda_device, tmp_path):
         import_PC.process_chunk(np.zeros((4, 3)), 0.0)             # open3d: voxel_size <= 0
     with pytest.raises(ValueError):
         import_PC.process_chunk(np.zeros((4, 2)), 0.1)
-    # index range that cannot be packed: huge extent with a tiny voxel
+    # open3d's own limit: the voxel index must fit an int
     pts = np.array([[0.0, 0.0, 0.0], [1e9, 1e9, 1e9]])
     with pytest.raises(ValueError):
         import_PC.process_chunk(pts, 1e-4)

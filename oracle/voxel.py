@@ -31,16 +31,19 @@ def voxel_down_sample(points, voxel_size, return_groups=False):
         return (out, np.zeros((0, 3), np.int64), np.zeros(0, np.int64)) if return_groups else out
     idx = voxel_indices(p, voxel_size)
     ext = idx.max(axis=0) + 1
-    assert float(ext[0]) * float(ext[1]) * float(ext[2]) < 2**62
-    key = (idx[:, 0] * ext[1] + idx[:, 1]) * ext[2] + idx[:, 2]
-    ukey, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
-    m = ukey.size
+    if float(ext[0]) * float(ext[1]) * float(ext[2]) < 2**62:
+        key = (idx[:, 0] * ext[1] + idx[:, 1]) * ext[2] + idx[:, 2]
+        ukey, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+        uidx = np.stack([ukey // (ext[1] * ext[2]), (ukey // ext[2]) % ext[1], ukey % ext[2]], axis=1)
+    else:  # index range too wide to pack: row-wise unique is the same lexicographic (ix, iy, iz) order
+        uidx, inv, cnt = np.unique(idx, axis=0, return_inverse=True, return_counts=True)
+        inv = inv.reshape(-1)
+    m = uidx.shape[0]
     means = np.empty((m, 3))
     for a in range(3):
         # bincount adds weights one by one in input order: the in-order float64 running sum
         means[:, a] = np.bincount(inv, weights=p[:, a], minlength=m) / cnt.astype(np.float64)
     if return_groups:
-        uidx = np.stack([ukey // (ext[1] * ext[2]), (ukey // ext[2]) % ext[1], ukey % ext[2]], axis=1)
         return means, uidx, cnt
     return means
 

@@ -166,3 +166,47 @@ def test_grid_min_ground_matches_self_oracle(cuda_device):
     ek, egz = og.grid_min_keep_mask(p, 2.0, 3.0)
     assert np.array_equal(gz.cpu().numpy(), egz)
     assert np.array_equal(keep.cpu().numpy().astype(bool), ek)
+
+
+def test_dbscan_randomised_against_sklearn(cuda_device):
+    """Random clouds, random eps / min_samples / chunk sizes (ragged last chunk, chunks smaller than a tile, a
+    single chunk), mixtures of dense blobs, sheets, lines and uniform noise: labels must equal scikit-learn's
+    chunk by chunk, including the running label offset."""
+    import torch
+    from sklearn.cluster import DBSCAN
+    from pointcloudhookup_b200 import device as dv
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        n = int(rng.integers(200, 60000))
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            k = int(rng.integers(50, max(60, n // 3)))
+            kind = rng.integers(0, 4)
+            c = rng.uniform(-200, 200, 3)
+            if kind == 0:
+                parts.append(c + rng.normal(0, rng.uniform(0.5, 6), (k, 3)))                       # blob
+            elif kind == 1:
+                parts.append(c + rng.uniform(-40, 40, (k, 3)) * np.array([1, 1, 0.01]))            # sheet
+            elif kind == 2:
+                t = rng.uniform(0, 1, (k, 1))
+                parts.append(c + t * rng.uniform(-150, 150, 3) + rng.normal(0, 0.2, (k, 3)))        # line
+            else:
+                parts.append(rng.uniform(-250, 250, (k, 3)))                                        # noise
+        pts = np.concatenate(parts)[:n].astype(np.float32)
+        pts = pts[rng.permutation(len(pts))]
+        if trial % 5 == 0:
+            pts = np.round(pts * 2) / 2            # lattice data: exact distance ties
+        eps = float(rng.choice([0.75, 2.0, 3.5, 8.0, 10.0]))
+        ms = int(rng.choice([3, 5, 20, 50, 80]))
+        chunk = int(rng.choice([len(pts), 50000, 4097, 1500, 997]))
+        res = dv.dbscan_chunked(torch.from_numpy(pts).to(cuda_device), eps, ms, chunk)
+        exp = np.full(len(pts), -1, np.int32)
+        cur = 0
+        for s in range(0, len(pts), chunk):
+            lab = DBSCAN(eps=eps, min_samples=ms, algorithm="ball_tree").fit(pts[s:s + chunk]).labels_
+            lab[lab != -1] += cur
+            exp[s:s + chunk] = lab
+            cur = lab.max() + 1 if (lab != -1).any() else cur
+        got = res.labels.cpu().numpy()
+        assert np.array_equal(got, exp), (trial, n, eps, ms, chunk, int((got != exp).sum()))
+        assert res.n_clusters == cur

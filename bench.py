@@ -353,6 +353,22 @@ def run_b200(args):
                    "GBps": (model.get(k) / ((v[1] / v[0]) / 1e3) / 1e9) if model.get(k) else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
+    # per-stage device time (sum of the stage's kernels, live events) -> input points/s per stage
+    stage_of = {"voxel_downsample": ("k_chunk_minmax", "k_init_minmax", "k_voxel_plan", "k_voxel_keys", "k_voxel_keys16",
+                                     "k_voxel_reduce"),
+                "ground": ("k_sum_", "k_seq_sum", "k_centroid", "k_shift", "k_sel_", "k_compact", "k_grid_", "k_minmax_f32"),
+                "tower": ("k_db_",), "geoid_crs": ("k_las_geodetic", "k_gk_inverse", "k_geoid_shift")}
+    stages = {}
+    sort_ms = sum(v[1] for k, v in prof.items() if k in ("k_hist", "k_scan", "k_pass")) / args.steps
+    for st_name, prefixes in stage_of.items():
+        ms_st = sum(v[1] for k, v in prof.items() if any(k.startswith(pf) for pf in prefixes)) / args.steps
+        if st_name == "voxel_downsample" and (pv + pd):
+            ms_st += sort_ms * (n * pv) / max(1, n * pv + info.get("G", 0) * pd)      # the voxel sort's share of k_pass
+        if st_name == "tower" and (pv + pd):
+            ms_st += sort_ms * (info.get("G", 0) * pd) / max(1, n * pv + info.get("G", 0) * pd)
+        if ms_st > 0:
+            stages[st_name] = {"ms_per_step": ms_st, "input_points_per_s": n / (ms_st / 1e3)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (voxel means, distances) / f32 (tower stage) / int32 lattice",
@@ -362,7 +378,7 @@ def run_b200(args):
                        "parallelism": f"tile-per-gpu x{world}, tower merge by all_gather",
                        "l2": "inputs (3.4 GB records per step) far exceed the 126 MB L2; no flush needed"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-            "stage_info": info, "kernels": kernels}
+            "stages": stages, "stage_info": info, "kernels": kernels}
     if rank == 0:
         line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline(args, cfg, bounded=True)
         print(json.dumps(line))

@@ -213,6 +213,14 @@ int pch_dbscan_run(const float* xyz_dev, int64_t G, int64_t chunk, double eps, i
                    int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
                    void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
+/* `cluster_points = filtered_points[all_labels == label]` for every label at once
+ * (utils/tower_extraction.py:133-134): pch_label_words builds (label << 32 | index) words (noise sorts
+ * last), pch_sort_u64_segmented orders them by label (stable), pch_gather_rows_f32 gathers the rows of
+ * the first m words; cluster k then occupies rows [sum(count[:k]), sum(count[:k+1])). */
+int pch_label_words(const int32_t* labels_dev, int64_t G, uint64_t* words_dev, pch_stream_t stream);
+int pch_gather_rows_f32(const float* xyz_dev, const uint64_t* words_dev, int64_t m, float* out_dev,
+                        int32_t* src_index_dev /* nullable */, pch_stream_t stream);
+
 /* ---------------------------------------------------------------- geoid shift + CRS */
 
 typedef struct pch_geoid_grid {

@@ -1087,3 +1087,54 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// cluster-major point order: what `filtered_points[all_labels == label]` (utils/tower_extraction.py:
+// 133-134) gathers for every label, done once for all labels: words (label << 32 | index) of the
+// labelled points are sorted by label (stable, so the index order inside a cluster is preserved) and
+// the rows gathered.  The reference's per-cluster mask scans are O(G*K); this is O(G).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_label_words(const int32_t* __restrict__ labels, int64_t G, uint64_t* __restrict__ words) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < G; i += stride) {
+        const int32_t l = labels[i];
+        // noise (-1) gets the largest label value so it sorts to the end
+        words[i] = ((uint64_t)(uint32_t)(l < 0 ? 0x7fffffff : l) << 32) | (uint64_t)i;
+    }
+}
+
+__global__ void k_gather_rows(const float* __restrict__ P, const uint64_t* __restrict__ words, int64_t m,
+                              float* __restrict__ out, int32_t* __restrict__ src_idx) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) {
+        const int64_t j = (int64_t)(words[i] & 0xffffffffull);
+        out[i * 3 + 0] = P[j * 3 + 0];
+        out[i * 3 + 1] = P[j * 3 + 1];
+        out[i * 3 + 2] = P[j * 3 + 2];
+        if (src_idx) src_idx[i] = (int32_t)j;
+    }
+}
+
+extern "C" int pch_label_words(const int32_t* labels, int64_t G, uint64_t* words, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(G >= 0 && G < (1ll << 31), "bad size");
+    if (G == 0) return PCH_OK;
+    PCH_CHECK_ARG(labels && words, "null pointer");
+    PCH_LAUNCH(st, "k_label_words", k_label_words<<<db_grid(G, 256), 256, 0, st>>>(labels, G, words));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_gather_rows_f32(const float* P, const uint64_t* words, int64_t m, float* out, int32_t* src_idx,
+                                   pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(m >= 0, "bad size");
+    if (m == 0) return PCH_OK;
+    PCH_CHECK_ARG(P && words && out, "null pointer");
+    PCH_LAUNCH(st, "k_gather_rows", k_gather_rows<<<db_grid(m, 256), 256, 0, st>>>(P, words, m, out, src_idx));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}

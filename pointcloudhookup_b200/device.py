@@ -412,3 +412,25 @@ def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Op
                                st), "pch_voxel_reduce")
     m = int(total.item())
     return VoxelResult(m, counts, mean[:m], plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_})
+
+
+def cluster_major_points(points: torch.Tensor, labels: torch.Tensor, counts: np.ndarray):
+    """All `points[labels == k]` at once: ((L,3) float32 rows grouped by label in ascending label order, each
+    group in original order; int64 offsets [K+1]).  L = number of labelled points."""
+    assert points.dtype == torch.float32 and points.is_contiguous() and labels.dtype == torch.int32
+    lib = _native.lib()
+    G = labels.numel()
+    K = len(counts)
+    offsets = np.zeros(K + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    L = int(offsets[-1])
+    out = torch.empty((L, 3), dtype=torch.float32, device=points.device)
+    if L == 0:
+        return out, offsets
+    words = torch.empty(G, dtype=torch.int64, device=points.device)
+    check(lib.pch_label_words(labels.data_ptr(), G, words.data_ptr(), _stream()), "pch_label_words")
+    bits = max(1, int(K).bit_length())
+    sw = sort_u64_segmented(words, G, 32, 32 + min(31, bits))
+    check(lib.pch_gather_rows_f32(points.data_ptr(), sw.data_ptr(), L, out.data_ptr(), None, _stream()),
+          "pch_gather_rows_f32")
+    return out, offsets

@@ -162,8 +162,15 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
                  (h_all / w_all > aspect_ratio_threshold)
         order = [l for l in order if ok[l]]
     towers, centres = [], []
-    labels_host = None
-    filtered_host = None
+    grouped = None   # cluster-major copy of the labelled points, built on the device on first use (O(G), not O(G*K))
+
+    def cluster_points(label):
+        nonlocal grouped
+        if grouped is None:
+            grouped = dv.cluster_major_points(stages.filtered, stages.labels, stats["count"][:K])
+        rows, off = grouped
+        return rows[int(off[label]): int(off[label + 1])].cpu().numpy()
+
     for li, label in enumerate(order):
         try:
             st = stats[label]
@@ -182,10 +189,7 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
                 diag = float(np.linalg.norm((st["max"] - st["min"]).astype(np.float64)))
                 if diag <= min_height:
                     continue
-                if labels_host is None:
-                    labels_host = stages.labels.cpu().numpy()
-                    filtered_host = stages.filtered.cpu().numpy()
-                cp = filtered_host[labels_host == label]
+                cp = cluster_points(label)
                 tr, ext = _obb.bounding_box_oriented(cp, ordered=(box == "obb_ordered"))
                 ctr, rot = tr[:3, 3], tr[:3, :3]
                 height, width = ext[2], max(ext[0], ext[1])
@@ -204,10 +208,7 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
             if dup:
                 continue
             if cp is None and want_points:
-                if labels_host is None:
-                    labels_host = stages.labels.cpu().numpy()
-                    filtered_host = stages.filtered.cpu().numpy()
-                cp = filtered_host[labels_host == label]
+                cp = cluster_points(label)
             towers.append({"label": int(label), "center": centre, "rotation": rot, "extent": ext,
                            "height": height, "width": width, "north_angle": north_angle_of(rot), "points": cp})
             centres.append(centre)

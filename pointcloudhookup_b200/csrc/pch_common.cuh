@@ -118,13 +118,13 @@ __device__ __forceinline__ void pch_st_volatile_u32(uint32_t* p, uint32_t v) {
 
 // 64-bit status: [63:62] flag, [61:0] value.  Called by ONE thread per tile.
 // `first` is the first tile of the scan domain (tile == first publishes inclusive directly).
-__device__ __forceinline__ uint64_t pch_lookback_u64(uint64_t* status, int64_t tile, int64_t first, uint64_t aggregate,
-                                                     int* err_flag) {
-    if (tile == first) {
-        pch_st_volatile_u64(&status[tile], (PCH_FLAG_INCL << 62) | aggregate);
-        return 0;
-    }
-    pch_st_volatile_u64(&status[tile], (PCH_FLAG_AGG << 62) | aggregate);
+// Split in two so a kernel can publish its aggregate early, do its heavy work, and only then walk back.
+__device__ __forceinline__ void pch_lookback_publish_u64(uint64_t* status, int64_t tile, int64_t first, uint64_t aggregate) {
+    pch_st_volatile_u64(&status[tile], ((tile == first ? PCH_FLAG_INCL : PCH_FLAG_AGG) << 62) | aggregate);
+}
+__device__ __forceinline__ uint64_t pch_lookback_walk_u64(uint64_t* status, int64_t tile, int64_t first, uint64_t aggregate,
+                                                          int* err_flag) {
+    if (tile == first) return 0;
     uint64_t excl = 0;
     // windowed walk: PCH_LB_WIN predecessors are fetched with independent loads, then consumed in order
     int64_t t = tile - 1;
@@ -154,6 +154,11 @@ __device__ __forceinline__ uint64_t pch_lookback_u64(uint64_t* status, int64_t t
     }
     pch_st_volatile_u64(&status[tile], (PCH_FLAG_INCL << 62) | (excl + aggregate));
     return excl;
+}
+__device__ __forceinline__ uint64_t pch_lookback_u64(uint64_t* status, int64_t tile, int64_t first, uint64_t aggregate,
+                                                     int* err_flag) {
+    pch_lookback_publish_u64(status, tile, first, aggregate);
+    return pch_lookback_walk_u64(status, tile, first, aggregate, err_flag);
 }
 
 // ---------------------------------------------------------------------------------------------

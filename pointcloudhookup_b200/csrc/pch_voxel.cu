@@ -330,18 +330,13 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         tile_total += c;
     }
     if (tid == 0) {
-        s_tile_off = pch_lookback_u64(status, tile, 0, tile_total, err);
+        pch_lookback_publish_u64(status, tile, 0, tile_total);   // publish early: successors never wait on our compute
         if (chunk_counts && tile_total) atomicAdd(&chunk_counts[chunk], (unsigned long long)tile_total);
-        if (tile == g.total_tiles - 1 && total_out) *total_out = (long long)(s_tile_off + tile_total);
     }
-    __syncthreads();
-    const uint64_t tile_off = s_tile_off;
 
-#pragma unroll
-    for (int j = 0; j < VR_ROWS; ++j) {
-        if (!(head_bits & (1u << j))) continue;
-        const int i = wbase + j * 32 + lane;
-        const uint64_t m = tile_off + wprefix + row_rank[j];
+    // One voxel = one run of equal key; its head thread folds the run IN INPUT ORDER (float64 running sum),
+    // mean = sum / count, then the LAS re-quantisation.  Returns the mean and the lattice triple.
+    auto fold_run = [&](int i, double& mx, double& my, double& mz, int& qx, int& qy, int& qz) {
         const uint64_t vkey = s_keys[i + 1] >> bi;
         const int32_t* vhead = vidx ? vidx + (cstart + (int64_t)(s_keys[i + 1] & idx_mask)) * 3 : nullptr;
         double sx = 0.0, sy = 0.0, sz = 0.0;
@@ -381,22 +376,57 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
             } else if ((k >> bi) != vkey) break;
         }
         const double dn = (double)cntp;
-        const double mx = __ddiv_rn(sx, dn), my = __ddiv_rn(sy, dn), mz = __ddiv_rn(sz, dn);
-        if (mean_out) {
-            mean_out[m * 3 + 0] = mx; mean_out[m * 3 + 1] = my; mean_out[m * 3 + 2] = mz;
+        mx = __ddiv_rn(sx, dn); my = __ddiv_rn(sy, dn); mz = __ddiv_rn(sz, dn);
+        qx = __double2int_rn(__ddiv_rn(__dsub_rn(mx, a.o[0]), a.s[0]));
+        qy = __double2int_rn(__ddiv_rn(__dsub_rn(my, a.o[1]), a.s[1]));
+        qz = __double2int_rn(__ddiv_rn(__dsub_rn(mz, a.o[2]), a.s[2]));
+    };
+
+    // When only the lattice / float32 outputs are wanted (the fused pipeline), the runs are folded BEFORE the
+    // look-back walk and the lattice triple is parked in the head's own s_xyz slot (nobody else reads a head
+    // slot), so the chain wait overlaps nothing but the final stores.
+    const bool deferred = (ALIGN > 0) && (mean_out == nullptr);
+    if (deferred) {
+#pragma unroll
+        for (int j = 0; j < VR_ROWS; ++j) {
+            if (!(head_bits & (1u << j))) continue;
+            const int i = wbase + j * 32 + lane;
+            double mx, my, mz;
+            int qx, qy, qz;
+            fold_run(i, mx, my, mz, qx, qy, qz);
+            s_xyz[ALIGN > 0 ? i : 0][0] = qx; s_xyz[ALIGN > 0 ? i : 0][1] = qy; s_xyz[ALIGN > 0 ? i : 0][2] = qz;
         }
-        if (lat_out || f32_out) {
-            int qx = __double2int_rn(__ddiv_rn(__dsub_rn(mx, a.o[0]), a.s[0]));
-            int qy = __double2int_rn(__ddiv_rn(__dsub_rn(my, a.o[1]), a.s[1]));
-            int qz = __double2int_rn(__ddiv_rn(__dsub_rn(mz, a.o[2]), a.s[2]));
-            if (lat_out) {
-                lat_out[m * 3 + 0] = qx; lat_out[m * 3 + 1] = qy; lat_out[m * 3 + 2] = qz;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_tile_off = pch_lookback_walk_u64(status, tile, 0, tile_total, err);
+        if (tile == g.total_tiles - 1 && total_out) *total_out = (long long)(s_tile_off + tile_total);
+    }
+    __syncthreads();
+    const uint64_t tile_off = s_tile_off;
+
+#pragma unroll
+    for (int j = 0; j < VR_ROWS; ++j) {
+        if (!(head_bits & (1u << j))) continue;
+        const int i = wbase + j * 32 + lane;
+        const uint64_t m = tile_off + wprefix + row_rank[j];
+        int qx, qy, qz;
+        if (deferred) {
+            qx = s_xyz[ALIGN > 0 ? i : 0][0]; qy = s_xyz[ALIGN > 0 ? i : 0][1]; qz = s_xyz[ALIGN > 0 ? i : 0][2];
+        } else {
+            double mx, my, mz;
+            fold_run(i, mx, my, mz, qx, qy, qz);
+            if (mean_out) {
+                mean_out[m * 3 + 0] = mx; mean_out[m * 3 + 1] = my; mean_out[m * 3 + 2] = mz;
             }
-            if (f32_out) {
-                f32_out[m * 3 + 0] = (float)pch_scaled(qx, a.s[0], a.o[0]);
-                f32_out[m * 3 + 1] = (float)pch_scaled(qy, a.s[1], a.o[1]);
-                f32_out[m * 3 + 2] = (float)pch_scaled(qz, a.s[2], a.o[2]);
-            }
+        }
+        if (lat_out) {
+            lat_out[m * 3 + 0] = qx; lat_out[m * 3 + 1] = qy; lat_out[m * 3 + 2] = qz;
+        }
+        if (f32_out) {
+            f32_out[m * 3 + 0] = (float)pch_scaled(qx, a.s[0], a.o[0]);
+            f32_out[m * 3 + 1] = (float)pch_scaled(qy, a.s[1], a.o[1]);
+            f32_out[m * 3 + 2] = (float)pch_scaled(qz, a.s[2], a.o[2]);
         }
     }
 }

@@ -174,8 +174,22 @@ k_db_cells(const uint64_t* __restrict__ keys, const float* __restrict__ P, DbGeo
         if (w < warp) wprefix += cc;
         total += cc;
     }
+    if (tid == 0) pch_lookback_publish_u64(status, tile, 0, total);
+    // gather the points BEFORE the look-back walk (the chain wait overlaps the loads)
+    float4 pv[DC_ROWS];
+#pragma unroll
+    for (int j = 0; j < DC_ROWS; ++j) {
+        const int i = wbase + j * 32 + lane;
+        pv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < cnt) {
+            const uint64_t k = s_keys[i + 1];
+            const int64_t orig = cstart + (int64_t)(k & idx_mask);
+            pv[j].x = P[orig * 3 + 0]; pv[j].y = P[orig * 3 + 1]; pv[j].z = P[orig * 3 + 2];
+            pv[j].w = __int_as_float((int)(k & idx_mask));
+        }
+    }
     if (tid == 0) {
-        s_off = pch_lookback_u64(status, tile, 0, total, err);
+        s_off = pch_lookback_walk_u64(status, tile, 0, total, err);
         if (tile == total_tiles - 1) {
             *o.n_cells = (long long)(s_off + total);
             o.cell_start[s_off + total] = (int32_t)g.G;
@@ -196,10 +210,7 @@ k_db_cells(const uint64_t* __restrict__ keys, const float* __restrict__ P, DbGeo
         const int64_t orig = cstart + (int64_t)(k & idx_mask);
         o.pt_cell[pos] = (int32_t)cell;
         o.inv_pos[orig] = (int32_t)pos;
-        float4 v;
-        v.x = P[orig * 3 + 0]; v.y = P[orig * 3 + 1]; v.z = P[orig * 3 + 2];
-        v.w = __int_as_float((int)(k & idx_mask));
-        o.spts[pos] = v;
+        o.spts[pos] = pv[j];
         if (head_bits & (1u << j)) {
             o.cell_start[cell] = (int32_t)pos;
             o.cell_key[cell] = k >> bi;

@@ -729,23 +729,39 @@ k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uin
         if (w < warp) wprefix += c;
         total += c;
     }
+    if (tid == 0) pch_lookback_publish_u64(status, tile, 0, total);
+    // fetch the kept rows BEFORE the look-back walk: the chain wait then overlaps the loads, and only the
+    // stores are left once the offset is known
+    float vx[CP_ROWS], vy[CP_ROWS], vz[CP_ROWS];
+    if (out_xyz) {
+        const float cx = centroid ? centroid[0] : 0.f, cy = centroid ? centroid[1] : 0.f, cz = centroid ? centroid[2] : 0.f;
+#pragma unroll
+        for (int j = 0; j < CP_ROWS; ++j) {
+            vx[j] = vy[j] = vz[j] = 0.f;
+            if (keep_bits & (1u << j)) {
+                const int64_t i = start + wbase + j * 32 + lane;
+                vx[j] = __fsub_rn(xyz[i * 3 + 0], cx);
+                vy[j] = __fsub_rn(xyz[i * 3 + 1], cy);
+                vz[j] = __fsub_rn(xyz[i * 3 + 2], cz);
+            }
+        }
+    }
     if (tid == 0) {
-        s_off = pch_lookback_u64(status, tile, 0, total, err);
+        s_off = pch_lookback_walk_u64(status, tile, 0, total, err);
         if (tile == n_tiles - 1) *count_out = (long long)(s_off + total);
     }
     __syncthreads();
     const uint64_t off = s_off + wprefix;
     if (!out_xyz && !out_src) return;
-    const float cx = centroid ? centroid[0] : 0.f, cy = centroid ? centroid[1] : 0.f, cz = centroid ? centroid[2] : 0.f;
 #pragma unroll
     for (int j = 0; j < CP_ROWS; ++j) {
         if (!(keep_bits & (1u << j))) continue;
         int64_t i = start + wbase + j * 32 + lane;
         uint64_t o = off + rank[j];
         if (out_xyz) {
-            out_xyz[o * 3 + 0] = __fsub_rn(xyz[i * 3 + 0], cx);
-            out_xyz[o * 3 + 1] = __fsub_rn(xyz[i * 3 + 1], cy);
-            out_xyz[o * 3 + 2] = __fsub_rn(xyz[i * 3 + 2], cz);
+            out_xyz[o * 3 + 0] = vx[j];
+            out_xyz[o * 3 + 1] = vy[j];
+            out_xyz[o * 3 + 2] = vz[j];
         }
         if (out_src) out_src[o] = (int32_t)i;
     }

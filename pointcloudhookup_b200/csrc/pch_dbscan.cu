@@ -500,30 +500,55 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
     // "already in one set" test instead of being searched exhaustively.
     const int64_t U = *U_dev;
     const uint64_t zmask = (1ull << g.bits_z) - 1ull;
-    // one warp per (cell A, neighbour column); only pairs with B > A are examined
+    // one warp per cell A.  The 25 neighbour columns are inspected by 25 lanes in parallel (the table
+    // and key look-ups are a chain of dependent loads: doing them lane-parallel instead of one warp task
+    // per column removes most of this kernel's latency); the surviving (A, B) pairs, B > A, are queued
+    // in shared memory and then processed by the whole warp one at a time.
     __shared__ float3 s_la[256 / 32][UN_CAP];
+    __shared__ int2 s_cand[256 / 32][128];
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double slack = g.eps2 * (1.0 + 1e-12);  // pruning must never drop a true neighbour pair
-    for (; w < U * 25; w += nw) {
-        const int32_t A = (int32_t)(w / 25);
-        const int col = (int)(w - (int64_t)A * 25);
+    for (; w < U; w += nw) {
+        const int32_t A = (int32_t)w;
         if (info[A].n_core == 0) continue;
-        const int ox = col / 5 - 2, oy = col % 5 - 2;
-        const bool near_xy = ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1;
-        if (pass == 0 && !near_xy) continue;
         const long long czA = (long long)(cell_key[A] & zmask);
         const unsigned long long mA = cell_mask[A];
-        const int32_t f = nbr_first[w];
-        const int nc = nbr_cnt[w];
-        for (int k = 0; k < nc; ++k) {
-            const int32_t B = f + k;
-            if (B <= A) continue;
-            if (info[B].n_core == 0) continue;
-            const long long dz = (long long)(cell_key[B] & zmask) - czA;
-            const bool near = near_xy && dz >= -1 && dz <= 1;
-            if ((pass == 0) != near) continue;
+        int n_cand = 0;
+        {
+            int32_t f = 0;
+            int nc = 0, ox_l = 0, oy_l = 0;
+            bool near_xy_l = false;
+            if (lane < 25) {
+                f = nbr_first[(int64_t)A * 25 + lane];
+                nc = nbr_cnt[(int64_t)A * 25 + lane];
+                ox_l = lane / 5 - 2; oy_l = lane % 5 - 2;
+                near_xy_l = ox_l >= -1 && ox_l <= 1 && oy_l >= -1 && oy_l <= 1;
+                if (pass == 0 && !near_xy_l) nc = 0;
+            }
+            for (int k = 0; k < 5; ++k) {
+                bool valid = false;
+                const int32_t Bc = f + k;
+                int dzl = 0;
+                if (k < nc && Bc > A && info[Bc].n_core > 0) {
+                    dzl = (int)((long long)(cell_key[Bc] & zmask) - czA);
+                    const bool near = near_xy_l && dzl >= -1 && dzl <= 1;
+                    valid = (pass == 0) == near;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+                if (valid)
+                    s_cand[warp_in_block][n_cand + __popc(bal & ((1u << lane) - 1u))] =
+                        make_int2(Bc, (ox_l + 2) | ((oy_l + 2) << 3) | ((dzl + 2) << 6));
+                n_cand += __popc(bal);
+            }
+            __syncwarp();
+        }
+        for (int ci = 0; ci < n_cand; ++ci) {
+            const int2 cd = s_cand[warp_in_block][ci];
+            const int32_t B = cd.x;
+            const int ox = (cd.y & 7) - 2, oy = ((cd.y >> 3) & 7) - 2;
+            const long long dz = (long long)((cd.y >> 6) & 7) - 2;
             int same = 0;  // already joined? (work saving only; decided by lane 0 so the warp stays uniform)
             if (lane == 0) same = uf_find(info, A) == uf_find(info, B);
             same = __shfl_sync(0xffffffffu, same, 0);

@@ -136,7 +136,8 @@ int pch_sort_u64_segmented(uint64_t* keys_dev, uint64_t* tmp_dev, int64_t n, int
  * mean = sum/count (open3d AccumulatedPoint, via ui/import_PC.py:12-13).  Any of the three outputs
  * may be NULL:  mean_dev (m,3) f64 = process_chunk's return;  lattice_dev (m,3) int32 = the
  * re-quantised values `las.x = final_points[:,0]` stores (ui/import_PC.py:61-63);  f32_dev (m,3) =
- * astype(float32) of that file read back (utils/tower_extraction.py:60-62).
+ * astype(float32) of that file read back (utils/tower_extraction.py:60-62);  z32_dev (m) = the z
+ * column of f32_dev as a dense array (the input of the percentile select, :82).
  * chunk_counts_dev[n_chunks] and total_dev[1] (int64) receive the voxel counts. */
 size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size);
 int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_size, int32_t bits_idx,
@@ -144,8 +145,8 @@ int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_s
                      const int32_t* xyz16_dev /* nullable: pch_voxel_keys' packed copy; gathers read it instead of rec_dev */,
                      const int32_t* vidx_dev /* nullable: (n,3) voxel indices for the wide-key path (see below) */,
                      const double* scales, const double* offsets,
-                     double* mean_dev, int32_t* lattice_dev, float* f32_dev, int64_t* chunk_counts_dev,
-                     int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+                     double* mean_dev, int32_t* lattice_dev, float* f32_dev, float* z32_dev /* nullable */,
+                     int64_t* chunk_counts_dev, int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
 /* ---------------------------------------------------------------- tower extraction, stages A/B */
 
@@ -163,6 +164,11 @@ int pch_f32_centroid(const float* xyz_dev, int64_t m, float* sums3_dev, float* c
 int pch_f32_shift(const float* xyz_dev, int64_t m, const float* centroid3_dev, float* zs_dev,
                   float* shifted_dev, pch_stream_t stream);
 
+/* One column of an (m,3) float32 cloud as a dense (m) array (z_values = points[:, 2],
+ * utils/tower_extraction.py:81, before the shift: x -> float32(x - c) is monotone, so the order
+ * statistics of the shifted column are the shifted order statistics of the raw column). */
+int pch_f32_column(const float* xyz_dev, int64_t m, int32_t column, float* out_dev, pch_stream_t stream);
+
 /* The two order statistics np.percentile(z_values, 25) interpolates between
  * (utils/tower_extraction.py:82): out2_dev = {sorted[rank0], sorted[rank1]} exactly. */
 size_t pch_select_workspace_bytes(void);
@@ -170,7 +176,8 @@ int pch_select_f32(const float* v_dev, int64_t n, int64_t rank0, int64_t rank1, 
                    void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
 /* filtered_points = points[z_values > thr] (utils/tower_extraction.py:83-89), order preserving.
- * keep[i] = zs_dev[i] > thr, or keep_mask_dev[i] != 0 when zs_dev is NULL.  out_xyz_dev (kept,3)
+ * keep[i] = zs_dev[i] > thr, or keep_mask_dev[i] != 0 when zs_dev is NULL, or — both NULL —
+ * float32(xyz[i].z - centroid.z) > thr computed on the fly (no shifted-z array needed).  out_xyz_dev (kept,3)
  * receives xyz - centroid (float32; centroid3_dev may be NULL = no shift), out_src_dev the source
  * index of every kept point, out_mask_dev (m) the keep flags; each may be NULL.  count_dev: int64. */
 size_t pch_compact_workspace_bytes(int64_t m);
@@ -265,6 +272,17 @@ int pch_las_geodetic(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const d
  * every pair of match_towers' double loop (:168-192): out_dev[i*n2 + j], degrees in. */
 int pch_haversine_matrix(const double* lat1_dev, const double* lon1_dev, int64_t n1, const double* lat2_dev,
                          const double* lon2_dev, int64_t n2, double* out_dev, pch_stream_t stream);
+
+/* ---------------------------------------------------------------- host staging for the PCIe hop */
+
+/* HOST function (no device work): gathers the X,Y,Z int32 triple at bytes 0..11 of each of the n
+ * `rec_len`-byte LAS point records — the only fields laspy's las.x/.y/.z read (ui/import_PC.py:47-48;
+ * utils/tower_extraction.py:60-62) — into a dense 12-byte record stream in `xyz12_host` (normally pinned
+ * staging memory; 16-byte aligned), with `n_threads` host threads (<= 0: all).  The result is a valid
+ * record stream with rec_len = 12 for every device entry point above, so a 34-byte PDRF-3 file crosses
+ * PCIe as 12 bytes per point.  No arithmetic is performed on the host. */
+int pch_host_pack_xyz(const void* records_host, int64_t n, int32_t rec_len, void* xyz12_host,
+                      int32_t n_threads);
 
 #ifdef __cplusplus
 }

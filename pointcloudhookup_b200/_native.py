@@ -50,7 +50,7 @@ SIGNATURES = {
     "pch_sort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "pch_sort_u64_segmented": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "pch_voxel_reduce_workspace_bytes": (_sz, [_i64, _i64]),
-    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _p, _p, _d3, _d3, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _p, _p, _d3, _d3, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "pch_voxel_index3_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
     "pch_voxel_wide_words": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p]),
 }
@@ -63,6 +63,7 @@ SIGNATURES.update({
     "pch_f32_centroid_workspace_bytes": (_sz, [_i64]),
     "pch_f32_centroid": (C.c_int, [_p, _i64, _p, _p, _p, _sz, _p]),
     "pch_f32_shift": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "pch_f32_column": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "pch_select_workspace_bytes": (_sz, []),
     "pch_select_f32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "pch_compact_workspace_bytes": (_sz, [_i64]),
@@ -92,6 +93,10 @@ SIGNATURES.update({
     "pch_gk_inverse": (C.c_int, [_p, _p, _i64, C.POINTER(TmParams), _p, _p, _p]),
     "pch_las_geodetic": (C.c_int, [_p, _i64, _i32, _d3, _d3, C.POINTER(TmParams), _p, C.POINTER(GeoidGrid),
                                    _i32, _i32, _i32, _i32, _f64, _p, _p]),
+})
+
+SIGNATURES.update({
+    "pch_host_pack_xyz": (C.c_int, [_p, _i64, _i32, _p, _i32]),
 })
 
 _lib = None

@@ -572,6 +572,12 @@ __global__ void k_shift(const float* __restrict__ xyz, int64_t m, const float* _
     }
 }
 
+__global__ void k_column(const float* __restrict__ xyz, int64_t m, int col, float* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) out[i] = xyz[i * 3 + col];
+}
+
 static unsigned grid_for(int64_t n, int threads, int per_sm) {
     int64_t b = pch_ceil_div(n, threads);
     int64_t cap = (int64_t)pch_sm_count() * per_sm;
@@ -587,6 +593,16 @@ extern "C" int pch_f32_shift(const float* xyz, int64_t m, const float* centroid3
     if (m == 0) return PCH_OK;
     PCH_CHECK_ARG(xyz && centroid3 && (zs || shifted), "null pointer");
     PCH_LAUNCH(st, "k_shift", k_shift<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, centroid3, zs, shifted));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_f32_column(const float* xyz, int64_t m, int32_t column, float* out, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(m >= 0 && column >= 0 && column < 3, "bad m/column");
+    if (m == 0) return PCH_OK;
+    PCH_CHECK_ARG(xyz && out, "null pointer");
+    PCH_LAUNCH(st, "k_column", k_column<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, column, out));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -690,7 +706,8 @@ extern "C" int pch_select_f32(const float* v, int64_t n, int64_t rank0, int64_t 
 
 extern "C" size_t pch_compact_workspace_bytes(int64_t m) { return 256 + (size_t)(pch_ceil_div(m > 0 ? m : 1, CP_TILE)) * 8; }
 
-// keep[i] = zs[i] > thr  (mode 0)   or   keep_mask[i] != 0 (mode 1, zs == nullptr)
+// keep[i] = zs[i] > thr  (mode 0)   or   keep_mask[i] != 0 (mode 1, zs == nullptr)   or
+// float32(z[i] - centroid.z) > thr from the cloud itself (mode 2, zs == keep_mask == nullptr)
 __global__ void __launch_bounds__(CP_THREADS)
 k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask,
           int64_t m, const float* __restrict__ centroid, float thr, float* __restrict__ out_xyz,
@@ -709,11 +726,12 @@ k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uin
     const int wbase = warp * (32 * CP_ROWS);
     uint32_t rank[CP_ROWS];
     uint32_t keep_bits = 0, wtotal = 0;
+    const float cz_keep = (!zs && !keep_mask && centroid) ? centroid[2] : 0.f;
 #pragma unroll
     for (int j = 0; j < CP_ROWS; ++j) {
         int64_t i = start + wbase + j * 32 + lane;
         bool keep = false;
-        if (i < m) keep = zs ? (zs[i] > thr) : (keep_mask[i] != 0);
+        if (i < m) keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(xyz[i * 3 + 2], cz_keep) > thr));
         if (out_mask && i < m) out_mask[i] = keep ? 1 : 0;
         uint32_t b = __ballot_sync(0xffffffffu, keep);
         rank[j] = wtotal + __popc(b & ((1u << lane) - 1u));
@@ -777,7 +795,7 @@ extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8
     PCH_CHECK_ARG(m < (1ll << 31), "more than 2^31-1 points per compaction");
     PCH_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int64_t), st));
     if (m == 0) return PCH_OK;
-    PCH_CHECK_ARG(xyz && (zs || keep_mask), "null pointer");
+    PCH_CHECK_ARG(xyz, "null pointer");
     size_t need = pch_compact_workspace_bytes(m);
     if (workspace_bytes < need) {
         pch_set_error("compact workspace too small: %zu < %zu", workspace_bytes, need);

@@ -234,7 +234,7 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
                const int4* __restrict__ xyz16, const int32_t* __restrict__ vidx /* (n,3) or NULL: wide keys */,
                PchAffine3 a,
                double* __restrict__ mean_out, int32_t* __restrict__ lat_out, float* __restrict__ f32_out,
-               unsigned long long* __restrict__ chunk_counts, long long* __restrict__ total_out,
+               float* __restrict__ z32_out, unsigned long long* __restrict__ chunk_counts, long long* __restrict__ total_out,
                uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
     __shared__ uint64_t s_keys[VR_TILE + 1];  // [0] = key preceding the tile
     __shared__ int s_xyz[ALIGN > 0 ? VR_TILE : 1][3];  // lattice coordinates of the tile's points (LAS source)
@@ -428,19 +428,20 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
             f32_out[m * 3 + 1] = (float)pch_scaled(qy, a.s[1], a.o[1]);
             f32_out[m * 3 + 2] = (float)pch_scaled(qz, a.s[2], a.o[2]);
         }
+        if (z32_out) z32_out[m] = (float)pch_scaled(qz, a.s[2], a.o[2]);
     }
 }
 
 extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
                                 const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const int32_t* vidx,
                                 const double* scales, const double* offsets,
-                                double* mean_out, int32_t* lat_out, float* f32_out, int64_t* chunk_counts,
-                                int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+                                double* mean_out, int32_t* lat_out, float* f32_out, float* z32_out,
+                                int64_t* chunk_counts, int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(n >= 0 && chunk_size > 0, "bad n/chunk_size");
     PCH_CHECK_ARG(rec_len == 0 || (rec_len >= 12 && rec_len <= 256), "bad record length");
     PCH_CHECK_ARG(bits_idx >= 0 && bits_idx <= 63, "bad bits_idx");
-    PCH_CHECK_ARG(rec_len != 0 || (lat_out == nullptr && f32_out == nullptr),
+    PCH_CHECK_ARG(rec_len != 0 || (lat_out == nullptr && f32_out == nullptr && z32_out == nullptr),
                   "float64 point input has no LAS lattice: only mean_dev is available");
     PchAffine3 a;
     int rc = make_affine3(scales, offsets, a);
@@ -469,7 +470,7 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     int al = rec_len == 0 ? 0 : pch_rec_align(rec_len);
 #define LAUNCH_RED(A)                                                                                          \
     PCH_LAUNCH(st, "k_voxel_reduce", k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
-        keys, g, rec, (const int4*)xyz16, vidx, a, mean_out, lat_out, f32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
+        keys, g, rec, (const int4*)xyz16, vidx, a, mean_out, lat_out, f32_out, z32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
         status, counter, err))
     if (al == 4) LAUNCH_RED(4);
     else if (al == 2) LAUNCH_RED(2);

@@ -143,12 +143,25 @@ class VoxelResult:
     f32: Optional[torch.Tensor] = None      # (M,3) float32 of the re-quantised values
     plan: Optional[dict] = None
     sorted_keys: Optional[torch.Tensor] = None
+    z32: Optional[torch.Tensor] = None      # (M,) the z column of f32 as a dense array
+
+
+class VoxelSink:
+    """Preallocated float32 outputs that several voxel_downsample calls append to (the sliced host-buffer
+    pipeline): rows [0, count) are filled."""
+
+    def __init__(self, capacity: int, device, want_z: bool = True):
+        self.f32 = torch.empty((int(capacity), 3), dtype=torch.float32, device=device)
+        self.z32 = torch.empty(int(capacity), dtype=torch.float32, device=device) if want_z else None
+        self.count = 0
 
 
 def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
-                     want: Sequence[str] = ("mean",), keep_keys: bool = False) -> VoxelResult:
+                     want: Sequence[str] = ("mean",), keep_keys: bool = False,
+                     sink: Optional[VoxelSink] = None) -> VoxelResult:
     """open3d voxel_down_sample over consecutive chunk_size-point slices of the records
-    (ui/import_PC.py:45-60), entirely on the device."""
+    (ui/import_PC.py:45-60), entirely on the device.  `want` selects the outputs ("mean", "lattice",
+    "f32", "z32"); with a `sink` the float32 outputs are appended to its buffers instead."""
     _require_cuda()
     if voxel_size <= 0:
         raise ValueError("voxel_size must be > 0")
@@ -178,15 +191,21 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
         del xyz16
         pts = decode_xyz(dl, torch.float64)
         w = voxel_downsample_points(pts, voxel_size, cs)
-        lat = quantise(w.mean, dl.scales, dl.offsets) if ("lattice" in want or "f32" in want) else None
+        lat = quantise(w.mean, dl.scales, dl.offsets) if (sink is not None or {"lattice", "f32", "z32"} & set(want)) else None
         f32 = None
-        if "f32" in want:
+        if "f32" in want or "z32" in want or sink is not None:
             # astype(float32) of the re-quantised values: encode the lattice into minimal records and run the
             # ordinary float32 decode kernel over them
             recs, _ = encode_records(lat, 20)
             f32 = decode_xyz(DeviceLas(recs, w.count, 20, dl.scales, dl.offsets), torch.float32)
+        if sink is not None:
+            sink.f32[sink.count: sink.count + w.count].copy_(f32)
+            if sink.z32 is not None:
+                sink.z32[sink.count: sink.count + w.count].copy_(f32[:, 2])
+            sink.count += w.count
         return VoxelResult(w.count, w.chunk_counts, w.mean if "mean" in want else None,
-                           lat if "lattice" in want else None, f32, plan=w.plan)
+                           lat if "lattice" in want else None, f32, plan=w.plan,
+                           z32=f32[:, 2].contiguous() if "z32" in want else None)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     check(lib.pch_voxel_keys_xyz16(xyz16.data_ptr(), n, cs, sc, of, float(voxel_size), origins.data_ptr(),
                                    C.byref(plan), keys.data_ptr(), st), "pch_voxel_keys_xyz16")
@@ -194,25 +213,34 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     # worst case every point is its own voxel; outputs are sized n and sliced after the count is known
     mean = torch.empty((n, 3), dtype=torch.float64, device=dev) if "mean" in want else None
     lat = torch.empty((n, 3), dtype=torch.int32, device=dev) if "lattice" in want else None
-    f32 = torch.empty((n, 3), dtype=torch.float32, device=dev) if "f32" in want else None
+    if sink is not None:
+        if sink.f32.shape[0] - sink.count < n:
+            raise ValueError("VoxelSink too small for this slice")
+        f32, z32 = sink.f32[sink.count:], (sink.z32[sink.count:] if sink.z32 is not None else None)
+    else:
+        f32 = torch.empty((n, 3), dtype=torch.float32, device=dev) if "f32" in want else None
+        z32 = torch.empty(n, dtype=torch.float32, device=dev) if "z32" in want else None
     counts = torch.empty(n_chunks, dtype=torch.int64, device=dev)
-    total = torch.empty(1, dtype=torch.int64, device=dev)
     ws_bytes = lib.pch_voxel_reduce_workspace_bytes(n, cs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    total = ws[8:16].view(torch.int64)      # next to the error word: one D2H fetches both
     check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, dl.rec.data_ptr(), dl.rec_len,
                                xyz16.data_ptr(), None, sc, of,
-                               _ptr(mean), _ptr(lat), _ptr(f32), counts.data_ptr(), total.data_ptr(),
+                               _ptr(mean), _ptr(lat), _ptr(f32), _ptr(z32), counts.data_ptr(), total.data_ptr(),
                                ws.data_ptr(), ws_bytes, st), "pch_voxel_reduce")
-    m = int(total.item())
-    err = int(ws[:4].view(torch.int32).item())
-    if err:
+    head = ws[:16].cpu().numpy()
+    m = int(head[8:16].view(np.int64)[0])
+    if int(head[:4].view(np.int32)[0]):
         raise _native.NativeError("device look-back spin limit hit in voxel_reduce")
+    if sink is not None:
+        sink.count += m
     res = VoxelResult(m, counts,
                       mean[:m] if mean is not None else None,
                       lat[:m] if lat is not None else None,
                       f32[:m] if f32 is not None else None,
                       plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_},
-                      sorted_keys=skeys if keep_keys else None)
+                      sorted_keys=skeys if keep_keys else None,
+                      z32=z32[:m] if z32 is not None else None)
     return res
 
 
@@ -247,6 +275,15 @@ def f32_shift(xyz: torch.Tensor, centroid: torch.Tensor, want_z=True, want_xyz=F
     return zs, sh
 
 
+def f32_column(xyz: torch.Tensor, column: int) -> torch.Tensor:
+    """xyz[:, column] as a dense (m,) float32 array."""
+    assert xyz.dtype == torch.float32 and xyz.is_contiguous()
+    out = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
+    check(_native.lib().pch_f32_column(xyz.data_ptr(), xyz.shape[0], int(column), out.data_ptr(), _stream()),
+          "pch_f32_column")
+    return out
+
+
 def select_f32(v: torch.Tensor, rank0: int, rank1: int) -> torch.Tensor:
     """Exact order statistics sorted(v)[rank0], sorted(v)[rank1] as a float32[2] device tensor."""
     assert v.dtype == torch.float32 and v.is_contiguous()
@@ -262,7 +299,10 @@ def select_f32(v: torch.Tensor, rank0: int, rank1: int) -> torch.Tensor:
 def compact_points(xyz: torch.Tensor, zs: Optional[torch.Tensor], thr: float,
                    centroid: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None,
                    want_src: bool = False, want_mask: bool = False):
-    """(filtered (G,3) float32 = xyz[keep] - centroid, G, src index or None, mask or None)."""
+    """(filtered (G,3) float32 = xyz[keep] - centroid, G, src index or None, mask or None).
+    keep = zs > thr, or keep_mask != 0, or (both None) float32(xyz.z - centroid.z) > thr on the fly."""
+    if zs is None and keep_mask is None and centroid is None:
+        raise ValueError("compact_points needs zs, keep_mask or a centroid")
     assert xyz.dtype == torch.float32 and xyz.is_contiguous()
     lib = _native.lib()
     m = xyz.shape[0]
@@ -408,7 +448,7 @@ def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Op
     wsb = lib.pch_voxel_reduce_workspace_bytes(n, cs)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, xyz.data_ptr(), 0, None, _ptr(vidx), None, None,
-                               mean.data_ptr(), None, None, counts.data_ptr(), total.data_ptr(), ws.data_ptr(), wsb,
+                               mean.data_ptr(), None, None, None, counts.data_ptr(), total.data_ptr(), ws.data_ptr(), wsb,
                                st), "pch_voxel_reduce")
     m = int(total.item())
     return VoxelResult(m, counts, mean[:m], plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_})

@@ -8,6 +8,8 @@ stages: the intermediate ``output/point_2.las`` is reproduced arithmetically (me
 from __future__ import annotations
 
 import dataclasses
+import os
+import threading
 from typing import List, Optional
 
 import numpy as np
@@ -32,61 +34,121 @@ class PipelineResult:
 def run_pipeline(dl: dv.DeviceLas, voxel_size: float = 0.1, chunk_size: int = 500000, eps: float = 8.0,
                  min_points: int = 80, ground: str = "percentile", box: str = "aabb", want_points: bool = False,
                  keep_stages: bool = False, **tower_kw) -> PipelineResult:
-    vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32",))
+    vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
     if vres.count == 0:
         return PipelineResult(dl.n, 0, 0, 0, [])
-    stages = tw.run_stages(vres.f32, eps, min_points, ground)
+    stages = tw.run_stages(vres.f32, eps, min_points, ground, zcol=vres.z32)
     towers = tw.select_towers(stages, box=box, want_points=want_points, **tower_kw)
     return PipelineResult(dl.n, vres.count, int(stages.filtered.shape[0]), stages.n_clusters, towers,
                           stages if keep_stages else None, vres.plan, stages.db_plan)
 
 
-def run_pipeline_from_host(host_records: torch.Tensor, n: int, rec_len: int, scales, offsets, voxel_size: float = 0.1,
-                           chunk_size: int = 500000, slice_chunks: int = 20, device=None, **kw) -> PipelineResult:
-    """End-to-end entry for HOST record buffers (pinned uint8 tensor): the H2D copy is cut into slices of
-    whole chunks on a copy stream, and the voxel stage of slice i runs while slice i+1 is still in flight
-    (chunks are independent, so the result is identical to one big call).  The tower stage follows on the
-    concatenated float32 cloud."""
+_STAGING = {}   # (device index, nbytes) -> pinned staging tensor, reused across calls (pinning costs ~0.3 s/GB)
+
+
+def _staging(nbytes: int) -> torch.Tensor:
+    key = int(nbytes)
+    buf = _STAGING.get(key)
+    if buf is None:
+        _STAGING.clear()      # one live staging buffer: a new size replaces the old one
+        buf = torch.empty(key, dtype=torch.uint8, pin_memory=True)
+        _STAGING[key] = buf
+    return buf
+
+
+def host_threads() -> int:
+    """Host threads for the staging gather: this process's share of the cores it may run on."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, cores // max(1, local_world))
+
+
+def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, voxel_size: float = 0.1,
+                           chunk_size: int = 500000, slice_chunks: int = 20, device=None, pack: str = "none",
+                           threads: int = 0, **kw) -> PipelineResult:
+    """End-to-end entry for HOST record buffers.  The transfer is cut into slices of whole chunks on a copy
+    stream, and the voxel stage of slice i runs while slice i+1 is still in flight (chunks are independent,
+    so the result is identical to one big call).  The tower stage follows on the concatenated float32 cloud.
+
+    pack="none": `host_records` is a (preferably pinned) uint8 tensor and whole records cross PCIe.
+    pack="xyz":  `host_records` is any host uint8 tensor / numpy array (pageable is fine); a worker thread
+                 gathers the 12 X,Y,Z bytes of each record into pinned staging (pch_host_pack_xyz, host
+                 threads, no arithmetic) slice by slice, so a 34-byte record crosses PCIe as 12 bytes and the
+                 gather of slice i+1 overlaps the copy and the voxel stage of slice i."""
     dv._require_cuda()
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     cs = max(1, min(int(chunk_size), max(n, 1)))
     per_slice = cs * max(1, int(slice_chunks))
-    if cs % 8:  # slice starts must stay 16-byte aligned (rec_len is even for every LAS format we stream)
+    if pack not in ("none", "xyz"):
+        raise ValueError(f"unknown pack mode {pack!r}")
+    dev_len = 12 if pack == "xyz" else rec_len
+    if (cs * dev_len) % 16:  # slice starts must stay 16-byte aligned
         per_slice = n
-    host = host_records.view(torch.uint8).reshape(-1)[: n * rec_len]
-    if not host.is_pinned():
+    if isinstance(host_records, torch.Tensor):
+        host = host_records.view(torch.uint8).reshape(-1)[: n * rec_len]
+    else:
+        host = torch.from_numpy(np.asarray(host_records).view(np.uint8).reshape(-1)[: n * rec_len])
+    if pack == "none" and not host.is_pinned():
         host = host.pin_memory()
-    dev = torch.empty(dv.padded_bytes(n, rec_len), dtype=torch.uint8, device=device)
-    dev[n * rec_len:].zero_()
+    dev = torch.empty(dv.padded_bytes(n, dev_len), dtype=torch.uint8, device=device)
+    dev[n * dev_len:].zero_()
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
     copy_stream.wait_stream(main)
-    events, bounds = [], []
-    with torch.cuda.stream(copy_stream):
-        for lo in range(0, n, per_slice):
-            hi = min(lo + per_slice, n)
-            dev[lo * rec_len: hi * rec_len].copy_(host[lo * rec_len: hi * rec_len], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-            events.append(ev)
-            bounds.append((lo, hi))
-    parts, total = [], 0
-    for ev, (lo, hi) in zip(events, bounds):
-        main.wait_event(ev)
-        view = dv.DeviceLas(dev[lo * rec_len:], hi - lo, rec_len, np.asarray(scales, dtype=np.float64),
+    bounds = [(lo, min(lo + per_slice, n)) for lo in range(0, n, per_slice)]
+    events = [torch.cuda.Event() for _ in bounds]
+    ready = [threading.Event() for _ in bounds]
+    failure = []
+
+    def feed():
+        # runs on a worker thread for pack="xyz" (ctypes releases the GIL during the gather) and inline otherwise
+        try:
+            torch.cuda.set_device(device)
+            stage = _staging(n * 12) if pack == "xyz" else host
+            lib = dv._native.lib()
+            nt = threads or host_threads()
+            for i, (lo, hi) in enumerate(bounds):
+                if pack == "xyz":
+                    dv.check(lib.pch_host_pack_xyz(host.data_ptr() + lo * rec_len, hi - lo, rec_len,
+                                                   stage.data_ptr() + lo * 12, nt), "pch_host_pack_xyz")
+                with torch.cuda.stream(copy_stream):
+                    dev[lo * dev_len: hi * dev_len].copy_(stage[lo * dev_len: hi * dev_len], non_blocking=True)
+                    events[i].record(copy_stream)
+                ready[i].set()
+        except BaseException as e:     # surface the failure on the calling thread
+            failure.append(e)
+            for r in ready:
+                r.set()
+
+    worker = None
+    if pack == "xyz":
+        worker = threading.Thread(target=feed, name="pch-host-pack", daemon=True)
+        worker.start()
+    else:
+        feed()
+    ground = kw.pop("ground", "percentile")
+    sink = dv.VoxelSink(n, device, want_z=(ground == "percentile"))
+    for i, (lo, hi) in enumerate(bounds):
+        ready[i].wait()
+        if failure:
+            raise failure[0]
+        main.wait_event(events[i])
+        view = dv.DeviceLas(dev[lo * dev_len:], hi - lo, dev_len, np.asarray(scales, dtype=np.float64),
                             np.asarray(offsets, dtype=np.float64))
-        v = dv.voxel_downsample(view, voxel_size, cs, want=("f32",))
-        parts.append(v.f32)
-        total += v.count
+        dv.voxel_downsample(view, voxel_size, cs, want=(), sink=sink)
+    if worker is not None:
+        worker.join()
+    total = sink.count
     if total == 0:
         return PipelineResult(n, 0, 0, 0, [])
-    f32 = parts[0] if len(parts) == 1 else torch.cat(parts)
-    del parts
+    f32 = sink.f32[:total]
     eps = kw.pop("eps", 8.0)
     min_points = kw.pop("min_points", 80)
-    ground = kw.pop("ground", "percentile")
     box = kw.pop("box", "aabb")
     want_points = kw.pop("want_points", False)
-    stages = tw.run_stages(f32, eps, min_points, ground)
+    stages = tw.run_stages(f32, eps, min_points, ground, zcol=sink.z32[:total] if sink.z32 is not None else None)
     towers = tw.select_towers(stages, box=box, want_points=want_points, **kw)
     return PipelineResult(n, total, int(stages.filtered.shape[0]), stages.n_clusters, towers, None, None, stages.db_plan)

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import dataclasses
 import os
+import threading
 from typing import Callable, List, Optional
 
 import numpy as np
@@ -69,49 +70,85 @@ class TowerStages:
     db_plan: Optional[dict] = None
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = (threading.get_ident(), torch.device(device).index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 def ground_filter_percentile(raw: torch.Tensor, pct: float = 25, offset: float = 3.0, min_keep: int = 1000,
-                             fallback_offset: float = 1.0, want_mask: bool = False):
-    """Stages A+B: centroid, shift, percentile threshold, compaction."""
+                             fallback_offset: float = 1.0, want_mask: bool = False,
+                             zcol: Optional[torch.Tensor] = None):
+    """Stages A+B: (filtered, centroid (device), base, offset used, mask)."""
+    return _ground_filter_percentile(raw, pct, offset, min_keep, fallback_offset, want_mask, zcol)[:5]
+
+
+def _ground_filter_percentile(raw: torch.Tensor, pct: float = 25, offset: float = 3.0, min_keep: int = 1000,
+                              fallback_offset: float = 1.0, want_mask: bool = False,
+                              zcol: Optional[torch.Tensor] = None):
+    """Stages A+B: centroid, shift, percentile threshold, compaction; also returns the host centroid.
+
+    `points = raw - centroid` is a float32 subtract per element and x -> float32(x - c) is monotone, so the
+    order statistics of the shifted z column are the shifted order statistics of the RAW z column: the radix
+    select runs on the raw column (`zcol`, emitted by the voxel reduce, or extracted here) on a side stream
+    while the bit-exact sequential-sum centroid is still being evaluated, and the shifted column is never
+    materialised (the compaction derives the keep flag from the cloud itself)."""
     m = raw.shape[0]
+    main = torch.cuda.current_stream(raw.device)
+    side = _side_stream(raw.device)
+    side.wait_stream(main)
+    r0, r1, gamma = percentile_ranks_f32(m, pct)
+    with torch.cuda.stream(side):
+        zraw = zcol if zcol is not None else dv.f32_column(raw, 2)
+        two_dev = dv.select_f32(zraw, r0, r1)
     if os.environ.get("PCH_TRACE"):
         cen_dev, _, st = dv.f32_centroid(raw, want_stats=True)
         print(f"[pch] centroid tiles via maps / via real adds per column: {st.tolist()}", flush=True)
     else:
         cen_dev, _ = dv.f32_centroid(raw)
-    zs, _ = dv.f32_shift(raw, cen_dev, want_z=True)
-    r0, r1, gamma = percentile_ranks_f32(m, pct)
-    two = dv.select_f32(zs, r0, r1).cpu().numpy()
+    main.wait_stream(side)
+    host = torch.cat([cen_dev, two_dev]).cpu().numpy()          # one D2H: centroid + the two raw order statistics
+    two = host[3:5] - host[2]                                   # float32 - float32 = the shifted order statistics
     base = percentile_lerp_f32(two[0], two[1], gamma)
     thr = base + offset                      # np.float32 + python float -> float32 (NEP 50)
-    filtered, g, _, mask = dv.compact_points(raw, zs, float(thr), cen_dev, want_mask=want_mask)
+    filtered, g, _, mask = dv.compact_points(raw, None, float(thr), cen_dev, want_mask=want_mask)
     used = offset
     if g < min_keep:
         thr = base + fallback_offset
-        filtered, g, _, mask = dv.compact_points(raw, zs, float(thr), cen_dev, want_mask=want_mask)
+        filtered, g, _, mask = dv.compact_points(raw, None, float(thr), cen_dev, want_mask=want_mask)
         used = fallback_offset
-    return filtered, cen_dev, np.float32(base), used, mask
+    return filtered, cen_dev, np.float32(base), used, mask, host[:3].copy()
 
 
 def ground_filter_grid(raw: torch.Tensor, cell: float = 2.0, hag: float = 3.0, want_mask: bool = False):
     """north_star grid min-z mode: keep points more than `hag` above their cell's lowest point."""
+    return _ground_filter_grid(raw, cell, hag, want_mask)[:5]
+
+
+def _ground_filter_grid(raw: torch.Tensor, cell: float = 2.0, hag: float = 3.0, want_mask: bool = False):
     cen_dev, _ = dv.f32_centroid(raw)
     _, shifted = dv.f32_shift(raw, cen_dev, want_z=False, want_xyz=True)
     keep, _ = dv.grid_min_ground(shifted, cell, hag)
     filtered, g, _, _ = dv.compact_points(shifted, None, 0.0, None, keep_mask=keep)
-    return filtered, cen_dev, np.float32("nan"), hag, (keep if want_mask else None)
+    return filtered, cen_dev, np.float32("nan"), hag, (keep if want_mask else None), cen_dev.cpu().numpy()
 
 
 def run_stages(raw: torch.Tensor, eps: float = 8.0, min_points: int = 80, ground: str = "percentile",
-               want_mask: bool = False, **ground_kw) -> TowerStages:
+               want_mask: bool = False, zcol: Optional[torch.Tensor] = None, **ground_kw) -> TowerStages:
     if ground == "percentile":
-        filtered, cen_dev, base, used, mask = ground_filter_percentile(raw, want_mask=want_mask, **ground_kw)
+        filtered, cen_dev, base, used, mask, cen = _ground_filter_percentile(raw, want_mask=want_mask, zcol=zcol,
+                                                                             **ground_kw)
     elif ground == "grid":
-        filtered, cen_dev, base, used, mask = ground_filter_grid(raw, want_mask=want_mask, **ground_kw)
+        filtered, cen_dev, base, used, mask, cen = _ground_filter_grid(raw, want_mask=want_mask, **ground_kw)
     else:
         raise ValueError(f"unknown ground mode {ground!r}")
     db = dv.dbscan_chunked(filtered, eps, min_points, DBSCAN_CHUNK)
-    return TowerStages(raw, cen_dev.cpu().numpy(), base, used, filtered, db.labels, db.n_clusters, db.stats, mask,
-                       db.plan)
+    return TowerStages(raw, cen, base, used, filtered, db.labels, db.n_clusters, db.stats, mask, db.plan)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -180,3 +180,22 @@ def test_extract_box_geometry():
     g = create_obb_geometries([{"center": np.zeros(3), "extent": np.array([2.0, 4, 6]), "rotation": np.eye(3)}])
     assert g[0].points.shape == (8, 3) and g[0].lines.shape == (12, 2)
     assert np.allclose(np.ptp(g[0].points, axis=0), [2, 4, 6])
+
+
+def test_host_pack_xyz_gathers_the_first_twelve_bytes_of_every_record():
+    """pch_host_pack_xyz is host code (no GPU needed): every record length / thread count / ragged tail."""
+    from pointcloudhookup_b200 import _native
+    lib = _native.lib()
+    for rec_len in (12, 20, 26, 28, 34, 37, 67):
+        for n in (0, 1, 3, 5, 1000, 70001, 262147):
+            rng = np.random.default_rng(n + rec_len)
+            src = rng.integers(0, 256, size=n * rec_len + 16, dtype=np.uint8)
+            dst = np.zeros(n * 12 + 32, dtype=np.uint8)
+            off = (-dst.ctypes.data) % 16
+            for threads in (1, 4):
+                dst[:] = 0
+                assert lib.pch_host_pack_xyz(src.ctypes.data, n, rec_len, dst.ctypes.data + off, threads) == 0
+                want = src[: n * rec_len].reshape(n, rec_len)[:, :12].reshape(-1)
+                assert np.array_equal(dst[off: off + n * 12], want), (rec_len, n, threads)
+                assert not dst[off + n * 12:].any()
+    assert lib.pch_host_pack_xyz(None, 5, 34, None, 1) != 0 and b"null" in lib.pch_last_error()

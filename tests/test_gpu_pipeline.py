@@ -37,6 +37,59 @@ def test_pipeline_equals_two_step_oracle(cuda_device):
             assert np.array_equal(a["center"], b["center"]) and np.array_equal(a["extent"], b["extent"])
 
 
+def test_host_pack_xyz_entry_equals_full_record_entry(cuda_device):
+    """pack="xyz": pageable host records -> 12-byte X,Y,Z stream (host threads) -> H2D -> the same kernels with
+    rec_len = 12; results identical to shipping whole 34-byte records."""
+    import torch
+    from pointcloudhookup_b200 import device as dv, pipeline, synth
+    n, chunk = 300_000, 100_000
+    rec = synth.corridor_records(n, 2, "hilly", 29, (0.86, 0.085, 0.005, 0.05))
+    dl = dv.upload_records(rec.view(np.uint8), n, 34, synth.SCALES, synth.OFFSETS)
+    ref = pipeline.run_pipeline(dl, 0.1, chunk, box="aabb", keep_stages=True)
+    pageable = rec.view(np.uint8).copy()
+    for slice_chunks, threads in ((1, 1), (2, 3), (100, 0)):
+        got = pipeline.run_pipeline_from_host(pageable, n, 34, synth.SCALES, synth.OFFSETS, 0.1, chunk,
+                                              slice_chunks=slice_chunks, pack="xyz", threads=threads, box="aabb")
+        assert (got.n_voxels, got.n_candidates, got.n_clusters) == (ref.n_voxels, ref.n_candidates, ref.n_clusters)
+        assert [t["label"] for t in got.towers] == [t["label"] for t in ref.towers]
+        for a, b in zip(got.towers, ref.towers):
+            assert np.array_equal(a["center"], b["center"]) and np.array_equal(a["extent"], b["extent"])
+    # the 12-byte stream is itself a valid record stream for every decode entry
+    lib = dv._native.lib()
+    packed = np.zeros(n * 12 + 16, dtype=np.uint8)
+    off = (-packed.ctypes.data) % 16
+    assert lib.pch_host_pack_xyz(pageable.ctypes.data, n, 34, packed.ctypes.data + off, 2) == 0
+    dl12 = dv.upload_records(packed[off: off + n * 12], n, 12, synth.SCALES, synth.OFFSETS)
+    assert torch.equal(dv.decode_xyz(dl12, torch.float64), dv.decode_xyz(dl, torch.float64))
+    v12 = dv.voxel_downsample(dl12, 0.1, chunk, want=("mean", "z32", "f32"))
+    v34 = dv.voxel_downsample(dl, 0.1, chunk, want=("mean", "f32"))
+    assert torch.equal(v12.mean, v34.mean) and torch.equal(v12.f32, v34.f32)
+    assert torch.equal(v12.z32, v34.f32[:, 2].contiguous())
+
+
+def test_percentile_on_raw_column_and_on_the_fly_compaction_equal_the_literal_order(cuda_device):
+    """The select on the RAW z column (side stream) + keep flag derived inside the compaction must equal the
+    reference's literal order: shift, percentile of the shifted column, mask, gather."""
+    import torch
+    from pointcloudhookup_b200 import device as dv, towers as tw
+    rng = np.random.default_rng(31)
+    for m in (1, 7, 1000, 300_001):
+        raw = np.stack([rng.uniform(437000, 437100, m), rng.uniform(3139000, 3139400, m),
+                        np.round(rng.gamma(2.0, 4.0, m) + 80, 3)], 1).astype(np.float32)
+        d = torch.from_numpy(raw).to(cuda_device)
+        filt, cen, base, used, mask = tw.ground_filter_percentile(d, want_mask=True)
+        pts = raw - np.mean(raw, axis=0)
+        z = pts[:, 2]
+        b = np.percentile(z, 25)
+        keep = z > b + 3.0
+        if keep.sum() < 1000:
+            keep = z > b + 1.0
+        assert np.array_equal(cen.cpu().numpy(), np.mean(raw, axis=0)) and base == b
+        assert np.array_equal(mask.cpu().numpy().astype(bool), keep)
+        assert np.array_equal(filt.cpu().numpy(), pts[keep])
+        assert torch.equal(dv.f32_column(d, 2), d[:, 2].contiguous())
+
+
 def test_pipeline_grid_ground_mode_runs_and_matches_self_oracle(cuda_device):
     import torch
     from pointcloudhookup_b200 import device as dv, towers as tw, synth

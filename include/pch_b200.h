@@ -273,6 +273,30 @@ int pch_las_geodetic(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const d
 int pch_haversine_matrix(const double* lat1_dev, const double* lon1_dev, int64_t n1, const double* lat2_dev,
                          const double* lon2_dev, int64_t n2, double* out_dev, pch_stream_t stream);
 
+/* ---------------------------------------------------------------- per-tower crop / preview */
+
+/* test/kuangxuan.py:69-79 for every tower at once: mask_b = (x>=xmin_b)&(x<=xmax_b)&(y...)&(z...) on the
+ * float64 decoded coordinates.  One streaming pass emits a word  b << 32 | point index  per hit, in no
+ * particular order, into words_dev (room for `capacity` words); total_dev[0] (int64) = number of hits, which
+ * may exceed capacity (re-run with more room).  Sorting the words on bits [0, 32+bits(n_boxes)) with
+ * pch_sort_u64_segmented restores `points[mask_b]` order per tower; pch_word_bounds then gives each tower's
+ * slice [bounds[b], bounds[b+1]) and pch_las_gather_f64 the points.  boxes_dev: [n_boxes][6] float64 =
+ * xmin,ymin,zmin,xmax,ymax,zmax. */
+int pch_las_box_crop(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const double* scales,
+                     const double* offsets, const double* boxes_dev, int32_t n_boxes, uint64_t* words_dev,
+                     int64_t capacity, int64_t* total_dev, pch_stream_t stream);
+int pch_word_bounds(const uint64_t* sorted_words_dev, int64_t m, int32_t n_boxes, int64_t* bounds_dev /* [n_boxes+1] */,
+                    pch_stream_t stream);
+/* out_dev (m,3) float64 = decoded points[words_dev[j] & 0xffffffff]  (`points[mask]`, `xyz[indices]`). */
+int pch_las_gather_f64(const uint8_t* rec_dev, int64_t n, int32_t rec_len, const double* scales,
+                       const double* offsets, const uint64_t* words_dev, int64_t m, double* out_dev,
+                       pch_stream_t stream);
+/* Preview subsample indices (pyGUI_towers_test.py:174-177 `np.random.choice(len(xyz), 200000, replace=False)`;
+ * ui/vtk_widget.py:115-118): k distinct indices of [0, n) as words.  seed == 0: evenly spaced floor(j*n/k);
+ * seed != 0: a keyed bijection of [0, n) (4-round Feistel network, cycle-walked) evaluated at 0..k-1.  The
+ * reference draws from numpy's unseeded global RNG, so only the distribution can be matched, not the draw. */
+int pch_sample_indices(int64_t n, int64_t k, uint64_t seed, uint64_t* words_dev, pch_stream_t stream);
+
 /* ---------------------------------------------------------------- host staging for the PCIe hop */
 
 /* HOST function (no device work): gathers the X,Y,Z int32 triple at bytes 0..11 of each of the n

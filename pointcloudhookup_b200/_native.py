@@ -97,6 +97,10 @@ SIGNATURES.update({
 
 SIGNATURES.update({
     "pch_host_pack_xyz": (C.c_int, [_p, _i64, _i32, _p, _i32]),
+    "pch_las_box_crop": (C.c_int, [_p, _i64, _i32, _d3, _d3, _p, _i32, _p, _i64, _p, _p]),
+    "pch_word_bounds": (C.c_int, [_p, _i64, _i32, _p, _p]),
+    "pch_las_gather_f64": (C.c_int, [_p, _i64, _i32, _d3, _d3, _p, _i64, _p, _p]),
+    "pch_sample_indices": (C.c_int, [_i64, _i64, C.c_uint64, _p, _p]),
 })
 
 _lib = None

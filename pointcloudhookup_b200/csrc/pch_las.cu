@@ -273,3 +273,229 @@ extern "C" int pch_las_encode(const int32_t* lattice, int64_t m, int32_t rec_len
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// per-tower box crop (test/kuangxuan.py:69-79) and preview subsample
+// (pyGUI_towers_test.py:174-177; ui/vtk_widget.py:115-118)
+//
+// The reference loops over towers and builds one boolean mask over ALL points per tower.  Here one
+// streaming pass over the raw records tests every point against every box (boxes in shared memory,
+// union-box early out) and emits a word  box << 32 | point index  per hit; sorting the (small) word list
+// restores `points[mask]` order for every tower at once.
+// ------------------------------------------------------------------------------------------------
+#define CROP_SMEM_BOXES 64   // 3 KB: keeps two CTAs of the 3-stage record ring resident per SM
+
+struct CropArgs {
+    const double* boxes;   // [n_boxes][6] xmin,ymin,zmin,xmax,ymax,zmax (inclusive, float64 compares)
+    int32_t n_boxes;
+    int32_t box0;          // id of boxes[0]
+    uint64_t* words;
+    long long capacity;
+    unsigned long long* total;   // hits so far (may exceed capacity: the caller re-runs with more room)
+};
+
+template <int ALIGN>
+__global__ void __launch_bounds__(PCH_TILE_THREADS, 2)
+k_box_crop(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine a, CropArgs c) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ double s_box[CROP_SMEM_BOXES][6];
+    __shared__ double s_union[6];
+    __shared__ uint32_t s_wsum[PCH_TILE_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < c.n_boxes * 6; i += PCH_TILE_THREADS) s_box[i / 6][i % 6] = c.boxes[i];
+    __syncthreads();
+    if (tid < 6) {
+        double v = s_box[0][tid];
+        for (int b = 1; b < c.n_boxes; ++b) v = tid < 3 ? fmin(v, s_box[b][tid]) : fmax(v, s_box[b][tid]);
+        s_union[tid] = v;
+    }
+    __syncthreads();
+    constexpr int MAXR = 4;   // tile_records <= 1024 = 4 records per thread
+    pch_stream_tiles(rec, g, smem, [&](const PchTile& t) {
+        double px[MAXR], py[MAXR], pz[MAXR];
+        uint32_t hits = 0;
+        bool cand[MAXR];
+#pragma unroll
+        for (int j = 0; j < MAXR; ++j) {
+            const int r = tid + j * PCH_TILE_THREADS;
+            cand[j] = false;
+            if (r < t.count) {
+                int X, Y, Z;
+                pch_load_xyz<ALIGN>(t.base + (size_t)r * g.rec_len, X, Y, Z);
+                px[j] = pch_scaled(X, a.sx, a.ox); py[j] = pch_scaled(Y, a.sy, a.oy); pz[j] = pch_scaled(Z, a.sz, a.oz);
+                cand[j] = px[j] >= s_union[0] && px[j] <= s_union[3] && py[j] >= s_union[1] && py[j] <= s_union[4] &&
+                          pz[j] >= s_union[2] && pz[j] <= s_union[5];
+            }
+            if (cand[j])
+                for (int b = 0; b < c.n_boxes; ++b)
+                    hits += (px[j] >= s_box[b][0] && px[j] <= s_box[b][3] && py[j] >= s_box[b][1] && py[j] <= s_box[b][4] &&
+                             pz[j] >= s_box[b][2] && pz[j] <= s_box[b][5]) ? 1u : 0u;
+        }
+        // block-exclusive scan of the per-thread hit counts, one global reservation per tile
+        uint32_t incl = hits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t wpre = 0, tile_hits = 0;
+#pragma unroll
+        for (int w = 0; w < PCH_TILE_THREADS / 32; ++w) {
+            const uint32_t v = s_wsum[w];
+            if (w < warp) wpre += v;
+            tile_hits += v;
+        }
+        if (tile_hits == 0) return;     // uniform for the CTA: the streamer's trailing barrier still runs
+        if (tid == 0) s_base = atomicAdd(c.total, (unsigned long long)tile_hits);
+        __syncthreads();
+        unsigned long long o = s_base + wpre + (incl - hits);
+        if (hits == 0) return;
+#pragma unroll
+        for (int j = 0; j < MAXR; ++j) {
+            if (!cand[j]) continue;
+            const uint64_t idx = (uint64_t)(t.r0 + tid + j * PCH_TILE_THREADS);
+            for (int b = 0; b < c.n_boxes; ++b)
+                if (px[j] >= s_box[b][0] && px[j] <= s_box[b][3] && py[j] >= s_box[b][1] && py[j] <= s_box[b][4] &&
+                    pz[j] >= s_box[b][2] && pz[j] <= s_box[b][5]) {
+                    if ((long long)o < c.capacity) c.words[o] = ((uint64_t)(uint32_t)(c.box0 + b) << 32) | idx;
+                    ++o;
+                }
+        }
+    });
+}
+
+extern "C" int pch_las_box_crop(const uint8_t* rec, int64_t n, int32_t rec_len, const double* scales,
+                                const double* offsets, const double* boxes_dev, int32_t n_boxes, uint64_t* words_dev,
+                                int64_t capacity, int64_t* total_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rec_args(rec, n, rec_len);
+    if (rc) return rc;
+    PchAffine a;
+    if ((rc = make_affine(scales, offsets, a))) return rc;
+    PCH_CHECK_ARG(n < (1ll << 32), "more than 2^32-1 points per crop");
+    PCH_CHECK_ARG(n_boxes >= 0 && capacity >= 0 && total_dev, "bad n_boxes/capacity/total");
+    PCH_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), st));
+    if (n == 0 || n_boxes == 0) return PCH_OK;
+    PCH_CHECK_ARG(boxes_dev && (words_dev || capacity == 0), "null pointer");
+    PchTileGeom g = pch_tile_geom(n, rec_len, n);
+    for (int32_t b0 = 0; b0 < n_boxes; b0 += CROP_SMEM_BOXES) {
+        CropArgs c;
+        c.boxes = boxes_dev + (size_t)b0 * 6;
+        c.n_boxes = n_boxes - b0 < CROP_SMEM_BOXES ? n_boxes - b0 : CROP_SMEM_BOXES;
+        c.box0 = b0;
+        c.words = words_dev;
+        c.capacity = capacity;
+        c.total = (unsigned long long*)total_dev;
+        PCH_DISPATCH_ALIGN(rec_len, k_box_crop, g, 2, st, rec, a, c);
+    }
+    return PCH_OK;
+}
+
+// first word >= (b << 32) for b = 0..n_boxes in the sorted word list: tower b owns [bounds[b], bounds[b+1])
+__global__ void k_word_bounds(const uint64_t* __restrict__ words, int64_t m, int32_t n_boxes, int64_t* __restrict__ bounds) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_boxes) return;
+    const uint64_t key = (uint64_t)(uint32_t)b << 32;
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (words[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    bounds[b] = lo;
+}
+
+extern "C" int pch_word_bounds(const uint64_t* sorted_words_dev, int64_t m, int32_t n_boxes, int64_t* bounds_dev,
+                               pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(m >= 0 && n_boxes >= 0 && bounds_dev && (m == 0 || sorted_words_dev), "bad arguments");
+    PCH_LAUNCH(st, "k_word_bounds", k_word_bounds<<<(unsigned)pch_ceil_div(n_boxes + 1, 128), 128, 0, st>>>(sorted_words_dev, m, n_boxes, bounds_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// points[index] decoded to float64 for a list of words (low 32 bits = point index)
+template <int ALIGN>
+__global__ void __launch_bounds__(256)
+k_gather_decode_f64(const uint8_t* __restrict__ rec, int32_t rec_len, PchAffine a, const uint64_t* __restrict__ words,
+                    int64_t m, double* __restrict__ out) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j < m; j += stride) {
+        const uint64_t i = words[j] & 0xffffffffull;
+        int X, Y, Z;
+        pch_load_xyz<ALIGN>(rec + (size_t)i * rec_len, X, Y, Z);
+        out[j * 3 + 0] = pch_scaled(X, a.sx, a.ox);
+        out[j * 3 + 1] = pch_scaled(Y, a.sy, a.oy);
+        out[j * 3 + 2] = pch_scaled(Z, a.sz, a.oz);
+    }
+}
+
+extern "C" int pch_las_gather_f64(const uint8_t* rec, int64_t n, int32_t rec_len, const double* scales,
+                                  const double* offsets, const uint64_t* words_dev, int64_t m, double* out_dev,
+                                  pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_rec_args(rec, n, rec_len);
+    if (rc) return rc;
+    PchAffine a;
+    if ((rc = make_affine(scales, offsets, a))) return rc;
+    PCH_CHECK_ARG(m >= 0, "m must be >= 0");
+    if (m == 0) return PCH_OK;
+    PCH_CHECK_ARG(n > 0 && words_dev && out_dev, "null pointer / empty source");
+    int64_t blocks = pch_ceil_div(m, 256);
+    int64_t cap = (int64_t)pch_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const int al = pch_rec_align(rec_len);
+    if (al == 4) { PCH_LAUNCH(st, "k_gather_decode_f64", k_gather_decode_f64<4><<<(unsigned)blocks, 256, 0, st>>>(rec, rec_len, a, words_dev, m, out_dev)); }
+    else if (al == 2) { PCH_LAUNCH(st, "k_gather_decode_f64", k_gather_decode_f64<2><<<(unsigned)blocks, 256, 0, st>>>(rec, rec_len, a, words_dev, m, out_dev)); }
+    else { PCH_LAUNCH(st, "k_gather_decode_f64", k_gather_decode_f64<1><<<(unsigned)blocks, 256, 0, st>>>(rec, rec_len, a, words_dev, m, out_dev)); }
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// Preview subsample: k distinct point indices out of n.  seed == 0: evenly spaced, idx_j = floor(j*n/k).
+// seed != 0: idx_j = P(j) for a keyed bijection P of [0, n) (4-round balanced Feistel network on the smallest
+// even number of bits covering n, cycle-walked back into range) = a sample without replacement.
+__device__ __forceinline__ uint32_t pch_mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+
+__global__ void k_sample_indices(int64_t n, int64_t k, uint64_t seed, int half_bits, uint64_t* __restrict__ words) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    if (seed == 0) {
+        words[j] = ((uint64_t)j * (uint64_t)n) / (uint64_t)k;   // j, n < 2^32: no overflow
+        return;
+    }
+    const uint32_t mask = half_bits >= 32 ? 0xffffffffu : ((1u << half_bits) - 1u);
+    uint64_t v = (uint64_t)j;
+    do {
+        uint32_t l = (uint32_t)(v >> half_bits) & mask, r = (uint32_t)v & mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            const uint32_t key = (uint32_t)(seed >> (16 * (round & 1))) ^ (0x9e3779b9u * (uint32_t)(round + 1)) ^ (uint32_t)(seed >> 32);
+            const uint32_t f = pch_mix32(r ^ key) & mask;
+            const uint32_t nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        v = ((uint64_t)l << half_bits) | (uint64_t)r;
+    } while (v >= (uint64_t)n);
+    words[j] = v;
+}
+
+extern "C" int pch_sample_indices(int64_t n, int64_t k, uint64_t seed, uint64_t* words_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && k >= 0 && k <= n && n < (1ll << 32), "need 0 <= k <= n < 2^32");
+    if (k == 0) return PCH_OK;
+    PCH_CHECK_ARG(words_dev, "null pointer");
+    int bits = 2;
+    while (bits < 64 && (1ull << bits) < (uint64_t)n) bits += 2;
+    PCH_LAUNCH(st, "k_sample_indices", k_sample_indices<<<(unsigned)pch_ceil_div(k, 256), 256, 0, st>>>(n, k, seed, bits / 2, words_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}

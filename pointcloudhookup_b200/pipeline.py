@@ -67,8 +67,8 @@ def host_threads() -> int:
 
 
 def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, voxel_size: float = 0.1,
-                           chunk_size: int = 500000, slice_chunks: int = 20, device=None, pack: str = "none",
-                           threads: int = 0, **kw) -> PipelineResult:
+                           chunk_size: int = 500000, slice_chunks: int = 10, device=None, pack: str = "none",
+                           threads: int = 0, raw_every: int = 0, **kw) -> PipelineResult:
     """End-to-end entry for HOST record buffers.  The transfer is cut into slices of whole chunks on a copy
     stream, and the voxel stage of slice i runs while slice i+1 is still in flight (chunks are independent,
     so the result is identical to one big call).  The tower stage follows on the concatenated float32 cloud.
@@ -77,15 +77,17 @@ def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, 
     pack="xyz":  `host_records` is any host uint8 tensor / numpy array (pageable is fine); a worker thread
                  gathers the 12 X,Y,Z bytes of each record into pinned staging (pch_host_pack_xyz, host
                  threads, no arithmetic) slice by slice, so a 34-byte record crosses PCIe as 12 bytes and the
-                 gather of slice i+1 overlaps the copy and the voxel stage of slice i."""
+                 gather of slice i+1 overlaps the copy and the voxel stage of slice i.
+    raw_every=k (with pack="xyz" and a pinned source): every k-th slice skips the gather and crosses PCIe as
+                 whole records while the host threads are busy with the slices around it, so the DMA engine
+                 and the host cores both carry part of the stream."""
     dv._require_cuda()
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     cs = max(1, min(int(chunk_size), max(n, 1)))
     per_slice = cs * max(1, int(slice_chunks))
     if pack not in ("none", "xyz"):
         raise ValueError(f"unknown pack mode {pack!r}")
-    dev_len = 12 if pack == "xyz" else rec_len
-    if (cs * dev_len) % 16:  # slice starts must stay 16-byte aligned
+    if (cs * 12) % 16 or (cs * rec_len) % 16:  # slice starts must stay 16-byte aligned in both layouts
         per_slice = n
     if isinstance(host_records, torch.Tensor):
         host = host_records.view(torch.uint8).reshape(-1)[: n * rec_len]
@@ -93,12 +95,21 @@ def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, 
         host = torch.from_numpy(np.asarray(host_records).view(np.uint8).reshape(-1)[: n * rec_len])
     if pack == "none" and not host.is_pinned():
         host = host.pin_memory()
-    dev = torch.empty(dv.padded_bytes(n, dev_len), dtype=torch.uint8, device=device)
-    dev[n * dev_len:].zero_()
+    if not host.is_pinned():
+        raw_every = 0
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
     copy_stream.wait_stream(main)
     bounds = [(lo, min(lo + per_slice, n)) for lo in range(0, n, per_slice)]
+    # record length of each slice on the device: whole records, or the gathered 12-byte stream
+    lens = [rec_len if (pack == "none" or (raw_every > 0 and i % raw_every == raw_every - 1)) else 12
+            for i in range(len(bounds))]
+    bufs = []
+    for (lo, hi), ln in zip(bounds, lens):
+        b = torch.empty(dv.padded_bytes(hi - lo, ln), dtype=torch.uint8, device=device)
+        b[(hi - lo) * ln:].zero_()
+        bufs.append(b)
+    copy_stream.wait_stream(main)
     events = [torch.cuda.Event() for _ in bounds]
     ready = [threading.Event() for _ in bounds]
     failure = []
@@ -107,15 +118,18 @@ def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, 
         # runs on a worker thread for pack="xyz" (ctypes releases the GIL during the gather) and inline otherwise
         try:
             torch.cuda.set_device(device)
-            stage = _staging(n * 12) if pack == "xyz" else host
+            stage = _staging(n * 12) if pack == "xyz" else None
             lib = dv._native.lib()
             nt = threads or host_threads()
             for i, (lo, hi) in enumerate(bounds):
-                if pack == "xyz":
+                if lens[i] == 12 and pack == "xyz":
                     dv.check(lib.pch_host_pack_xyz(host.data_ptr() + lo * rec_len, hi - lo, rec_len,
                                                    stage.data_ptr() + lo * 12, nt), "pch_host_pack_xyz")
+                    src = stage[lo * 12: hi * 12]
+                else:
+                    src = host[lo * rec_len: hi * rec_len]
                 with torch.cuda.stream(copy_stream):
-                    dev[lo * dev_len: hi * dev_len].copy_(stage[lo * dev_len: hi * dev_len], non_blocking=True)
+                    bufs[i][: src.numel()].copy_(src, non_blocking=True)
                     events[i].record(copy_stream)
                 ready[i].set()
         except BaseException as e:     # surface the failure on the calling thread
@@ -136,7 +150,7 @@ def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, 
         if failure:
             raise failure[0]
         main.wait_event(events[i])
-        view = dv.DeviceLas(dev[lo * dev_len:], hi - lo, dev_len, np.asarray(scales, dtype=np.float64),
+        view = dv.DeviceLas(bufs[i], hi - lo, lens[i], np.asarray(scales, dtype=np.float64),
                             np.asarray(offsets, dtype=np.float64))
         dv.voxel_downsample(view, voxel_size, cs, want=(), sink=sink)
     if worker is not None:

@@ -138,3 +138,20 @@ def test_oracle_match_towers_matches_reference_run():
     for i, g in enumerate(m["gim"]):
         for j, c in enumerate(conv):
             assert abs(match.haversine(g["lat"], g["lng"], c[1], c[0]) - m["haversine"][i][j]) < 1e-6
+
+
+def test_crop_oracle_bounds_and_sample_restatement():
+    """oracle/crop.py: the kuangxuan box of the reference's first logged tower (test/kuangxuan.py:29-30, 63-71)
+    and the sample restatement being a bijection of [0, n)."""
+    from oracle import crop as oc
+    t = {"id": 8, "height": 17.4, "width": 20.1, "x": 4.37587898e+05, "y": 3.14069158e+06, "z": 1.31457350e+02}
+    b = oc.kuangxuan_bounds(t)
+    assert np.allclose(b, [437587.898 - 20.1, 3140691.58 - 10.05, 131.45735 - 17.4,
+                           437587.898 + 33.5, 3140691.58 + 20.1, 131.45735 + 34.8], rtol=0, atol=1e-9)
+    pts = np.array([[b[0], b[1], b[2]], [b[3], b[4], b[5]], [b[0] - 1e-6, b[1], b[2]], [b[3], b[4], b[5] + 1e-6]])
+    assert np.array_equal(oc.crop_boxes(pts, b[None])[0], pts[:2])          # bounds are inclusive
+    for n in (1, 2, 5, 1000, 70001):
+        v = oc.sample_indices(n, n, 99)
+        assert np.array_equal(np.sort(v), np.arange(n, dtype=np.uint64))
+        k = max(1, n // 3)
+        assert np.unique(oc.sample_indices(n, k, 0)).size == k

@@ -47,9 +47,12 @@ def test_host_pack_xyz_entry_equals_full_record_entry(cuda_device):
     dl = dv.upload_records(rec.view(np.uint8), n, 34, synth.SCALES, synth.OFFSETS)
     ref = pipeline.run_pipeline(dl, 0.1, chunk, box="aabb", keep_stages=True)
     pageable = rec.view(np.uint8).copy()
-    for slice_chunks, threads in ((1, 1), (2, 3), (100, 0)):
-        got = pipeline.run_pipeline_from_host(pageable, n, 34, synth.SCALES, synth.OFFSETS, 0.1, chunk,
-                                              slice_chunks=slice_chunks, pack="xyz", threads=threads, box="aabb")
+    pinned = torch.from_numpy(pageable.copy()).pin_memory()
+    for src, slice_chunks, threads, raw_every in ((pageable, 1, 1, 0), (pageable, 2, 3, 2), (pageable, 100, 0, 0),
+                                                  (pinned, 1, 2, 2), (pinned, 1, 0, 1), (pinned, 1, 0, 3)):
+        got = pipeline.run_pipeline_from_host(src, n, 34, synth.SCALES, synth.OFFSETS, 0.1, chunk,
+                                              slice_chunks=slice_chunks, pack="xyz", threads=threads,
+                                              raw_every=raw_every, box="aabb")
         assert (got.n_voxels, got.n_candidates, got.n_clusters) == (ref.n_voxels, ref.n_candidates, ref.n_clusters)
         assert [t["label"] for t in got.towers] == [t["label"] for t in ref.towers]
         for a, b in zip(got.towers, ref.towers):

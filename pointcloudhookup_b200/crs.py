@@ -36,7 +36,7 @@ def convert_las_coordinates(input_path, grid_path=None, multiplier=-1.0):
     returns an (n,3) float64 array [lon, lat, H]."""
     from . import device as dv, las as _las
     hdr, rec = _las.read_raw(input_path)
-    dl = dv.upload_records(rec, hdr.point_count, hdr.record_length, hdr.scales, hdr.offsets)
+    dl = dv.upload_records_xyz(rec, hdr.point_count, hdr.record_length, hdr.scales, hdr.offsets)
     return _geo.las_to_geodetic(dl, _grid(grid_path), multiplier, _geo.EPSG4547).cpu().numpy()
 
 

@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import os
+import threading
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -75,6 +76,65 @@ def upload_records(records, n: int, rec_len: int, scales, offsets, device=None,
     dev[nbytes:].zero_()
     return DeviceLas(dev, int(n), int(rec_len), np.asarray(scales, dtype=np.float64),
                      np.asarray(offsets, dtype=np.float64))
+
+
+_XYZ_STAGE = {}
+
+
+def host_threads() -> int:
+    """Host threads for the staging gather: this process's share of the cores it may run on."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, cores // max(1, local_world))
+
+
+def upload_records_xyz(records, n: int, rec_len: int, scales, offsets, device=None,
+                       block_points: int = 1 << 22, threads: int = 0) -> DeviceLas:
+    """Host record bytes (ndarray, np.memmap of the LAS file, or tensor; pageable is fine) -> HBM as the
+    dense 12-byte X,Y,Z stream (rec_len = 12), double-buffered: host threads gather block i+1 into pinned
+    staging (pch_host_pack_xyz; page-cache reads of a memmap happen inside those threads) while block i is
+    still crossing PCIe.  Everything the drop-in modules compute reads only X,Y,Z, so the other
+    rec_len-12 bytes of each record never leave the host."""
+    _require_cuda()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    lib = _native.lib()
+    dev = torch.empty(padded_bytes(n, 12), dtype=torch.uint8, device=device)
+    dev[n * 12:].zero_()
+    out = DeviceLas(dev, int(n), 12, np.asarray(scales, dtype=np.float64), np.asarray(offsets, dtype=np.float64))
+    if n == 0:
+        return out
+    if isinstance(records, torch.Tensor):
+        keep = records.view(torch.uint8).reshape(-1)
+        base, have = keep.data_ptr(), keep.numel()
+    else:
+        keep = np.asarray(records).view(np.uint8).reshape(-1)
+        base, have = keep.ctypes.data, keep.size
+    if have < n * rec_len:
+        raise ValueError("record buffer shorter than n * rec_len")
+    block = max(4, int(block_points) // 4 * 4)
+    key = (threading.get_ident(), block)
+    stage = _XYZ_STAGE.get(key)
+    if stage is None:
+        stage = _XYZ_STAGE[key] = [torch.empty(block * 12, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    nt = threads or host_threads()
+    busy = [None, None]
+    with torch.cuda.device(device):
+        for bi, lo in enumerate(range(0, n, block)):
+            cnt = min(block, n - lo)
+            b = bi & 1
+            if busy[b] is not None:
+                busy[b].synchronize()          # the copy that last read this staging block has finished
+            check(lib.pch_host_pack_xyz(base + lo * rec_len, cnt, rec_len, stage[b].data_ptr(), nt), "pch_host_pack_xyz")
+            dev[lo * 12: (lo + cnt) * 12].copy_(stage[b][: cnt * 12], non_blocking=True)
+            busy[b] = torch.cuda.Event()
+            busy[b].record()
+        for e in busy:
+            if e is not None:
+                e.synchronize()                 # staging blocks are reused by the next call
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -56,14 +56,7 @@ def _staging(nbytes: int) -> torch.Tensor:
     return buf
 
 
-def host_threads() -> int:
-    """Host threads for the staging gather: this process's share of the cores it may run on."""
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, cores // max(1, local_world))
+host_threads = dv.host_threads
 
 
 def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, voxel_size: float = 0.1,

@@ -22,7 +22,7 @@ def _read_points_f64(las_path):
     if not os.path.exists(las_path):
         raise FileNotFoundError(f"未找到文件: {las_path}")
     hdr, rec = _las.read_raw(las_path)
-    dl = dv.upload_records(rec, hdr.point_count, hdr.record_length, hdr.scales, hdr.offsets)
+    dl = dv.upload_records_xyz(rec, hdr.point_count, hdr.record_length, hdr.scales, hdr.offsets)
     return dv.decode_xyz(dl, torch.float64).cpu().numpy()
 
 

@@ -28,7 +28,7 @@ def _downsample_file(input_path, output_path, voxel_size, chunk_size, progress_c
     if log_callback:
         log_callback(f"📂 原始点数: {total_points}")
         log_callback(f"✨ 开始下采样（voxel_size={voxel_size}, chunk_size={chunk_size}）")
-    dl = dv.upload_records(rec, total_points, hdr.record_length, hdr.scales, hdr.offsets)
+    dl = dv.upload_records_xyz(rec, total_points, hdr.record_length, hdr.scales, hdr.offsets)
     res = dv.voxel_downsample(dl, float(voxel_size), int(chunk_size), want=("lattice",))
     for i, start in enumerate(range(0, total_points, int(chunk_size))):
         end = min(start + int(chunk_size), total_points)

@@ -54,7 +54,7 @@ def extract_towers(
         log("📂 读取点云文件...")
         progress(5)
         hdr, rec = _las.read_raw(str(input_las_path))
-        dl = dv.upload_records(rec, hdr.point_count, hdr.record_length, hdr.scales, hdr.offsets)
+        dl = dv.upload_records_xyz(rec, hdr.point_count, hdr.record_length, hdr.scales, hdr.offsets)
         raw = dv.decode_xyz(dl, torch.float32)
         if raw.shape[0] == 0:
             raise ValueError("empty point cloud")

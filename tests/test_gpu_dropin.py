@@ -120,3 +120,26 @@ def test_threaded_call_like_the_gui(cuda_device, workdir):
     th.start()
     th.join(120)
     assert not err and os.path.exists(out)
+
+
+def test_upload_records_xyz_streams_any_host_buffer(cuda_device, tmp_path):
+    """Double-buffered gather + H2D of a memmapped LAS file, an ndarray and a tensor: the 12-byte stream decodes
+    to exactly what the whole records decode to, for ragged block sizes."""
+    import torch
+    from pointcloudhookup_b200 import device as dv, las as _las, synth
+    n = 123_457
+    rec = synth.corridor_records(n, 2, "hilly", 77)
+    path = str(tmp_path / "in.las")
+    hdr = _las.LasHeader(point_format=3, record_length=34, scales=np.array(synth.SCALES), offsets=np.array(synth.OFFSETS))
+    _las.write_raw(path, hdr, rec.view(np.uint8).reshape(-1))
+    h2, mm = _las.read_raw(path)
+    full = dv.upload_records(rec.view(np.uint8).reshape(-1), n, 34, synth.SCALES, synth.OFFSETS)
+    want = dv.decode_xyz(full, torch.float64)
+    for src, block, threads in ((mm, 1 << 22, 0), (mm, 10_000, 3), (rec.view(np.uint8).reshape(-1).copy(), 40_001, 1),
+                                (torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()), 4, 2)):
+        dl = dv.upload_records_xyz(src, n, 34, h2.scales, h2.offsets, block_points=block, threads=threads)
+        assert dl.rec_len == 12 and torch.equal(dv.decode_xyz(dl, torch.float64), want)
+    e = dv.upload_records_xyz(np.zeros(0, np.uint8), 0, 34, synth.SCALES, synth.OFFSETS)
+    assert e.n == 0 and dv.decode_xyz(e, torch.float64).shape == (0, 3)
+    with pytest.raises(ValueError):
+        dv.upload_records_xyz(np.zeros(33, np.uint8), 1, 34, synth.SCALES, synth.OFFSETS)

@@ -148,6 +148,12 @@ int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_s
                      double* mean_dev, int32_t* lattice_dev, float* f32_dev, float* z32_dev /* nullable */,
                      int64_t* chunk_counts_dev, int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
+/* Self-test: the voxel kernels evaluate `sum/count`, `(mean-offset)/scale` and `(p-origin)/voxel` as a
+ * reciprocal product plus two FMA corrections (Markstein), which must equal the IEEE divide bit for bit.
+ * mismatches_dev[0] (int64) = number of a_dev[i] for which it does not (expected: 0).  Returns
+ * PCH_ERR_INVALID for divisors the kernels themselves would route to the true divide. */
+int pch_selftest_fastdiv(const double* a_dev, int64_t n, double b, int64_t* mismatches_dev, pch_stream_t stream);
+
 /* ---------------------------------------------------------------- tower extraction, stages A/B */
 
 /* centroid = np.mean(raw_points_f32, axis=0) (utils/tower_extraction.py:63): numpy's SEQUENTIAL

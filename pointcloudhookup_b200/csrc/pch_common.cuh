@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <limits.h>
+#include <string.h>
 #include "../../include/pch_b200.h"
 
 #define PCH_SM_COUNT_FALLBACK 148
@@ -191,6 +192,40 @@ __device__ __forceinline__ void pch_load_xyz(const uint8_t* p, int& X, int& Y, i
 // (never contracted into an FMA).
 __device__ __forceinline__ double pch_scaled(int X, double scale, double offset) {
     return __dadd_rn(__dmul_rn((double)X, scale), offset);
+}
+
+// Correctly rounded a / b from y = RN(1/b) (a true IEEE divide done once, on the host or per CTA): a product
+// and two FMA refinement steps.  The last step is Markstein's: with q faithful, r = a - b*q exact (FMA) and
+// y the correctly rounded reciprocal, RN(q + r*y) = RN(a/b) provided b's significand is not all ones and
+// nothing under/overflows.  pch_recip_ok(b) vets b; operands outside a comfortable range take __ddiv_rn.
+// (Checked against IEEE division on 1.5e9 CPU samples and on the device by pch_selftest_fastdiv.)
+__device__ __forceinline__ double pch_div_by_nocheck(double a, double b, double y) {
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+// operands for which the FMA sequence cannot under/overflow (zero, inf and nan are NOT in range)
+__device__ __forceinline__ bool pch_div_inrange(double a) {
+    const double m = fabs(a);
+    return m > 1e-200 && m < 1e200;
+}
+__device__ __forceinline__ bool pch_div_inrange3(double a, double b, double c) {
+    const double x = fabs(a), y = fabs(b), z = fabs(c);
+    return fmin(fmin(x, y), z) > 1e-200 && fmax(fmax(x, y), z) < 1e200;
+}
+__device__ __forceinline__ double pch_div_by(double a, double b, double y) {
+    if (!pch_div_inrange(a)) return __ddiv_rn(a, b);   // zero, denormal-ish, inf, nan: the slow exact path
+    return pch_div_by_nocheck(a, b, y);
+}
+static inline bool pch_recip_ok(double b) {
+    if (!(b == b) || b == 0.0) return false;
+    const double m = b < 0 ? -b : b;
+    if (!(m > 1e-60 && m < 1e60)) return false;
+    uint64_t u;
+    memcpy(&u, &b, 8);
+    return (u & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull;
 }
 
 __device__ __forceinline__ int pch_warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }

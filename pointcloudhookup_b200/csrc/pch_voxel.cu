@@ -12,7 +12,35 @@
 
 struct PchAffine3 {
     double s[3], o[3];
+    double r[3];   // RN(1/s[i]) for pch_div_by
+    int fast;      // every scale passed pch_recip_ok
 };
+struct VoxelDiv {
+    double v, r;   // voxel size, RN(1/voxel)
+    int fast;
+};
+static VoxelDiv make_voxel_div(double voxel) {
+    VoxelDiv d;
+    d.v = voxel;
+    d.r = 1.0 / voxel;
+    d.fast = pch_recip_ok(voxel) ? 1 : 0;
+#ifdef PCH_NO_FASTDIV
+    d.fast = 0;
+#endif
+    return d;
+}
+// floor((p - origin) / voxel) for the three axes: one range guard, then either three reciprocal sequences or
+// three true divides (the divide code exists once per kernel)
+__device__ __forceinline__ void pch_voxel_index3(double dx, double dy, double dz, const VoxelDiv& d, uint64_t& ix,
+                                                 uint64_t& iy, uint64_t& iz) {
+    double qx, qy, qz;
+    if (d.fast && pch_div_inrange3(dx, dy, dz)) {
+        qx = pch_div_by_nocheck(dx, d.v, d.r); qy = pch_div_by_nocheck(dy, d.v, d.r); qz = pch_div_by_nocheck(dz, d.v, d.r);
+    } else {
+        qx = __ddiv_rn(dx, d.v); qy = __ddiv_rn(dy, d.v); qz = __ddiv_rn(dz, d.v);
+    }
+    ix = (uint64_t)(long long)floor(qx); iy = (uint64_t)(long long)floor(qy); iz = (uint64_t)(long long)floor(qz);
+}
 
 __device__ __forceinline__ int bits_for(long long v) {  // bits needed to store values 0..v
     int b = 0;
@@ -56,8 +84,9 @@ __global__ void k_voxel_plan(const int32_t* __restrict__ mm, int64_t n_chunks, i
 }
 
 static int make_affine3(const double* scales, const double* offsets, PchAffine3& a) {
+    a.fast = 1;
     if (!scales && !offsets) {  // float64 point input: identity
-        for (int i = 0; i < 3; ++i) { a.s[i] = 1.0; a.o[i] = 0.0; }
+        for (int i = 0; i < 3; ++i) { a.s[i] = 1.0; a.o[i] = 0.0; a.r[i] = 1.0; }
         return PCH_OK;
     }
     PCH_CHECK_ARG(scales && offsets, "null scales/offsets");
@@ -65,7 +94,12 @@ static int make_affine3(const double* scales, const double* offsets, PchAffine3&
         a.s[i] = scales[i];
         a.o[i] = offsets[i];
         PCH_CHECK_ARG(scales[i] != 0.0, "zero LAS scale");
+        a.r[i] = 1.0 / scales[i];
+        if (!pch_recip_ok(scales[i])) a.fast = 0;
     }
+#ifdef PCH_NO_FASTDIV
+    a.fast = 0;
+#endif
     return PCH_OK;
 }
 
@@ -91,7 +125,7 @@ struct KeyLayout {
 
 template <int ALIGN>
 __global__ void __launch_bounds__(PCH_TILE_THREADS, 2)
-k_voxel_keys(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine3 a, double voxel,
+k_voxel_keys(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine3 a, VoxelDiv voxel,
              const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys, int4* __restrict__ xyz16) {
     extern __shared__ __align__(128) uint8_t smem[];
     pch_stream_tiles(rec, g, smem, [&](const PchTile& t) {
@@ -104,9 +138,8 @@ k_voxel_keys(const uint8_t* __restrict__ rec, PchTileGeom g, PchAffine3 a, doubl
             double y = pch_scaled(Y, a.s[1], a.o[1]);
             double z = pch_scaled(Z, a.s[2], a.o[2]);
             // (p - origin) / voxel with a correctly rounded divide, then floor -> int (open3d)
-            uint64_t ix = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(x, ox), voxel));
-            uint64_t iy = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(y, oy), voxel));
-            uint64_t iz = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(z, oz), voxel));
+            uint64_t ix, iy, iz;
+            pch_voxel_index3(__dsub_rn(x, ox), __dsub_rn(y, oy), __dsub_rn(z, oz), voxel, ix, iy, iz);
             uint64_t local = (uint64_t)(t.r0 + r - chunk_start);
             keys[t.r0 + r] = (ix << kl.sh_x) | (iy << kl.sh_y) | (iz << kl.sh_z) | local;
             // 16-byte aligned copy of the lattice coordinates: the reduce pass gathers ONE aligned
@@ -145,7 +178,7 @@ extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, in
 #define LAUNCH_KEYS(A)                                                                                       \
     do {                                                                                                     \
         PCH_CUDA(cudaFuncSetAttribute(k_voxel_keys<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        PCH_LAUNCH(st, "k_voxel_keys", k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, voxel, origins, kl, keys, (int4*)xyz16));          \
+        PCH_LAUNCH(st, "k_voxel_keys", k_voxel_keys<A><<<grid, PCH_TILE_THREADS, smem, st>>>(rec, g, a, make_voxel_div(voxel), origins, kl, keys, (int4*)xyz16));          \
     } while (0)
     if (al == 4) LAUNCH_KEYS(4);
     else if (al == 2) LAUNCH_KEYS(2);
@@ -157,7 +190,7 @@ extern "C" int pch_voxel_keys(const uint8_t* rec, int64_t n, int32_t rec_len, in
 
 // keys from the packed lattice copy (plain coalesced 16-byte loads; no second pass over the records)
 __global__ void __launch_bounds__(256)
-k_voxel_keys16(const int4* __restrict__ xyz16, int64_t n, int64_t chunk, PchAffine3 a, double voxel,
+k_voxel_keys16(const int4* __restrict__ xyz16, int64_t n, int64_t chunk, PchAffine3 a, VoxelDiv voxel,
                const double* __restrict__ origins, KeyLayout kl, uint64_t* __restrict__ keys) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -167,9 +200,9 @@ k_voxel_keys16(const int4* __restrict__ xyz16, int64_t n, int64_t chunk, PchAffi
         const double x = pch_scaled(v.x, a.s[0], a.o[0]);
         const double y = pch_scaled(v.y, a.s[1], a.o[1]);
         const double z = pch_scaled(v.z, a.s[2], a.o[2]);
-        const uint64_t ix = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(x, origins[c * 3 + 0]), voxel));
-        const uint64_t iy = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(y, origins[c * 3 + 1]), voxel));
-        const uint64_t iz = (uint64_t)(long long)floor(__ddiv_rn(__dsub_rn(z, origins[c * 3 + 2]), voxel));
+        uint64_t ix, iy, iz;
+        pch_voxel_index3(__dsub_rn(x, origins[c * 3 + 0]), __dsub_rn(y, origins[c * 3 + 1]),
+                         __dsub_rn(z, origins[c * 3 + 2]), voxel, ix, iy, iz);
         keys[i] = (ix << kl.sh_x) | (iy << kl.sh_y) | (iz << kl.sh_z) | (uint64_t)(i - c * chunk);
     }
 }
@@ -198,7 +231,7 @@ extern "C" int pch_voxel_keys_xyz16(const int32_t* xyz16, int64_t n, int64_t chu
     int64_t blocks = pch_ceil_div(n, 256);
     int64_t cap = (int64_t)pch_sm_count() * 16;
     PCH_LAUNCH(st, "k_voxel_keys16", k_voxel_keys16<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
-                                         (const int4*)xyz16, n, chunk_size, a, voxel, origins, kl, keys));
+                                         (const int4*)xyz16, n, chunk_size, a, make_voxel_div(voxel), origins, kl, keys));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
@@ -212,6 +245,10 @@ extern "C" int pch_voxel_keys_xyz16(const int32_t* xyz16, int64_t n, int64_t chu
 #endif
 #define VR_TILE (VR_THREADS * VR_ROWS)
 #define VR_WARPS (VR_THREADS / 32)
+#define VR_RECIP 64
+#ifndef VR_MINB
+#define VR_MINB 4
+#endif
 
 struct ReduceGeom {
     int64_t n, chunk_size, tiles_per_chunk, total_tiles;
@@ -228,8 +265,19 @@ extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size
 
 // ALIGN > 0: `rec` is a raw LAS byte stream (record alignment ALIGN); ALIGN == 0: `rec` is an
 // (n,3) float64 array (process_chunk's arbitrary point input).
+//
+// One voxel = one run of equal key in the sorted chunk.  Per tile of VR_TILE sorted slots:
+//   1. every thread loads its slots' keys and gathers their points (all loads in flight at once);
+//   2. head flags -> ballots -> the tile's head LIST (s_heads[r] = slot of the r-th run), tile count published;
+//   3. the runs are folded VR_THREADS at a time, run r by thread r % VR_THREADS: every lane has a run (no
+//      idle non-head lanes), the fold code exists once, and output rows r, r+1, ... are written by
+//      consecutive lanes.  A run is summed IN INPUT ORDER in float64 (open3d's AccumulatedPoint), then
+//      mean = sum/count and the LAS re-quantisation;
+//   4. when only lattice / float32 outputs are wanted (the fused pipeline) the folds run BEFORE the
+//      look-back wait and park their lattice triple in s_xyz[r] (slot r is never read again: round k only
+//      reads slots >= k*VR_THREADS, and writes slots < (k+1)*VR_THREADS after a barrier).
 template <int ALIGN>
-__global__ void __launch_bounds__(VR_THREADS)
+__global__ void __launch_bounds__(VR_THREADS, VR_MINB)
 k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec,
                const int4* __restrict__ xyz16, const int32_t* __restrict__ vidx /* (n,3) or NULL: wide keys */,
                PchAffine3 a,
@@ -238,11 +286,14 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
                uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
     __shared__ uint64_t s_keys[VR_TILE + 1];  // [0] = key preceding the tile
     __shared__ int s_xyz[ALIGN > 0 ? VR_TILE : 1][3];  // lattice coordinates of the tile's points (LAS source)
+    __shared__ uint16_t s_heads[VR_TILE + 2];
     __shared__ uint32_t s_wcount[VR_WARPS];
+    __shared__ double s_recip[VR_RECIP + 1];   // RN(1/count) for the common small voxel populations
     __shared__ uint64_t s_tile_off;
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    if (tid <= VR_RECIP) s_recip[tid] = tid ? __ddiv_rn(1.0, (double)tid) : 0.0;
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= g.total_tiles) return;
@@ -257,9 +308,7 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     const uint64_t idx_mask = bi >= 64 ? ~0ull : ((1ull << bi) - 1ull);
 
     {
-        // every thread gathers the points of its own sorted slots: first all key loads, then all
-        // point gathers, so the whole tile's loads are in flight at once instead of being serialised
-        // inside the per-voxel loops below
+        // first all key loads, then all point gathers, so the whole tile's loads are in flight at once
         uint64_t kk[VR_ROWS];
 #pragma unroll
         for (int j = 0; j < VR_ROWS; ++j) {
@@ -293,7 +342,7 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     if (tid == 0) s_keys[0] = lt > 0 ? keys[start - 1] : ~0ull;
     __syncthreads();
 
-    // head flags in warp-blocked order: warp w owns [w*256, w*256+256), row j = 32 consecutive items
+    // head flags in warp-blocked order: warp w owns [w*32*VR_ROWS, ...), row j = 32 consecutive slots
     uint32_t row_rank[VR_ROWS];
     uint32_t head_bits = 0;
     uint32_t wtotal = 0;
@@ -329,74 +378,119 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         if (w < warp) wprefix += c;
         tile_total += c;
     }
+#pragma unroll
+    for (int j = 0; j < VR_ROWS; ++j)
+        if (head_bits & (1u << j)) s_heads[wprefix + row_rank[j]] = (uint16_t)(wbase + j * 32 + lane);
     if (tid == 0) {
+        s_heads[tile_total] = (uint16_t)cnt;
         pch_lookback_publish_u64(status, tile, 0, tile_total);   // publish early: successors never wait on our compute
         if (chunk_counts && tile_total) atomicAdd(&chunk_counts[chunk], (unsigned long long)tile_total);
     }
+    const bool deferred = (ALIGN > 0) && (mean_out == nullptr);
+    if (!deferred && tid == 0) {
+        s_tile_off = pch_lookback_walk_u64(status, tile, 0, tile_total, err);
+        if (tile == g.total_tiles - 1 && total_out) *total_out = (long long)(s_tile_off + tile_total);
+    }
+    __syncthreads();
 
-    // One voxel = one run of equal key; its head thread folds the run IN INPUT ORDER (float64 running sum),
-    // mean = sum / count, then the LAS re-quantisation.  Returns the mean and the lattice triple.
-    auto fold_run = [&](int i, double& mx, double& my, double& mz, int& qx, int& qy, int& qz) {
-        const uint64_t vkey = s_keys[i + 1] >> bi;
-        const int32_t* vhead = vidx ? vidx + (cstart + (int64_t)(s_keys[i + 1] & idx_mask)) * 3 : nullptr;
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        long long cntp = 0;
-        int64_t p = start + i;
-        uint64_t k = s_keys[i + 1];
-        int li = i;
-        while (true) {
-            if (ALIGN > 0) {
-                int X, Y, Z;
-                if (li < cnt) {
-                    X = s_xyz[li][0]; Y = s_xyz[li][1]; Z = s_xyz[li][2];
-                } else if (xyz16) {   // the run continues past this tile
-                    const int4 v = __ldg(xyz16 + cstart + (int64_t)(k & idx_mask));
-                    X = v.x; Y = v.y; Z = v.z;
-                } else {
-                    const uint8_t* q = rec + (size_t)(cstart + (int64_t)(k & idx_mask)) * g.rec_len;
-                    pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(q, X, Y, Z);
-                }
-                sx = __dadd_rn(sx, pch_scaled(X, a.s[0], a.o[0]));
-                sy = __dadd_rn(sy, pch_scaled(Y, a.s[1], a.o[1]));
-                sz = __dadd_rn(sz, pch_scaled(Z, a.s[2], a.o[2]));
-            } else {
-                const double* q = reinterpret_cast<const double*>(rec) + (size_t)(cstart + (int64_t)(k & idx_mask)) * 3;
-                sx = __dadd_rn(sx, q[0]);
-                sy = __dadd_rn(sy, q[1]);
-                sz = __dadd_rn(sz, q[2]);
-            }
-            ++cntp;
-            ++p;
-            if (p >= cend) break;
-            li = (int)(p - start);
-            k = li < cnt ? s_keys[li + 1] : keys[p];
-            if (vidx) {
-                const int32_t* vn = vidx + (cstart + (int64_t)(k & idx_mask)) * 3;
-                if (vn[0] != vhead[0] || vn[1] != vhead[1] || vn[2] != vhead[2]) break;
-            } else if ((k >> bi) != vkey) break;
+    auto store_row = [&](uint64_t m, int qx, int qy, int qz) {
+        if (lat_out) {
+            lat_out[m * 3 + 0] = qx; lat_out[m * 3 + 1] = qy; lat_out[m * 3 + 2] = qz;
         }
-        const double dn = (double)cntp;
-        mx = __ddiv_rn(sx, dn); my = __ddiv_rn(sy, dn); mz = __ddiv_rn(sz, dn);
-        qx = __double2int_rn(__ddiv_rn(__dsub_rn(mx, a.o[0]), a.s[0]));
-        qy = __double2int_rn(__ddiv_rn(__dsub_rn(my, a.o[1]), a.s[1]));
-        qz = __double2int_rn(__ddiv_rn(__dsub_rn(mz, a.o[2]), a.s[2]));
+        const float fz = (float)pch_scaled(qz, a.s[2], a.o[2]);
+        if (f32_out) {
+            f32_out[m * 3 + 0] = (float)pch_scaled(qx, a.s[0], a.o[0]);
+            f32_out[m * 3 + 1] = (float)pch_scaled(qy, a.s[1], a.o[1]);
+            f32_out[m * 3 + 2] = fz;
+        }
+        if (z32_out) z32_out[m] = fz;
     };
 
-    // When only the lattice / float32 outputs are wanted (the fused pipeline), the runs are folded BEFORE the
-    // look-back walk and the lattice triple is parked in the head's own s_xyz slot (nobody else reads a head
-    // slot), so the chain wait overlaps nothing but the final stores.
-    const bool deferred = (ALIGN > 0) && (mean_out == nullptr);
-    if (deferred) {
-#pragma unroll
-        for (int j = 0; j < VR_ROWS; ++j) {
-            if (!(head_bits & (1u << j))) continue;
-            const int i = wbase + j * 32 + lane;
-            double mx, my, mz;
-            int qx, qy, qz;
-            fold_run(i, mx, my, mz, qx, qy, qz);
-            s_xyz[ALIGN > 0 ? i : 0][0] = qx; s_xyz[ALIGN > 0 ? i : 0][1] = qy; s_xyz[ALIGN > 0 ? i : 0][2] = qz;
+    const int rounds = ((int)tile_total + VR_THREADS - 1) / VR_THREADS;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int r = rd * VR_THREADS + tid;
+        const bool valid = r < (int)tile_total;
+        double mx = 0.0, my = 0.0, mz = 0.0;
+        int qx = 0, qy = 0, qz = 0;
+        if (valid) {
+            const int i0 = s_heads[r], i1 = s_heads[r + 1];
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            long long cntp = i1 - i0;
+#pragma unroll 1
+            for (int li = i0; li < i1; ++li) {
+                if (ALIGN > 0) {
+                    sx = __dadd_rn(sx, pch_scaled(s_xyz[ALIGN > 0 ? li : 0][0], a.s[0], a.o[0]));
+                    sy = __dadd_rn(sy, pch_scaled(s_xyz[ALIGN > 0 ? li : 0][1], a.s[1], a.o[1]));
+                    sz = __dadd_rn(sz, pch_scaled(s_xyz[ALIGN > 0 ? li : 0][2], a.s[2], a.o[2]));
+                } else {
+                    const double* q = reinterpret_cast<const double*>(rec) + (size_t)(cstart + (int64_t)(s_keys[li + 1] & idx_mask)) * 3;
+                    sx = __dadd_rn(sx, q[0]); sy = __dadd_rn(sy, q[1]); sz = __dadd_rn(sz, q[2]);
+                }
+            }
+            if (r == (int)tile_total - 1 && start + cnt < cend) {
+                // the tile's last run may continue into the following tiles of the chunk
+                const uint64_t hk = s_keys[i0 + 1];
+                const int32_t* vhead = vidx ? vidx + (cstart + (int64_t)(hk & idx_mask)) * 3 : nullptr;
+                for (int64_t p = start + cnt; p < cend; ++p) {
+                    const uint64_t k = keys[p];
+                    const int64_t src = cstart + (int64_t)(k & idx_mask);
+                    if (vidx) {
+                        const int32_t* vn = vidx + src * 3;
+                        if (vn[0] != vhead[0] || vn[1] != vhead[1] || vn[2] != vhead[2]) break;
+                    } else if ((k >> bi) != (hk >> bi)) break;
+                    if (ALIGN > 0) {
+                        int X, Y, Z;
+                        if (xyz16) {
+                            const int4 v = __ldg(xyz16 + src);
+                            X = v.x; Y = v.y; Z = v.z;
+                        } else {
+                            pch_load_xyz<(ALIGN > 0 ? ALIGN : 1)>(rec + (size_t)src * g.rec_len, X, Y, Z);
+                        }
+                        sx = __dadd_rn(sx, pch_scaled(X, a.s[0], a.o[0]));
+                        sy = __dadd_rn(sy, pch_scaled(Y, a.s[1], a.o[1]));
+                        sz = __dadd_rn(sz, pch_scaled(Z, a.s[2], a.o[2]));
+                    } else {
+                        const double* q = reinterpret_cast<const double*>(rec) + (size_t)src * 3;
+                        sx = __dadd_rn(sx, q[0]); sy = __dadd_rn(sy, q[1]); sz = __dadd_rn(sz, q[2]);
+                    }
+                    ++cntp;
+                }
+            }
+            const double dn = (double)cntp;
+            // same values as true divides (pch_div_by), at a fraction of the FP64 issue slots; one range guard
+            // per stage, and a single copy of the true-divide code for everything the guards turn away
+            bool fast = a.fast && cntp <= VR_RECIP && pch_div_inrange3(sx, sy, sz);
+            if (fast) {
+                const double yn = s_recip[cntp];
+                mx = pch_div_by_nocheck(sx, dn, yn); my = pch_div_by_nocheck(sy, dn, yn); mz = pch_div_by_nocheck(sz, dn, yn);
+                const double dx = __dsub_rn(mx, a.o[0]), dy = __dsub_rn(my, a.o[1]), dz = __dsub_rn(mz, a.o[2]);
+                fast = pch_div_inrange3(dx, dy, dz);
+                if (fast) {
+                    qx = __double2int_rn(pch_div_by_nocheck(dx, a.s[0], a.r[0]));
+                    qy = __double2int_rn(pch_div_by_nocheck(dy, a.s[1], a.r[1]));
+                    qz = __double2int_rn(pch_div_by_nocheck(dz, a.s[2], a.r[2]));
+                }
+            }
+            if (!fast) {
+                mx = __ddiv_rn(sx, dn); my = __ddiv_rn(sy, dn); mz = __ddiv_rn(sz, dn);
+                qx = __double2int_rn(__ddiv_rn(__dsub_rn(mx, a.o[0]), a.s[0]));
+                qy = __double2int_rn(__ddiv_rn(__dsub_rn(my, a.o[1]), a.s[1]));
+                qz = __double2int_rn(__ddiv_rn(__dsub_rn(mz, a.o[2]), a.s[2]));
+            }
+        }
+        if (deferred) {
+            __syncthreads();   // every read of this round (slots >= rd*VR_THREADS) is done before slots < (rd+1)*VR_THREADS change
+            if (valid) { s_xyz[ALIGN > 0 ? r : 0][0] = qx; s_xyz[ALIGN > 0 ? r : 0][1] = qy; s_xyz[ALIGN > 0 ? r : 0][2] = qz; }
+        } else if (valid) {
+            const uint64_t m = s_tile_off + (uint64_t)r;
+            if (mean_out) {
+                mean_out[m * 3 + 0] = mx; mean_out[m * 3 + 1] = my; mean_out[m * 3 + 2] = mz;
+            }
+            if (ALIGN > 0) store_row(m, qx, qy, qz);
         }
     }
+    if (!deferred) return;
     __syncthreads();
     if (tid == 0) {
         s_tile_off = pch_lookback_walk_u64(status, tile, 0, tile_total, err);
@@ -404,32 +498,8 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     }
     __syncthreads();
     const uint64_t tile_off = s_tile_off;
-
-#pragma unroll
-    for (int j = 0; j < VR_ROWS; ++j) {
-        if (!(head_bits & (1u << j))) continue;
-        const int i = wbase + j * 32 + lane;
-        const uint64_t m = tile_off + wprefix + row_rank[j];
-        int qx, qy, qz;
-        if (deferred) {
-            qx = s_xyz[ALIGN > 0 ? i : 0][0]; qy = s_xyz[ALIGN > 0 ? i : 0][1]; qz = s_xyz[ALIGN > 0 ? i : 0][2];
-        } else {
-            double mx, my, mz;
-            fold_run(i, mx, my, mz, qx, qy, qz);
-            if (mean_out) {
-                mean_out[m * 3 + 0] = mx; mean_out[m * 3 + 1] = my; mean_out[m * 3 + 2] = mz;
-            }
-        }
-        if (lat_out) {
-            lat_out[m * 3 + 0] = qx; lat_out[m * 3 + 1] = qy; lat_out[m * 3 + 2] = qz;
-        }
-        if (f32_out) {
-            f32_out[m * 3 + 0] = (float)pch_scaled(qx, a.s[0], a.o[0]);
-            f32_out[m * 3 + 1] = (float)pch_scaled(qy, a.s[1], a.o[1]);
-            f32_out[m * 3 + 2] = (float)pch_scaled(qz, a.s[2], a.o[2]);
-        }
-        if (z32_out) z32_out[m] = (float)pch_scaled(qz, a.s[2], a.o[2]);
-    }
+    for (int r = tid; r < (int)tile_total; r += VR_THREADS)
+        store_row(tile_off + (uint64_t)r, s_xyz[ALIGN > 0 ? r : 0][0], s_xyz[ALIGN > 0 ? r : 0][1], s_xyz[ALIGN > 0 ? r : 0][2]);
 }
 
 extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
@@ -663,6 +733,34 @@ extern "C" int pch_voxel_wide_words(const uint64_t* prev, const int32_t* vidx, i
     if (chunk_size > n) chunk_size = n;
     int64_t blocks = pch_ceil_div(n, 256), cap = (int64_t)pch_sm_count() * 8;
     PCH_LAUNCH(st, "k_wide_words", k_wide_words<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(prev, vidx, n, chunk_size, bits_idx, axis, out));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-test of pch_div_by against the hardware-sequence IEEE divide (used by the parity tests)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_selftest_fastdiv(const double* __restrict__ a, int64_t n, double b, double y,
+                                   unsigned long long* __restrict__ bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
+    for (; i < n; i += stride)
+        mine += __double_as_longlong(pch_div_by(a[i], b, y)) != __double_as_longlong(__ddiv_rn(a[i], b));
+    if (mine) atomicAdd(bad, mine);
+}
+
+extern "C" int pch_selftest_fastdiv(const double* a_dev, int64_t n, double b, int64_t* mismatches_dev,
+                                    pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && mismatches_dev && (n == 0 || a_dev), "bad arguments");
+    PCH_CHECK_ARG(pch_recip_ok(b), "divisor %g is not eligible for the reciprocal path", b);
+    PCH_CUDA(cudaMemsetAsync(mismatches_dev, 0, sizeof(int64_t), st));
+    if (n == 0) return PCH_OK;
+    int64_t blocks = pch_ceil_div(n, 256);
+    int64_t cap = (int64_t)pch_sm_count() * 8;
+    PCH_LAUNCH(st, "k_selftest_fastdiv", k_selftest_fastdiv<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+                                              a_dev, n, b, 1.0 / b, (unsigned long long*)mismatches_dev));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

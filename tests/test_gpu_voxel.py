@@ -102,3 +102,57 @@ def test_encode_roundtrip(cuda_device):
         assert not raw[:, 12:].any()
         if m:
             assert np.array_equal(mm.cpu().numpy(), np.concatenate([lat.min(0), lat.max(0)]))
+
+
+def test_reciprocal_division_equals_ieee_divide(cuda_device):
+    """The voxel kernels replace `sum/count`, `(mean-offset)/scale` and `(p-origin)/voxel` by a reciprocal
+    product + two FMA corrections; on the device that must equal __ddiv_rn bit for bit (pch_selftest_fastdiv
+    counts the mismatches) for lattice-like, uniform, decode-then-subtract and random-mantissa operands,
+    including the values the range guard turns away (0, denormals, inf, nan)."""
+    import ctypes
+    import torch
+    from pointcloudhookup_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(2024)
+    n = 4_000_000
+    k = rng.integers(-2**31, 2**31, n)
+    cases = [k * 0.001 * 0.5,                                       # half-lattice values (the common .5 ties)
+             rng.uniform(0, 1e7, n),
+             (rng.integers(0, 2**31, n) * 0.001 + 437000.0) - 437000.0,
+             (rng.integers(0, 2**31, n) * 0.001 + 3139000.0) * rng.integers(1, 65, n),
+             np.ldexp(rng.uniform(1, 2, n), rng.integers(-40, 40, n)) * rng.choice([-1.0, 1.0], n),
+             np.array([0.0, -0.0, 5e-324, 1e-310, -1e-250, 1e250, np.inf, -np.inf, np.nan, 1e-199, 1e199] * 1000)]
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    divisors = [0.001, 0.01, 0.1, 1e-4, 2.5e-4, 0.25, 0.5, 0.3, 1 / 3, 1e-5, 0.05, 1.7, -0.001, 1e-7] + \
+               [float(c) for c in range(1, 65)]
+    for b in divisors:
+        for a in cases:
+            d = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(cuda_device)
+            rc = lib.pch_selftest_fastdiv(d.data_ptr(), d.numel(), ctypes.c_double(b), bad.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream)
+            assert rc == 0 and int(bad.item()) == 0, (b, int(bad.item()))
+    # divisors the kernels route to the true divide are refused here
+    allones = np.frombuffer(np.uint64(0x3FEFFFFFFFFFFFFF).tobytes(), dtype=np.float64)[0]
+    for b in (0.0, float("nan"), 1e80, 1e-80, float(allones)):
+        assert lib.pch_selftest_fastdiv(d.data_ptr(), 10, ctypes.c_double(b), bad.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream) != 0
+
+
+def test_voxel_downsample_with_ineligible_scale_takes_the_true_divide(cuda_device):
+    """A LAS scale whose significand is all ones is not eligible for the reciprocal path: still bit-exact."""
+    import torch
+    from pointcloudhookup_b200 import device as dv, synth
+    from oracle import voxel as ov
+    allones = float(np.frombuffer(np.uint64(0x3F4FFFFFFFFFFFFF).tobytes(), dtype=np.float64)[0])   # ~0.000977
+    scales = (allones, 0.001, allones)
+    n = 120_000
+    rec = synth.corridor_records(n, 2, "flat", 5)
+    dl = dv.upload_records(rec.view(np.uint8), n, 34, scales, synth.OFFSETS)
+    las = {"scales": np.array(scales), "offsets": np.array(synth.OFFSETS), "X": rec["X"].copy(), "Y": rec["Y"].copy(),
+           "Z": rec["Z"].copy(), "n": n}
+    ref, _ = ov.downsample_las_arrays(las, 0.1, 50_000)
+    got = dv.voxel_downsample(dl, 0.1, 50_000, want=("mean", "lattice"))
+    assert np.array_equal(got.mean.cpu().numpy(), ref)
+    from oracle import las_io
+    q = np.stack([las_io.quantise(ref[:, i], scales[i], synth.OFFSETS[i]) for i in range(3)], 1)
+    assert np.array_equal(got.lattice.cpu().numpy(), q)

@@ -202,6 +202,34 @@ __device__ __forceinline__ void sq_elem(uint32_t bits, int k, uint32_t& q, uint3
     }
 }
 
+// All SQ_W window slots of one element at once: a / 2^(k0+w), w = 0..SQ_W-1.  Logical right shifts compose
+// ((x >> s) >> w == x >> (s+w)), so the slots share one variable 64-bit shift and differ by constant shifts;
+// the values are exactly those of sq_elem(bits, k0 + w, ...).
+__device__ __forceinline__ void sq_elem_window(uint32_t bits, int k0, unsigned long long acc[SQ_W], uint32_t ties[SQ_W]) {
+    int ea = (int)((bits >> 23) & 0xffu);
+    uint32_t ma = bits & 0x7fffffu;
+    if (ea == 0) ea = 1; else ma |= 0x800000u;
+    const int shift0 = k0 - (ea - 150);
+    if (shift0 >= 0) {
+        const unsigned long long T = shift0 < 64 ? (((unsigned long long)ma << 32) >> shift0) : 0ull;
+#pragma unroll
+        for (int w = 0; w < SQ_W; ++w) {
+            const unsigned long long t = T >> w;
+            const uint32_t f = (uint32_t)t;
+            acc[w] += (t >> 32) + (f > 0x80000000u ? 1u : 0u);
+            ties[w] += f == 0x80000000u ? 1u : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < SQ_W; ++w) {
+            uint32_t q, gt, eq;
+            sq_elem(bits, k0 + w, q, gt, eq);
+            acc[w] += (unsigned long long)q + gt;
+            ties[w] += eq;
+        }
+    }
+}
+
 // Per tile, column and window slot: the composed map.  Fast path: when no element of the tile is an
 // exact tie for this k, the map does not depend on parity and is a plain (order-free) sum, so the
 // threads read the tile strided/coalesced and one block reduction finishes it; a (column, slot) that
@@ -226,13 +254,7 @@ k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const Sq
             for (int e = 0; e < SQ_EPT; ++e) {
                 const int64_t i = base + e * SQ_THREADS + tid;
                 const uint32_t bits = i < m ? __float_as_uint(__ldg(&xyz[i * 3 + c])) : 0u;
-#pragma unroll
-                for (int w = 0; w < SQ_W; ++w) {
-                    uint32_t q, gt, eq;
-                    sq_elem(bits, k0 + w, q, gt, eq);
-                    acc[w] += (unsigned long long)q + gt;
-                    ties[w] += eq;
-                }
+                sq_elem_window(bits, k0, acc, ties);
             }
 #pragma unroll
             for (int w = 0; w < SQ_W; ++w) {
@@ -331,6 +353,43 @@ k_sum_super(int64_t n_tiles, int64_t n_super, const SqTileInfo* __restrict__ inf
     }
 }
 
+// Level 3: 32 consecutive super-tiles (= one SQ_BATCH of 1024 tiles, 2 M elements) sharing one window are
+// composed once more (one warp per batch), so the chain crosses a whole batch with a single map wherever the
+// running sum stays inside one binade — which is most of a large cloud, and all of it once the sum stagnates.
+__global__ void __launch_bounds__(256)
+k_sum_super2(int64_t n_super, int64_t n_batch, const SqMap* __restrict__ stable, const int32_t* __restrict__ sklo,
+             SqMap* __restrict__ btable /*[3][n_batch][SQ_W]*/, int32_t* __restrict__ bklo /*[3][n_batch]*/) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; w < 3 * n_batch; w += nw) {
+        const int c = (int)(w / n_batch);
+        const int64_t b = w - (int64_t)c * n_batch;
+        const int64_t su = b * SQ_SUPER + lane;
+        const bool have = su < n_super;
+        const int k_me = have ? sklo[c * n_super + su] : INT_MIN;
+        const int k0 = __shfl_sync(0xffffffffu, k_me, 0);
+        const bool uniform = __all_sync(0xffffffffu, have && k_me != INT_MIN && k_me == k0);
+        if (!uniform) {
+            if (lane == 0) bklo[c * n_batch + b] = INT_MIN;
+            continue;
+        }
+#pragma unroll
+        for (int ww = 0; ww < SQ_W; ++ww) {
+            SqMap F = stable[((size_t)c * n_super + su) * SQ_W + ww];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                SqMap pv;
+                pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
+                pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
+                if (lane >= o) F = sq_compose(pv, F);
+            }
+            if (lane == 31) btable[((size_t)c * n_batch + b) * SQ_W + ww] = F;
+        }
+        if (lane == 0) bklo[c * n_batch + b] = k0;
+    }
+}
+
 // One CTA per column.  All 256 threads stage the maps of SQ_BATCH tiles into shared memory (coalesced,
 // many loads in flight); warp 0 then walks the batch 32 tiles at a time with warp scans — no global
 // latency on the serial path.
@@ -340,7 +399,8 @@ k_sum_super(int64_t n_tiles, int64_t n_super, const SqTileInfo* __restrict__ inf
 __global__ void __launch_bounds__(SQ_CHAIN_THREADS)
 k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqTileInfo* __restrict__ info,
             const int32_t* __restrict__ klo, const SqMap* __restrict__ table, int64_t n_super,
-            const SqMap* __restrict__ stable, const int32_t* __restrict__ sklo, float* __restrict__ sums,
+            const SqMap* __restrict__ stable, const int32_t* __restrict__ sklo, const SqMap* __restrict__ btable,
+            const int32_t* __restrict__ bklo, float* __restrict__ sums,
             int* __restrict__ stats /*[3][2]: tiles via maps, tiles via real adds*/) {
     __shared__ SqMap s_tab[SQ_BATCH * SQ_W];
     __shared__ int32_t s_klo[SQ_BATCH];
@@ -348,11 +408,41 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
     __shared__ SqMap s_stab[(SQ_BATCH / SQ_SUPER) * SQ_W];
     __shared__ int32_t s_sklo[SQ_BATCH / SQ_SUPER];
     __shared__ float s_col[SQ_TILE];
+    __shared__ float s_state;
+    __shared__ int s_skip;
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_batch = (n_tiles + SQ_BATCH - 1) / SQ_BATCH;
     float s = 0.0f;
     int n_map = 0, n_real = 0;
+    if (tid == 0) s_state = 0.0f;
+    __syncthreads();
     for (int64_t b0 = 0; b0 < n_tiles; b0 += SQ_BATCH) {
         const int nb = (int)min((int64_t)SQ_BATCH, n_tiles - b0);
+        // ---- level 3: the whole batch with one map (thread 0 decides; nothing is staged when it applies)
+        if (tid == 0) {
+            int skip = 0;
+            const int32_t bk = bklo[c * n_batch + b0 / SQ_BATCH];
+            const uint32_t sb = __float_as_uint(s);
+            const int es = (int)((sb >> 23) & 0xffu);
+            if (bk != INT_MIN && es != 0 && es != 0xff && !(sb >> 31)) {
+                const int idx = (es - 150) - bk;
+                if (idx >= 0 && idx < SQ_W) {
+                    const SqMap F = btable[((size_t)c * n_batch + b0 / SQ_BATCH) * SQ_W + idx];
+                    const uint32_t ms = (sb & 0x7fffffu) | 0x800000u;
+                    const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
+                    if (D < SQ_SAT && (uint64_t)ms + D < (1ull << 24)) {
+                        s = __uint_as_float(((uint32_t)es << 23) | ((ms + D) & 0x7fffffu));
+                        n_map += nb;
+                        skip = 1;
+                    }
+                }
+            }
+            s_state = s;
+            s_skip = skip;
+        }
+        __syncthreads();
+        s = s_state;
+        if (s_skip) continue;    // block-uniform
         const int nsb = (int)min((int64_t)(SQ_BATCH / SQ_SUPER), n_super - b0 / SQ_SUPER);   // super-tiles in this batch
         for (int i = tid; i < nsb * SQ_W; i += SQ_CHAIN_THREADS)
             s_stab[i] = stable[((size_t)c * n_super + b0 / SQ_SUPER) * SQ_W + i];
@@ -496,8 +586,10 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
                     ++n_real;
                 }
             }
+            if (lane == 0) s_state = s;
         }
         __syncthreads();
+        s = s_state;
     }
     if (tid == 0) {
         sums[c] = s;
@@ -508,9 +600,11 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
 extern "C" size_t pch_f32_centroid_workspace_bytes(int64_t m) {
     int64_t nt = pch_ceil_div(m > 0 ? m : 1, SQ_TILE);
     int64_t ns = pch_ceil_div(nt, 32);
+    int64_t nbt = pch_ceil_div(nt, SQ_BATCH);
     return 256 + pch_align_up((size_t)3 * nt * sizeof(SqTileInfo), 256) + pch_align_up((size_t)3 * nt * 4, 256) +
            pch_align_up((size_t)3 * nt * SQ_W * sizeof(SqMap), 256) + pch_align_up((size_t)3 * ns * SQ_W * sizeof(SqMap), 256) +
-           pch_align_up((size_t)3 * ns * 4, 256);
+           pch_align_up((size_t)3 * ns * 4, 256) + pch_align_up((size_t)3 * nbt * SQ_W * sizeof(SqMap), 256) +
+           pch_align_up((size_t)3 * nbt * 4, 256);
 }
 
 extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float* centroid3, void* workspace,
@@ -536,15 +630,20 @@ extern "C" int pch_f32_centroid(const float* xyz, int64_t m, float* sums3, float
         SqMap* table = (SqMap*)(base + off); off += pch_align_up((size_t)3 * nt * SQ_W * sizeof(SqMap), 256);
         const int64_t ns = pch_ceil_div(nt, SQ_SUPER);
         SqMap* stable = (SqMap*)(base + off); off += pch_align_up((size_t)3 * ns * SQ_W * sizeof(SqMap), 256);
-        int32_t* sklo = (int32_t*)(base + off);
+        int32_t* sklo = (int32_t*)(base + off); off += pch_align_up((size_t)3 * ns * 4, 256);
+        const int64_t nbt = pch_ceil_div(nt, SQ_BATCH);
+        SqMap* btable = (SqMap*)(base + off); off += pch_align_up((size_t)3 * nbt * SQ_W * sizeof(SqMap), 256);
+        int32_t* bklo = (int32_t*)(base + off);
         unsigned grid = (unsigned)(nt < (int64_t)pch_sm_count() * 8 ? nt : (int64_t)pch_sm_count() * 8);
         PCH_LAUNCH(st, "k_sum_prep", k_sum_prep<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info));
         PCH_LAUNCH(st, "k_sum_window", k_sum_window<<<3, 1024, 0, st>>>(info, nt, klo));
         PCH_LAUNCH(st, "k_sum_tables", k_sum_tables<<<grid, SQ_THREADS, 0, st>>>(xyz, m, nt, info, klo, table));
         PCH_LAUNCH(st, "k_sum_super", k_sum_super<<<(unsigned)(pch_ceil_div(3 * ns, 8) < 1184 ? pch_ceil_div(3 * ns, 8) : 1184), 256, 0, st>>>(
                                           nt, ns, info, klo, table, stable, sklo));
+        PCH_LAUNCH(st, "k_sum_super2", k_sum_super2<<<(unsigned)(pch_ceil_div(3 * nbt, 8) < 1184 ? pch_ceil_div(3 * nbt, 8) : 1184), 256, 0, st>>>(
+                                           ns, nbt, stable, sklo, btable, bklo));
         PCH_LAUNCH(st, "k_sum_chain", k_sum_chain<<<3, SQ_CHAIN_THREADS, 0, st>>>(xyz, m, nt, info, klo, table, ns, stable, sklo,
-                                                                                 sums3, stats));
+                                                                                 btable, bklo, sums3, stats));
         PCH_LAUNCH_CHECK();
     }
     PCH_LAUNCH(st, "k_centroid_from_sums", k_centroid_from_sums<<<1, 32, 0, st>>>(sums3, m, centroid3));
@@ -785,6 +884,188 @@ k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uin
     }
 }
 
+// Staged variant for the hot case (a float32 cloud in, compacted cloud out): the tile's 2048 rows are fetched
+// with coalesced 16-byte loads into shared memory, the kept rows are packed there (after every warp has its
+// rows in registers), and the packed span leaves with fully coalesced stores — instead of 4-byte accesses at
+// a 12-byte stride on both sides.  Same flags, same order, same outputs as k_compact.
+__global__ void __launch_bounds__(CP_THREADS)
+k_compact_xyz(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask,
+              int64_t m, const float* __restrict__ centroid, float thr, float* __restrict__ out_xyz,
+              int32_t* __restrict__ out_src, uint8_t* __restrict__ out_mask, long long* __restrict__ count_out,
+              uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
+    __shared__ __align__(16) float s_row[CP_TILE * 3];
+    __shared__ uint32_t s_wcount[CP_THREADS / 32];
+    __shared__ uint64_t s_off;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t n_tiles = (m + CP_TILE - 1) / CP_TILE;
+    if (tile >= n_tiles) return;
+    const int64_t start = tile * CP_TILE;
+    const int cnt = (int)min((int64_t)CP_TILE, m - start);
+    if (cnt == CP_TILE) {
+        const float4* src = reinterpret_cast<const float4*>(xyz + start * 3);   // 24 576-byte tiles of a 16-byte aligned base
+        float4* dst = reinterpret_cast<float4*>(s_row);
+#pragma unroll
+        for (int k = 0; k < CP_TILE * 3 / 4 / CP_THREADS; ++k) dst[tid + k * CP_THREADS] = __ldg(src + tid + k * CP_THREADS);
+    } else {
+        for (int w = tid; w < cnt * 3; w += CP_THREADS) s_row[w] = xyz[start * 3 + w];
+    }
+    __syncthreads();
+    const float cx = centroid ? centroid[0] : 0.f, cy = centroid ? centroid[1] : 0.f, cz = centroid ? centroid[2] : 0.f;
+    const int wbase = warp * (32 * CP_ROWS);
+    uint32_t rank[CP_ROWS];
+    uint32_t keep_bits = 0, wtotal = 0;
+#pragma unroll
+    for (int j = 0; j < CP_ROWS; ++j) {
+        const int li = wbase + j * 32 + lane;
+        const int64_t i = start + li;
+        bool keep = false;
+        if (li < cnt) keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(s_row[li * 3 + 2], cz) > thr));
+        if (out_mask && li < cnt) out_mask[i] = keep ? 1 : 0;
+        uint32_t b = __ballot_sync(0xffffffffu, keep);
+        rank[j] = wtotal + __popc(b & ((1u << lane) - 1u));
+        wtotal += __popc(b);
+        if (keep) keep_bits |= 1u << j;
+    }
+    if (lane == 0) s_wcount[warp] = wtotal;
+    float vx[CP_ROWS], vy[CP_ROWS], vz[CP_ROWS];
+#pragma unroll
+    for (int j = 0; j < CP_ROWS; ++j) {
+        const int li = wbase + j * 32 + lane;
+        vx[j] = vy[j] = vz[j] = 0.f;
+        if (keep_bits & (1u << j)) {
+            vx[j] = __fsub_rn(s_row[li * 3 + 0], cx);
+            vy[j] = __fsub_rn(s_row[li * 3 + 1], cy);
+            vz[j] = __fsub_rn(s_row[li * 3 + 2], cz);
+        }
+    }
+    __syncthreads();      // counts visible; every warp holds its kept rows in registers: s_row may be overwritten
+    uint32_t wprefix = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+        uint32_t c = s_wcount[w];
+        if (w < warp) wprefix += c;
+        total += c;
+    }
+    if (tid == 0) pch_lookback_publish_u64(status, tile, 0, total);
+#pragma unroll
+    for (int j = 0; j < CP_ROWS; ++j)
+        if (keep_bits & (1u << j)) {
+            const uint32_t p = wprefix + rank[j];
+            s_row[p * 3 + 0] = vx[j]; s_row[p * 3 + 1] = vy[j]; s_row[p * 3 + 2] = vz[j];
+        }
+    if (tid == 0) {
+        s_off = pch_lookback_walk_u64(status, tile, 0, total, err);
+        if (tile == n_tiles - 1) *count_out = (long long)(s_off + total);
+    }
+    __syncthreads();
+    const uint64_t off = s_off;
+    if (out_xyz) {
+        float* dst = out_xyz + off * 3;
+        for (int w = tid; w < (int)total * 3; w += CP_THREADS) dst[w] = s_row[w];
+    }
+    if (out_src) {
+#pragma unroll
+        for (int j = 0; j < CP_ROWS; ++j)
+            if (keep_bits & (1u << j)) out_src[off + wprefix + rank[j]] = (int32_t)(start + wbase + j * 32 + lane);
+    }
+}
+
+// Index list of the set flags of a byte mask (DBSCAN cluster heads: a few thousand set bytes in tens of
+// millions).  16 flags per 16-byte load, 8192 flags per tile, so the look-back chain is 4x shorter than with
+// k_compact's 2048-element tiles and no row data is touched.
+#define CF_ROWS 2
+#define CF_TILE (CP_THREADS * 16 * CF_ROWS)
+__global__ void __launch_bounds__(CP_THREADS)
+k_compact_flags(const uint8_t* __restrict__ mask, int64_t m, int32_t* __restrict__ out_src, long long* __restrict__ count_out,
+                uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
+    __shared__ uint32_t s_wsum[CF_ROWS][CP_THREADS / 32];
+    __shared__ uint64_t s_off;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t n_tiles = (m + CF_TILE - 1) / CF_TILE;
+    if (tile >= n_tiles) return;
+    const int64_t start = tile * CF_TILE;
+    uint32_t w[CF_ROWS][4];
+    uint32_t c[CF_ROWS], incl[CF_ROWS];
+#pragma unroll
+    for (int r = 0; r < CF_ROWS; ++r) {
+        const int64_t i0 = start + (int64_t)r * (CP_THREADS * 16) + tid * 16;
+        if (i0 + 16 <= m) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(mask + i0));
+            w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int64_t i = i0 + q * 4 + b;
+                    if (i < m) x |= (uint32_t)mask[i] << (8 * b);
+                }
+                w[r][q] = x;
+            }
+        }
+        uint32_t n = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // a byte is "set" when non-zero: fold every byte onto its bit 0
+            uint32_t x = w[r][q];
+            x |= x >> 4; x |= x >> 2; x |= x >> 1;
+            x &= 0x01010101u;
+            w[r][q] = x;
+            n += __popc(x);
+        }
+        c[r] = n;
+        uint32_t x = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl[r] = x;
+        if (lane == 31) s_wsum[r][warp] = x;
+    }
+    __syncthreads();
+    uint32_t total = 0, pre[CF_ROWS];
+#pragma unroll
+    for (int r = 0; r < CF_ROWS; ++r) {
+        uint32_t wp = 0, rt = 0;
+#pragma unroll
+        for (int ww = 0; ww < CP_THREADS / 32; ++ww) {
+            const uint32_t v = s_wsum[r][ww];
+            if (ww < warp) wp += v;
+            rt += v;
+        }
+        pre[r] = total + wp + incl[r] - c[r];
+        total += rt;
+    }
+    if (tid == 0) {
+        s_off = pch_lookback_u64(status, tile, 0, total, err);
+        if (tile == n_tiles - 1) *count_out = (long long)(s_off + total);
+    }
+    __syncthreads();
+    if (!out_src) return;
+    const uint64_t off = s_off;
+#pragma unroll
+    for (int r = 0; r < CF_ROWS; ++r) {
+        if (c[r] == 0) continue;
+        uint64_t o = off + pre[r];
+        const int64_t i0 = start + (int64_t)r * (CP_THREADS * 16) + tid * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (w[r][q] & (1u << (8 * b))) out_src[o++] = (int32_t)(i0 + q * 4 + b);
+    }
+}
+
 extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8_t* keep_mask, int64_t m,
                                   const float* centroid3, float thr, float* out_xyz, int32_t* out_src,
                                   uint8_t* out_mask, int64_t* count_dev, void* workspace, size_t workspace_bytes,
@@ -806,8 +1087,17 @@ extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8
     uint32_t* counter = (uint32_t*)((uint8_t*)workspace + 64);
     uint64_t* status = (uint64_t*)((uint8_t*)workspace + 256);
     int64_t tiles = pch_ceil_div(m, CP_TILE);
-    PCH_LAUNCH(st, "k_compact", k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src, out_mask,
-                                                      (long long*)count_dev, status, counter, err));
+    if (keep_mask && !zs && !out_xyz && !out_mask && (reinterpret_cast<uintptr_t>(keep_mask) & 15) == 0) {
+        // flags -> index list only (needs CF_TILE/CP_TILE times fewer status words than were zeroed above)
+        PCH_LAUNCH(st, "k_compact_flags", k_compact_flags<<<(unsigned)pch_ceil_div(m, CF_TILE), CP_THREADS, 0, st>>>(
+                                              keep_mask, m, out_src, (long long*)count_dev, status, counter, err));
+    } else if (out_xyz && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
+        PCH_LAUNCH(st, "k_compact_xyz", k_compact_xyz<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src,
+                                                              out_mask, (long long*)count_dev, status, counter, err));
+    } else {
+        PCH_LAUNCH(st, "k_compact", k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src, out_mask,
+                                                          (long long*)count_dev, status, counter, err));
+    }
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

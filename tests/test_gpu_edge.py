@@ -160,3 +160,45 @@ def test_errors(cuda_device, tmp_path):
     open(src, "wb").write(bytes(raw))
     with pytest.raises(Exception):
         import_PC.run_voxel_downsampling(src, str(tmp_path / "o" / "y.las"))
+
+
+def test_compaction_variants_agree_with_numpy(cuda_device):
+    """The three compaction kernels (generic, staged xyz, flags-only) on ragged sizes and every keep source."""
+    import torch
+    from pointcloudhookup_b200 import _native, device as dv
+    lib = _native.lib()
+    rng = np.random.default_rng(17)
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    for m in (1, 15, 16, 17, 2047, 2048, 2049, 8191, 8192, 8193, 100_003):
+        xyz = rng.normal(0, 50, (m, 3)).astype(np.float32)
+        cen = np.array([1.5, -2.25, 3.0], dtype=np.float32)
+        d = torch.from_numpy(xyz).to(cuda_device)
+        c = torch.from_numpy(cen).to(cuda_device)
+        thr = 4.0
+        # (a) keep flag derived from the cloud, (b) from a z column, (c) from a byte mask with arbitrary non-zero values
+        keep = (xyz[:, 2] - cen[2]) > np.float32(thr)
+        got, g, src, mask = dv.compact_points(d, None, thr, c, want_src=True, want_mask=True)
+        assert g == keep.sum() and np.array_equal(got.cpu().numpy(), (xyz - cen)[keep])
+        assert np.array_equal(src.cpu().numpy(), np.nonzero(keep)[0]) and np.array_equal(mask.cpu().numpy().astype(bool), keep)
+        zs = torch.from_numpy((xyz[:, 2] - cen[2]).astype(np.float32)).to(cuda_device)
+        got2, g2, _, _ = dv.compact_points(d, zs, thr, c)
+        assert g2 == g and torch.equal(got2, got)
+        bm = (rng.random(m) < 0.3) * rng.integers(1, 256, m)
+        bmask = torch.from_numpy(bm.astype(np.uint8)).to(cuda_device)
+        got3, g3, src3, _ = dv.compact_points(d, None, 0.0, None, keep_mask=bmask, want_src=True)
+        assert g3 == (bm != 0).sum() and np.array_equal(got3.cpu().numpy(), xyz[bm != 0])
+        assert np.array_equal(src3.cpu().numpy(), np.nonzero(bm)[0])
+        # flags-only entry (no rows out): the DBSCAN head list path
+        for dens in (0.3, 0.0005):
+            bm = (rng.random(m) < dens) * rng.integers(1, 256, m)
+            bmask = torch.from_numpy(bm.astype(np.uint8)).to(cuda_device)
+            out = torch.full((m,), -1, dtype=torch.int32, device=cuda_device)
+            cnt = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+            wsb = lib.pch_compact_workspace_bytes(m)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=cuda_device)
+            rc = lib.pch_compact_points(d.data_ptr(), None, bmask.data_ptr(), m, None, 0.0, None, out.data_ptr(), None,
+                                        cnt.data_ptr(), ws.data_ptr(), wsb, st())
+            assert rc == 0
+            k = int(cnt.item())
+            assert k == (bm != 0).sum() and np.array_equal(out[:k].cpu().numpy(), np.nonzero(bm)[0])
+            assert bool((out[k:] == -1).all())

@@ -728,62 +728,6 @@ __global__ void k_db_cluster_ids(const long long* __restrict__ K_dev, const int3
     for (; r < K; r += stride) root_label[cell_root[pt_cell[inv_pos[head_list[r]]]]] = (int32_t)r;
 }
 
-// ---------------------------------------------------------------- D6: labels (core + border + noise)
-// core points take their cell's cluster id (thread per point); the non-core points (again the work
-// list of D3, minus those that turned out core) are searched by one warp each: smallest cluster id
-// among the core points within eps, else -1.
-__global__ void __launch_bounds__(256)
-k_db_labels_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
-                 const uint8_t* __restrict__ core, const int32_t* __restrict__ cell_root,
-                 const int32_t* __restrict__ root_label, int32_t* __restrict__ labels) {
-    int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; pos < g.G; pos += stride) {
-        if (!core[pos]) continue;
-        const int64_t c = pos / g.chunk;
-        const int64_t orig = c * g.chunk + __float_as_int(spts[pos].w);
-        labels[orig] = root_label[cell_root[pt_cell[pos]]];
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
-                   const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
-                   const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt,
-                   const int32_t* __restrict__ cell_root, const int32_t* __restrict__ root_label,
-                   const int32_t* __restrict__ worklist, const unsigned int* __restrict__ n_work,
-                   int32_t* __restrict__ labels) {
-    const int lane = threadIdx.x & 31;
-    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t n = *n_work;
-    for (; w < n; w += nw) {
-        const int32_t pos = worklist[w];
-        if (core[pos]) continue;  // warp-uniform
-        const int32_t u = pt_cell[pos];
-        const float4 p = spts[pos];
-        int32_t best = INT_MAX;
-        for (int col = 0; col < 25; ++col) {
-            const int nc = nbr_cnt[(int64_t)u * 25 + col];
-            if (nc == 0) continue;
-            const int32_t f = nbr_first[(int64_t)u * 25 + col];
-            const int32_t b = cell_start[f], e = cell_start[f + nc];
-            for (int32_t q0 = b; q0 < e; q0 += 32) {
-                const int32_t q = q0 + lane;
-                if (q < e && core[q]) {
-                    const int32_t cl = root_label[cell_root[pt_cell[q]]];
-                    if (cl < best && db_dist2(p, spts[q]) <= g.eps2) best = cl;
-                }
-            }
-        }
-        best = __reduce_min_sync(0xffffffffu, best);
-        if (lane == 0) {
-            const int64_t c = pos / g.chunk;
-            labels[c * g.chunk + __float_as_int(p.w)] = best == INT_MAX ? -1 : best;
-        }
-    }
-}
-
 // ---------------------------------------------------------------- D7: per-cluster reduction
 // acc[k]: count, float32 AABB (ordered-uint encoded while reducing), float64 coordinate sums
 struct DbClusterAcc {
@@ -843,6 +787,124 @@ __device__ __forceinline__ void db_warp_flush(DbClusterAcc* __restrict__ acc, Db
 }
 
 #define CR_ROWS 64
+
+// ---------------------------------------------------------------- D6: labels (core + border + noise)
+// core points take their cell's cluster id (thread per point); the non-core points (again the work
+// list of D3, minus those that turned out core) are searched by one warp each: smallest cluster id
+// among the core points within eps, else -1.
+// k_db_labels_core also performs the per-cluster reduction (D7) for the core points in the same pass: in
+// cell-sorted order the cluster id is constant over long stretches, so a warp reads rows of 32 consecutive
+// sorted points, keeps a lane-local running accumulator while the row's label matches, and merges + flushes
+// (one set of atomics) only when the label changes.  Border points add themselves in k_db_labels_border.
+__global__ void __launch_bounds__(256)
+k_db_labels_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+                 const uint8_t* __restrict__ core, const int32_t* __restrict__ cell_root,
+                 const int32_t* __restrict__ root_label, int32_t* __restrict__ labels, int64_t cap,
+                 DbClusterAcc* __restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_rows = (g.G + 31) / 32;
+    const int64_t n_groups = (n_rows + CR_ROWS - 1) / CR_ROWS;
+    int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t ngw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (; grp < n_groups; grp += ngw) {
+        DbRun run;
+        db_run_reset(run, -1);
+        for (int j = 0; j < CR_ROWS; ++j) {
+            if ((grp * CR_ROWS + j) >= n_rows) break;   // warp-uniform
+            const int64_t pos = (grp * CR_ROWS + j) * 32 + lane;
+            int32_t lab = -1;
+            float v[3] = {0.f, 0.f, 0.f};
+            if (pos < g.G && core[pos]) {
+                const float4 p = spts[pos];
+                lab = root_label[cell_root[pt_cell[pos]]];
+                const int64_t c = pos / g.chunk;
+                labels[c * g.chunk + __float_as_int(p.w)] = lab;
+                if (lab >= cap) lab = -1;       // statistics only for the clusters the caller made room for
+                v[0] = p.x; v[1] = p.y; v[2] = p.z;
+            }
+            const uint32_t valid = __ballot_sync(0xffffffffu, lab >= 0);
+            if (valid == 0) continue;
+            const int32_t cand = __shfl_sync(0xffffffffu, lab, __ffs(valid) - 1);
+            if (run.lab < 0) db_run_reset(run, cand);
+            if (!__any_sync(0xffffffffu, lab == run.lab)) {   // the current run ended before this row
+                db_warp_flush(acc, run, lane);
+                db_run_reset(run, cand);
+            }
+            if (lab == run.lab) {
+                run.cnt += 1;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const uint32_t u = pch_f32_to_ordered(v[a]);
+                    run.mn[a] = min(run.mn[a], u);
+                    run.mx[a] = max(run.mx[a], u);
+                    run.sum[a] += (double)v[a];
+                }
+            } else if (lab >= 0) {                            // a second label inside the row: rare, direct atomics
+                DbClusterAcc* a = &acc[lab];
+                atomicAdd(&a->count, 1ull);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t u = pch_f32_to_ordered(v[k]);
+                    atomicMin(&a->mn[k], u);
+                    atomicMax(&a->mx[k], u);
+                    atomicAdd(&a->sum[k], (double)v[k]);
+                }
+            }
+        }
+        db_warp_flush(acc, run, lane);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict__ pt_cell,
+                   const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
+                   const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt,
+                   const int32_t* __restrict__ cell_root, const int32_t* __restrict__ root_label,
+                   const int32_t* __restrict__ worklist, const unsigned int* __restrict__ n_work,
+                   int32_t* __restrict__ labels, int64_t cap, DbClusterAcc* __restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n = *n_work;
+    for (; w < n; w += nw) {
+        const int32_t pos = worklist[w];
+        if (core[pos]) continue;  // warp-uniform
+        const int32_t u = pt_cell[pos];
+        const float4 p = spts[pos];
+        int32_t best = INT_MAX;
+        for (int col = 0; col < 25; ++col) {
+            const int nc = nbr_cnt[(int64_t)u * 25 + col];
+            if (nc == 0) continue;
+            const int32_t f = nbr_first[(int64_t)u * 25 + col];
+            const int32_t b = cell_start[f], e = cell_start[f + nc];
+            for (int32_t q0 = b; q0 < e; q0 += 32) {
+                const int32_t q = q0 + lane;
+                if (q < e && core[q]) {
+                    const int32_t cl = root_label[cell_root[pt_cell[q]]];
+                    if (cl < best && db_dist2(p, spts[q]) <= g.eps2) best = cl;
+                }
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0) {
+            const int64_t c = pos / g.chunk;
+            labels[c * g.chunk + __float_as_int(p.w)] = best == INT_MAX ? -1 : best;
+            if (best != INT_MAX && best < cap) {     // the border point joins its cluster's statistics
+                DbClusterAcc* a = &acc[best];
+                atomicAdd(&a->count, 1ull);
+                const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t u = pch_f32_to_ordered(v[k]);
+                    atomicMin(&a->mn[k], u);
+                    atomicMax(&a->mx[k], u);
+                    atomicAdd(&a->sum[k], (double)v[k]);
+                }
+            }
+        }
+    }
+}
+
 // Labels are spatially coherent (the candidates are in voxel-sorted order).  A warp reads rows of 32
 // consecutive points (coalesced); a row whose 32 labels agree is reduced with shuffles into the warp's
 // running accumulator (held redundantly by all lanes), which is flushed with one set of atomics only
@@ -1109,15 +1171,16 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     PCH_LAUNCH(st, "k_db_cluster_ids", k_db_cluster_ids<<<db_grid(G, 256), 256, 0, st>>>((const long long*)n_clusters_dev, head_list, o.inv_pos, o.pt_cell,
                                                       cell_root, root_label));
     PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_labels_core", k_db_labels_core<<<db_grid(G, 256), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_label, labels_dev));
+    // labels + per-cluster reduction in one pass over the cell-sorted points (core points: run-merged; border
+    // points: per-point atomics from the border search)
+    PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
+    PCH_LAUNCH_CHECK();
+    PCH_LAUNCH(st, "k_db_labels_core", k_db_labels_core<<<db_grid(G, 8 * 32 * CR_ROWS, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_label,
+                                                                                            labels_dev, max_clusters, acc));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_labels_border", k_db_labels_border<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first,
                                                                                     nbr_cnt, cell_root, root_label, worklist, n_work,
-                                                                                    labels_dev));
-    PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
-    PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_db_cluster_reduce", k_db_cluster_reduce<<<db_grid(G, 8 * 32 * CR_ROWS, 16), 256, 0, st>>>(P, labels_dev, G, max_clusters, acc));
+                                                                                    labels_dev, max_clusters, acc));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_finish", k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev));
     PCH_LAUNCH_CHECK();

@@ -244,6 +244,10 @@ k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const Sq
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t base = t * SQ_TILE;
+        // the fast path is order-free, so each thread takes 8 consecutive points with six 16-byte loads
+        float v[24];
+        sq_load8(xyz, base + (int64_t)tid * SQ_EPT, m, v);
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
             const int k0 = klo[c * n_tiles + t];
             unsigned long long acc[SQ_W];
@@ -251,11 +255,7 @@ k_sum_tables(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const Sq
 #pragma unroll
             for (int w = 0; w < SQ_W; ++w) { acc[w] = 0; ties[w] = 0; }
 #pragma unroll
-            for (int e = 0; e < SQ_EPT; ++e) {
-                const int64_t i = base + e * SQ_THREADS + tid;
-                const uint32_t bits = i < m ? __float_as_uint(__ldg(&xyz[i * 3 + c])) : 0u;
-                sq_elem_window(bits, k0, acc, ties);
-            }
+            for (int e = 0; e < SQ_EPT; ++e) sq_elem_window(__float_as_uint(v[e * 3 + c]), k0, acc, ties);
 #pragma unroll
             for (int w = 0; w < SQ_W; ++w) {
 #pragma unroll

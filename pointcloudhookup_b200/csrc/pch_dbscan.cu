@@ -41,19 +41,38 @@ __global__ void k_db_bounds_init(uint32_t* mm, int64_t n_chunks) {
 }
 
 __global__ void __launch_bounds__(256) k_db_bounds(const float* __restrict__ P, int64_t G, int64_t chunk, uint32_t* __restrict__ mm) {
-    // one block handles a 4096-point slab inside one chunk
+    // one block handles a 4096-point slab inside one chunk; a thread takes runs of 4 consecutive points
+    // (48 bytes = three 16-byte loads when the run starts on a 16-byte boundary)
     const int64_t slabs_per_chunk = (chunk + 4095) / 4096;
     const int64_t n_chunks = (G + chunk - 1) / chunk;
+    const bool base16 = (reinterpret_cast<uintptr_t>(P) & 15) == 0;
     for (int64_t s = blockIdx.x; s < n_chunks * slabs_per_chunk; s += gridDim.x) {
         int64_t c = s / slabs_per_chunk, ls = s - c * slabs_per_chunk;
         int64_t lo = c * chunk + ls * 4096, hi = min(min(lo + 4096, (c + 1) * chunk), G);
         uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0, 0, 0};
-        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+        for (int64_t i0 = lo + (int64_t)threadIdx.x * 4; i0 < hi; i0 += 256 * 4) {
+            if (base16 && (i0 & 3) == 0 && i0 + 4 <= hi) {
+                const float4* src = reinterpret_cast<const float4*>(P + i0 * 3);
+                float v[12];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                uint32_t u = pch_f32_to_ordered(P[i * 3 + a]);
-                mn[a] = min(mn[a], u);
-                mx[a] = max(mx[a], u);
+                for (int k = 0; k < 3; ++k) {
+                    const float4 f = __ldg(src + k);
+                    v[4 * k + 0] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const uint32_t u = pch_f32_to_ordered(v[k]);
+                    mn[k % 3] = min(mn[k % 3], u);
+                    mx[k % 3] = max(mx[k % 3], u);
+                }
+            } else {
+                for (int64_t i = i0; i < min(i0 + 4, hi); ++i)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const uint32_t u = pch_f32_to_ordered(P[i * 3 + a]);
+                        mn[a] = min(mn[a], u);
+                        mx[a] = max(mx[a], u);
+                    }
             }
         }
 #pragma unroll
@@ -103,16 +122,63 @@ __global__ void k_db_plan(const uint32_t* __restrict__ mm, int64_t n_chunks, int
 }
 
 // ---------------------------------------------------------------- D2: cell keys
-__global__ void k_db_keys(const float* __restrict__ P, DbGeom g, const uint32_t* __restrict__ mm, uint64_t* __restrict__ keys) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// floor((v - mn) / cell) for the three axes with one range guard: the reciprocal sequence returns exactly what
+// the true divide returns (pch_div_by), so the cell grid is the same either way
+__device__ __forceinline__ void db_cell3(float x, float y, float z, float mnx, float mny, float mnz, double cell,
+                                         double rcell, int fast, uint64_t& cx, uint64_t& cy, uint64_t& cz) {
+    const double dx = __dsub_rn((double)x, (double)mnx), dy = __dsub_rn((double)y, (double)mny),
+                 dz = __dsub_rn((double)z, (double)mnz);
+    double qx, qy, qz;
+    if (fast && pch_div_inrange3(dx, dy, dz)) {
+        qx = pch_div_by_nocheck(dx, cell, rcell); qy = pch_div_by_nocheck(dy, cell, rcell); qz = pch_div_by_nocheck(dz, cell, rcell);
+    } else {
+        qx = __ddiv_rn(dx, cell); qy = __ddiv_rn(dy, cell); qz = __ddiv_rn(dz, cell);
+    }
+    cx = (uint64_t)(long long)floor(qx); cy = (uint64_t)(long long)floor(qy); cz = (uint64_t)(long long)floor(qz);
+}
+
+// four consecutive points per thread: three 16-byte loads in, two 16-byte stores out
+__global__ void __launch_bounds__(256)
+k_db_keys(const float* __restrict__ P, DbGeom g, const uint32_t* __restrict__ mm, double rcell, int fast,
+          uint64_t* __restrict__ keys) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < g.G; i += stride) {
-        int64_t c = i / g.chunk;
-        float mnx = pch_ordered_to_f32(mm[c * 6 + 0]), mny = pch_ordered_to_f32(mm[c * 6 + 1]), mnz = pch_ordered_to_f32(mm[c * 6 + 2]);
-        uint64_t cx = (uint64_t)db_cell_of(P[i * 3 + 0], mnx, g.cell);
-        uint64_t cy = (uint64_t)db_cell_of(P[i * 3 + 1], mny, g.cell);
-        uint64_t cz = (uint64_t)db_cell_of(P[i * 3 + 2], mnz, g.cell);
-        keys[i] = (cx << g.sh_x) | (cy << g.sh_y) | (cz << g.sh_z) | (uint64_t)(i - c * g.chunk);
+    const int64_t n_quads = (g.G + 3) / 4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(keys)) & 15) == 0;
+    for (; q < n_quads; q += stride) {
+        const int64_t i0 = q * 4;
+        float v[12];
+        if (aligned && i0 + 4 <= g.G) {
+            const float4* src = reinterpret_cast<const float4*>(P + i0 * 3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 f = __ldg(src + k);
+                v[4 * k + 0] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) v[k] = (i0 * 3 + k < g.G * 3) ? P[i0 * 3 + k] : 0.f;
+        }
+        uint64_t out[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i0 + e;
+            const int64_t c = (i < g.G ? i : g.G - 1) / g.chunk;
+            const float mnx = pch_ordered_to_f32(mm[c * 6 + 0]), mny = pch_ordered_to_f32(mm[c * 6 + 1]),
+                        mnz = pch_ordered_to_f32(mm[c * 6 + 2]);
+            uint64_t cx, cy, cz;
+            db_cell3(v[e * 3 + 0], v[e * 3 + 1], v[e * 3 + 2], mnx, mny, mnz, g.cell, rcell, fast, cx, cy, cz);
+            out[e] = (cx << g.sh_x) | (cy << g.sh_y) | (cz << g.sh_z) | (uint64_t)(i - c * g.chunk);
+        }
+        if (aligned && i0 + 4 <= g.G) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(keys + i0);
+            dst[0] = make_ulonglong2(out[0], out[1]);
+            dst[1] = make_ulonglong2(out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i0 + e < g.G) keys[i0 + e] = out[e];
+        }
     }
 }
 
@@ -1103,7 +1169,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     g.sh_z = plan->bits_idx; g.sh_y = g.sh_z + plan->bits_z; g.sh_x = g.sh_y + plan->bits_y;
 
     PCH_CUDA(cudaMemsetAsync(base + w.scalars, 0, 256, st));
-    PCH_LAUNCH(st, "k_db_keys", k_db_keys<<<db_grid(G, 256), 256, 0, st>>>(P, g, bounds_dev, keys));
+    PCH_LAUNCH(st, "k_db_keys", k_db_keys<<<db_grid((G + 3) / 4, 256, 16), 256, 0, st>>>(P, g, bounds_dev, 1.0 / g.cell, pch_recip_ok(g.cell) ? 1 : 0, keys));
     PCH_LAUNCH_CHECK();
     int rc = pch_sort_u64_segmented(keys, tmp, G, chunk, plan->bits_idx, plan->bits_idx + plan->key_bits,
                                     base + w.sortws, w.sortws_bytes, stream);

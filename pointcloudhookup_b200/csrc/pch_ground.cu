@@ -407,17 +407,16 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
     __shared__ uint8_t s_ok[SQ_BATCH];
     __shared__ SqMap s_stab[(SQ_BATCH / SQ_SUPER) * SQ_W];
     __shared__ int32_t s_sklo[SQ_BATCH / SQ_SUPER];
-    __shared__ float s_col[SQ_TILE];
-    __shared__ float s_state;
-    __shared__ int s_skip;
+    __shared__ __align__(16) float s_col[SQ_TILE];
+    __shared__ float s_state[2];   // double-buffered by batch parity: the next batch's decision never races this one's readers
+    __shared__ int s_skip[2];
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_batch = (n_tiles + SQ_BATCH - 1) / SQ_BATCH;
     float s = 0.0f;
     int n_map = 0, n_real = 0;
-    if (tid == 0) s_state = 0.0f;
-    __syncthreads();
     for (int64_t b0 = 0; b0 < n_tiles; b0 += SQ_BATCH) {
         const int nb = (int)min((int64_t)SQ_BATCH, n_tiles - b0);
+        const int slot = (int)((b0 / SQ_BATCH) & 1);
         // ---- level 3: the whole batch with one map (thread 0 decides; nothing is staged when it applies)
         if (tid == 0) {
             int skip = 0;
@@ -437,12 +436,12 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
                     }
                 }
             }
-            s_state = s;
-            s_skip = skip;
+            s_state[slot] = s;
+            s_skip[slot] = skip;
         }
         __syncthreads();
-        s = s_state;
-        if (s_skip) continue;    // block-uniform
+        s = s_state[slot];
+        if (s_skip[slot]) continue;    // block-uniform
         const int nsb = (int)min((int64_t)(SQ_BATCH / SQ_SUPER), n_super - b0 / SQ_SUPER);   // super-tiles in this batch
         for (int i = tid; i < nsb * SQ_W; i += SQ_CHAIN_THREADS)
             s_stab[i] = stable[((size_t)c * n_super + b0 / SQ_SUPER) * SQ_W + i];
@@ -457,7 +456,9 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
             }
         }
         __syncthreads();
-        if (warp == 0) {
+        {
+            // Every warp runs the same walk redundantly (identical state in all threads), so the whole CTA can
+            // take part in the rare tile that needs real adds.
             int t = 0;   // tile index inside the batch
             while (t < nb) {
                 const uint32_t sb = __float_as_uint(s);
@@ -524,72 +525,36 @@ k_sum_chain(const float* __restrict__ xyz, int64_t m, int64_t n_tiles, const SqT
                 t += advanced;
                 if (t >= cap) continue;   // reached the boundary without a failing tile
                 {
-                    // tile b0+t leaves the binade / is outside its window / has negative data
+                    // Tile b0+t leaves the binade / is outside its window / has negative data: the literal float32
+                    // running sum.  The CTA stages the column in shared memory (coalesced, all loads in flight), then
+                    // every thread performs the same 2048 dependent adds from broadcast shared-memory reads (~4 cycles
+                    // each) — cheaper than any map construction for the handful of tiles per column that get here.
                     const int64_t tg = b0 + t;
                     const int64_t lo = tg * SQ_TILE, hi = min(lo + (int64_t)SQ_TILE, m);
-                    const bool tile_ok = s_ok[t] != 0;
-#pragma unroll 16
-                    for (int j = 0; j < SQ_TILE / 32; ++j) {      // 64 independent loads per lane in flight
-                        const int64_t i = lo + j * 32 + lane;
-                        s_col[j * 32 + lane] = i < hi ? __ldg(&xyz[i * 3 + c]) : 0.0f;
-                    }
-                    __syncwarp();
-                    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
-                        const int64_t i = i0 + lane;
-                        const float v = i < hi ? s_col[(int)(i - lo)] : 0.0f;
-                        const int cnt = (int)min((int64_t)32, hi - i0);
-                        if (!tile_ok) {                       // negative / non-finite data: real float32 adds
-                            for (int j = 0; j < cnt; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, j));
-                            continue;
-                        }
-                        // non-negative data: on-the-fly maps for the current binade; only the element that
-                        // actually crosses a binade boundary takes a real add
-                        int start = 0;
-                        while (start < cnt) {
-                            const uint32_t sb2 = __float_as_uint(s);
-                            const int es2 = (int)((sb2 >> 23) & 0xffu);
-                            if (es2 != 0 && es2 != 0xff) {
-                                const int k = es2 - 150;
-                                const uint32_t ms = (sb2 & 0x7fffffu) | 0x800000u;
-                                SqMap F; F.d0 = 0; F.d1 = 0;
-                                if (lane >= start && lane < cnt) {
-                                    uint32_t q, gt, eq;
-                                    sq_elem(__float_as_uint(v), k, q, gt, eq);
-                                    const uint32_t bb = sq_sat_add(q, gt);
-                                    F.d0 = sq_sat_add(bb, eq & (q & 1u));
-                                    F.d1 = sq_sat_add(bb, eq & ((1u + q) & 1u));
-                                }
+                    const int n_el = (int)(hi - lo);
+                    __syncthreads();     // previous use of s_col is over
 #pragma unroll
-                                for (int o = 1; o < 32; o <<= 1) {
-                                    SqMap pv;
-                                    pv.d0 = __shfl_up_sync(0xffffffffu, F.d0, o);
-                                    pv.d1 = __shfl_up_sync(0xffffffffu, F.d1, o);
-                                    if (lane >= o) F = sq_compose(pv, F);
-                                }
-                                const uint32_t D = (ms & 1u) ? F.d1 : F.d0;
-                                const bool ok = lane < cnt && D < SQ_SAT && (uint64_t)ms + D < (1ull << 24);
-                                const uint32_t okmask = __ballot_sync(0xffffffffu, ok) | ((1u << start) - 1u);
-                                const int first_bad = okmask == 0xffffffffu ? 32 : (__ffs(~okmask) - 1);
-                                if (first_bad > start) {
-                                    const uint32_t Dl = __shfl_sync(0xffffffffu, D, first_bad - 1);
-                                    s = __uint_as_float(((uint32_t)es2 << 23) | ((ms + Dl) & 0x7fffffu));
-                                    start = first_bad;
-                                }
-                            }
-                            if (start < cnt) {   // the element that crosses the binade (or s is still 0/denormal)
-                                s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, start));
-                                ++start;
-                            }
+                    for (int j = 0; j < SQ_TILE / SQ_CHAIN_THREADS; ++j) {
+                        const int e = j * SQ_CHAIN_THREADS + tid;
+                        s_col[e] = e < n_el ? __ldg(&xyz[(lo + e) * 3 + c]) : 0.0f;
+                    }
+                    __syncthreads();
+                    if (n_el == SQ_TILE) {
+                        const float4* q = reinterpret_cast<const float4*>(s_col);
+#pragma unroll 4
+                        for (int j = 0; j < SQ_TILE / 4; ++j) {
+                            const float4 v = q[j];
+                            s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
                         }
+                    } else {
+                        for (int j = 0; j < n_el; ++j) s = __fadd_rn(s, s_col[j]);
                     }
                     ++t;
                     ++n_real;
                 }
             }
-            if (lane == 0) s_state = s;
         }
         __syncthreads();
-        s = s_state;
     }
     if (tid == 0) {
         sums[c] = s;

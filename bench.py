@@ -183,12 +183,17 @@ def kernel_bytes_model(cfg, info):
         "k_shift": M * 12 + M * 4,
         "k_sel_hist": M * 4,
         "k_compact": M * 12 + G * 12,                         # keep flag derived from the cloud itself
+        "k_compact_xyz": M * 12 + G * 12,
+        "k_compact_flags": G,
         "k_column": M * 12 + M * 4,
+        "k_sum_prep": M * 12,
+        "k_sum_tables": M * 12,
+        "k_db_bounds": G * 12,
+        "k_db_labels_core": G * (16 + 1 + 4) + G * 4,
         "k_db_keys": G * 12 + G * 8,
         "k_db_cells": G * 8 + G * 12 + G * (16 + 4 + 4),
         "k_db_core": G * 16 + G,
         "k_db_labels": G * 16 + G * 4,
-        "k_db_cluster_reduce": G * 16,
         "k_las_geodetic": n * R + n * 24,
     }
 

@@ -853,6 +853,9 @@ __device__ __forceinline__ void db_warp_flush(DbClusterAcc* __restrict__ acc, Db
 }
 
 #define CR_ROWS 64
+#ifndef CR_UNROLL
+#define CR_UNROLL 4
+#endif
 
 // ---------------------------------------------------------------- D6: labels (core + border + noise)
 // core points take their cell's cluster id (thread per point); the non-core points (again the work
@@ -875,45 +878,65 @@ k_db_labels_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __res
     for (; grp < n_groups; grp += ngw) {
         DbRun run;
         db_run_reset(run, -1);
-        for (int j = 0; j < CR_ROWS; ++j) {
-            if ((grp * CR_ROWS + j) >= n_rows) break;   // warp-uniform
-            const int64_t pos = (grp * CR_ROWS + j) * 32 + lane;
-            int32_t lab = -1;
-            float v[3] = {0.f, 0.f, 0.f};
-            if (pos < g.G && core[pos]) {
-                const float4 p = spts[pos];
-                lab = root_label[cell_root[pt_cell[pos]]];
-                const int64_t c = pos / g.chunk;
-                labels[c * g.chunk + __float_as_int(p.w)] = lab;
-                if (lab >= cap) lab = -1;       // statistics only for the clusters the caller made room for
-                v[0] = p.x; v[1] = p.y; v[2] = p.z;
-            }
-            const uint32_t valid = __ballot_sync(0xffffffffu, lab >= 0);
-            if (valid == 0) continue;
-            const int32_t cand = __shfl_sync(0xffffffffu, lab, __ffs(valid) - 1);
-            if (run.lab < 0) db_run_reset(run, cand);
-            if (!__any_sync(0xffffffffu, lab == run.lab)) {   // the current run ended before this row
-                db_warp_flush(acc, run, lane);
-                db_run_reset(run, cand);
-            }
-            if (lab == run.lab) {
-                run.cnt += 1;
+        for (int j0 = 0; j0 < CR_ROWS; j0 += CR_UNROLL) {
+            if ((grp * CR_ROWS + j0) >= n_rows) break;   // warp-uniform
+            // the label of a core point sits behind three dependent gathers (pt_cell -> cell_root -> root_label):
+            // issue each level for CR_UNROLL rows at once so that many loads are in flight per lane
+            int64_t pos[CR_UNROLL];
+            bool isc[CR_UNROLL];
+            float4 p[CR_UNROLL];
+            int32_t lab_u[CR_UNROLL];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const uint32_t u = pch_f32_to_ordered(v[a]);
-                    run.mn[a] = min(run.mn[a], u);
-                    run.mx[a] = max(run.mx[a], u);
-                    run.sum[a] += (double)v[a];
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                pos[u] = (grp * CR_ROWS + j0 + u) * 32 + lane;
+                isc[u] = (grp * CR_ROWS + j0 + u) < n_rows && pos[u] < g.G && core[pos[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                lab_u[u] = isc[u] ? pt_cell[pos[u]] : 0;
+                p[u] = isc[u] ? spts[pos[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) lab_u[u] = isc[u] ? cell_root[lab_u[u]] : 0;
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) lab_u[u] = isc[u] ? root_label[lab_u[u]] : -1;
+#pragma unroll
+            for (int u = 0; u < CR_UNROLL; ++u) {
+                if ((grp * CR_ROWS + j0 + u) >= n_rows) break;   // warp-uniform
+                int32_t lab = lab_u[u];
+                float v[3] = {p[u].x, p[u].y, p[u].z};
+                if (isc[u]) {
+                    const int64_t c = pos[u] / g.chunk;
+                    labels[c * g.chunk + __float_as_int(p[u].w)] = lab;
+                    if (lab >= cap) lab = -1;       // statistics only for the clusters the caller made room for
                 }
-            } else if (lab >= 0) {                            // a second label inside the row: rare, direct atomics
-                DbClusterAcc* a = &acc[lab];
-                atomicAdd(&a->count, 1ull);
+                const uint32_t valid = __ballot_sync(0xffffffffu, lab >= 0);
+                if (valid == 0) continue;
+                const int32_t cand = __shfl_sync(0xffffffffu, lab, __ffs(valid) - 1);
+                if (run.lab < 0) db_run_reset(run, cand);
+                if (!__any_sync(0xffffffffu, lab == run.lab)) {   // the current run ended before this row
+                    db_warp_flush(acc, run, lane);
+                    db_run_reset(run, cand);
+                }
+                if (lab == run.lab) {
+                    run.cnt += 1;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const uint32_t u = pch_f32_to_ordered(v[k]);
-                    atomicMin(&a->mn[k], u);
-                    atomicMax(&a->mx[k], u);
-                    atomicAdd(&a->sum[k], (double)v[k]);
+                    for (int a = 0; a < 3; ++a) {
+                        const uint32_t uo = pch_f32_to_ordered(v[a]);
+                        run.mn[a] = min(run.mn[a], uo);
+                        run.mx[a] = max(run.mx[a], uo);
+                        run.sum[a] += (double)v[a];
+                    }
+                } else if (lab >= 0) {                            // a second label inside the row: rare, direct atomics
+                    DbClusterAcc* a = &acc[lab];
+                    atomicAdd(&a->count, 1ull);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t uo = pch_f32_to_ordered(v[k]);
+                        atomicMin(&a->mn[k], uo);
+                        atomicMax(&a->mx[k], uo);
+                        atomicAdd(&a->sum[k], (double)v[k]);
+                    }
                 }
             }
         }

@@ -144,14 +144,14 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
        const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
        int* __restrict__ err) {
     __shared__ uint64_t s_keys[RS_TILE];
-    __shared__ uint16_t s_whist[RS_WARPS][256];   // a warp ranks 32*RS_KPT = 512 keys: counts fit 16 bits
+    __shared__ uint16_t s_whist[RS_WARPS][258];   // a warp ranks 32*RS_KPT = 512 keys: counts fit 16 bits; [256] = spare slot for out-of-range lanes
     __shared__ uint32_t s_dstart[256];
     __shared__ int64_t s_goff[256];
     __shared__ uint32_t s_scan[RS_THREADS / 32];
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
-    for (int i = tid; i < RS_WARPS * 256 / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&s_whist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * 258 / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&s_whist[0][0])[i] = 0;
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= g.total_tiles) return;
@@ -173,9 +173,30 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
     for (int j = 0; j < RS_KPT; ++j) {
         int idx = wbase + j * 32 + lane;
         uint32_t d = idx < cnt ? ((uint32_t)(key[j] >> shift) & dmask) : 256u;
+#ifdef RS_BALLOT
+        // peers = lanes holding the same digit, from one ballot per digit bit (+ one for the out-of-range
+        // flag): MATCH.ANY has a long, poorly pipelined latency on sm_100, ballots issue back to back
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+#else
         uint32_t peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
+#endif
         uint32_t before = __popc(peers & ((1u << lane) - 1u));
+#ifdef RS_NOBRANCH
+        // every lane reads its digit's running count (peers read the same word: a broadcast), then the last
+        // peer alone stores the new count: no divergent region, no shuffle.  d == 256 uses the spare slot.
+        uint32_t old = s_whist[warp][d];
+        __syncwarp();
+        if (before + 1 == __popc(peers)) s_whist[warp][d] = (uint16_t)(old + before + 1);
+        rank[j] = (uint16_t)(old + before);
+        __syncwarp();
+#else
+        int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader && d < 256u) {
             old = s_whist[warp][d];
@@ -184,6 +205,7 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[j] = (uint16_t)(old + before);
         __syncwarp();
+#endif
     }
     __syncthreads();
 

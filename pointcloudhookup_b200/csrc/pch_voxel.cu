@@ -239,7 +239,9 @@ extern "C" int pch_voxel_keys_xyz16(const int32_t* xyz16, int64_t n, int64_t chu
 // ------------------------------------------------------------------------------------------------
 // segmented in-order reduction
 // ------------------------------------------------------------------------------------------------
+#ifndef VR_THREADS
 #define VR_THREADS 256
+#endif
 #ifndef VR_ROWS
 #define VR_ROWS 8
 #endif

@@ -15,4 +15,7 @@ buf = ctypes.create_string_buffer(65536); lib.pch_profile_report(buf, 65536)
 out = {}
 for line in buf.value.decode().splitlines():
     nm, c, t = line.split(); out[nm] = float(t) / 3
-print(os.environ.get("PCH_LIB_PATH", "default").split("_")[-1], {k: round(v, 3) for k, v in sorted(out.items(), key=lambda kv: -kv[1])[:5]})
+r = dv.voxel_downsample(dl, 0.1, 500000, want=("f32",))
+chk = int(r.f32.view(torch.int32).to(torch.int64).sum().item()) ^ r.count          # identical across variants or the variant is wrong
+print(os.environ.get("PCH_LIB_PATH", "default").split("_")[-1], "M", r.count, "chk", chk,
+      {k: round(v, 3) for k, v in sorted(out.items(), key=lambda kv: -kv[1])[:5]})

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import dataclasses
 import os
+import queue
 import threading
 from typing import List, Optional
 
@@ -43,20 +44,136 @@ def run_pipeline(dl: dv.DeviceLas, voxel_size: float = 0.1, chunk_size: int = 50
                           stages if keep_stages else None, vres.plan, stages.db_plan)
 
 
-_STAGING = {}   # (device index, nbytes) -> pinned staging tensor, reused across calls (pinning costs ~0.3 s/GB)
+# pinned staging buffers are expensive to create (~0.3 s/GB), so they are pooled; a buffer is owned by exactly one
+# transfer between acquire and release (concurrent calls from several threads never share one)
+_POOL = []
+_POOL_LOCK = threading.Lock()
 
 
-def _staging(nbytes: int) -> torch.Tensor:
-    key = int(nbytes)
-    buf = _STAGING.get(key)
+def _alloc_pinned(nbytes: int) -> torch.Tensor:
+    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+
+def _acquire_staging(nbytes: int) -> torch.Tensor:
+    nbytes = max(int(nbytes), 16)
+    with _POOL_LOCK:
+        fit = [i for i, b in enumerate(_POOL) if b.numel() >= nbytes]
+        if fit:
+            return _POOL.pop(min(fit, key=lambda i: _POOL[i].numel()))     # by index: tensors compare elementwise
+    return _alloc_pinned(nbytes)
+
+
+def _release_staging(buf) -> None:
     if buf is None:
-        _STAGING.clear()      # one live staging buffer: a new size replaces the old one
-        buf = torch.empty(key, dtype=torch.uint8, pin_memory=True)
-        _STAGING[key] = buf
-    return buf
+        return
+    with _POOL_LOCK:
+        if any(b is buf for b in _POOL):
+            return
+        _POOL.append(buf)
+        _POOL.sort(key=lambda b: -b.numel())
+        del _POOL[4:]
 
 
 host_threads = dv.host_threads
+FEED_TIMEOUT_S = 120.0      # a slice that has not arrived by then is a bug or a dead feeder, never a wait worth keeping
+
+
+class _TileFeed:
+    """One tile's host -> device transfer plan: slices of whole chunks, each either gathered to the 12-byte X,Y,Z
+    stream (pch_host_pack_xyz) or shipped as whole records, each with its own device buffer and CUDA event."""
+
+    def __init__(self, host_records, n, rec_len, chunk_size, slice_chunks, pack, raw_every, device, slot=0, stage=None):
+        if pack not in ("none", "xyz"):
+            raise ValueError(f"unknown pack mode {pack!r}")
+        self.n, self.rec_len, self.pack, self.slot, self.device = int(n), int(rec_len), pack, slot, device
+        self.stage = stage          # pinned staging for the gathered stream (pack="xyz"); set before feed()
+        self.cs = max(1, min(int(chunk_size), max(self.n, 1)))
+        per_slice = self.cs * max(1, int(slice_chunks))
+        if (self.cs * 12) % 16 or (self.cs * rec_len) % 16:  # slice starts must stay 16-byte aligned in both layouts
+            per_slice = max(self.n, 1)
+        if isinstance(host_records, torch.Tensor):
+            host = host_records.view(torch.uint8).reshape(-1)[: self.n * rec_len]
+        else:
+            host = torch.from_numpy(np.asarray(host_records).view(np.uint8).reshape(-1)[: self.n * rec_len])
+        if pack == "none" and not host.is_pinned():
+            host = host.pin_memory()
+        if not host.is_pinned():
+            raw_every = 0
+        self.host = host
+        self.bounds = [(lo, min(lo + per_slice, self.n)) for lo in range(0, self.n, per_slice)]
+        # record length of each slice on the device: whole records, or the gathered 12-byte stream
+        self.lens = [rec_len if (pack == "none" or (raw_every > 0 and i % raw_every == raw_every - 1)) else 12
+                     for i in range(len(self.bounds))]
+        self.bufs = []
+        for (lo, hi), ln in zip(self.bounds, self.lens):
+            b = torch.empty(dv.padded_bytes(hi - lo, ln), dtype=torch.uint8, device=device)
+            b[(hi - lo) * ln:].zero_()
+            self.bufs.append(b)
+        self.zeroed = torch.cuda.Event()
+        self.zeroed.record(torch.cuda.current_stream(device))
+        self.events = [torch.cuda.Event() for _ in self.bounds]
+        self.ready = [threading.Event() for _ in self.bounds]
+        self.failure = []
+
+    def feed(self, copy_stream, threads):
+        """Gather (pack="xyz") and enqueue the copies, slice by slice.  Runs on a worker thread for pack="xyz"
+        (ctypes releases the GIL during the gather)."""
+        try:
+            torch.cuda.set_device(self.device)
+            copy_stream.wait_event(self.zeroed)
+            stage = self.stage
+            lib = dv._native.lib()
+            for i, (lo, hi) in enumerate(self.bounds):
+                if self.lens[i] == 12 and self.pack == "xyz":
+                    dv.check(lib.pch_host_pack_xyz(self.host.data_ptr() + lo * self.rec_len, hi - lo, self.rec_len,
+                                                   stage.data_ptr() + lo * 12, threads), "pch_host_pack_xyz")
+                    src = stage[lo * 12: hi * 12]
+                else:
+                    src = self.host[lo * self.rec_len: hi * self.rec_len]
+                with torch.cuda.stream(copy_stream):
+                    self.bufs[i][: src.numel()].copy_(src, non_blocking=True)
+                    self.events[i].record(copy_stream)
+                self.ready[i].set()
+        except BaseException as e:     # surface the failure on the consuming thread
+            self.fail(e)
+
+    def fail(self, e):
+        self.failure.append(e)
+        for r in self.ready:
+            r.set()
+
+    def wait_copied(self):
+        if self.events:
+            self.events[-1].synchronize()
+
+
+def _consume(feed: _TileFeed, scales, offsets, voxel_size, kw) -> PipelineResult:
+    """Voxel stage per slice as the slices land, then the ground / tower stages on the whole tile."""
+    kw = dict(kw)
+    device, n = feed.device, feed.n
+    main = torch.cuda.current_stream(device)
+    ground = kw.pop("ground", "percentile")
+    sink = dv.VoxelSink(max(n, 1), device, want_z=(ground == "percentile"))
+    for i, (lo, hi) in enumerate(feed.bounds):
+        if not feed.ready[i].wait(timeout=FEED_TIMEOUT_S):
+            raise RuntimeError(f"host feed stalled: slice {i} not delivered within {FEED_TIMEOUT_S} s")
+        if feed.failure:
+            raise feed.failure[0]
+        main.wait_event(feed.events[i])
+        view = dv.DeviceLas(feed.bufs[i], hi - lo, feed.lens[i], np.asarray(scales, dtype=np.float64),
+                            np.asarray(offsets, dtype=np.float64))
+        dv.voxel_downsample(view, voxel_size, feed.cs, want=(), sink=sink)
+    total = sink.count
+    if total == 0:
+        return PipelineResult(n, 0, 0, 0, [])
+    f32 = sink.f32[:total]
+    eps = kw.pop("eps", 8.0)
+    min_points = kw.pop("min_points", 80)
+    box = kw.pop("box", "aabb")
+    want_points = kw.pop("want_points", False)
+    stages = tw.run_stages(f32, eps, min_points, ground, zcol=sink.z32[:total] if sink.z32 is not None else None)
+    towers = tw.select_towers(stages, box=box, want_points=want_points, **kw)
+    return PipelineResult(n, total, int(stages.filtered.shape[0]), stages.n_clusters, towers, None, None, stages.db_plan)
 
 
 def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, voxel_size: float = 0.1,
@@ -76,86 +193,88 @@ def run_pipeline_from_host(host_records, n: int, rec_len: int, scales, offsets, 
                  and the host cores both carry part of the stream."""
     dv._require_cuda()
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-    cs = max(1, min(int(chunk_size), max(n, 1)))
-    per_slice = cs * max(1, int(slice_chunks))
-    if pack not in ("none", "xyz"):
-        raise ValueError(f"unknown pack mode {pack!r}")
-    if (cs * 12) % 16 or (cs * rec_len) % 16:  # slice starts must stay 16-byte aligned in both layouts
-        per_slice = n
-    if isinstance(host_records, torch.Tensor):
-        host = host_records.view(torch.uint8).reshape(-1)[: n * rec_len]
-    else:
-        host = torch.from_numpy(np.asarray(host_records).view(np.uint8).reshape(-1)[: n * rec_len])
-    if pack == "none" and not host.is_pinned():
-        host = host.pin_memory()
-    if not host.is_pinned():
-        raw_every = 0
     copy_stream = torch.cuda.Stream(device=device)
-    main = torch.cuda.current_stream(device)
-    copy_stream.wait_stream(main)
-    bounds = [(lo, min(lo + per_slice, n)) for lo in range(0, n, per_slice)]
-    # record length of each slice on the device: whole records, or the gathered 12-byte stream
-    lens = [rec_len if (pack == "none" or (raw_every > 0 and i % raw_every == raw_every - 1)) else 12
-            for i in range(len(bounds))]
-    bufs = []
-    for (lo, hi), ln in zip(bounds, lens):
-        b = torch.empty(dv.padded_bytes(hi - lo, ln), dtype=torch.uint8, device=device)
-        b[(hi - lo) * ln:].zero_()
-        bufs.append(b)
-    copy_stream.wait_stream(main)
-    events = [torch.cuda.Event() for _ in bounds]
-    ready = [threading.Event() for _ in bounds]
-    failure = []
-
-    def feed():
-        # runs on a worker thread for pack="xyz" (ctypes releases the GIL during the gather) and inline otherwise
-        try:
-            torch.cuda.set_device(device)
-            stage = _staging(n * 12) if pack == "xyz" else None
-            lib = dv._native.lib()
-            nt = threads or host_threads()
-            for i, (lo, hi) in enumerate(bounds):
-                if lens[i] == 12 and pack == "xyz":
-                    dv.check(lib.pch_host_pack_xyz(host.data_ptr() + lo * rec_len, hi - lo, rec_len,
-                                                   stage.data_ptr() + lo * 12, nt), "pch_host_pack_xyz")
-                    src = stage[lo * 12: hi * 12]
-                else:
-                    src = host[lo * rec_len: hi * rec_len]
-                with torch.cuda.stream(copy_stream):
-                    bufs[i][: src.numel()].copy_(src, non_blocking=True)
-                    events[i].record(copy_stream)
-                ready[i].set()
-        except BaseException as e:     # surface the failure on the calling thread
-            failure.append(e)
-            for r in ready:
-                r.set()
-
+    stage = _acquire_staging(n * 12) if pack == "xyz" else None
+    feed = _TileFeed(host_records, n, rec_len, chunk_size, slice_chunks, pack, raw_every, device, stage=stage)
+    nt = threads or host_threads()
     worker = None
     if pack == "xyz":
-        worker = threading.Thread(target=feed, name="pch-host-pack", daemon=True)
+        worker = threading.Thread(target=feed.feed, args=(copy_stream, nt), name="pch-host-pack", daemon=True)
         worker.start()
     else:
-        feed()
-    ground = kw.pop("ground", "percentile")
-    sink = dv.VoxelSink(n, device, want_z=(ground == "percentile"))
-    for i, (lo, hi) in enumerate(bounds):
-        ready[i].wait()
-        if failure:
-            raise failure[0]
-        main.wait_event(events[i])
-        view = dv.DeviceLas(bufs[i], hi - lo, lens[i], np.asarray(scales, dtype=np.float64),
-                            np.asarray(offsets, dtype=np.float64))
-        dv.voxel_downsample(view, voxel_size, cs, want=(), sink=sink)
-    if worker is not None:
+        feed.feed(copy_stream, nt)
+    try:
+        return _consume(feed, scales, offsets, voxel_size, kw)
+    finally:
+        if worker is not None:
+            worker.join()
+        feed.wait_copied()
+        _release_staging(stage)
+
+
+def run_tiles_from_host(tiles, scales, offsets, voxel_size: float = 0.1, chunk_size: int = 500000,
+                        slice_chunks: int = 10, device=None, pack: str = "xyz", threads: int = 0, raw_every: int = 0,
+                        **kw):
+    """A corridor as a STREAM of tiles on one GPU (more tiles than GPUs): generator yielding one
+    PipelineResult per tile of `tiles` (an iterable of (host_records, n_points, rec_len)), in order.  Each
+    tile is processed exactly like run_pipeline_from_host; in addition, while tile k is in its ground / tower
+    stages the records of tile k+1 are already being gathered and copied (one tile of look-ahead, two pinned
+    staging buffers), so in steady state the device never waits for PCIe and the host never waits for the
+    device."""
+    dv._require_cuda()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    copy_stream = torch.cuda.Stream(device=device)
+    nt = threads or host_threads()
+    jobs: "queue.Queue" = queue.Queue()
+
+    stages = {}                         # staging slot -> pinned buffer (owned by this call until the end)
+
+    def feeder():
+        last = {}                       # staging slot -> the feed that last used it
+        while True:
+            f = jobs.get()
+            if f is None:
+                return
+            try:
+                prev = last.get(f.slot)
+                if prev is not None:
+                    prev.wait_copied()      # its copies have finished reading this staging buffer
+                if pack == "xyz":
+                    buf = stages.get(f.slot)
+                    if buf is None or buf.numel() < f.n * 12:
+                        stages.pop(f.slot, None)
+                        _release_staging(buf)
+                        buf = stages[f.slot] = _acquire_staging(f.n * 12)
+                    f.stage = buf
+                f.feed(copy_stream, nt)
+                last[f.slot] = f
+            except BaseException as e:      # never leave the consumer waiting on a feed that will not come
+                f.fail(e)
+
+    worker = threading.Thread(target=feeder, name="pch-tile-feeder", daemon=True)
+    worker.start()
+    try:
+        it = iter(tiles)
+
+        def prep(tile, slot):
+            if tile is None:
+                return None
+            rec, n, rec_len = tile
+            f = _TileFeed(rec, n, rec_len, chunk_size, slice_chunks, pack, raw_every, device, slot)
+            jobs.put(f)
+            return f
+
+        slot = 0
+        cur = prep(next(it, None), slot)
+        while cur is not None:
+            slot ^= 1
+            nxt = prep(next(it, None), slot)     # queued now: gathered / copied while `cur` is processed
+            yield _consume(cur, scales, offsets, voxel_size, kw)
+            cur = nxt
+    finally:
+        jobs.put(None)
         worker.join()
-    total = sink.count
-    if total == 0:
-        return PipelineResult(n, 0, 0, 0, [])
-    f32 = sink.f32[:total]
-    eps = kw.pop("eps", 8.0)
-    min_points = kw.pop("min_points", 80)
-    box = kw.pop("box", "aabb")
-    want_points = kw.pop("want_points", False)
-    stages = tw.run_stages(f32, eps, min_points, ground, zcol=sink.z32[:total] if sink.z32 is not None else None)
-    towers = tw.select_towers(stages, box=box, want_points=want_points, **kw)
-    return PipelineResult(n, total, int(stages.filtered.shape[0]), stages.n_clusters, towers, None, None, stages.db_plan)
+        torch.cuda.current_stream(device).synchronize()
+        copy_stream.synchronize()
+        for buf in stages.values():
+            _release_staging(buf)

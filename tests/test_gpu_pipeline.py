@@ -70,6 +70,35 @@ def test_host_pack_xyz_entry_equals_full_record_entry(cuda_device):
     assert torch.equal(v12.z32, v34.f32[:, 2].contiguous())
 
 
+def test_tile_stream_equals_per_tile_calls(cuda_device):
+    """run_tiles_from_host (one tile of look-ahead, two staging buffers) yields, tile by tile, exactly what
+    independent calls yield — for tiles of different sizes and record lengths, gathered or whole-record."""
+    import torch
+    from pointcloudhookup_b200 import device as dv, pipeline, synth
+    tiles = []
+    for k, (n, seed) in enumerate(((200_000, 51), (90_001, 52), (310_000, 53), (4, 54), (150_000, 55))):
+        rec = synth.corridor_records(n, 2, "hilly", seed, (0.86, 0.085, 0.005, 0.05))
+        raw = rec.view(np.uint8).reshape(n, 34)
+        if k == 2:      # a 36-byte format with two trailing bytes
+            raw = np.concatenate([raw, np.full((n, 2), 7, np.uint8)], axis=1)
+        tiles.append((np.ascontiguousarray(raw).reshape(-1), n, raw.shape[1]))
+    want = []
+    for rec, n, rl in tiles:
+        dl = dv.upload_records(rec, n, rl, synth.SCALES, synth.OFFSETS)
+        want.append(pipeline.run_pipeline(dl, 0.1, 50_000, box="aabb"))
+    for pack, pin in (("xyz", False), ("none", True), ("xyz", True)):
+        src = [((torch.from_numpy(r).pin_memory() if pin else r), n, rl) for r, n, rl in tiles]
+        got = list(pipeline.run_tiles_from_host(iter(src), synth.SCALES, synth.OFFSETS, 0.1, 50_000, slice_chunks=2,
+                                                pack=pack, raw_every=3 if pin else 0, box="aabb"))
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert (a.n_points, a.n_voxels, a.n_candidates, a.n_clusters) == (b.n_points, b.n_voxels, b.n_candidates, b.n_clusters)
+            assert [t["label"] for t in a.towers] == [t["label"] for t in b.towers]
+            for x, y in zip(a.towers, b.towers):
+                assert np.array_equal(x["center"], y["center"]) and np.array_equal(x["extent"], y["extent"])
+    assert list(pipeline.run_tiles_from_host([], synth.SCALES, synth.OFFSETS)) == []
+
+
 def test_percentile_on_raw_column_and_on_the_fly_compaction_equal_the_literal_order(cuda_device):
     """The select on the RAW z column (side stream) + keep flag derived inside the compaction must equal the
     reference's literal order: shift, percentile of the shifted column, mask, gather."""

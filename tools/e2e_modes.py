@@ -9,7 +9,7 @@ n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 pinned = torch.empty(n * 34, dtype=torch.uint8, pin_memory=True)
 synth.corridor_records(n, max(2, n // 2_000_000), "hilly", 3, out=pinned.numpy())
 lib = _native.lib()
-stage = pipeline._staging(n * 12)
+stage = pipeline._acquire_staging(n * 12)
 for t in (4, 8, 12, 14, 15, 16, 24, 32):
     lib.pch_host_pack_xyz(pinned.data_ptr(), n, 34, stage.data_ptr(), t)
     t0 = time.perf_counter()

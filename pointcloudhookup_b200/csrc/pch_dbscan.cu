@@ -994,65 +994,6 @@ k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __r
     }
 }
 
-// Labels are spatially coherent (the candidates are in voxel-sorted order).  A warp reads rows of 32
-// consecutive points (coalesced); a row whose 32 labels agree is reduced with shuffles into the warp's
-// running accumulator (held redundantly by all lanes), which is flushed with one set of atomics only
-// when the label changes; mixed rows fall back to per-point atomics.
-__global__ void __launch_bounds__(256)
-k_db_cluster_reduce(const float* __restrict__ P, const int32_t* __restrict__ labels, int64_t G, int64_t cap,
-                    DbClusterAcc* __restrict__ acc) {
-    const int lane = threadIdx.x & 31;
-    const int64_t n_rows = (G + 31) / 32;
-    const int64_t n_groups = (n_rows + CR_ROWS - 1) / CR_ROWS;
-    int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t ngw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (; grp < n_groups; grp += ngw) {
-        DbRun run;
-        db_run_reset(run, -1);
-        for (int j = 0; j < CR_ROWS; ++j) {
-            const int64_t i = (grp * CR_ROWS + j) * 32 + lane;
-            if ((grp * CR_ROWS + j) >= n_rows) break;   // warp-uniform
-            int32_t lab = -1;
-            float v[3] = {0.f, 0.f, 0.f};
-            if (i < G) {
-                lab = labels[i];
-                if (lab >= cap) lab = -1;
-                if (lab >= 0) { v[0] = P[i * 3 + 0]; v[1] = P[i * 3 + 1]; v[2] = P[i * 3 + 2]; }
-            }
-            // noise (-1) lanes simply do not contribute; the row's first labelled lane proposes the run label
-            const uint32_t valid = __ballot_sync(0xffffffffu, lab >= 0);
-            if (valid == 0) continue;
-            const int32_t cand = __shfl_sync(0xffffffffu, lab, __ffs(valid) - 1);
-            if (run.lab < 0) db_run_reset(run, cand);
-            if (!__any_sync(0xffffffffu, lab == run.lab)) {   // the current run ended before this row
-                db_warp_flush(acc, run, lane);
-                db_run_reset(run, cand);
-            }
-            if (lab == run.lab) {                             // lane-local accumulation, merged when the run ends
-                run.cnt += 1;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const uint32_t u = pch_f32_to_ordered(v[a]);
-                    run.mn[a] = min(run.mn[a], u);
-                    run.mx[a] = max(run.mx[a], u);
-                    run.sum[a] += (double)v[a];
-                }
-            } else if (lab >= 0) {                            // a second label inside the row: rare, direct atomics
-                DbClusterAcc* a = &acc[lab];
-                atomicAdd(&a->count, 1ull);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const uint32_t u = pch_f32_to_ordered(v[k]);
-                    atomicMin(&a->mn[k], u);
-                    atomicMax(&a->mx[k], u);
-                    atomicAdd(&a->sum[k], (double)v[k]);
-                }
-            }
-        }
-        db_warp_flush(acc, run, lane);
-    }
-}
-
 __global__ void k_db_acc_finish(int64_t cap, const long long* __restrict__ K_dev, const DbClusterAcc* __restrict__ acc,
                                 pch_cluster_stats* __restrict__ out) {
     const int64_t K = min((int64_t)*K_dev, cap);

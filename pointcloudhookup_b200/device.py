@@ -438,22 +438,22 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
     if plan.status != 0:
         raise ValueError("DBSCAN cell grid does not fit the packed key")
     labels = torch.empty(G, dtype=torch.int32, device=dev)
-    nclu = torch.empty(1, dtype=torch.int64, device=dev)
     cap = max(4096, G // 256)
     while True:
         stats = torch.empty(cap * STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         wsb = lib.pch_dbscan_workspace_bytes(G, ch, C.byref(plan), cap)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        nclu = ws[136:144].view(torch.int64)      # inside the workspace's scalar block: one D2H fetches count + error word
         check(lib.pch_dbscan_run(points.data_ptr(), G, ch, float(eps), int(min_samples), bounds.data_ptr(),
                                  C.byref(plan), labels.data_ptr(), nclu.data_ptr(), stats.data_ptr(), cap,
                                  ws.data_ptr(), wsb, st), "pch_dbscan_run")
-        k = int(nclu.item())
+        sc = ws[:256].cpu().numpy()
+        k = int(sc[136:144].view(np.int64)[0])
         if os.environ.get("PCH_TRACE"):
-            sc = ws[:256].cpu().numpy()
             print(f"[pch] dbscan G={G} chunks={n_chunks} cells={int(sc[128:136].view(np.int64)[0])} "
                   f"non-dense points={int(sc[192:196].view(np.uint32)[0])} clusters={k} plan={plan.bits_x},{plan.bits_y},{plan.bits_z}",
                   flush=True)
-        if int(ws[:4].view(torch.int32).item()):
+        if int(sc[:4].view(np.int32)[0]):
             raise _native.NativeError("device look-back spin limit hit in dbscan")
         if k <= cap:
             break

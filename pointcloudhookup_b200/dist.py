@@ -45,26 +45,54 @@ def dedup_towers(towers: List[dict], duplicate_threshold: float = 30.0) -> List[
     return kept
 
 
+FAST_CAP = 255   # towers per rank that travel in the single fixed-size collective
+
+
+def _gather_rows(block: torch.Tensor, world: int) -> torch.Tensor:
+    """all-gather of one equally shaped block per rank -> (world, *block.shape)."""
+    out = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
+    try:
+        dist.all_gather_into_tensor(out, block)
+    except (RuntimeError, NotImplementedError, AttributeError):   # backend without the flat variant
+        parts = [torch.empty_like(block) for _ in range(world)]
+        dist.all_gather(parts, block)
+        out = torch.stack(parts)
+    return out
+
+
 def merge_towers(towers: List[dict], duplicate_threshold: float = 30.0, device=None) -> List[dict]:
-    """All ranks contribute their tile's towers; every rank returns the same merged list."""
+    """All ranks contribute their tile's towers; every rank returns the same merged list.
+
+    One collective and one device->host read per call: every rank sends a fixed (FAST_CAP+1, REC) block whose
+    first row carries its tower count (a corridor tile has a few dozen towers at most).  Only if some rank has
+    more than FAST_CAP towers — announced in that same block, so all ranks agree — a second, max-sized gather
+    follows."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return dedup_towers(unpack_towers(pack_towers(towers, 0)), duplicate_threshold)
     rank, world = dist.get_rank(), dist.get_world_size()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    mine = torch.from_numpy(pack_towers(towers, rank)).to(device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([mine.shape[0]], dtype=torch.int64, device=device))
-    cmax = max(int(c.item()) for c in counts)
+    mine = pack_towers(towers, rank)
+    k = mine.shape[0]
+    block = np.zeros((FAST_CAP + 1, REC), dtype=np.float64)
+    block[0, 0] = k
+    if k <= FAST_CAP:
+        block[1: k + 1] = mine
+    host = _gather_rows(torch.from_numpy(block).to(device), world).cpu().numpy()
+    counts = [int(host[r, 0, 0]) for r in range(world)]
+    cmax = max(counts)
     if cmax == 0:
         return []
-    padded = torch.zeros((cmax, REC), dtype=torch.float64, device=device)
-    padded[: mine.shape[0]] = mine
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded)
+    if cmax > FAST_CAP:
+        padded = np.zeros((cmax, REC), dtype=np.float64)
+        padded[:k] = mine
+        big = _gather_rows(torch.from_numpy(padded).to(device), world).cpu().numpy()
+        rows = [big[r, : counts[r]] for r in range(world)]
+    else:
+        rows = [host[r, 1: counts[r] + 1] for r in range(world)]
     allt = []
     for r in range(world):
-        allt += unpack_towers(gathered[r][: int(counts[r].item())].cpu().numpy())
+        allt += unpack_towers(rows[r])
     return dedup_towers(allt, duplicate_threshold)
 
 

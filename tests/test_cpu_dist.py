@@ -30,6 +30,9 @@ def _worker(rank, world, port, q):
            [tower(355.0, 5.0, 1), tower(700.0, 0.0, 4), tower(710.0, 0.0, 6)]
     merged = pdist.merge_towers(mine, 30.0)
     empty = pdist.merge_towers([], 30.0)
+    pdist.FAST_CAP = 2          # rank 1 now exceeds the fixed block: the announced second gather must give the same list
+    merged2 = pdist.merge_towers(mine, 30.0)
+    assert [(t["rank"], t["label"]) for t in merged2] == [(t["rank"], t["label"]) for t in merged]
     q.put((rank, [(t["rank"], t["label"], t["center"].tolist()) for t in merged], len(empty),
            pdist.tile_for_rank(rank, 50)))
     dist.destroy_process_group()

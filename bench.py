@@ -64,8 +64,9 @@ def workload_config(args):
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed regions (NVML from a thread, every 5 ms;
-    the nvidia-smi loop of B200_PROFILING.md is the fallback)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (NVML from a thread, every 20 ms — often
+    enough for several samples inside the shortest timed region, rare enough not to take the GIL from the
+    thread that launches the kernels; the nvidia-smi loop of B200_PROFILING.md is the fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -122,7 +123,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.02)
 
     def _read(self):
         for line in self.proc.stdout:

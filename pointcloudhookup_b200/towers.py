@@ -176,6 +176,23 @@ def label_iteration_order(n_clusters: int, present: np.ndarray) -> List[int]:
     return list(s)
 
 
+_ORDER_CACHE = {}
+
+
+def _label_order_array(n_clusters: int, present: np.ndarray) -> np.ndarray:
+    """label_iteration_order as an int64 array; memoised for the usual case "every label 0..K-1 occurs" (the set is
+    still built literally once per K, so a CPython whose table layout differs is followed, not assumed)."""
+    full = len(present) == n_clusters
+    if full and n_clusters in _ORDER_CACHE:
+        return _ORDER_CACHE[n_clusters]
+    arr = np.asarray(label_iteration_order(n_clusters, present), dtype=np.int64)
+    if full:
+        if len(_ORDER_CACHE) > 64:
+            _ORDER_CACHE.clear()
+        _ORDER_CACHE[n_clusters] = arr
+    return arr
+
+
 def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15.0, max_width=50.0, min_width=8,
                   duplicate_threshold=30.0, box: str = "obb", log: Optional[Callable[[str], None]] = None,
                   progress: Optional[Callable[[int], None]] = None, want_points: bool = True):
@@ -187,7 +204,7 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
     present = np.nonzero(stats["count"][:K] > 0)[0].astype(np.int32)
     # every label 0..K-1 carries at least its head core point, so `present` is all of them; the
     # set() is still built from the values to reproduce the reference's order
-    order = label_iteration_order(K, present)
+    order = _label_order_array(K, present)
     if box == "aabb" and K:
         # vectorised size filter (test/008.py:302-319 arithmetic in float32, like the reference's numpy):
         # only labels that pass reach the python loop below, in the same set() order
@@ -197,7 +214,8 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
         with np.errstate(divide="ignore", invalid="ignore"):
             ok = (w_all > 0) & (h_all > min_height) & (min_width < w_all) & (w_all < max_width) & \
                  (h_all / w_all > aspect_ratio_threshold)
-        order = [l for l in order if ok[l]]
+        order = order[ok[order]]
+    order = [int(l) for l in order]
     towers, centres = [], []
     grouped = None   # cluster-major copy of the labelled points, built on the device on first use (O(G), not O(G*K))
 

@@ -96,5 +96,58 @@ def extract_towers_arrays(las, eps=8.0, min_points=80, aspect_ratio_threshold=0.
     return towers
 
 
+def merge_adjacent_clusters(filtered, all_labels, merge_threshold=6.0):
+    """test/tttt.py:93-175, literally: cluster centres = np.mean(cluster_points, axis=0) in set() order, sklearn KDTree
+    radius query, union by cluster size, new labels max+1.. in order of first member.  Returns merged_labels."""
+    from sklearn.neighbors import KDTree
+    unique_labels = set(all_labels) - {-1}
+    if not unique_labels:
+        return all_labels
+    cluster_centers, label_to_index, valid_labels = [], {}, []
+    for label in unique_labels:
+        cluster_points = filtered[all_labels == label]
+        if len(cluster_points) > 0:
+            cluster_centers.append(np.mean(cluster_points, axis=0))
+            label_to_index[label] = len(cluster_centers) - 1
+            valid_labels.append(label)
+    if not cluster_centers:
+        return all_labels
+    cluster_centers = np.array(cluster_centers)
+    tree = KDTree(cluster_centers)
+    neighbors = tree.query_radius(cluster_centers, r=merge_threshold)
+    parent = list(range(len(cluster_centers)))
+
+    def find(x):
+        if parent[x] != x:
+            parent[x] = find(parent[x])
+        return parent[x]
+
+    def union(x, y):
+        root_x, root_y = find(x), find(y)
+        if root_x != root_y:
+            size_x = np.sum(all_labels == valid_labels[x])
+            size_y = np.sum(all_labels == valid_labels[y])
+            if size_x > size_y:
+                parent[root_y] = root_x
+            else:
+                parent[root_x] = root_y
+
+    for i, neighbor_indices in enumerate(neighbors):
+        for j in neighbor_indices:
+            if i < j:
+                union(i, j)
+    new_labels = {}
+    current_max_label = max(unique_labels) + 1
+    for i in range(len(cluster_centers)):
+        root = find(i)
+        if root not in new_labels:
+            new_labels[root] = current_max_label
+            current_max_label += 1
+    merged_labels = all_labels.copy()
+    for label in valid_labels:
+        merged_labels[all_labels == label] = new_labels[find(label_to_index[label])]
+    return merged_labels
+
+
 def extract_towers(input_las_path, **kw):
     return extract_towers_arrays(las_io.read_las(input_las_path), **kw)

@@ -193,18 +193,91 @@ def _label_order_array(n_clusters: int, present: np.ndarray) -> np.ndarray:
     return arr
 
 
+def merge_adjacent_clusters(stats: np.ndarray, n_clusters: int, merge_threshold: float = 6.0):
+    """The cluster post-processing of test/tttt.py:93-175 on the per-cluster reduction instead of on the points:
+    clusters whose centres lie within `merge_threshold` of each other (inclusive, like KDTree.query_radius) are
+    joined transitively.  Returns (component id per original label [K], merged stats [C]) where component ids are
+    ranked by their first member in the reference's set() iteration order — the reference's new labels are
+    max(label)+1+id — and the merged rows carry count = sum, AABB = union, coordinate sums = sum, i.e. exactly what
+    re-reducing the relabelled points would give.
+
+    Centres are float64 sum/count here and float32 np.mean (a sequential float32 sum) in the reference: they agree
+    to ~1e-3 m on 50 000-point clusters, so only a pair whose distance is within that of the threshold can differ
+    (tolerance-level parity; the component structure is otherwise identical)."""
+    K = int(n_clusters)
+    if K == 0:
+        return np.zeros(0, dtype=np.int64), stats[:0].copy()
+    present = np.nonzero(stats["count"][:K] > 0)[0].astype(np.int32)
+    order = _label_order_array(K, present)                     # valid_labels in the reference's iteration order
+    centres = stats["sum"][order] / stats["count"][order][:, None].astype(np.float64)
+    n = len(order)
+    parent = np.arange(n)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    # all pairs within the threshold: sort along x and sweep (K is a few thousand at most)
+    xs = np.argsort(centres[:, 0], kind="stable")
+    cx = centres[xs, 0]
+    hi = np.searchsorted(cx, cx + merge_threshold, side="right")
+    thr2 = float(merge_threshold) ** 2
+    for a in range(n):
+        b = np.arange(a + 1, hi[a])
+        if b.size == 0:
+            continue
+        d = centres[xs[b]] - centres[xs[a]]
+        close = b[np.einsum("ij,ij->i", d, d) <= thr2]
+        for j in close:
+            ra, rb = find(xs[a]), find(xs[j])
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+    roots = np.array([find(i) for i in range(n)])
+    # component id = rank of the component's first member (index order = the reference's `for i in range(len(...))`)
+    first_seen, comp_of_root = {}, np.empty(n, dtype=np.int64)
+    for i in range(n):
+        r = roots[i]
+        if r not in first_seen:
+            first_seen[r] = len(first_seen)
+        comp_of_root[i] = first_seen[r]
+    C = len(first_seen)
+    comp = np.full(K, -1, dtype=np.int64)
+    comp[order] = comp_of_root
+    merged = np.zeros(C, dtype=stats.dtype)
+    merged["min"] = np.inf
+    merged["max"] = -np.inf
+    np.add.at(merged["count"], comp_of_root, stats["count"][order])
+    np.add.at(merged["sum"], comp_of_root, stats["sum"][order])
+    np.minimum.at(merged["min"], comp_of_root, stats["min"][order])
+    np.maximum.at(merged["max"], comp_of_root, stats["max"][order])
+    return comp, merged
+
+
 def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15.0, max_width=50.0, min_width=8,
                   duplicate_threshold=30.0, box: str = "obb", log: Optional[Callable[[str], None]] = None,
-                  progress: Optional[Callable[[int], None]] = None, want_points: bool = True):
-    """Stages D+E.  Returns the reference's tower dict list (+ 'label')."""
+                  progress: Optional[Callable[[int], None]] = None, want_points: bool = True,
+                  merge_threshold: Optional[float] = None):
+    """Stages D+E.  Returns the reference's tower dict list (+ 'label').  merge_threshold (default off) first joins
+    clusters whose centres are that close (the variant of test/tttt.py:93-175); the merged clusters carry the labels
+    K, K+1, ... like the reference's max(label)+1 numbering."""
     from . import obb as _obb
     centroid = stages.centroid
     stats = stages.stats
     K = stages.n_clusters
+    members, label_base, orig_counts = None, 0, stats["count"][:K]
+    if merge_threshold is not None and K:
+        comp, stats = merge_adjacent_clusters(stats, K, float(merge_threshold))
+        members = [np.nonzero(comp == c)[0] for c in range(len(stats))]
+        label_base, K = K, len(stats)
     present = np.nonzero(stats["count"][:K] > 0)[0].astype(np.int32)
     # every label 0..K-1 carries at least its head core point, so `present` is all of them; the
     # set() is still built from the values to reproduce the reference's order
-    order = _label_order_array(K, present)
+    if members is None:
+        order = _label_order_array(K, present)
+    else:   # the reference iterates set(merged_labels) - {-1}: the set of the NEW label values, built literally
+        order = np.asarray(label_iteration_order(K, present + label_base), dtype=np.int64) - label_base
     if box == "aabb" and K:
         # vectorised size filter (test/008.py:302-319 arithmetic in float32, like the reference's numpy):
         # only labels that pass reach the python loop below, in the same set() order
@@ -222,9 +295,11 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
     def cluster_points(label):
         nonlocal grouped
         if grouped is None:
-            grouped = dv.cluster_major_points(stages.filtered, stages.labels, stats["count"][:K])
+            grouped = dv.cluster_major_points(stages.filtered, stages.labels, orig_counts)
         rows, off = grouped
-        return rows[int(off[label]): int(off[label + 1])].cpu().numpy()
+        if members is None:
+            return rows[int(off[label]): int(off[label + 1])].cpu().numpy()
+        return np.concatenate([rows[int(off[m]): int(off[m + 1])].cpu().numpy() for m in members[label]])
 
     for li, label in enumerate(order):
         try:
@@ -264,7 +339,7 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
                 continue
             if cp is None and want_points:
                 cp = cluster_points(label)
-            towers.append({"label": int(label), "center": centre, "rotation": rot, "extent": ext,
+            towers.append({"label": int(label) + label_base, "center": centre, "rotation": rot, "extent": ext,
                            "height": height, "width": width, "north_angle": north_angle_of(rot), "points": cp})
             centres.append(centre)
             if log:

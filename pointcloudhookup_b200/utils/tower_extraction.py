@@ -5,7 +5,9 @@ towers_info.xlsx when an Excel writer is installed) and error behaviour (never r
 what it has).  The LAS decode, float32 cast, centroid, percentile filter, chunked DBSCAN, the
 per-cluster reduction and the per-tower LAS encode run on the GPU (..towers, ..device).
 Extra keyword-only options (defaults reproduce the reference): ``box`` ("obb" | "obb_ordered" |
-"aabb" — test/008.py:302-319), ``ground`` ("percentile" | "grid" — the north_star grid min-z mode).
+"aabb" — test/008.py:302-319), ``ground`` ("percentile" | "grid" — the north_star grid min-z mode),
+``merge_threshold`` (metres; joins clusters whose centres are that close before the box test — the
+post-processing of test/tttt.py:93-175; None = off).
 """
 import math  # noqa: F401  (kept: the reference module exposes the same top-level names)
 import time
@@ -30,7 +32,7 @@ def extract_towers(
         max_width=50.0,
         min_width=8,
         duplicate_threshold=30.0,
-        *, box="obb", ground="percentile", write_outputs=True
+        *, box="obb", ground="percentile", write_outputs=True, merge_threshold=None
 ):
     tower_obbs = []
     tower_info_list = []
@@ -103,7 +105,7 @@ def extract_towers(
     log(f"\n=== 开始杆塔检测（候选簇：{db.n_clusters}个） ===")
     progress(75)
     towers = _tw.select_towers(stages, aspect_ratio_threshold, min_height, max_width, min_width, duplicate_threshold,
-                               box=box, log=log, progress=progress)
+                               box=box, log=log, progress=progress, merge_threshold=merge_threshold)
     for t in towers:
         label = t.pop("label")
         tower_obbs.append(t)

@@ -231,3 +231,59 @@ def test_staging_pool_hands_out_each_buffer_once(monkeypatch):
         pipeline._release_staging(t)
     assert len(pipeline._POOL) == 4                    # the pool keeps the four largest
     pipeline._release_staging(None)
+
+
+def test_merge_adjacent_clusters_matches_the_reference_variant():
+    """towers.merge_adjacent_clusters (on per-cluster stats) against the literal restatement of test/tttt.py:93-175
+    (on points + labels, real sklearn KDTree): same partition, same new-label order, merged stats = stats of the
+    relabelled points."""
+    from oracle import towers as ot
+    from pointcloudhookup_b200 import towers as tw, device as dv
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        K = int(rng.integers(1, 60))
+        centres = rng.uniform(0, 60, (K, 3)) * np.array([1.0, 1.0, 0.2])
+        sizes = rng.integers(3, 200, K)
+        pts, labs = [], []
+        for k in range(K):
+            pts.append((centres[k] + rng.normal(0, 0.4, (sizes[k], 3))).astype(np.float32))
+            labs.append(np.full(sizes[k], k, dtype=np.int32))
+        pts.append(rng.uniform(0, 60, (50, 3)).astype(np.float32))
+        labs.append(np.full(50, -1, dtype=np.int32))
+        pts, labs = np.concatenate(pts), np.concatenate(labs)
+        perm = rng.permutation(len(labs))
+        pts, labs = pts[perm], labs[perm]
+        stats = np.zeros(K, dtype=dv.STATS_DTYPE)
+        for k in range(K):
+            cp = pts[labs == k]
+            stats[k] = (len(cp), cp.min(0), cp.max(0), cp.astype(np.float64).sum(0))
+        thr = 6.0
+        want = ot.merge_adjacent_clusters(pts, labs, thr)
+        comp, merged = tw.merge_adjacent_clusters(stats, K, thr)
+        base = labs.max() + 1
+        got = np.where(labs >= 0, base + comp[np.maximum(labs, 0)], -1)
+        assert np.array_equal(got, want), trial
+        for c in range(len(merged)):
+            cp = pts[want == base + c]
+            assert merged["count"][c] == len(cp)
+            assert np.array_equal(merged["min"][c], cp.min(0)) and np.array_equal(merged["max"][c], cp.max(0))
+            assert np.allclose(merged["sum"][c], cp.astype(np.float64).sum(0), rtol=0, atol=1e-6)
+    comp, merged = tw.merge_adjacent_clusters(np.zeros(0, dtype=dv.STATS_DTYPE), 0, 6.0)
+    assert len(comp) == 0 and len(merged) == 0
+
+
+def test_select_towers_with_merge_threshold_uses_merged_boxes():
+    """select_towers(merge_threshold=...) in AABB mode is pure host logic on the cluster stats: two halves of a tower
+    that fail the size filter alone pass once merged, and carry the reference's max(label)+1 numbering."""
+    from pointcloudhookup_b200 import towers as tw, device as dv
+    stats = np.zeros(3, dtype=dv.STATS_DTYPE)
+    # lower and upper half of one tower (each 12 x 12 x 10 m: too short alone), and a far-away bush
+    stats[0] = (500, (0, 0, 0), (12, 12, 10), (500 * 6.0, 500 * 6.0, 500 * 5.0))
+    stats[1] = (400, (0, 0, 10), (12, 12, 20), (400 * 6.0, 400 * 6.0, 400 * 9.0))     # centre (6,6,9): 4 m from (6,6,5)
+    stats[2] = (300, (200, 0, 0), (203, 3, 2), (300 * 201.5, 300 * 1.5, 300 * 1.0))
+    st = tw.TowerStages(None, np.array([1000.0, 2000.0, 50.0], dtype=np.float32), np.float32(0), 3.0, None, None, 3, stats)
+    assert tw.select_towers(st, box="aabb", want_points=False) == []
+    got = tw.select_towers(st, box="aabb", want_points=False, merge_threshold=6.0)
+    assert [t["label"] for t in got] == [3]                       # first merged component -> max(label)+1
+    assert np.allclose(got[0]["extent"], [12, 12, 20]) and np.allclose(got[0]["center"], [1006, 2006, 60])
+    assert tw.select_towers(st, box="aabb", want_points=False, merge_threshold=1.0) == []

@@ -210,3 +210,25 @@ def test_dbscan_randomised_against_sklearn(cuda_device):
         got = res.labels.cpu().numpy()
         assert np.array_equal(got, exp), (trial, n, eps, ms, chunk, int((got != exp).sum()))
         assert res.n_clusters == cur
+
+
+def test_ground_filter_variants_of_the_reference_scripts(cuda_device):
+    """The height-filter variants of the scratch scripts are the same kernel path with other parameters:
+    pct10 + 4 (test/main_ground.py:118-131), pct20 + 2.5 (test/008.py:212-224), min(z) + 6 (test/zzzzz.py:64-65,
+    = percentile 0), plus the extreme q = 100; each against numpy on the shifted float32 column."""
+    import torch
+    from pointcloudhookup_b200 import towers as tw
+    rng = np.random.default_rng(77)
+    m = 400_003
+    raw = np.stack([rng.uniform(437000, 437500, m), rng.uniform(3139000, 3139300, m),
+                    np.round(80 + rng.gamma(2.0, 3.0, m), 3)], 1).astype(np.float32)
+    d = torch.from_numpy(raw).to(cuda_device)
+    pts = raw - np.mean(raw, axis=0)
+    z = pts[:, 2]
+    for pct, off in ((10, 4.0), (20, 2.5), (0, 6.0), (25, 3.0), (50, 0.0), (100, -1.0), (33.3, 1.25)):
+        filt, cen, base, used, mask = tw.ground_filter_percentile(d, pct=pct, offset=off, min_keep=0, want_mask=True)
+        b = np.percentile(z, pct)
+        keep = z > b + off
+        assert base == b and used == off, (pct, float(base), float(b))
+        assert np.array_equal(mask.cpu().numpy().astype(bool), keep), pct
+        assert np.array_equal(filt.cpu().numpy(), pts[keep]), pct

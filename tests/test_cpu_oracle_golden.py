@@ -3,6 +3,7 @@
 import hashlib
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -155,3 +156,52 @@ def test_crop_oracle_bounds_and_sample_restatement():
         assert np.array_equal(np.sort(v), np.arange(n, dtype=np.uint64))
         k = max(1, n // 3)
         assert np.unique(oc.sample_indices(n, k, 0)).size == k
+
+
+def _variants():
+    import json
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import variant_inputs as vi
+    return json.load(open(os.path.join(HERE, "golden", "variants_run.json"), encoding="utf-8")), vi
+
+
+def test_crop_oracle_reproduces_the_reference_lines():
+    """tests/golden/variants_run.json holds what test/kuangxuan.py:60-79 (the reference's own lines, exec'd by
+    make_golden_variants.py) produced for the reference's four logged towers on seeded clouds: oracle/crop.py must
+    give the same boxes (exactly) and the same `points[mask]` arrays (sha256)."""
+    from oracle import crop as oc
+    gold, vi = _variants()
+    towers = gold["tower_data"]
+    assert [t["id"] for t in towers] == [8, 188, 199, 235]
+    for case in gold["crop"]:
+        pts = vi.crop_inputs(towers, case["seed"])
+        assert vi.digest(pts) == case["points_sha256"]
+        boxes = np.stack([oc.kuangxuan_bounds(t) for t in towers])
+        got = oc.crop_boxes(pts, boxes)
+        for t, g, want in zip(towers, got, case["towers"]):
+            assert list(oc.kuangxuan_bounds(t)) == want["bounds"]
+            assert len(g) == want["count"] and vi.digest(g) == want["sha256"]
+
+
+def test_cluster_merge_reproduces_the_reference_lines():
+    """The merge block test/tttt.py:93-175 exec'd on seeded clusters: the oracle's restatement AND the product's
+    stats-based merge (towers.merge_adjacent_clusters) must give the same merged labels, in the same set() order."""
+    from oracle import towers as ot
+    from pointcloudhookup_b200 import device as dv, towers as tw
+    gold, vi = _variants()
+    for case in gold["merge"]:
+        pts, labs = vi.merge_inputs(case["seed"])
+        assert vi.digest(labs) == case["labels_sha256"] and vi.digest(pts) == case["points_sha256"]
+        thr = case["merge_threshold"]
+        merged = ot.merge_adjacent_clusters(pts, labs, thr)
+        assert vi.digest(np.asarray(merged).astype(np.int64)) == case["merged_sha256"]
+        assert [int(v) for v in (set(merged) - {-1})] == case["iteration_order"]
+        K = int(labs.max()) + 1
+        stats = np.zeros(K, dtype=dv.STATS_DTYPE)
+        for k in range(K):
+            cp = pts[labs == k]
+            stats[k] = (len(cp), cp.min(0), cp.max(0), cp.astype(np.float64).sum(0))
+        comp, mstats = tw.merge_adjacent_clusters(stats, K, thr)
+        got = np.where(labs >= 0, K + comp[np.maximum(labs, 0)], -1).astype(np.int64)
+        assert vi.digest(got) == case["merged_sha256"]
+        assert len(mstats) == case["n_merged_clusters"]

@@ -287,3 +287,14 @@ def test_select_towers_with_merge_threshold_uses_merged_boxes():
     assert [t["label"] for t in got] == [3]                       # first merged component -> max(label)+1
     assert np.allclose(got[0]["extent"], [12, 12, 20]) and np.allclose(got[0]["center"], [1006, 2006, 60])
     assert tw.select_towers(st, box="aabb", want_points=False, merge_threshold=1.0) == []
+
+
+def test_pack_mode_resolution(monkeypatch):
+    from pointcloudhookup_b200 import pipeline
+    assert pipeline.resolve_pack("xyz") == "xyz" and pipeline.resolve_pack("none", 64) == "none"
+    assert pipeline.resolve_pack("auto", 16) == "xyz" and pipeline.resolve_pack("auto", 4) == "none"
+    monkeypatch.setattr(pipeline, "host_threads", lambda: 2)
+    assert pipeline.resolve_pack("auto") == "none"
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    from pointcloudhookup_b200 import device as dv
+    assert dv.host_threads() >= 1

@@ -88,32 +88,44 @@ def resolve_pack(pack: str, threads: int = 0) -> str:
     return "xyz" if (threads or host_threads()) >= AUTO_PACK_MIN_THREADS else "none"
 
 
+def slice_plan(n: int, rec_len: int, chunk_size: int, slice_chunks: int, pack: str, raw_every: int, pinned: bool):
+    """How one tile crosses PCIe: (chunk size used, [(first, last) point of each slice], [device record length of
+    each slice]).  Slices are whole chunks (chunks are independent, so the voxel stage can run per slice); a slice
+    start must be 16-byte aligned in both layouts (34 B records and the 12 B stream), else the tile is one slice;
+    with pack="xyz" every raw_every-th slice of a PINNED source is shipped as whole records instead of gathered."""
+    if pack not in ("none", "xyz"):
+        raise ValueError(f"unknown pack mode {pack!r}")
+    n = int(n)
+    cs = max(1, min(int(chunk_size), max(n, 1)))
+    per_slice = cs * max(1, int(slice_chunks))
+    if (cs * 12) % 16 or (cs * int(rec_len)) % 16:
+        per_slice = max(n, 1)
+    if not pinned:
+        raw_every = 0
+    bounds = [(lo, min(lo + per_slice, n)) for lo in range(0, n, per_slice)]
+    lens = [int(rec_len) if (pack == "none" or (raw_every > 0 and i % raw_every == raw_every - 1)) else 12
+            for i in range(len(bounds))]
+    return cs, bounds, lens
+
+
 class _TileFeed:
     """One tile's host -> device transfer plan: slices of whole chunks, each either gathered to the 12-byte X,Y,Z
     stream (pch_host_pack_xyz) or shipped as whole records, each with its own device buffer and CUDA event."""
 
     def __init__(self, host_records, n, rec_len, chunk_size, slice_chunks, pack, raw_every, device, slot=0, stage=None):
-        if pack not in ("none", "xyz"):
-            raise ValueError(f"unknown pack mode {pack!r}")
         self.n, self.rec_len, self.pack, self.slot, self.device = int(n), int(rec_len), pack, slot, device
         self.stage = stage          # pinned staging for the gathered stream (pack="xyz"); set before feed()
-        self.cs = max(1, min(int(chunk_size), max(self.n, 1)))
-        per_slice = self.cs * max(1, int(slice_chunks))
-        if (self.cs * 12) % 16 or (self.cs * rec_len) % 16:  # slice starts must stay 16-byte aligned in both layouts
-            per_slice = max(self.n, 1)
+        if pack not in ("none", "xyz"):
+            raise ValueError(f"unknown pack mode {pack!r}")
         if isinstance(host_records, torch.Tensor):
             host = host_records.view(torch.uint8).reshape(-1)[: self.n * rec_len]
         else:
             host = torch.from_numpy(np.asarray(host_records).view(np.uint8).reshape(-1)[: self.n * rec_len])
         if pack == "none" and not host.is_pinned():
             host = host.pin_memory()
-        if not host.is_pinned():
-            raw_every = 0
         self.host = host
-        self.bounds = [(lo, min(lo + per_slice, self.n)) for lo in range(0, self.n, per_slice)]
-        # record length of each slice on the device: whole records, or the gathered 12-byte stream
-        self.lens = [rec_len if (pack == "none" or (raw_every > 0 and i % raw_every == raw_every - 1)) else 12
-                     for i in range(len(self.bounds))]
+        self.cs, self.bounds, self.lens = slice_plan(self.n, rec_len, chunk_size, slice_chunks, pack, raw_every,
+                                                     host.is_pinned())
         self.bufs = []
         for (lo, hi), ln in zip(self.bounds, self.lens):
             b = torch.empty(dv.padded_bytes(hi - lo, ln), dtype=torch.uint8, device=device)

@@ -298,3 +298,23 @@ def test_pack_mode_resolution(monkeypatch):
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
     from pointcloudhookup_b200 import device as dv
     assert dv.host_threads() >= 1
+
+
+def test_slice_plan_of_the_host_entries():
+    """pipeline.slice_plan is pure host logic: whole-chunk slices, 16-byte aligned starts in both layouts, the
+    raw-slice pattern only for pinned sources."""
+    from pointcloudhookup_b200 import pipeline
+    cs, b, l = pipeline.slice_plan(1_200_001, 34, 500_000, 1, "xyz", 0, False)
+    assert cs == 500_000 and b == [(0, 500_000), (500_000, 1_000_000), (1_000_000, 1_200_001)] and l == [12, 12, 12]
+    cs, b, l = pipeline.slice_plan(1_200_001, 34, 500_000, 2, "none", 3, True)
+    assert b == [(0, 1_000_000), (1_000_000, 1_200_001)] and l == [34, 34]
+    cs, b, l = pipeline.slice_plan(100, 34, 8, 1, "xyz", 3, True)            # every third slice as whole records
+    assert len(b) == 13 and l[:6] == [12, 12, 34, 12, 12, 34] and all((lo * 12) % 16 == 0 and (lo * 34) % 16 == 0 for lo, _ in b)
+    assert pipeline.slice_plan(100, 34, 8, 1, "xyz", 3, False)[2] == [12] * 13                        # pageable source: no raw slices
+    cs, b, l = pipeline.slice_plan(100, 34, 6, 1, "xyz", 0, True)            # 6*34 % 16 != 0 -> one slice
+    assert cs == 6 and b == [(0, 100)] and l == [12]
+    cs, b, l = pipeline.slice_plan(4, 36, 50_000, 2, "xyz", 0, False)        # tile smaller than a chunk
+    assert cs == 4 and b == [(0, 4)]
+    assert pipeline.slice_plan(0, 34, 500_000, 10, "none", 0, True)[1] == []
+    with pytest.raises(ValueError):
+        pipeline.slice_plan(10, 34, 5, 1, "zip", 0, True)

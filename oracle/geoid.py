@@ -35,7 +35,7 @@ def grid_from_npz(path):
 
 
 def geoid_height(grid, lat, lon):
-    """N(lat, lon) in float64; NaN outside the grid's latitude range or where all corners are nodata."""
+    """N(lat, lon) in float64; NaN outside the grid or where all four corners are nodata."""
     lat = np.asarray(lat, dtype=np.float64)
     lon = np.asarray(lon, dtype=np.float64)
     g, rows, cols = grid["grid"], grid["rows"], grid["cols"]
@@ -58,9 +58,21 @@ def geoid_height(grid, lat, lon):
     g00 = g[iy, ix].astype(np.float64); g01 = g[iy, ix2].astype(np.float64)
     g10 = g[iy2, ix].astype(np.float64); g11 = g[iy2, ix2].astype(np.float64)
     w00 = (1.0 - fx) * (1.0 - fy); w01 = fx * (1.0 - fy); w10 = (1.0 - fx) * fy; w11 = fx * fy
-    n = w00 * g00 + w01 * g01 + w10 * g10 + w11 * g11
-    nod = (g00 == np.float32(NODATA)) | (g01 == np.float32(NODATA)) | (g10 == np.float32(NODATA)) | (g11 == np.float32(NODATA))
-    n = np.where(bad | nod, np.nan, n)
+    # PROJ's nodata rule (grids.cpp, vertical grid value): corners equal to the nodata value are left out, the
+    # sum is divided by the total weight of the valid corners, and only a cell without any valid corner has no
+    # value (PROJ: HUGE_VAL and an error; NaN here).
+    nd = np.float32(NODATA)
+    n = np.zeros(np.broadcast(gx, gy).shape, dtype=np.float64)
+    tw = np.zeros_like(n)
+    nw = np.zeros(n.shape, dtype=np.int64)
+    for w, gv, fv in ((w00, g00, g[iy, ix]), (w01, g01, g[iy, ix2]), (w10, g10, g[iy2, ix]), (w11, g11, g[iy2, ix2])):
+        ok = fv != nd
+        n = np.where(ok, n + w * gv, n)
+        tw = np.where(ok, tw + w, tw)
+        nw = nw + ok
+    with np.errstate(divide="ignore", invalid="ignore"):
+        n = np.where(nw == 4, n, n / tw)
+    n = np.where(bad | (nw == 0), np.nan, n)
     return n
 
 

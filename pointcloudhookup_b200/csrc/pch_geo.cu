@@ -35,14 +35,18 @@ __device__ __forceinline__ double geoid_bilinear(const pch_geoid_grid& g, double
     long long iy2 = iy + 1 < g.rows ? iy + 1 : g.rows - 1;
     const float f00 = node((int)iy, (int)ix), f01 = node((int)iy, (int)ix2);
     const float f10 = node((int)iy2, (int)ix), f11 = node((int)iy2, (int)ix2);
-    if (f00 == PCH_GEOID_NODATA || f01 == PCH_GEOID_NODATA || f10 == PCH_GEOID_NODATA || f11 == PCH_GEOID_NODATA)
-        return geo_nan();
     const double ofx = __dsub_rn(1.0, fx), ofy = __dsub_rn(1.0, fy);
     const double w00 = __dmul_rn(ofx, ofy), w01 = __dmul_rn(fx, ofy), w10 = __dmul_rn(ofx, fy), w11 = __dmul_rn(fx, fy);
-    double n = __dmul_rn(w00, (double)f00);
-    n = __dadd_rn(n, __dmul_rn(w01, (double)f01));
-    n = __dadd_rn(n, __dmul_rn(w10, (double)f10));
-    n = __dadd_rn(n, __dmul_rn(w11, (double)f11));
+    // PROJ's nodata rule (grids.cpp, vertical grid value): nodata corners are left out, the sum is divided by
+    // the weight of the valid ones, and only a cell with no valid corner has no value.
+    double n = 0.0, tw = 0.0;
+    int nw = 0;
+    if (f00 != PCH_GEOID_NODATA) { n = __dadd_rn(n, __dmul_rn(w00, (double)f00)); tw = __dadd_rn(tw, w00); ++nw; }
+    if (f01 != PCH_GEOID_NODATA) { n = __dadd_rn(n, __dmul_rn(w01, (double)f01)); tw = __dadd_rn(tw, w01); ++nw; }
+    if (f10 != PCH_GEOID_NODATA) { n = __dadd_rn(n, __dmul_rn(w10, (double)f10)); tw = __dadd_rn(tw, w10); ++nw; }
+    if (f11 != PCH_GEOID_NODATA) { n = __dadd_rn(n, __dmul_rn(w11, (double)f11)); tw = __dadd_rn(tw, w11); ++nw; }
+    if (nw == 0) return geo_nan();
+    if (nw != 4) n = __ddiv_rn(n, tw);
     return n;
 }
 

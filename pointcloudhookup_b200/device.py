@@ -78,7 +78,36 @@ def upload_records(records, n: int, rec_len: int, scales, offsets, device=None,
                      np.asarray(offsets, dtype=np.float64))
 
 
-_XYZ_STAGE = {}
+# Pinned staging is expensive to create (~0.3 s/GB) and must not accumulate per worker thread (the reference GUI
+# starts a new thread per action): one locked, size-bounded pool serves every host->device path.  A buffer is owned
+# by exactly one transfer between acquire and release.
+_POOL = []
+_POOL_LOCK = threading.Lock()
+_POOL_KEEP = 4
+
+
+def _alloc_pinned(nbytes: int) -> torch.Tensor:
+    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+
+def acquire_staging(nbytes: int) -> torch.Tensor:
+    nbytes = max(int(nbytes), 16)
+    with _POOL_LOCK:
+        fit = [i for i, b in enumerate(_POOL) if b.numel() >= nbytes]
+        if fit:
+            return _POOL.pop(min(fit, key=lambda i: _POOL[i].numel()))     # by index: tensors compare elementwise
+    return _alloc_pinned(nbytes)
+
+
+def release_staging(buf) -> None:
+    if buf is None:
+        return
+    with _POOL_LOCK:
+        if any(b is buf for b in _POOL):
+            return
+        _POOL.append(buf)
+        _POOL.sort(key=lambda b: -b.numel())
+        del _POOL[_POOL_KEEP:]
 
 
 def host_threads() -> int:
@@ -114,26 +143,27 @@ def upload_records_xyz(records, n: int, rec_len: int, scales, offsets, device=No
         base, have = keep.ctypes.data, keep.size
     if have < n * rec_len:
         raise ValueError("record buffer shorter than n * rec_len")
-    block = max(4, int(block_points) // 4 * 4)
-    key = (threading.get_ident(), block)
-    stage = _XYZ_STAGE.get(key)
-    if stage is None:
-        stage = _XYZ_STAGE[key] = [torch.empty(block * 12, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    block = max(4, min(int(block_points), n + 3) // 4 * 4)
+    stage = [acquire_staging(block * 12) for _ in range(2)]
     nt = threads or host_threads()
     busy = [None, None]
-    with torch.cuda.device(device):
-        for bi, lo in enumerate(range(0, n, block)):
-            cnt = min(block, n - lo)
-            b = bi & 1
-            if busy[b] is not None:
-                busy[b].synchronize()          # the copy that last read this staging block has finished
-            check(lib.pch_host_pack_xyz(base + lo * rec_len, cnt, rec_len, stage[b].data_ptr(), nt), "pch_host_pack_xyz")
-            dev[lo * 12: (lo + cnt) * 12].copy_(stage[b][: cnt * 12], non_blocking=True)
-            busy[b] = torch.cuda.Event()
-            busy[b].record()
+    try:
+        with torch.cuda.device(device):
+            for bi, lo in enumerate(range(0, n, block)):
+                cnt = min(block, n - lo)
+                b = bi & 1
+                if busy[b] is not None:
+                    busy[b].synchronize()          # the copy that last read this staging block has finished
+                check(lib.pch_host_pack_xyz(base + lo * rec_len, cnt, rec_len, stage[b].data_ptr(), nt), "pch_host_pack_xyz")
+                dev[lo * 12: (lo + cnt) * 12].copy_(stage[b][: cnt * 12], non_blocking=True)
+                busy[b] = torch.cuda.Event()
+                busy[b].record()
+    finally:
         for e in busy:
             if e is not None:
-                e.synchronize()                 # staging blocks are reused by the next call
+                e.synchronize()                 # the blocks go back to the pool only once their copies are done
+        for b in stage:
+            release_staging(b)
     return out
 
 
@@ -259,6 +289,8 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
             recs, _ = encode_records(lat, 20)
             f32 = decode_xyz(DeviceLas(recs, w.count, 20, dl.scales, dl.offsets), torch.float32)
         if sink is not None:
+            if sink.f32.shape[0] - sink.count < w.count:
+                raise ValueError("VoxelSink too small for this slice")
             sink.f32[sink.count: sink.count + w.count].copy_(f32)
             if sink.z32 is not None:
                 sink.z32[sink.count: sink.count + w.count].copy_(f32[:, 2])

@@ -44,34 +44,8 @@ def run_pipeline(dl: dv.DeviceLas, voxel_size: float = 0.1, chunk_size: int = 50
                           stages if keep_stages else None, vres.plan, stages.db_plan)
 
 
-# pinned staging buffers are expensive to create (~0.3 s/GB), so they are pooled; a buffer is owned by exactly one
-# transfer between acquire and release (concurrent calls from several threads never share one)
-_POOL = []
-_POOL_LOCK = threading.Lock()
-
-
-def _alloc_pinned(nbytes: int) -> torch.Tensor:
-    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-
-
-def _acquire_staging(nbytes: int) -> torch.Tensor:
-    nbytes = max(int(nbytes), 16)
-    with _POOL_LOCK:
-        fit = [i for i, b in enumerate(_POOL) if b.numel() >= nbytes]
-        if fit:
-            return _POOL.pop(min(fit, key=lambda i: _POOL[i].numel()))     # by index: tensors compare elementwise
-    return _alloc_pinned(nbytes)
-
-
-def _release_staging(buf) -> None:
-    if buf is None:
-        return
-    with _POOL_LOCK:
-        if any(b is buf for b in _POOL):
-            return
-        _POOL.append(buf)
-        _POOL.sort(key=lambda b: -b.numel())
-        del _POOL[4:]
+_acquire_staging = dv.acquire_staging      # one bounded pinned pool for every host->device path (device.py)
+_release_staging = dv.release_staging
 
 
 host_threads = dv.host_threads

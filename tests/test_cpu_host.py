@@ -202,34 +202,34 @@ def test_host_pack_xyz_gathers_the_first_twelve_bytes_of_every_record():
 
 
 def test_staging_pool_hands_out_each_buffer_once(monkeypatch):
-    """The pinned staging pool (pipeline._acquire_staging / _release_staging) is host logic: buffers are matched by
+    """The pinned staging pool (device.acquire_staging / release_staging, shared by pipeline and upload_records_xyz) is host logic: buffers are matched by
     identity (tensors compare elementwise), the smallest fitting one is reused, and nothing is handed out twice."""
     import torch
-    from pointcloudhookup_b200 import pipeline
+    from pointcloudhookup_b200 import device as dvm, pipeline
     made = []
 
     def fake(nbytes):
         t = torch.zeros(nbytes, dtype=torch.uint8)
         made.append(t)
         return t
-    monkeypatch.setattr(pipeline, "_alloc_pinned", fake)
-    monkeypatch.setattr(pipeline, "_POOL", [])
+    monkeypatch.setattr(dvm, "_alloc_pinned", fake)
+    monkeypatch.setattr(dvm, "_POOL", [])
     a = pipeline._acquire_staging(3_600_000)
     b = pipeline._acquire_staging(3_720_000)
     assert a is not b and len(made) == 2
     pipeline._release_staging(a)
     pipeline._release_staging(b)
     pipeline._release_staging(b)                       # double release is ignored
-    assert len(pipeline._POOL) == 2
+    assert len(dvm._POOL) == 2
     c = pipeline._acquire_staging(3_600_001)           # only b fits
     assert c is b and len(made) == 2
     d = pipeline._acquire_staging(100)                 # smallest fitting = a
-    assert d is a and not pipeline._POOL
+    assert d is a and not dvm._POOL
     e = pipeline._acquire_staging(100)
     assert e is not a and e is not b and len(made) == 3 and e.numel() == 100
     for t in (a, b, e, pipeline._acquire_staging(5), pipeline._acquire_staging(6), pipeline._acquire_staging(7)):
         pipeline._release_staging(t)
-    assert len(pipeline._POOL) == 4                    # the pool keeps the four largest
+    assert len(dvm._POOL) == 4                    # the pool keeps the four largest
     pipeline._release_staging(None)
 
 

@@ -205,3 +205,29 @@ def test_cluster_merge_reproduces_the_reference_lines():
         got = np.where(labs >= 0, K + comp[np.maximum(labs, 0)], -1).astype(np.int64)
         assert vi.digest(got) == case["merged_sha256"]
         assert len(mstats) == case["n_merged_clusters"]
+
+
+def test_geoid_nodata_corners_are_reweighted_like_proj():
+    """PROJ vgridshift: nodata corners (-88.8888) are dropped and the remaining weights renormalised; only a cell
+    with four nodata corners has no value."""
+    from oracle import geoid
+    nd = np.float32(geoid.NODATA)
+    g = np.array([[1.0, 2.0, nd], [3.0, nd, nd], [5.0, 6.0, 7.0]], dtype=np.float32)
+    grid = {"ll_lat": 10.0, "ll_lon": 100.0, "dlat": 1.0, "dlon": 1.0, "rows": 3, "cols": 3, "grid": g}
+    fx, fy = 0.25, 0.5
+    # cell (0,0): corners 1, 2 (east), 3 (north), nodata (north-east)
+    w00, w01, w10 = (1 - fx) * (1 - fy), fx * (1 - fy), (1 - fx) * fy
+    exp = (w00 * 1.0 + w01 * 2.0 + w10 * 3.0) / (w00 + w01 + w10)
+    got = geoid.geoid_height(grid, [10.0 + fy], [100.0 + fx])
+    assert got[0] == exp
+    # cell (0,1): only the south-west corner (2.0) is valid -> exactly that value
+    assert geoid.geoid_height(grid, [10.5], [101.5])[0] == 2.0
+    # all four valid elsewhere: plain bilinear; all nodata: NaN
+    g2 = g.copy()
+    g2[0, 1] = nd
+    g2[:, 2] = nd
+    g2[1, 1] = nd
+    grid2 = dict(grid, grid=g2)
+    assert np.isnan(geoid.geoid_height(grid2, [10.5], [101.5])[0])
+    full = dict(grid, grid=np.array([[1, 2, 3], [3, 4, 5], [5, 6, 7]], dtype=np.float32))
+    assert geoid.geoid_height(full, [10.5], [100.25])[0] == (0.375 * 1 + 0.125 * 2 + 0.375 * 3 + 0.125 * 4)

@@ -67,6 +67,31 @@ def test_geoid_regional_egm96_and_reference_golden(cuda_device):
     assert np.isnan(geo.geoid_shift(dg, [50.0], [113.0], [0.0], 1.0).cpu().numpy()[0])
 
 
+def test_geoid_nodata_reweighting_matches_oracle(cuda_device):
+    """Regional grid with nodata nodes: valid corners are re-weighted (PROJ), all-nodata cells give NaN."""
+    from pointcloudhookup_b200 import geo
+    from oracle import geoid
+    rng = np.random.default_rng(11)
+    rows, cols = 41, 57
+    g = rng.uniform(-40, 40, (rows, cols)).astype(np.float32)
+    holes = rng.random((rows, cols)) < 0.3
+    g[holes] = np.float32(geoid.NODATA)
+    g[10:14, 20:25] = np.float32(geoid.NODATA)          # a block with all-nodata cells
+    og = {"ll_lat": 20.0, "ll_lon": 105.0, "dlat": 0.25, "dlon": 0.25, "rows": rows, "cols": cols, "grid": g}
+    dg = geo.upload_grid(geo.HostGrid(20.0, 105.0, 0.25, 0.25, g))
+    lat = rng.uniform(19.9, 30.1, 200000)
+    lon = rng.uniform(104.9, 119.1, 200000)
+    h = rng.uniform(0, 500, lat.size)
+    got, n = geo.geoid_shift(dg, lat, lon, h, -1.0, want_n=True)
+    exp_n = geoid.geoid_height(og, lat, lon)
+    gn = n.cpu().numpy()
+    assert np.array_equal(np.isnan(gn), np.isnan(exp_n))
+    ok = ~np.isnan(exp_n)
+    assert ok.sum() > 100000 and (~ok).sum() > 1000
+    assert np.array_equal(gn[ok], exp_n[ok])
+    assert np.abs(got.cpu().numpy()[ok] - geoid.vgridshift(og, lon, lat, h, -1.0)[ok]).max() <= 1e-4
+
+
 @pytest.mark.parametrize("window", ["auto", None])
 def test_las_to_geodetic_fused(cuda_device, window):
     from pointcloudhookup_b200 import device as dv, geo, synth

@@ -148,6 +148,27 @@ int pch_voxel_reduce(const uint64_t* sorted_keys_dev, int64_t n, int64_t chunk_s
                      double* mean_dev, int32_t* lattice_dev, float* f32_dev, float* z32_dev /* nullable */,
                      int64_t* chunk_counts_dev, int64_t* total_dev, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
+/* The whole voxel stage of ui/import_PC.py:45-63 (every chunk of the file: open3d grid per chunk, concat,
+ * LAS re-quantisation, float32 read-back) as ONE call without a host round trip inside: chunk extrema + the
+ * 16-byte lattice copy -> plan (kept in plan_dev, DEVICE memory) -> keys + radix digit histograms -> scan and
+ * radix passes (launched for the widest key the chunk size allows; the passes the plan does not need exit at
+ * once) -> in-order reduce (reads the plan to know which of keys_dev / tmp_dev holds the sorted keys).
+ * Scratch owned by the caller: xyz16_dev (n,4) int32, keys_dev / tmp_dev (n) uint64, minmax_dev [n_chunks][6]
+ * int32, origins_dev [n_chunks][3] float64.  Outputs as for pch_voxel_reduce (each nullable, sized n rows).
+ * After the call the first 64 bytes of workspace_dev hold, for ONE device->host read:
+ *   int32 @0  error word of the look-backs (0 = fine)
+ *   int64 @8  M, the number of voxels; -1 = the voxel index range does not fit one 64-bit key word
+ *             (voxel_size far too small for the chunk extent): nothing was reduced, take the wide-key path
+ *   pch_voxel_plan @32  the plan the device used. */
+size_t pch_voxel_downsample_las_workspace_bytes(int64_t n, int64_t chunk_size);
+int pch_voxel_downsample_las(const uint8_t* rec_dev, int64_t n, int32_t rec_len, int64_t chunk_size,
+                             const double* scales, const double* offsets, double voxel_size,
+                             int32_t* xyz16_dev, uint64_t* keys_dev, uint64_t* tmp_dev, int32_t* minmax_dev,
+                             double* origins_dev, pch_voxel_plan* plan_dev,
+                             double* mean_dev, int32_t* lattice_dev, float* f32_dev, float* z32_dev,
+                             int64_t* chunk_counts_dev, void* workspace_dev, size_t workspace_bytes,
+                             pch_stream_t stream);
+
 /* Self-test: the voxel kernels evaluate `sum/count`, `(mean-offset)/scale` and `(p-origin)/voxel` as a
  * reciprocal product plus two FMA corrections (Markstein), which must equal the IEEE divide bit for bit.
  * mismatches_dev[0] (int64) = number of a_dev[i] for which it does not (expected: 0).  Returns
@@ -225,6 +246,17 @@ int pch_dbscan_run(const float* xyz_dev, int64_t G, int64_t chunk, double eps, i
                    const uint32_t* bounds_dev, const pch_voxel_plan* plan, int32_t* labels_dev,
                    int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
                    void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+
+/* The same clustering as ONE call with no host round trip inside (the plan stays in device memory and every
+ * kernel reads the key layout from it): bounds -> plan -> pch_dbscan_run's kernels.  After the call the first
+ * 256 bytes of workspace_dev are the scalar block, for ONE device->host read:
+ *   int32 @0 error word (0 = fine) | int64 @128 occupied cells | int64 @136 clusters K | uint32 @192 points
+ *   outside dense cells | pch_voxel_plan @208 (status != 0: the cell grid does not fit one key word and nothing
+ *   was clustered).  K > max_clusters: stats_dev holds only the first max_clusters rows; call again with more. */
+size_t pch_dbscan_fused_workspace_bytes(int64_t G, int64_t chunk, int64_t max_clusters);
+int pch_dbscan(const float* xyz_dev, int64_t G, int64_t chunk, double eps, int32_t min_samples,
+               int32_t* labels_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
+               void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
 /* `cluster_points = filtered_points[all_labels == label]` for every label at once
  * (utils/tower_extraction.py:133-134): pch_label_words builds (label << 32 | index) words (noise sorts

@@ -51,6 +51,9 @@ SIGNATURES = {
     "pch_sort_u64_segmented": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _sz, _p]),
     "pch_voxel_reduce_workspace_bytes": (_sz, [_i64, _i64]),
     "pch_voxel_reduce": (C.c_int, [_p, _i64, _i64, _i32, _p, _i32, _p, _p, _d3, _d3, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_voxel_downsample_las_workspace_bytes": (_sz, [_i64, _i64]),
+    "pch_voxel_downsample_las": (C.c_int, [_p, _i64, _i32, _i64, _d3, _d3, _f64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                           _sz, _p]),
     "pch_voxel_index3_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
     "pch_voxel_wide_words": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p]),
     "pch_selftest_fastdiv": (C.c_int, [_p, _i64, _f64, _p, _p]),
@@ -75,6 +78,8 @@ SIGNATURES.update({
     "pch_gather_rows_f32": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "pch_dbscan_plan": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
     "pch_dbscan_workspace_bytes": (_sz, [_i64, _i64, C.POINTER(VoxelPlan), _i64]),
+    "pch_dbscan_fused_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "pch_dbscan": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, _p, _i64, _p, _sz, _p]),
     "pch_dbscan_run": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, C.POINTER(VoxelPlan), _p, _p, _p, _i64, _p, _sz, _p]),
 })
 

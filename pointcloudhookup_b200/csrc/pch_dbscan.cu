@@ -14,6 +14,7 @@
 // points is all-core and all core points of a cell share a cluster), and neighbours of a point lie
 // within +-2 cells per axis.  Clusters are a union-find over CELLS that hold a core point.
 #include "pch_common.cuh"
+#include "pch_sort.cuh"
 
 struct DbPlan {
     int32_t bits_x, bits_y, bits_z, bits_idx, key_bits, n_passes, status, reserved;
@@ -24,8 +25,24 @@ struct DbGeom {
     double cell, eps2;
     int32_t min_pts;
     int32_t sh_x, sh_y, sh_z, bits_idx;  // key layout
-    int32_t bits_x, bits_y, bits_z;
+    int32_t bits_x, bits_y, bits_z, key_bits;
+    const DbPlan* dplan;                 // non-NULL: the key layout is read from this plan in DEVICE memory
 };
+
+// Device-planned runs (pch_dbscan): every kernel that needs the key layout takes it from the plan the plan
+// kernel left in device memory, so the host never waits for it.  false = the plan is unusable (cell grid too
+// wide for one key word); the kernels then do nothing and the host learns it from the scalar block.
+__device__ __forceinline__ bool db_resolve(DbGeom& g) {
+    if (g.dplan) {
+        const DbPlan p = *g.dplan;
+        if (p.status != PCH_OK) return false;
+        g.bits_idx = p.bits_idx;
+        g.bits_x = p.bits_x; g.bits_y = p.bits_y; g.bits_z = p.bits_z;
+        g.key_bits = p.key_bits;
+        g.sh_z = p.bits_idx; g.sh_y = g.sh_z + p.bits_z; g.sh_x = g.sh_y + p.bits_y;
+    }
+    return true;
+}
 
 static unsigned db_grid(int64_t n, int threads, int per_sm = 8) {
     int64_t b = pch_ceil_div(n > 0 ? n : 1, threads);
@@ -141,6 +158,7 @@ __device__ __forceinline__ void db_cell3(float x, float y, float z, float mnx, f
 __global__ void __launch_bounds__(256)
 k_db_keys(const float* __restrict__ P, DbGeom g, const uint32_t* __restrict__ mm, double rcell, int fast,
           uint64_t* __restrict__ keys) {
+    if (!db_resolve(g)) return;
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_quads = (g.G + 3) / 4;
@@ -198,8 +216,10 @@ struct DbCells {
 };
 
 __global__ void __launch_bounds__(DC_THREADS)
-k_db_cells(const uint64_t* __restrict__ keys, const float* __restrict__ P, DbGeom g, DbCells o, int64_t tiles_per_chunk,
+k_db_cells(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ keys_odd, const float* __restrict__ P, DbGeom g, DbCells o, int64_t tiles_per_chunk,
            int64_t total_tiles, uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
+    if (!db_resolve(g)) return;
+    if (g.dplan && (((g.key_bits + 7) >> 3) & 1)) keys = keys_odd;   // odd pass count: the sorted keys are in the ping-pong partner
     __shared__ uint64_t s_keys[DC_TILE + 1];
     __shared__ uint32_t s_wcount[DC_THREADS / 32];
     __shared__ uint64_t s_off;
@@ -291,6 +311,7 @@ k_db_cells(const uint64_t* __restrict__ keys, const float* __restrict__ P, DbGeo
 __global__ void k_db_nbr(DbGeom g, const uint64_t* __restrict__ cell_key, const int32_t* __restrict__ cell_start,
                          const int32_t* __restrict__ chunk_cell0, const long long* __restrict__ U_dev,
                          int32_t* __restrict__ nbr_first, uint8_t* __restrict__ nbr_cnt) {
+    if (!db_resolve(g)) return;
     const int64_t U = *U_dev;
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -341,6 +362,7 @@ __device__ __forceinline__ double db_dist2(const float4& a, const float4& b) {
 __global__ void __launch_bounds__(256)
 k_db_core1(DbGeom g, const int32_t* __restrict__ pt_cell, const int32_t* __restrict__ cell_start,
            uint8_t* __restrict__ core, int32_t* __restrict__ worklist, unsigned int* __restrict__ n_work) {
+    if (!db_resolve(g)) return;
     const int lane = threadIdx.x & 31;
     const int64_t Gpad = (g.G + 31) / 32 * 32;
     int64_t pos = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -393,6 +415,7 @@ k_db_core2(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict_
            const uint8_t* __restrict__ nbr_cnt, const int32_t* __restrict__ worklist,
            const unsigned int* __restrict__ n_work, uint8_t* __restrict__ core,
            const uint64_t* __restrict__ cell_key, const uint32_t* __restrict__ bounds) {
+    if (!db_resolve(g)) return;
     const int lane = threadIdx.x & 31;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -461,6 +484,7 @@ k_db_cellinfo(const long long* __restrict__ U_dev, const float4* __restrict__ sp
               const uint8_t* __restrict__ core, DbCellInfo* __restrict__ info, int64_t chunk,
               int32_t* __restrict__ cell_mincore, DbGeom g, const uint64_t* __restrict__ cell_key,
               const uint32_t* __restrict__ bounds, unsigned long long* __restrict__ cell_mask) {
+    if (!db_resolve(g)) return;
     const int64_t U = *U_dev;
     const int bxy = g.bits_y + g.bits_z;
     const uint64_t mzk = (1ull << g.bits_z) - 1ull, myk = (1ull << g.bits_y) - 1ull;
@@ -561,6 +585,7 @@ k_db_union(DbGeom g, const long long* __restrict__ U_dev, const float4* __restri
            const int32_t* __restrict__ cell_start, const uint8_t* __restrict__ core,
            const int32_t* __restrict__ nbr_first, const uint8_t* __restrict__ nbr_cnt, DbCellInfo* __restrict__ info,
            const uint64_t* __restrict__ cell_key, int pass, const unsigned long long* __restrict__ cell_mask) {
+    if (!db_resolve(g)) return;
     // pass 0: only face/edge/corner-adjacent cells (|offset| <= 1): cheap hits that merge almost every
     // dense region; pass 1: the remaining (distance-2) cells, most of which are then skipped by the
     // "already in one set" test instead of being searched exhaustively.
@@ -870,6 +895,7 @@ k_db_labels_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __res
                  const uint8_t* __restrict__ core, const int32_t* __restrict__ cell_root,
                  const int32_t* __restrict__ root_label, int32_t* __restrict__ labels, int64_t cap,
                  DbClusterAcc* __restrict__ acc) {
+    if (!db_resolve(g)) return;
     const int lane = threadIdx.x & 31;
     const int64_t n_rows = (g.G + 31) / 32;
     const int64_t n_groups = (n_rows + CR_ROWS - 1) / CR_ROWS;
@@ -951,6 +977,7 @@ k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __r
                    const int32_t* __restrict__ cell_root, const int32_t* __restrict__ root_label,
                    const int32_t* __restrict__ worklist, const unsigned int* __restrict__ n_work,
                    int32_t* __restrict__ labels, int64_t cap, DbClusterAcc* __restrict__ acc) {
+    if (!db_resolve(g)) return;
     const int lane = threadIdx.x & 31;
     int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1038,7 +1065,7 @@ struct DbWs {
     size_t total;
     size_t keys, tmp, sortws, sortws_bytes, spts, pt_cell, inv_pos, cell_start, cell_key, chunk_cell0, scalars,
         nbr_first, nbr_cnt, core, info, cell_root, root_min, root_label, is_head, head_list, scan_status, acc,
-        worklist, cell_mincore, cell_mask;
+        worklist, cell_mincore, cell_mask, bounds, plan;
 };
 
 extern "C" size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi);
@@ -1050,7 +1077,14 @@ extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8
                                   uint8_t* out_mask, int64_t* count_dev, void* workspace, size_t workspace_bytes,
                                   pch_stream_t stream);
 
-static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t max_clusters) {
+static int db_max_passes(int64_t chunk) {   // radix passes of the widest cell key a chunk of this size allows (62 bits in all)
+    int bits_idx = 0;
+    for (int64_t v = chunk - 1; v > 0; v >>= 1) ++bits_idx;
+    int p = (62 - bits_idx + 7) / 8;
+    return p < 1 ? 1 : (p > RS_MAX_PASSES ? RS_MAX_PASSES : p);
+}
+
+static DbWs db_ws(int64_t G, int64_t chunk, int sort_passes, int64_t max_clusters) {
     DbWs w;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += pch_align_up(bytes, 256); return o; };
@@ -1059,7 +1093,7 @@ static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t 
     w.scalars = take(256);  // [0]=err int, [64]=tile counter, [128]=n_cells (i64), [136]=n_clusters (i64)
     w.keys = take((size_t)G * 8);
     w.tmp = take((size_t)G * 8);
-    w.sortws_bytes = pch_sort_workspace_bytes(G, chunk, plan->bits_idx, plan->bits_idx + plan->key_bits);
+    w.sortws_bytes = pch_sort_ws(pch_sort_geom(G, chunk, 0, 0, sort_passes < 1 ? 1 : sort_passes), nullptr).bytes;
     w.sortws = take(w.sortws_bytes);
     w.spts = take((size_t)G * 16);
     w.pt_cell = take((size_t)G * 4);
@@ -1083,6 +1117,8 @@ static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t 
     w.worklist = take((size_t)(G + 32) * 4);
     w.cell_mincore = take((size_t)G * 4);
     w.cell_mask = take((size_t)G * 8);
+    w.bounds = take((size_t)n_chunks * 6 * 4);
+    w.plan = take(256);
     w.total = off;
     return w;
 }
@@ -1090,24 +1126,17 @@ static DbWs db_ws(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t 
 extern "C" size_t pch_dbscan_workspace_bytes(int64_t G, int64_t chunk, const pch_voxel_plan* plan, int64_t max_clusters) {
     if (G <= 0 || !plan) return 256;
     if (chunk > G) chunk = G;
-    return db_ws(G, chunk, plan, max_clusters).total;
+    return db_ws(G, chunk, plan->n_passes, max_clusters).total;
 }
 
-extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts,
-                              const uint32_t* bounds_dev, const pch_voxel_plan* plan, int32_t* labels_dev,
-                              int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
-                              void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+// hplan: the plan on the HOST (pch_dbscan_plan + a read-back, the two-call interface) or NULL;
+// dplan: the same plan in DEVICE memory (pch_dbscan, no read-back between planning and clustering).
+static int dbscan_impl(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts,
+                       const uint32_t* bounds_dev, const pch_voxel_plan* hplan, const pch_voxel_plan* dplan,
+                       int sort_passes, int32_t* labels_dev, int64_t* n_clusters_dev, pch_cluster_stats* stats_dev,
+                       int64_t max_clusters, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    PCH_CHECK_ARG(G >= 1 && chunk >= 1 && min_pts >= 1 && eps > 0.0, "bad G/chunk/min_samples/eps");
-    PCH_CHECK_ARG(G < (1ll << 31), "more than 2^31-1 candidate points");
-    PCH_CHECK_ARG(P && bounds_dev && plan && labels_dev && n_clusters_dev && workspace, "null pointer");
-    PCH_CHECK_ARG(max_clusters >= 1 && (stats_dev != nullptr), "stats buffer required");
-    if (plan->status != PCH_OK) {
-        pch_set_error("DBSCAN cell grid needs %d+%d key bits", plan->key_bits, plan->bits_idx);
-        return PCH_ERR_RANGE;
-    }
-    if (chunk > G) chunk = G;
-    DbWs w = db_ws(G, chunk, plan, max_clusters);
+    DbWs w = db_ws(G, chunk, sort_passes, max_clusters);
     if (workspace_bytes < w.total) {
         pch_set_error("dbscan workspace too small: %zu < %zu", workspace_bytes, w.total);
         return PCH_ERR_WORKSPACE;
@@ -1128,17 +1157,30 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     g.cell = db_cell_side(eps);
     g.eps2 = eps * eps;
     g.min_pts = min_pts;
-    g.bits_idx = plan->bits_idx;
-    g.bits_x = plan->bits_x; g.bits_y = plan->bits_y; g.bits_z = plan->bits_z;
-    g.sh_z = plan->bits_idx; g.sh_y = g.sh_z + plan->bits_z; g.sh_x = g.sh_y + plan->bits_y;
+    g.dplan = (const DbPlan*)dplan;
+    g.bits_idx = g.bits_x = g.bits_y = g.bits_z = g.key_bits = g.sh_x = g.sh_y = g.sh_z = 0;
+    if (hplan) {
+        g.bits_idx = hplan->bits_idx;
+        g.bits_x = hplan->bits_x; g.bits_y = hplan->bits_y; g.bits_z = hplan->bits_z;
+        g.key_bits = hplan->key_bits;
+        g.sh_z = hplan->bits_idx; g.sh_y = g.sh_z + hplan->bits_z; g.sh_x = g.sh_y + hplan->bits_y;
+    }
 
     PCH_CUDA(cudaMemsetAsync(base + w.scalars, 0, 256, st));
     PCH_LAUNCH(st, "k_db_keys", k_db_keys<<<db_grid((G + 3) / 4, 256, 16), 256, 0, st>>>(P, g, bounds_dev, 1.0 / g.cell, pch_recip_ok(g.cell) ? 1 : 0, keys));
     PCH_LAUNCH_CHECK();
-    int rc = pch_sort_u64_segmented(keys, tmp, G, chunk, plan->bits_idx, plan->bits_idx + plan->key_bits,
+    int rc;
+    const uint64_t* skeys = keys;
+    if (hplan) {
+        rc = pch_sort_u64_segmented(keys, tmp, G, chunk, hplan->bits_idx, hplan->bits_idx + hplan->key_bits,
                                     base + w.sortws, w.sortws_bytes, stream);
-    if (rc) return rc;
-    const uint64_t* skeys = (plan->n_passes % 2) ? tmp : keys;
+        if (rc) return rc;
+        skeys = (hplan->n_passes % 2) ? tmp : keys;
+    } else {
+        SortGeom sg = pch_sort_geom(G, chunk, 0, 0, sort_passes);
+        if ((rc = pch_sort_prepare(sg, base + w.sortws, w.sortws_bytes, st))) return rc;
+        if ((rc = pch_sort_run(keys, tmp, sg, dplan, sort_passes, false, base + w.sortws, w.sortws_bytes, st))) return rc;
+    }
 
     DbCells o;
     o.spts = (float4*)(base + w.spts);
@@ -1153,7 +1195,7 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
     int64_t total_tiles = (g.n_chunks - 1) * tiles_per_chunk + pch_ceil_div(last, DC_TILE);
     uint64_t* status = (uint64_t*)(base + w.scan_status);
     PCH_CUDA(cudaMemsetAsync(status, 0, (size_t)total_tiles * 8, st));
-    PCH_LAUNCH(st, "k_db_cells", k_db_cells<<<(unsigned)total_tiles, DC_THREADS, 0, st>>>(skeys, P, g, o, tiles_per_chunk, total_tiles, status, counter, err));
+    PCH_LAUNCH(st, "k_db_cells", k_db_cells<<<(unsigned)total_tiles, DC_THREADS, 0, st>>>(skeys, tmp, P, g, o, tiles_per_chunk, total_tiles, status, counter, err));
     PCH_LAUNCH_CHECK();
 
     int32_t* nbr_first = (int32_t*)(base + w.nbr_first);
@@ -1213,6 +1255,70 @@ extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double e
                                                                                     labels_dev, max_clusters, acc));
     PCH_LAUNCH_CHECK();
     PCH_LAUNCH(st, "k_db_acc_finish", k_db_acc_finish<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, (const long long*)n_clusters_dev, acc, stats_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+
+extern "C" int pch_dbscan_run(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts,
+                              const uint32_t* bounds_dev, const pch_voxel_plan* plan, int32_t* labels_dev,
+                              int64_t* n_clusters_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
+                              void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    PCH_CHECK_ARG(G >= 1 && chunk >= 1 && min_pts >= 1 && eps > 0.0, "bad G/chunk/min_samples/eps");
+    PCH_CHECK_ARG(G < (1ll << 31), "more than 2^31-1 candidate points");
+    PCH_CHECK_ARG(P && bounds_dev && plan && labels_dev && n_clusters_dev && workspace, "null pointer");
+    PCH_CHECK_ARG(max_clusters >= 1 && (stats_dev != nullptr), "stats buffer required");
+    if (plan->status != PCH_OK) {
+        pch_set_error("DBSCAN cell grid needs %d+%d key bits", plan->key_bits, plan->bits_idx);
+        return PCH_ERR_RANGE;
+    }
+    if (chunk > G) chunk = G;
+    return dbscan_impl(P, G, chunk, eps, min_pts, bounds_dev, plan, nullptr, plan->n_passes, labels_dev, n_clusters_dev,
+                       stats_dev, max_clusters, workspace, workspace_bytes, stream);
+}
+
+// One call, no host round trip inside: chunk bounds -> plan (device) -> clustering.  The first 256 bytes of the
+// workspace are the scalar block the caller reads back once: int32 @0 error word, int64 @128 cells, int64 @136
+// clusters, uint32 @192 points outside dense cells, pch_voxel_plan @208 (status != 0: the cell grid does not fit
+// one key word and nothing was clustered).
+__global__ void k_db_head(const DbPlan* __restrict__ plan, uint8_t* __restrict__ scalars, const int* __restrict__ sort_err) {
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<DbPlan*>(scalars + 208) = *plan;
+        if (*sort_err) atomicExch(reinterpret_cast<int*>(scalars), *sort_err);
+    }
+}
+
+extern "C" size_t pch_dbscan_fused_workspace_bytes(int64_t G, int64_t chunk, int64_t max_clusters) {
+    if (G <= 0) return 256;
+    if (chunk <= 0 || chunk > G) chunk = G;
+    return db_ws(G, chunk, db_max_passes(chunk), max_clusters).total;
+}
+
+extern "C" int pch_dbscan(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts, int32_t* labels_dev,
+                          pch_cluster_stats* stats_dev, int64_t max_clusters, void* workspace, size_t workspace_bytes,
+                          pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(G >= 1 && chunk >= 1 && min_pts >= 1 && eps > 0.0, "bad G/chunk/min_samples/eps");
+    PCH_CHECK_ARG(G < (1ll << 31), "more than 2^31-1 candidate points");
+    PCH_CHECK_ARG(P && labels_dev && workspace, "null pointer");
+    PCH_CHECK_ARG(max_clusters >= 1 && (stats_dev != nullptr), "stats buffer required");
+    if (chunk > G) chunk = G;
+    const int passes = db_max_passes(chunk);
+    DbWs w = db_ws(G, chunk, passes, max_clusters);
+    if (workspace_bytes < w.total) {
+        pch_set_error("dbscan workspace too small: %zu < %zu", workspace_bytes, w.total);
+        return PCH_ERR_WORKSPACE;
+    }
+    uint8_t* base = (uint8_t*)workspace;
+    uint32_t* bounds = (uint32_t*)(base + w.bounds);
+    pch_voxel_plan* plan_dev = (pch_voxel_plan*)(base + w.plan);
+    int rc = pch_dbscan_plan(P, G, chunk, eps, bounds, plan_dev, stream);
+    if (rc) return rc;
+    int64_t* n_clusters_dev = (int64_t*)(base + w.scalars + 136);
+    rc = dbscan_impl(P, G, chunk, eps, min_pts, bounds, nullptr, plan_dev, passes, labels_dev, n_clusters_dev, stats_dev,
+                     max_clusters, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    PCH_LAUNCH(st, "k_db_head", k_db_head<<<1, 32, 0, st>>>((const DbPlan*)plan_dev, base + w.scalars, (const int*)(base + w.sortws)));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

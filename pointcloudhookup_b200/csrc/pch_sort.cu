@@ -1,5 +1,6 @@
 // Segmented stable LSD radix sort of 64-bit keys (8-bit digits), one-sweep style:
-//   k_hist  : ONE read of the keys builds the digit histograms of every pass, per segment
+//   k_hist  : ONE read of the keys builds the digit histograms of every pass, per segment (skipped when the
+//             kernel that produced the keys already built them: pch_sort.cuh)
 //   k_scan  : exclusive scan of each 256-bin histogram -> digit bases inside the segment
 //   k_pass  : per pass, one kernel: tile-local ranking (warp match_any multi-split), chained
 //             decoupled look-back across the tiles of a segment, scatter via shared memory.
@@ -7,106 +8,71 @@
 // are sorted, and segments (voxel chunks / DBSCAN chunks) never mix because every offset is
 // segment-relative.  Used for open3d's voxel grouping (ui/import_PC.py:12) and for the DBSCAN
 // cell grid (utils/tower_extraction.py:107-112).
-#include "pch_common.cuh"
+#include "pch_sort.cuh"
 
-#define RS_THREADS 256
-#ifndef RS_KPT
-#define RS_KPT 16
-#endif
-#ifndef RS_MINB
-#define RS_MINB 4
-#endif
-#define RS_TILE (RS_THREADS * RS_KPT)
-#define RS_WARPS (RS_THREADS / 32)
-#define RS_MAX_PASSES 8
+#ifndef LB_WIN
 #define LB_WIN 8
+#endif
 
-struct SortGeom {
-    int64_t n, seg_size, tiles_per_seg, total_tiles, n_segs;
-    int32_t bit_lo, n_passes;
-    int32_t pass_bits[RS_MAX_PASSES];
-};
-
-static SortGeom sort_geom(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi) {
-    SortGeom g;
-    g.n = n;
-    if (seg_size <= 0 || seg_size > n) seg_size = n > 0 ? n : 1;
-    g.seg_size = seg_size;
-    g.tiles_per_seg = pch_ceil_div(seg_size, RS_TILE);
-    g.n_segs = pch_ceil_div(n, seg_size);
-    int64_t last = n - (g.n_segs - 1) * seg_size;
-    g.total_tiles = n > 0 ? (g.n_segs - 1) * g.tiles_per_seg + pch_ceil_div(last, RS_TILE) : 0;
-    g.bit_lo = bit_lo;
-    int bits = bit_hi - bit_lo;
-    g.n_passes = (bits + 7) / 8;
-    for (int p = 0; p < RS_MAX_PASSES; ++p) {
-        int b = bits - 8 * p;
-        g.pass_bits[p] = b >= 8 ? 8 : (b > 0 ? b : 0);
-    }
-    return g;
-}
-
-// workspace: [0,256): int err; uint32 counters[8] at +64 | hist: n_segs*passes*256 u32 | status: passes*tiles*256 u32
-struct SortWs {
-    int* err;
-    uint32_t* counters;
-    uint32_t* hist;
-    uint32_t* status;
-    size_t bytes;
-    size_t zero_bytes;  // everything is zeroed in one memset
-};
-static SortWs sort_ws(const SortGeom& g, void* base) {
-    SortWs w;
-    uint8_t* p = (uint8_t*)base;
-    w.err = (int*)p;
-    w.counters = (uint32_t*)(p + 64);
-    size_t off = 256;
-    w.hist = (uint32_t*)(p + off);
-    off += pch_align_up((size_t)g.n_segs * g.n_passes * 256 * 4, 256);
-    w.status = (uint32_t*)(p + off);
-    off += pch_align_up((size_t)g.n_passes * g.total_tiles * 256 * 4, 256);
-    w.bytes = off;
-    w.zero_bytes = off;
-    return w;
-}
-
-__device__ __forceinline__ void tile_span(const SortGeom& g, int64_t tile, int64_t& seg, int64_t& seg_start,
-                                          int64_t& start, int& cnt) {
-    seg = tile / g.tiles_per_seg;
-    int64_t lt = tile - seg * g.tiles_per_seg;
+// ticket -> tile.  Tickets are handed out group by group (RS_GROUP segments), and inside a group tile-index
+// major: (lt 0 of every segment of the group), (lt 1 of every segment), ...  A tile's predecessors in its
+// own segment therefore always hold smaller tickets (forward progress of the look-back), and the tiles that
+// run concurrently belong to different segments.
+__device__ __forceinline__ bool tile_of_ticket(const SortGeom& g, int64_t ticket, int64_t& seg, int64_t& lt,
+                                               int64_t& seg_start, int64_t& start, int& cnt) {
+    const int64_t per_group = (int64_t)RS_GROUP * g.tiles_per_seg;
+    const int64_t grp = ticket / per_group;
+    const int64_t r = ticket - grp * per_group;
+    int64_t sg = g.n_segs - grp * RS_GROUP;
+    if (sg > RS_GROUP) sg = RS_GROUP;
+    lt = r / sg;
+    seg = grp * RS_GROUP + (r - lt * sg);
     seg_start = seg * g.seg_size;
     int64_t seg_end = seg_start + g.seg_size;
     if (seg_end > g.n) seg_end = g.n;
     start = seg_start + lt * RS_TILE;
-    int64_t c = seg_end - start;
+    const int64_t c = seg_end - start;
     cnt = (int)(c > RS_TILE ? RS_TILE : c);
+    return c > 0;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
-k_hist(const uint64_t* __restrict__ keys, SortGeom g, uint32_t* __restrict__ hist) {
+k_hist(const uint64_t* __restrict__ keys, SortGeom g, const pch_voxel_plan* __restrict__ dplan, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[RS_MAX_PASSES * 256];
     const int tid = threadIdx.x;
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        int64_t seg, seg_start, start;
-        int cnt;
-        tile_span(g, tile, seg, seg_start, start, cnt);
-        for (int i = tid; i < g.n_passes * 256; i += RS_THREADS) sh[i] = 0;
-        __syncthreads();
-#pragma unroll 4
-        for (int i = tid; i < cnt; i += RS_THREADS) {
-            uint64_t k = keys[start + i] >> g.bit_lo;
-            for (int p = 0; p < g.n_passes; ++p) {
-                uint32_t d = (uint32_t)(k >> (8 * p)) & ((1u << g.pass_bits[p]) - 1u);
-                atomicAdd(&sh[p * 256 + d], 1u);
+    int bit_lo, n_bits;
+    if (!pch_sort_range(g, dplan, bit_lo, n_bits)) return;
+    const int n_passes = (n_bits + 7) >> 3;
+    if (n_passes > g.hist_passes) return;
+    for (int i = tid; i < RS_MAX_PASSES * 256; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    // canonical tile order here (no look-back): consecutive tiles of a CTA mostly share a segment, so the
+    // table row is flushed once per segment change
+    const int64_t tiles = g.total_tickets;
+    const int64_t per = (tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = t0 + per < tiles ? t0 + per : tiles;
+    int64_t cur_seg = -1;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t seg = tile / g.tiles_per_seg, lt = tile - seg * g.tiles_per_seg;
+        const int64_t seg_start = seg * g.seg_size;
+        int64_t seg_end = seg_start + g.seg_size;
+        if (seg_end > g.n) seg_end = g.n;
+        const int64_t start = seg_start + lt * RS_TILE;
+        if (start >= seg_end) continue;
+        const int cnt = (int)(seg_end - start > RS_TILE ? RS_TILE : seg_end - start);
+        if (seg != cur_seg) {
+            if (cur_seg >= 0) {
+                __syncthreads();
+                pch_sort_hist_flush(sh, hist, cur_seg, g.hist_passes, n_bits);
+                __syncthreads();
             }
+            cur_seg = seg;
         }
-        __syncthreads();
-        for (int i = tid; i < g.n_passes * 256; i += RS_THREADS) {
-            uint32_t c = sh[i];
-            if (c) atomicAdd(&hist[(seg * g.n_passes) * 256 + i], c);
-        }
-        __syncthreads();
+#pragma unroll 4
+        for (int i = tid; i < cnt; i += RS_THREADS) pch_sort_hist_add(sh, keys[start + i], bit_lo, n_bits);
     }
+    __syncthreads();
+    if (cur_seg >= 0) pch_sort_hist_flush(sh, hist, cur_seg, g.hist_passes, n_bits);
 }
 
 // exclusive scan of one value per thread over the whole block (threads beyond the 256 digits pass 0)
@@ -140,8 +106,8 @@ __global__ void __launch_bounds__(256) k_scan(uint32_t* __restrict__ hist, int64
 #define ST_VAL 0x3fffffffu
 
 __global__ void __launch_bounds__(RS_THREADS, RS_MINB)
-k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, int pass, int shift, uint32_t dmask,
-       const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
+k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, const pch_voxel_plan* __restrict__ dplan,
+       int pass, const uint32_t* __restrict__ hist, uint32_t* __restrict__ status, uint32_t* __restrict__ counter,
        int* __restrict__ err) {
     __shared__ uint64_t s_keys[RS_TILE];
     __shared__ uint16_t s_whist[RS_WARPS][258];   // a warp ranks 32*RS_KPT = 512 keys: counts fit 16 bits; [256] = spare slot for out-of-range lanes
@@ -150,14 +116,22 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
     __shared__ uint32_t s_scan[RS_THREADS / 32];
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bit_lo, n_bits;
+    if (!pch_sort_range(g, dplan, bit_lo, n_bits)) return;
+    if (((n_bits + 7) >> 3) > g.hist_passes) {       // a device plan wider than the launched passes: flag, do not sort
+        if (blockIdx.x == 0 && tid == 0) atomicExch(err, 2);
+        return;
+    }
+    if (pass * 8 >= n_bits) return;                  // launched for the widest possible key; this key is narrower
+    const int shift = bit_lo + 8 * pass;
+    const uint32_t dmask = (1u << (n_bits - 8 * pass < 8 ? n_bits - 8 * pass : 8)) - 1u;
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
     for (int i = tid; i < RS_WARPS * 258 / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&s_whist[0][0])[i] = 0;
     __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= g.total_tiles) return;
-    int64_t seg, seg_start, start;
+    int64_t seg, lt, seg_start, start;
     int cnt;
-    tile_span(g, tile, seg, seg_start, start, cnt);
+    if (!tile_of_ticket(g, (int64_t)s_tile, seg, lt, seg_start, start, cnt)) return;
+    const int64_t tile = seg * g.tiles_per_seg + lt;          // canonical id: status row
     const int64_t first_tile = seg * g.tiles_per_seg;
 
     // ---- load (warp-blocked so that the in-tile order is the input order) and rank
@@ -275,7 +249,7 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
             }
             pch_st_volatile_u32(status + ((size_t)tile * 256 + d), ST_INCL | ((excl + my_sum) & ST_VAL));
         }
-        s_goff[d] = seg_start + (int64_t)hist[(seg * g.n_passes + pass) * 256 + d] + (int64_t)excl - (int64_t)s_dstart[d];
+        s_goff[d] = seg_start + (int64_t)hist[(seg * g.hist_passes + pass) * 256 + d] + (int64_t)excl - (int64_t)s_dstart[d];
     }
     __syncthreads();
     for (int i = tid; i < cnt; i += RS_THREADS) {
@@ -287,8 +261,48 @@ k_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, SortGeom g, 
 
 extern "C" size_t pch_sort_workspace_bytes(int64_t n, int64_t seg_size, int32_t bit_lo, int32_t bit_hi) {
     if (n <= 0 || bit_hi <= bit_lo) return 256;
-    SortGeom g = sort_geom(n, seg_size, bit_lo, bit_hi);
-    return sort_ws(g, nullptr).bytes;
+    SortGeom g = pch_sort_geom(n, seg_size, bit_lo, bit_hi - bit_lo, (bit_hi - bit_lo + 7) / 8);
+    return pch_sort_ws(g, nullptr).bytes;
+}
+
+int pch_sort_prepare(const SortGeom& g, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    SortWs w = pch_sort_ws(g, workspace);
+    if (workspace_bytes < w.bytes) {
+        pch_set_error("sort workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+        return PCH_ERR_WORKSPACE;
+    }
+    PCH_CHECK_ARG(g.seg_size < (1ll << 30), "segment size must be < 2^30");
+    PCH_CHECK_ARG(g.hist_passes >= 1 && g.hist_passes <= RS_MAX_PASSES, "1..%d radix passes", RS_MAX_PASSES);
+    PCH_CUDA(cudaMemsetAsync(workspace, 0, w.bytes, st));
+    return PCH_OK;
+}
+
+int pch_sort_run(uint64_t* keys, uint64_t* tmp, const SortGeom& g, const pch_voxel_plan* dplan, int passes, bool prehist,
+                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    SortWs w = pch_sort_ws(g, workspace);
+    if (workspace_bytes < w.bytes) {
+        pch_set_error("sort workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+        return PCH_ERR_WORKSPACE;
+    }
+    if (g.total_tickets == 0) return PCH_OK;
+    if (!prehist) {
+        int64_t hgrid = (int64_t)pch_sm_count() * 8;
+        if (hgrid > g.total_tickets) hgrid = g.total_tickets;
+        PCH_LAUNCH(st, "k_hist", k_hist<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys, g, dplan, w.hist));
+        PCH_LAUNCH_CHECK();
+    }
+    int64_t rows = g.n_segs * g.hist_passes;
+    PCH_LAUNCH(st, "k_scan", k_scan<<<(unsigned)(rows < 4096 ? rows : 4096), 256, 0, st>>>(w.hist, rows));
+    PCH_LAUNCH_CHECK();
+    uint64_t* src = keys;
+    uint64_t* dst = tmp;
+    for (int p = 0; p < passes; ++p) {
+        PCH_LAUNCH(st, "k_pass", k_pass<<<(unsigned)g.total_tickets, RS_THREADS, 0, st>>>(
+                                     src, dst, g, dplan, p, w.hist, w.status + (size_t)p * g.total_tickets * 256, w.counters + p, w.err));
+        PCH_LAUNCH_CHECK();
+        uint64_t* t = src; src = dst; dst = t;
+    }
+    return PCH_OK;
 }
 
 extern "C" int pch_sort_u64_segmented(uint64_t* keys, uint64_t* tmp, int64_t n, int64_t seg_size, int32_t bit_lo,
@@ -298,29 +312,9 @@ extern "C" int pch_sort_u64_segmented(uint64_t* keys, uint64_t* tmp, int64_t n, 
     PCH_CHECK_ARG(bit_lo >= 0 && bit_hi <= 64 && bit_hi >= bit_lo, "bad bit range [%d,%d)", bit_lo, bit_hi);
     if (n == 0 || bit_hi == bit_lo) return PCH_OK;
     PCH_CHECK_ARG(keys && tmp && workspace, "null pointer");
-    SortGeom g = sort_geom(n, seg_size, bit_lo, bit_hi);
-    PCH_CHECK_ARG(g.seg_size < (1ll << 30), "segment size must be < 2^30");
-    SortWs w = sort_ws(g, workspace);
-    if (workspace_bytes < w.bytes) {
-        pch_set_error("sort workspace too small: %zu < %zu", workspace_bytes, w.bytes);
-        return PCH_ERR_WORKSPACE;
-    }
-    PCH_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));
-    int64_t hgrid = (int64_t)pch_sm_count() * 8;
-    if (hgrid > g.total_tiles) hgrid = g.total_tiles;
-    PCH_LAUNCH(st, "k_hist", k_hist<<<(unsigned)hgrid, RS_THREADS, 0, st>>>(keys, g, w.hist));
-    PCH_LAUNCH_CHECK();
-    int64_t rows = g.n_segs * g.n_passes;
-    PCH_LAUNCH(st, "k_scan", k_scan<<<(unsigned)(rows < 4096 ? rows : 4096), 256, 0, st>>>(w.hist, rows));
-    PCH_LAUNCH_CHECK();
-    uint64_t* src = keys;
-    uint64_t* dst = tmp;
-    for (int p = 0; p < g.n_passes; ++p) {
-        PCH_LAUNCH(st, "k_pass", k_pass<<<(unsigned)g.total_tiles, RS_THREADS, 0, st>>>(src, dst, g, p, g.bit_lo + 8 * p, (1u << g.pass_bits[p]) - 1u, w.hist,
-                                                               w.status + (size_t)p * g.total_tiles * 256,
-                                                               w.counters + p, w.err));
-        PCH_LAUNCH_CHECK();
-        uint64_t* t = src; src = dst; dst = t;
-    }
-    return PCH_OK;
+    const int passes = (bit_hi - bit_lo + 7) / 8;
+    SortGeom g = pch_sort_geom(n, seg_size, bit_lo, bit_hi - bit_lo, passes);
+    int rc = pch_sort_prepare(g, workspace, workspace_bytes, st);
+    if (rc) return rc;
+    return pch_sort_run(keys, tmp, g, nullptr, passes, false, workspace, workspace_bytes, st);
 }

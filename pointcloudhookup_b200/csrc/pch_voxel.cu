@@ -9,6 +9,7 @@
 //            (utils/tower_extraction.py:60-62) fused into the same pass.
 #include "pch_common.cuh"
 #include "pch_tiles.cuh"
+#include "pch_sort.cuh"
 
 struct PchAffine3 {
     double s[3], o[3];
@@ -236,6 +237,62 @@ extern "C" int pch_voxel_keys_xyz16(const int32_t* xyz16, int64_t n, int64_t chu
     return PCH_OK;
 }
 
+// Device-planned variant for the fused stage (pch_voxel_downsample_las): the key layout is read from the plan in
+// DEVICE memory (no host round trip after the plan kernel), a CTA walks a contiguous range of RS_TILE-point
+// tiles (a tile lies in one chunk, so the origin is loaded once per chunk instead of one 64-bit division per
+// point), and the digit histograms of every radix pass are built on the way (pch_sort.cuh) — the sort then
+// starts at its scan and never re-reads the keys for k_hist.
+__global__ void __launch_bounds__(256)
+k_voxel_keys16_plan(const int4* __restrict__ xyz16, SortGeom sg, PchAffine3 a, VoxelDiv voxel,
+                    const double* __restrict__ origins, const pch_voxel_plan* __restrict__ dplan,
+                    uint64_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[RS_MAX_PASSES * 256];
+    const int tid = threadIdx.x;
+    const pch_voxel_plan plan = *dplan;
+    if (plan.status != PCH_OK || ((plan.key_bits + 7) >> 3) > sg.hist_passes) return;
+    const int sh_z = plan.bits_idx, sh_y = sh_z + plan.bits_z, sh_x = sh_y + plan.bits_y;
+    for (int i = tid; i < RS_MAX_PASSES * 256; i += 256) sh[i] = 0;
+    __syncthreads();
+    const int64_t tiles = sg.total_tickets;
+    const int64_t per = (tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per, t1 = t0 + per < tiles ? t0 + per : tiles;
+    int64_t cur = -1;
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    for (int64_t tile = t0; tile < t1; ++tile) {
+        const int64_t c = tile / sg.tiles_per_seg, lt = tile - c * sg.tiles_per_seg;
+        const int64_t cstart = c * sg.seg_size;
+        int64_t cend = cstart + sg.seg_size;
+        if (cend > sg.n) cend = sg.n;
+        const int64_t start = cstart + lt * RS_TILE;
+        if (start >= cend) continue;
+        const int cnt = (int)(cend - start > RS_TILE ? RS_TILE : cend - start);
+        if (c != cur) {
+            if (cur >= 0) {
+                __syncthreads();
+                pch_sort_hist_flush(sh, hist, cur, sg.hist_passes, plan.key_bits);
+                __syncthreads();
+            }
+            cur = c;
+            ox = origins[c * 3 + 0]; oy = origins[c * 3 + 1]; oz = origins[c * 3 + 2];
+        }
+        const uint64_t local0 = (uint64_t)(start - cstart);
+#pragma unroll 4
+        for (int i = tid; i < cnt; i += 256) {
+            const int4 v = __ldg(xyz16 + start + i);
+            const double x = pch_scaled(v.x, a.s[0], a.o[0]);
+            const double y = pch_scaled(v.y, a.s[1], a.o[1]);
+            const double z = pch_scaled(v.z, a.s[2], a.o[2]);
+            uint64_t ix, iy, iz;
+            pch_voxel_index3(__dsub_rn(x, ox), __dsub_rn(y, oy), __dsub_rn(z, oz), voxel, ix, iy, iz);
+            const uint64_t key = (ix << sh_x) | (iy << sh_y) | (iz << sh_z) | (local0 + (uint64_t)i);
+            keys[start + i] = key;
+            pch_sort_hist_add(sh, key, plan.bits_idx, plan.key_bits);
+        }
+    }
+    __syncthreads();
+    if (cur >= 0) pch_sort_hist_flush(sh, hist, cur, sg.hist_passes, plan.key_bits);
+}
+
 // ------------------------------------------------------------------------------------------------
 // segmented in-order reduction
 // ------------------------------------------------------------------------------------------------
@@ -280,7 +337,8 @@ extern "C" size_t pch_voxel_reduce_workspace_bytes(int64_t n, int64_t chunk_size
 //      reads slots >= k*VR_THREADS, and writes slots < (k+1)*VR_THREADS after a barrier).
 template <int ALIGN>
 __global__ void __launch_bounds__(VR_THREADS, VR_MINB)
-k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* __restrict__ rec,
+k_voxel_reduce(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ keys_odd,
+               const pch_voxel_plan* __restrict__ dplan, ReduceGeom g, const uint8_t* __restrict__ rec,
                const int4* __restrict__ xyz16, const int32_t* __restrict__ vidx /* (n,3) or NULL: wide keys */,
                PchAffine3 a,
                double* __restrict__ mean_out, int32_t* __restrict__ lat_out, float* __restrict__ f32_out,
@@ -294,6 +352,18 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     __shared__ uint64_t s_tile_off;
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bi = g.bits_idx;
+    if (dplan) {
+        // device-planned run: key layout and the buffer that holds the sorted keys (odd pass count -> the
+        // ping-pong partner) come from the plan; an unusable plan is reported through total_out = -1
+        const int st_plan = dplan->status, kb = dplan->key_bits;
+        if (st_plan != PCH_OK) {
+            if (blockIdx.x == 0 && tid == 0 && total_out) *total_out = -1;
+            return;
+        }
+        bi = dplan->bits_idx;
+        if (((kb + 7) >> 3) & 1) keys = keys_odd;
+    }
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
     if (tid <= VR_RECIP) s_recip[tid] = tid ? __ddiv_rn(1.0, (double)tid) : 0.0;
     __syncthreads();
@@ -306,7 +376,6 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
     if (cend > g.n) cend = g.n;
     const int64_t start = cstart + lt * VR_TILE;
     const int cnt = (int)min((int64_t)VR_TILE, cend - start);
-    const int bi = g.bits_idx;
     const uint64_t idx_mask = bi >= 64 ? ~0ull : ((1ull << bi) - 1ull);
 
     {
@@ -504,12 +573,12 @@ k_voxel_reduce(const uint64_t* __restrict__ keys, ReduceGeom g, const uint8_t* _
         store_row(tile_off + (uint64_t)r, s_xyz[ALIGN > 0 ? r : 0][0], s_xyz[ALIGN > 0 ? r : 0][1], s_xyz[ALIGN > 0 ? r : 0][2]);
 }
 
-extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
-                                const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const int32_t* vidx,
-                                const double* scales, const double* offsets,
-                                double* mean_out, int32_t* lat_out, float* f32_out, float* z32_out,
-                                int64_t* chunk_counts, int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int voxel_reduce_impl(const uint64_t* keys, const uint64_t* keys_odd, const pch_voxel_plan* dplan, int64_t n,
+                             int64_t chunk_size, int32_t bits_idx,
+                             const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const int32_t* vidx,
+                             const double* scales, const double* offsets,
+                             double* mean_out, int32_t* lat_out, float* f32_out, float* z32_out,
+                             int64_t* chunk_counts, int64_t* total_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     PCH_CHECK_ARG(n >= 0 && chunk_size > 0, "bad n/chunk_size");
     PCH_CHECK_ARG(rec_len == 0 || (rec_len >= 12 && rec_len <= 256), "bad record length");
     PCH_CHECK_ARG(bits_idx >= 0 && bits_idx <= 63, "bad bits_idx");
@@ -542,13 +611,116 @@ extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_s
     int al = rec_len == 0 ? 0 : pch_rec_align(rec_len);
 #define LAUNCH_RED(A)                                                                                          \
     PCH_LAUNCH(st, "k_voxel_reduce", k_voxel_reduce<A><<<(unsigned)g.total_tiles, VR_THREADS, 0, st>>>(                                         \
-        keys, g, rec, (const int4*)xyz16, vidx, a, mean_out, lat_out, f32_out, z32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
+        keys, keys_odd, dplan, g, rec, (const int4*)xyz16, vidx, a, mean_out, lat_out, f32_out, z32_out, (unsigned long long*)chunk_counts, (long long*)total_out, \
         status, counter, err))
     if (al == 4) LAUNCH_RED(4);
     else if (al == 2) LAUNCH_RED(2);
     else if (al == 1) LAUNCH_RED(1);
     else LAUNCH_RED(0);
 #undef LAUNCH_RED
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_voxel_reduce(const uint64_t* keys, int64_t n, int64_t chunk_size, int32_t bits_idx,
+                                const uint8_t* rec, int32_t rec_len, const int32_t* xyz16, const int32_t* vidx,
+                                const double* scales, const double* offsets,
+                                double* mean_out, int32_t* lat_out, float* f32_out, float* z32_out,
+                                int64_t* chunk_counts, int64_t* total_out, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    return voxel_reduce_impl(keys, nullptr, nullptr, n, chunk_size, bits_idx, rec, rec_len, xyz16, vidx, scales, offsets,
+                             mean_out, lat_out, f32_out, z32_out, chunk_counts, total_out, workspace, workspace_bytes,
+                             (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole voxel stage of the LAS path as ONE host call with no host round trip inside
+// (ui/import_PC.py:45-63 for all chunks at once): chunk extrema + the 16-byte lattice copy -> plan (stays in
+// device memory) -> keys + radix histograms -> scan + the radix passes the plan needs (launched for the
+// widest key the chunk size allows; surplus passes exit at once) -> in-order reduce, which reads the plan to
+// know which ping-pong buffer holds the sorted keys.  The caller reads back the 64-byte head of the
+// workspace once: [0] error word of the look-backs, [8] M (or -1: the index range does not fit one key word,
+// take the wide-key path), [32..64) the plan.
+// ------------------------------------------------------------------------------------------------
+extern "C" int pch_las_chunk_minmax(const uint8_t* rec, int64_t n, int32_t rec_len, int64_t chunk_size, int32_t* mm,
+                                    int32_t* xyz16, pch_stream_t stream);
+
+struct VoxelFusedWs {
+    size_t head, sort, sort_bytes, reduce, reduce_bytes, total;
+    int passes;
+};
+static VoxelFusedWs voxel_fused_ws(int64_t n, int64_t chunk_size) {
+    VoxelFusedWs w;
+    if (chunk_size <= 0 || chunk_size > n) chunk_size = n > 0 ? n : 1;
+    int bits_idx = 0;
+    for (int64_t v = chunk_size - 1; v > 0; v >>= 1) ++bits_idx;
+    w.passes = (64 - bits_idx + 7) / 8;
+    if (w.passes > RS_MAX_PASSES) w.passes = RS_MAX_PASSES;
+    if (w.passes < 1) w.passes = 1;
+    SortGeom sg = pch_sort_geom(n, chunk_size, 0, 0, w.passes);
+    w.head = 0;
+    w.sort = 256;
+    w.sort_bytes = pch_sort_ws(sg, nullptr).bytes;
+    w.reduce = w.sort + pch_align_up(w.sort_bytes, 256);
+    w.reduce_bytes = pch_voxel_reduce_workspace_bytes(n, chunk_size);
+    w.total = w.reduce + pch_align_up(w.reduce_bytes, 256);
+    return w;
+}
+
+extern "C" size_t pch_voxel_downsample_las_workspace_bytes(int64_t n, int64_t chunk_size) {
+    if (n <= 0) return 256;
+    return voxel_fused_ws(n, chunk_size).total;
+}
+
+__global__ void k_voxel_head(const pch_voxel_plan* __restrict__ plan, const int* __restrict__ sort_err,
+                             const int* __restrict__ red_err, uint8_t* __restrict__ head) {
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<int*>(head) = (*sort_err) | (*red_err);
+        *reinterpret_cast<pch_voxel_plan*>(head + 32) = *plan;
+    }
+}
+
+extern "C" int pch_voxel_downsample_las(const uint8_t* rec, int64_t n, int32_t rec_len, int64_t chunk_size,
+                                        const double* scales, const double* offsets, double voxel,
+                                        int32_t* xyz16, uint64_t* keys, uint64_t* tmp, int32_t* minmax, double* origins,
+                                        pch_voxel_plan* plan_dev,
+                                        double* mean_out, int32_t* lat_out, float* f32_out, float* z32_out,
+                                        int64_t* chunk_counts, void* workspace, size_t workspace_bytes,
+                                        pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 1 && rec_len >= 12 && rec_len <= 256, "bad n/rec_len");
+    PCH_CHECK_ARG(chunk_size > 0 && voxel > 0.0, "chunk_size and voxel_size must be > 0");
+    PCH_CHECK_ARG(rec && xyz16 && keys && tmp && minmax && origins && plan_dev && workspace, "null pointer");
+    if (chunk_size > n) chunk_size = n;
+    const int64_t n_chunks = pch_ceil_div(n, chunk_size);
+    VoxelFusedWs w = voxel_fused_ws(n, chunk_size);
+    if (workspace_bytes < w.total) {
+        pch_set_error("voxel_downsample_las workspace too small: %zu < %zu", workspace_bytes, w.total);
+        return PCH_ERR_WORKSPACE;
+    }
+    uint8_t* base = (uint8_t*)workspace;
+    PCH_CUDA(cudaMemsetAsync(base, 0, 256, st));
+    int rc = pch_las_chunk_minmax(rec, n, rec_len, chunk_size, minmax, xyz16, stream);
+    if (rc) return rc;
+    rc = pch_voxel_plan_build(minmax, n_chunks, chunk_size, scales, offsets, voxel, origins, plan_dev, stream);
+    if (rc) return rc;
+    PchAffine3 a;
+    if ((rc = make_affine3(scales, offsets, a))) return rc;
+    SortGeom sg = pch_sort_geom(n, chunk_size, 0, 0, w.passes);
+    if ((rc = pch_sort_prepare(sg, base + w.sort, w.sort_bytes, st))) return rc;
+    SortWs sw = pch_sort_ws(sg, base + w.sort);
+    {
+        int64_t grid = (int64_t)pch_sm_count() * 8;
+        if (grid > sg.total_tickets) grid = sg.total_tickets;
+        PCH_LAUNCH(st, "k_voxel_keys16", k_voxel_keys16_plan<<<(unsigned)grid, 256, 0, st>>>(
+                                             (const int4*)xyz16, sg, a, make_voxel_div(voxel), origins, plan_dev, keys, sw.hist));
+        PCH_LAUNCH_CHECK();
+    }
+    if ((rc = pch_sort_run(keys, tmp, sg, plan_dev, w.passes, true, base + w.sort, w.sort_bytes, st))) return rc;
+    int64_t* total = reinterpret_cast<int64_t*>(base + 8);
+    rc = voxel_reduce_impl(keys, tmp, plan_dev, n, chunk_size, 0, rec, rec_len, xyz16, nullptr, scales, offsets, mean_out, lat_out,
+                           f32_out, z32_out, chunk_counts, total, base + w.reduce, w.reduce_bytes, st);
+    if (rc) return rc;
+    PCH_LAUNCH(st, "k_voxel_head", k_voxel_head<<<1, 32, 0, st>>>(plan_dev, (const int*)(base + w.sort), (const int*)(base + w.reduce), base));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

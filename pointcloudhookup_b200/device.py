@@ -268,40 +268,6 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
                            z(torch.float32) if "f32" in want else None)
     st = _stream()
     sc, of = d3(dl.scales), d3(dl.offsets)
-    xyz16 = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    mm = chunk_minmax(dl, cs, xyz16)
-    origins = torch.empty((n_chunks, 3), dtype=torch.float64, device=dev)
-    plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
-    check(lib.pch_voxel_plan_build(mm.data_ptr(), n_chunks, cs, sc, of, float(voxel_size), origins.data_ptr(),
-                                   plan_dev.data_ptr(), st), "pch_voxel_plan_build")
-    ph = plan_dev.cpu().numpy()
-    plan = VoxelPlan(*[int(v) for v in ph])
-    if plan.status != 0:
-        # index range does not fit one sort word: decode to float64 and take the wide-key path
-        del xyz16
-        pts = decode_xyz(dl, torch.float64)
-        w = voxel_downsample_points(pts, voxel_size, cs)
-        lat = quantise(w.mean, dl.scales, dl.offsets) if (sink is not None or {"lattice", "f32", "z32"} & set(want)) else None
-        f32 = None
-        if "f32" in want or "z32" in want or sink is not None:
-            # astype(float32) of the re-quantised values: encode the lattice into minimal records and run the
-            # ordinary float32 decode kernel over them
-            recs, _ = encode_records(lat, 20)
-            f32 = decode_xyz(DeviceLas(recs, w.count, 20, dl.scales, dl.offsets), torch.float32)
-        if sink is not None:
-            if sink.f32.shape[0] - sink.count < w.count:
-                raise ValueError("VoxelSink too small for this slice")
-            sink.f32[sink.count: sink.count + w.count].copy_(f32)
-            if sink.z32 is not None:
-                sink.z32[sink.count: sink.count + w.count].copy_(f32[:, 2])
-            sink.count += w.count
-        return VoxelResult(w.count, w.chunk_counts, w.mean if "mean" in want else None,
-                           lat if "lattice" in want else None, f32, plan=w.plan,
-                           z32=f32[:, 2].contiguous() if "z32" in want else None)
-    keys = torch.empty(n, dtype=torch.int64, device=dev)
-    check(lib.pch_voxel_keys_xyz16(xyz16.data_ptr(), n, cs, sc, of, float(voxel_size), origins.data_ptr(),
-                                   C.byref(plan), keys.data_ptr(), st), "pch_voxel_keys_xyz16")
-    skeys = sort_u64_segmented(keys, cs, plan.bits_idx, plan.bits_idx + plan.key_bits)
     # worst case every point is its own voxel; outputs are sized n and sliced after the count is known
     mean = torch.empty((n, 3), dtype=torch.float64, device=dev) if "mean" in want else None
     lat = torch.empty((n, 3), dtype=torch.int32, device=dev) if "lattice" in want else None
@@ -312,28 +278,63 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
     else:
         f32 = torch.empty((n, 3), dtype=torch.float32, device=dev) if "f32" in want else None
         z32 = torch.empty(n, dtype=torch.float32, device=dev) if "z32" in want else None
+    xyz16 = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    tmp = torch.empty(n, dtype=torch.int64, device=dev)
+    mm = torch.empty((n_chunks, 6), dtype=torch.int32, device=dev)
+    origins = torch.empty((n_chunks, 3), dtype=torch.float64, device=dev)
+    plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
     counts = torch.empty(n_chunks, dtype=torch.int64, device=dev)
-    ws_bytes = lib.pch_voxel_reduce_workspace_bytes(n, cs)
+    ws_bytes = lib.pch_voxel_downsample_las_workspace_bytes(n, cs)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    total = ws[8:16].view(torch.int64)      # next to the error word: one D2H fetches both
-    check(lib.pch_voxel_reduce(skeys.data_ptr(), n, cs, plan.bits_idx, dl.rec.data_ptr(), dl.rec_len,
-                               xyz16.data_ptr(), None, sc, of,
-                               _ptr(mean), _ptr(lat), _ptr(f32), _ptr(z32), counts.data_ptr(), total.data_ptr(),
-                               ws.data_ptr(), ws_bytes, st), "pch_voxel_reduce")
-    head = ws[:16].cpu().numpy()
+    # one call, no host round trip inside: extrema -> plan (device) -> keys + digit histograms -> radix passes -> reduce
+    check(lib.pch_voxel_downsample_las(dl.rec.data_ptr(), n, dl.rec_len, cs, sc, of, float(voxel_size),
+                                       xyz16.data_ptr(), keys.data_ptr(), tmp.data_ptr(), mm.data_ptr(),
+                                       origins.data_ptr(), plan_dev.data_ptr(), _ptr(mean), _ptr(lat), _ptr(f32), _ptr(z32),
+                                       counts.data_ptr(), ws.data_ptr(), ws_bytes, st), "pch_voxel_downsample_las")
+    head = ws[:64].cpu().numpy()            # the stage's only device->host read: error word, M, plan
     m = int(head[8:16].view(np.int64)[0])
+    plan = VoxelPlan(*[int(v) for v in head[32:64].view(np.int32)])
     if int(head[:4].view(np.int32)[0]):
-        raise _native.NativeError("device look-back spin limit hit in voxel_reduce")
+        raise _native.NativeError("device look-back spin limit hit in voxel_downsample")
+    if m < 0 or plan.status != 0:
+        del xyz16, keys, tmp, mean, lat
+        return _voxel_downsample_wide(dl, voxel_size, cs, want, sink)
     if sink is not None:
         sink.count += m
-    res = VoxelResult(m, counts,
-                      mean[:m] if mean is not None else None,
-                      lat[:m] if lat is not None else None,
-                      f32[:m] if f32 is not None else None,
-                      plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_},
-                      sorted_keys=skeys if keep_keys else None,
-                      z32=z32[:m] if z32 is not None else None)
-    return res
+    skeys = None
+    if keep_keys:
+        skeys = tmp if plan.n_passes % 2 else keys
+    return VoxelResult(m, counts,
+                       mean[:m] if mean is not None else None,
+                       lat[:m] if lat is not None else None,
+                       f32[:m] if f32 is not None else None,
+                       plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_},
+                       sorted_keys=skeys,
+                       z32=z32[:m] if z32 is not None else None)
+
+
+def _voxel_downsample_wide(dl: DeviceLas, voxel_size: float, cs: int, want, sink) -> VoxelResult:
+    """The voxel index range does not fit one sort word: decode to float64 and take the wide-key path."""
+    pts = decode_xyz(dl, torch.float64)
+    w = voxel_downsample_points(pts, voxel_size, cs)
+    lat = quantise(w.mean, dl.scales, dl.offsets) if (sink is not None or {"lattice", "f32", "z32"} & set(want)) else None
+    f32 = None
+    if "f32" in want or "z32" in want or sink is not None:
+        # astype(float32) of the re-quantised values: encode the lattice into minimal records and run the
+        # ordinary float32 decode kernel over them
+        recs, _ = encode_records(lat, 20)
+        f32 = decode_xyz(DeviceLas(recs, w.count, 20, dl.scales, dl.offsets), torch.float32)
+    if sink is not None:
+        if sink.f32.shape[0] - sink.count < w.count:
+            raise ValueError("VoxelSink too small for this slice")
+        sink.f32[sink.count: sink.count + w.count].copy_(f32)
+        if sink.z32 is not None:
+            sink.z32[sink.count: sink.count + w.count].copy_(f32[:, 2])
+        sink.count += w.count
+    return VoxelResult(w.count, w.chunk_counts, w.mean if "mean" in want else None,
+                       lat if "lattice" in want else None, f32, plan=w.plan,
+                       z32=f32[:, 2].contiguous() if "z32" in want else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -446,6 +447,7 @@ class DbscanResult:
     plan: Optional[dict] = None   # cell-grid key layout (bits per axis, radix passes)
 
 
+DB_STATS_PEEK = 4096     # rows of the per-cluster table fetched together with the scalar block
 STATS_DTYPE = np.dtype([("count", "<i8"), ("min", "<f4", 3), ("max", "<f4", 3), ("sum", "<f8", 3)])
 assert STATS_DTYPE.itemsize == C.sizeof(_native.ClusterStats) == 56
 
@@ -462,25 +464,24 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
     ch = max(1, min(int(chunk), G))
     n_chunks = -(-G // ch)
     st = _stream()
-    bounds = torch.empty(n_chunks * 6, dtype=torch.int32, device=dev)
-    plan_dev = torch.empty(8, dtype=torch.int32, device=dev)
-    check(lib.pch_dbscan_plan(points.data_ptr(), G, ch, float(eps), bounds.data_ptr(), plan_dev.data_ptr(), st),
-          "pch_dbscan_plan")
-    plan = VoxelPlan(*[int(v) for v in plan_dev.cpu().numpy()])
-    if plan.status != 0:
-        raise ValueError("DBSCAN cell grid does not fit the packed key")
     labels = torch.empty(G, dtype=torch.int32, device=dev)
-    cap = max(4096, G // 256)
+    cap = max(DB_STATS_PEEK, G // 256)
+    item = STATS_DTYPE.itemsize
     while True:
-        stats = torch.empty(cap * STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-        wsb = lib.pch_dbscan_workspace_bytes(G, ch, C.byref(plan), cap)
+        stats = torch.empty(cap * item, dtype=torch.uint8, device=dev)
+        wsb = lib.pch_dbscan_fused_workspace_bytes(G, ch, cap)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        nclu = ws[136:144].view(torch.int64)      # inside the workspace's scalar block: one D2H fetches count + error word
-        check(lib.pch_dbscan_run(points.data_ptr(), G, ch, float(eps), int(min_samples), bounds.data_ptr(),
-                                 C.byref(plan), labels.data_ptr(), nclu.data_ptr(), stats.data_ptr(), cap,
-                                 ws.data_ptr(), wsb, st), "pch_dbscan_run")
-        sc = ws[:256].cpu().numpy()
+        # one call, no host round trip inside (the cell-grid plan stays on the device)
+        check(lib.pch_dbscan(points.data_ptr(), G, ch, float(eps), int(min_samples), labels.data_ptr(), stats.data_ptr(), cap,
+                             ws.data_ptr(), wsb, st), "pch_dbscan")
+        # ONE device->host read: the scalar block and the first DB_STATS_PEEK rows of the per-cluster table
+        peek = min(cap, DB_STATS_PEEK)
+        both = torch.cat([ws[:256], stats[: peek * item]]).cpu().numpy()
+        sc = both[:256]
         k = int(sc[136:144].view(np.int64)[0])
+        plan = VoxelPlan(*[int(v) for v in sc[208:240].view(np.int32)])
+        if plan.status != 0:
+            raise ValueError("DBSCAN cell grid does not fit the packed key")
         if os.environ.get("PCH_TRACE"):
             print(f"[pch] dbscan G={G} chunks={n_chunks} cells={int(sc[128:136].view(np.int64)[0])} "
                   f"non-dense points={int(sc[192:196].view(np.uint32)[0])} clusters={k} plan={plan.bits_x},{plan.bits_y},{plan.bits_z}",
@@ -490,7 +491,10 @@ def dbscan_chunked(points: torch.Tensor, eps: float = 8.0, min_samples: int = 80
         if k <= cap:
             break
         cap = k
-    host = stats[: k * STATS_DTYPE.itemsize].cpu().numpy().view(STATS_DTYPE).copy()
+    if k <= peek:
+        host = both[256: 256 + k * item].view(STATS_DTYPE).copy()
+    else:
+        host = stats[: k * item].cpu().numpy().view(STATS_DTYPE).copy()
     return DbscanResult(labels, k, host, {f: getattr(plan, f) for f, _ in VoxelPlan._fields_})
 
 

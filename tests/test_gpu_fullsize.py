@@ -124,3 +124,24 @@ def test_fullsize_geodetic_properties(corridor):
     # corridor geometry: longitudes/latitudes fall in the expected window around 113.4E / 28.4N
     assert 113.0 < float(out[:, 0].min()) and float(out[:, 0].max()) < 114.5
     assert 28.0 < float(out[:, 1].min()) and float(out[:, 1].max()) < 30.5
+
+
+def test_fullsize_sampled_chunks_match_oracle(corridor):
+    """Oracle parity at the BASELINE sizes on sampled units: random 500 k-point voxel chunks against
+    oracle.voxel (means, lattice and float32 cloud bit-exact; ui/import_PC.py:45-58), centroid / percentile
+    base / keep mask of the WHOLE float32 cloud against numpy (utils/tower_extraction.py:63-89), random
+    50 k-point DBSCAN chunks against the real scikit-learn minus the running offset (:96-116)."""
+    import sampled_parity as sp
+    from pointcloudhookup_b200 import device as dv, towers as tw
+    n, dl = corridor
+    chunk = 500_000
+    res = dv.voxel_downsample(dl, 0.1, chunk, want=("mean", "lattice", "f32"))
+    ids = sp.check_voxel_chunks(dl, res, 0.1, chunk, n_samples=3, seed=n % 1000)
+    assert len(ids) >= 3
+    raw = res.f32
+    del res
+    stages = tw.run_stages(raw, 8.0, 80, "percentile", want_mask=True)
+    g = sp.check_ground_whole_cloud(raw, stages)
+    assert g == stages.filtered.shape[0] and g > 1000
+    checked = sp.check_dbscan_chunks(stages.filtered, stages.labels, 8.0, 80, 50_000, n_samples=5, seed=n % 997)
+    assert len(checked) >= 5

@@ -258,6 +258,38 @@ int pch_dbscan(const float* xyz_dev, int64_t G, int64_t chunk, double eps, int32
                int32_t* labels_dev, pch_cluster_stats* stats_dev, int64_t max_clusters,
                void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
+/* Two-phase clustering for spatial tiles with a halo (parity definition: the un-chunked variant
+ * test/zzzzz.py:79-84 on the concatenated cloud).  xyz_dev = [halo from the left neighbour | own points | halo
+ * from the right neighbour] in one common frame.
+ *   pch_dbscan_cores : clusters the array up to the ids of the CORE points: labels_dev[i] = local cluster id
+ *                      (ordered by smallest core index) for core points, -1 elsewhere; scalar block as for
+ *                      pch_dbscan.  workspace = pch_dbscan_fused_workspace_bytes(G, chunk, max_clusters).
+ *   -- the ranks exchange (point, local id) of the core points both sides know exactly, join local clusters that
+ *      share a point, and number the global clusters by their smallest core index (dist.py) --
+ *   pch_dbscan_finish: map_dev[local id] = global id or -1; rewrites the core labels, gives every border point the
+ *                      smallest GLOBAL id among the clusters owning a core point within eps (scikit-learn's rule on
+ *                      the concatenated cloud) and reduces count / AABB / sums over the original indices
+ *                      [own_lo, own_hi) only into stats_dev[n_global].  Same workspace, untouched in between;
+ *                      acc_dev = pch_dbscan_acc_bytes(n_global) bytes of scratch.
+ *   pch_label_min_index: table_dev[k] = min(table_dev[k], base + i - lo) over i in [lo, hi) with labels_dev[i] == k. */
+int pch_dbscan_cores(const float* xyz_dev, int64_t G, int64_t chunk, double eps, int32_t min_samples, int32_t* labels_dev,
+                     int64_t max_clusters, void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+size_t pch_dbscan_acc_bytes(int64_t n_clusters);
+int pch_dbscan_finish(const float* xyz_dev, int64_t G, int64_t chunk, double eps, int32_t min_samples,
+                      const int32_t* map_dev, int64_t n_global, int64_t own_lo, int64_t own_hi,
+                      int32_t* labels_dev, pch_cluster_stats* stats_dev, void* acc_dev, int64_t max_clusters_phase1,
+                      void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+int pch_label_min_index(const int32_t* labels_dev, int64_t lo, int64_t hi, int64_t base, int64_t n_labels,
+                        int64_t* table_dev, pch_stream_t stream);
+
+/* Projection of (n,3) float32 points on a horizontal axis, s = x*ux + y*uy in float64: the coordinate along which
+ * corridor tiles abut.  pch_axis_extent: minmax_dev[2] = min, max of s.  pch_axis_band_mask: mask_dev[i] =
+ * (lo <= s_i <= hi) and (labels_dev == NULL or labels_dev[i] >= 0): the halo a tile sends to its neighbour, and
+ * the zone next to a cut in which both ranks know a point's core status exactly. */
+int pch_axis_extent(const float* xyz_dev, int64_t n, double ux, double uy, double* minmax_dev, pch_stream_t stream);
+int pch_axis_band_mask(const float* xyz_dev, int64_t n, double ux, double uy, double lo, double hi,
+                       const int32_t* labels_dev /* nullable */, uint8_t* mask_dev, pch_stream_t stream);
+
 /* `cluster_points = filtered_points[all_labels == label]` for every label at once
  * (utils/tower_extraction.py:133-134): pch_label_words builds (label << 32 | index) words (noise sorts
  * last), pch_sort_u64_segmented orders them by label (stable), pch_gather_rows_f32 gathers the rows of

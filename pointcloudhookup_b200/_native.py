@@ -80,6 +80,12 @@ SIGNATURES.update({
     "pch_dbscan_workspace_bytes": (_sz, [_i64, _i64, C.POINTER(VoxelPlan), _i64]),
     "pch_dbscan_fused_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "pch_dbscan": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, _p, _i64, _p, _sz, _p]),
+    "pch_dbscan_cores": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, _i64, _p, _sz, _p]),
+    "pch_dbscan_acc_bytes": (_sz, [_i64]),
+    "pch_dbscan_finish": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _p, _sz, _p]),
+    "pch_label_min_index": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
+    "pch_axis_extent": (C.c_int, [_p, _i64, _f64, _f64, _p, _p]),
+    "pch_axis_band_mask": (C.c_int, [_p, _i64, _f64, _f64, _f64, _f64, _p, _p, _p]),
     "pch_dbscan_run": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, C.POINTER(VoxelPlan), _p, _p, _p, _i64, _p, _sz, _p]),
 })
 

@@ -190,8 +190,14 @@ __device__ __forceinline__ void pch_load_xyz(const uint8_t* p, int& X, int& Y, i
 
 // x = X*scale + offset exactly as numpy/laspy evaluate it: one rounded multiply, one rounded add
 // (never contracted into an FMA).
+// int32 -> float64, exact, without the conversion unit: the XU pipe that executes I2F.F64 issues a quarter
+// warp per cycle and was the top stall of the key kernel (56 % of its samples); 2^52 + 2^31 + X is assembled
+// from two integer words and one exact float64 subtract brings X back.
+__device__ __forceinline__ double pch_i2d(int X) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((unsigned)X ^ 0x80000000u)), 4503601774854144.0);
+}
 __device__ __forceinline__ double pch_scaled(int X, double scale, double offset) {
-    return __dadd_rn(__dmul_rn((double)X, scale), offset);
+    return __dadd_rn(__dmul_rn(pch_i2d(X), scale), offset);
 }
 
 // Correctly rounded a / b from y = RN(1/b) (a true IEEE divide done once, on the host or per CTA): a product

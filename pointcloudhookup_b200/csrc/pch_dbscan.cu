@@ -27,6 +27,7 @@ struct DbGeom {
     int32_t sh_x, sh_y, sh_z, bits_idx;  // key layout
     int32_t bits_x, bits_y, bits_z, key_bits;
     const DbPlan* dplan;                 // non-NULL: the key layout is read from this plan in DEVICE memory
+    int64_t own_lo, own_hi;              // original indices that count in the per-cluster statistics (halo points do not)
 };
 
 // Device-planned runs (pch_dbscan): every kernel that needs the key layout takes it from the plan the plan
@@ -933,8 +934,10 @@ k_db_labels_core(DbGeom g, const float4* __restrict__ spts, const int32_t* __res
                 float v[3] = {p[u].x, p[u].y, p[u].z};
                 if (isc[u]) {
                     const int64_t c = pos[u] / g.chunk;
-                    labels[c * g.chunk + __float_as_int(p[u].w)] = lab;
-                    if (lab >= cap) lab = -1;       // statistics only for the clusters the caller made room for
+                    const int64_t orig = c * g.chunk + __float_as_int(p[u].w);
+                    labels[orig] = lab;
+                    // statistics only for the clusters the caller made room for, and only for this rank's own points
+                    if (lab >= cap || orig < g.own_lo || orig >= g.own_hi) lab = -1;
                 }
                 const uint32_t valid = __ballot_sync(0xffffffffu, lab >= 0);
                 if (valid == 0) continue;
@@ -997,15 +1000,16 @@ k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __r
                 const int32_t q = q0 + lane;
                 if (q < e && core[q]) {
                     const int32_t cl = root_label[cell_root[pt_cell[q]]];
-                    if (cl < best && db_dist2(p, spts[q]) <= g.eps2) best = cl;
+                    if (cl >= 0 && cl < best && db_dist2(p, spts[q]) <= g.eps2) best = cl;
                 }
             }
         }
         best = __reduce_min_sync(0xffffffffu, best);
         if (lane == 0) {
             const int64_t c = pos / g.chunk;
-            labels[c * g.chunk + __float_as_int(p.w)] = best == INT_MAX ? -1 : best;
-            if (best != INT_MAX && best < cap) {     // the border point joins its cluster's statistics
+            const int64_t orig = c * g.chunk + __float_as_int(p.w);
+            labels[orig] = best == INT_MAX ? -1 : best;
+            if (best != INT_MAX && best < cap && orig >= g.own_lo && orig < g.own_hi) {     // the border point joins its cluster's statistics
                 DbClusterAcc* a = &acc[best];
                 atomicAdd(&a->count, 1ull);
                 const float v[3] = {p.x, p.y, p.z};
@@ -1023,7 +1027,7 @@ k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __r
 
 __global__ void k_db_acc_finish(int64_t cap, const long long* __restrict__ K_dev, const DbClusterAcc* __restrict__ acc,
                                 pch_cluster_stats* __restrict__ out) {
-    const int64_t K = min((int64_t)*K_dev, cap);
+    const int64_t K = K_dev ? min((int64_t)*K_dev, cap) : cap;
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; k < K; k += stride) {
@@ -1134,7 +1138,8 @@ extern "C" size_t pch_dbscan_workspace_bytes(int64_t G, int64_t chunk, const pch
 static int dbscan_impl(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts,
                        const uint32_t* bounds_dev, const pch_voxel_plan* hplan, const pch_voxel_plan* dplan,
                        int sort_passes, int32_t* labels_dev, int64_t* n_clusters_dev, pch_cluster_stats* stats_dev,
-                       int64_t max_clusters, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+                       int64_t max_clusters, void* workspace, size_t workspace_bytes, pch_stream_t stream,
+                       bool core_only = false) {
     cudaStream_t st = (cudaStream_t)stream;
     DbWs w = db_ws(G, chunk, sort_passes, max_clusters);
     if (workspace_bytes < w.total) {
@@ -1158,6 +1163,7 @@ static int dbscan_impl(const float* P, int64_t G, int64_t chunk, double eps, int
     g.eps2 = eps * eps;
     g.min_pts = min_pts;
     g.dplan = (const DbPlan*)dplan;
+    g.own_lo = 0; g.own_hi = G;
     g.bits_idx = g.bits_x = g.bits_y = g.bits_z = g.key_bits = g.sh_x = g.sh_y = g.sh_z = 0;
     if (hplan) {
         g.bits_idx = hplan->bits_idx;
@@ -1247,9 +1253,11 @@ static int dbscan_impl(const float* P, int64_t G, int64_t chunk, double eps, int
     // points: per-point atomics from the border search)
     PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(max_clusters, 256), 256, 0, st>>>(max_clusters, acc));
     PCH_LAUNCH_CHECK();
+    if (core_only) PCH_CUDA(cudaMemsetAsync(labels_dev, 0xff, (size_t)G * 4, st));   // non-core points stay -1 until pch_dbscan_finish
     PCH_LAUNCH(st, "k_db_labels_core", k_db_labels_core<<<db_grid(G, 8 * 32 * CR_ROWS, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, core, cell_root, root_label,
                                                                                             labels_dev, max_clusters, acc));
     PCH_LAUNCH_CHECK();
+    if (core_only) return PCH_OK;
     PCH_LAUNCH(st, "k_db_labels_border", k_db_labels_border<<<db_grid(G, 8, 16), 256, 0, st>>>(g, o.spts, o.pt_cell, o.cell_start, core, nbr_first,
                                                                                     nbr_cnt, cell_root, root_label, worklist, n_work,
                                                                                     labels_dev, max_clusters, acc));
@@ -1319,6 +1327,209 @@ extern "C" int pch_dbscan(const float* P, int64_t G, int64_t chunk, double eps, 
                      max_clusters, workspace, workspace_bytes, stream);
     if (rc) return rc;
     PCH_LAUNCH(st, "k_db_head", k_db_head<<<1, 32, 0, st>>>((const DbPlan*)plan_dev, base + w.scalars, (const int*)(base + w.sortws)));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Two-phase clustering for spatial tiles with a halo (DBSCAN row; parity definition = the
+// un-chunked variant test/zzzzz.py:79-84 on the concatenated cloud):
+//   pch_dbscan_cores : everything up to the cluster ids of the CORE points (labels_dev: local id for core
+//                      points, -1 elsewhere).  Between the phases the ranks exchange which local clusters are
+//                      the same global cluster (shared halo points) and agree on global ids.
+//   pch_dbscan_finish: the local ids are replaced by global ids (map_dev[local] = global id or -1), core labels
+//                      are rewritten, border points take the smallest GLOBAL id among the clusters that own a
+//                      core point within eps (sklearn's rule on the concatenated cloud), and the per-cluster
+//                      statistics count only original indices in [own_lo, own_hi) (halo points belong to the
+//                      neighbour).  Uses the workspace of the first phase unchanged.
+// ------------------------------------------------------------------------------------------------
+extern "C" int pch_dbscan_cores(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts, int32_t* labels_dev,
+                                int64_t max_clusters, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(G >= 1 && chunk >= 1 && min_pts >= 1 && eps > 0.0, "bad G/chunk/min_samples/eps");
+    PCH_CHECK_ARG(G < (1ll << 31), "more than 2^31-1 candidate points");
+    PCH_CHECK_ARG(P && labels_dev && workspace && max_clusters >= 1, "null pointer");
+    if (chunk > G) chunk = G;
+    const int passes = db_max_passes(chunk);
+    DbWs w = db_ws(G, chunk, passes, max_clusters);
+    if (workspace_bytes < w.total) {
+        pch_set_error("dbscan workspace too small: %zu < %zu", workspace_bytes, w.total);
+        return PCH_ERR_WORKSPACE;
+    }
+    uint8_t* base = (uint8_t*)workspace;
+    uint32_t* bounds = (uint32_t*)(base + w.bounds);
+    pch_voxel_plan* plan_dev = (pch_voxel_plan*)(base + w.plan);
+    int rc = pch_dbscan_plan(P, G, chunk, eps, bounds, plan_dev, stream);
+    if (rc) return rc;
+    int64_t* n_clusters_dev = (int64_t*)(base + w.scalars + 136);
+    rc = dbscan_impl(P, G, chunk, eps, min_pts, bounds, nullptr, plan_dev, passes, labels_dev, n_clusters_dev, nullptr,
+                     max_clusters, workspace, workspace_bytes, stream, true);
+    if (rc) return rc;
+    PCH_LAUNCH(st, "k_db_head", k_db_head<<<1, 32, 0, st>>>((const DbPlan*)plan_dev, base + w.scalars, (const int*)(base + w.sortws)));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+__global__ void k_db_relabel_roots(const long long* __restrict__ U_dev, const long long* __restrict__ K_dev,
+                                   const int32_t* __restrict__ cell_root, const int32_t* __restrict__ map,
+                                   int32_t* __restrict__ root_label) {
+    const int64_t U = *U_dev, K = *K_dev;
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; u < U; u += stride)
+        if (cell_root[u] == (int32_t)u) {
+            const int32_t l = root_label[u];
+            root_label[u] = (l >= 0 && l < K) ? map[l] : -1;
+        }
+}
+
+extern "C" size_t pch_dbscan_acc_bytes(int64_t n_clusters) { return (size_t)(n_clusters > 0 ? n_clusters : 1) * sizeof(DbClusterAcc); }
+
+extern "C" int pch_dbscan_finish(const float* P, int64_t G, int64_t chunk, double eps, int32_t min_pts,
+                                 const int32_t* map_dev, int64_t n_global, int64_t own_lo, int64_t own_hi,
+                                 int32_t* labels_dev, pch_cluster_stats* stats_dev, void* acc_dev,
+                                 int64_t max_clusters_phase1, void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(G >= 1 && chunk >= 1 && min_pts >= 1 && eps > 0.0, "bad G/chunk/min_samples/eps");
+    PCH_CHECK_ARG(P && map_dev && labels_dev && workspace, "null pointer");
+    PCH_CHECK_ARG(n_global >= 0 && own_lo >= 0 && own_hi >= own_lo && own_hi <= G, "bad global cluster count / own range");
+    PCH_CHECK_ARG(n_global == 0 || (stats_dev && acc_dev), "stats and accumulator buffers required");
+    if (chunk > G) chunk = G;
+    const int passes = db_max_passes(chunk);
+    DbWs w = db_ws(G, chunk, passes, max_clusters_phase1);
+    if (workspace_bytes < w.total) {
+        pch_set_error("dbscan workspace too small: %zu < %zu", workspace_bytes, w.total);
+        return PCH_ERR_WORKSPACE;
+    }
+    uint8_t* base = (uint8_t*)workspace;
+    long long* U_dev = (long long*)(base + w.scalars + 128);
+    long long* K_dev = (long long*)(base + w.scalars + 136);
+    unsigned int* n_work = (unsigned int*)(base + w.scalars + 192);
+    DbGeom g;
+    g.G = G; g.chunk = chunk; g.n_chunks = pch_ceil_div(G, chunk);
+    g.cell = db_cell_side(eps);
+    g.eps2 = eps * eps;
+    g.min_pts = min_pts;
+    g.dplan = (const DbPlan*)(base + w.plan);
+    g.own_lo = own_lo; g.own_hi = own_hi;
+    g.bits_idx = g.bits_x = g.bits_y = g.bits_z = g.key_bits = g.sh_x = g.sh_y = g.sh_z = 0;
+    const float4* spts = (const float4*)(base + w.spts);
+    const int32_t* pt_cell = (const int32_t*)(base + w.pt_cell);
+    const int32_t* cell_start = (const int32_t*)(base + w.cell_start);
+    const int32_t* nbr_first = (const int32_t*)(base + w.nbr_first);
+    const uint8_t* nbr_cnt = (const uint8_t*)(base + w.nbr_cnt);
+    const uint8_t* core = base + w.core;
+    const int32_t* cell_root = (const int32_t*)(base + w.cell_root);
+    int32_t* root_label = (int32_t*)(base + w.root_label);
+    const int32_t* worklist = (const int32_t*)(base + w.worklist);
+    DbClusterAcc* acc = (DbClusterAcc*)acc_dev;
+    const int64_t cap = n_global > 0 ? n_global : 1;
+    PCH_LAUNCH(st, "k_db_relabel_roots", k_db_relabel_roots<<<db_grid(G, 256), 256, 0, st>>>(U_dev, K_dev, cell_root, map_dev, root_label));
+    PCH_LAUNCH_CHECK();
+    PCH_CUDA(cudaMemsetAsync(labels_dev, 0xff, (size_t)G * 4, st));
+    if (n_global > 0) {
+        PCH_LAUNCH(st, "k_db_acc_init", k_db_acc_init<<<db_grid(cap, 256), 256, 0, st>>>(cap, acc));
+        PCH_LAUNCH_CHECK();
+    }
+    PCH_LAUNCH(st, "k_db_labels_core", k_db_labels_core<<<db_grid(G, 8 * 32 * CR_ROWS, 16), 256, 0, st>>>(g, spts, pt_cell, core, cell_root, root_label,
+                                                                                            labels_dev, n_global, acc));
+    PCH_LAUNCH_CHECK();
+    PCH_LAUNCH(st, "k_db_labels_border", k_db_labels_border<<<db_grid(G, 8, 16), 256, 0, st>>>(g, spts, pt_cell, cell_start, core, nbr_first,
+                                                                                    nbr_cnt, cell_root, root_label, worklist, n_work,
+                                                                                    labels_dev, n_global, acc));
+    PCH_LAUNCH_CHECK();
+    if (n_global > 0) {
+        PCH_LAUNCH(st, "k_db_acc_finish", k_db_acc_finish<<<db_grid(cap, 256), 256, 0, st>>>(n_global, nullptr, acc, stats_dev));
+        PCH_LAUNCH_CHECK();
+    }
+    return PCH_OK;
+}
+
+// smallest value of base + i over the points i in [lo, hi) that carry label k, for every k (atomicMin into
+// table_dev[k], which the caller initialises): "smallest core index of a cluster" in a numbering that spans ranks
+__global__ void k_label_min_index(const int32_t* __restrict__ labels, int64_t lo, int64_t hi, long long base, int64_t K,
+                                  long long* __restrict__ table) {
+    int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < hi; i += stride) {
+        const int32_t l = labels[i];
+        if (l >= 0 && l < K) atomicMin(&table[l], base + (long long)(i - lo));
+    }
+}
+
+extern "C" int pch_label_min_index(const int32_t* labels_dev, int64_t lo, int64_t hi, int64_t base, int64_t n_labels,
+                                   int64_t* table_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(lo >= 0 && hi >= lo && n_labels >= 0, "bad range");
+    if (hi == lo || n_labels == 0) return PCH_OK;
+    PCH_CHECK_ARG(labels_dev && table_dev, "null pointer");
+    PCH_LAUNCH(st, "k_label_min_index", k_label_min_index<<<db_grid(hi - lo, 256), 256, 0, st>>>(labels_dev, lo, hi, (long long)base, n_labels, (long long*)table_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// projection of (n,3) float32 points on a horizontal axis (ux, uy), float64: s = x*ux + y*uy.
+//   pch_axis_extent   : minmax_dev[2] (float64) = min and max of s (the caller initialises to +inf / -inf)
+//   pch_axis_band_mask: mask_dev[i] = lo <= s_i <= hi, and (labels_dev != NULL) labels_dev[i] >= 0
+// Used to pick the halo a tile sends to its neighbour and the zone in which both ranks know a point's core
+// status exactly.
+__device__ __forceinline__ double axis_s(const float* __restrict__ P, int64_t i, double ux, double uy) {
+    return __dadd_rn(__dmul_rn((double)P[i * 3 + 0], ux), __dmul_rn((double)P[i * 3 + 1], uy));
+}
+__global__ void k_axis_extent(const float* __restrict__ P, int64_t n, double ux, double uy, unsigned long long* __restrict__ mm) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double lo = __longlong_as_double(0x7ff0000000000000ll), hi = -lo;
+    for (; i < n; i += stride) {
+        const double s = axis_s(P, i, ux, uy);
+        lo = fmin(lo, s); hi = fmax(hi, s);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // order-preserving encoding of the doubles so that integer atomics reduce them
+        auto enc = [](double d) { unsigned long long u = (unsigned long long)__double_as_longlong(d); return (u >> 63) ? ~u : (u | 0x8000000000000000ull); };
+        atomicMin(&mm[0], enc(lo));
+        atomicMax(&mm[1], enc(hi));
+    }
+}
+__global__ void k_axis_extent_init(unsigned long long* mm) { mm[0] = ~0ull; mm[1] = 0ull; }
+__global__ void k_axis_extent_finish(unsigned long long* mm) {
+    for (int k = 0; k < 2; ++k) {
+        const unsigned long long u = mm[k];
+        mm[k] = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    }
+}
+__global__ void k_axis_band_mask(const float* __restrict__ P, int64_t n, double ux, double uy, double lo, double hi,
+                                 const int32_t* __restrict__ labels, uint8_t* __restrict__ mask) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double s = axis_s(P, i, ux, uy);
+        mask[i] = (s >= lo && s <= hi && (!labels || labels[i] >= 0)) ? 1 : 0;
+    }
+}
+
+extern "C" int pch_axis_extent(const float* xyz_dev, int64_t n, double ux, double uy, double* minmax_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && minmax_dev && (n == 0 || xyz_dev), "bad arguments");
+    PCH_LAUNCH(st, "k_axis_extent_init", k_axis_extent_init<<<1, 1, 0, st>>>((unsigned long long*)minmax_dev));
+    if (n > 0) PCH_LAUNCH(st, "k_axis_extent", k_axis_extent<<<db_grid(n, 256), 256, 0, st>>>(xyz_dev, n, ux, uy, (unsigned long long*)minmax_dev));
+    PCH_LAUNCH(st, "k_axis_extent_finish", k_axis_extent_finish<<<1, 1, 0, st>>>((unsigned long long*)minmax_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_axis_band_mask(const float* xyz_dev, int64_t n, double ux, double uy, double lo, double hi,
+                                  const int32_t* labels_dev, uint8_t* mask_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && (n == 0 || (xyz_dev && mask_dev)), "bad arguments");
+    if (n == 0) return PCH_OK;
+    PCH_LAUNCH(st, "k_axis_band_mask", k_axis_band_mask<<<db_grid(n, 256), 256, 0, st>>>(xyz_dev, n, ux, uy, lo, hi, labels_dev, mask_dev));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

@@ -277,3 +277,84 @@ def run_tiles_from_host(tiles, scales, offsets, voxel_size: float = 0.1, chunk_s
         copy_stream.synchronize()
         for buf in stages.values():
             _release_staging(buf)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole-corridor mode: spatial tiles over several GPUs with a DBSCAN halo exchange (tiles.py)
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class TiledResult:
+    n_points: int                 # input points of this rank
+    n_voxels: int
+    n_candidates: int             # this rank's candidates
+    n_clusters: int               # global
+    towers: List[dict]            # the same list on every rank
+    labels: Optional[torch.Tensor] = None      # int32 [n_candidates]: global cluster ids
+    candidates: Optional[torch.Tensor] = None  # (n_candidates,3) float32 in the common frame
+    origin: Optional[np.ndarray] = None        # float32[3] common frame origin
+    halo: Optional[dict] = None                # exchange sizes (points sent / received, bytes)
+
+
+def corridor_axis(azimuth_deg: float):
+    """Unit vector (east, north) of a corridor whose azimuth is measured clockwise from north."""
+    a = np.radians(float(azimuth_deg))
+    return float(np.sin(a)), float(np.cos(a))
+
+
+def tile_candidates(dl: dv.DeviceLas, origin_dev: Optional[torch.Tensor], voxel_size: float, chunk_size: int):
+    """Voxel downsample + the reference's height filter on ONE tile (its own centroid and percentile, i.e. the
+    reference run on that tile's LAS, utils/tower_extraction.py:57-93); the kept points are then expressed
+    relative to `origin_dev` (float32[3], common to all tiles) instead of the tile's own centroid, so that
+    every rank computes distances on identical coordinates.  origin_dev None: returns this tile's centroid
+    as the origin.  -> (candidates (G,3) float32, voxel count, origin_dev)."""
+    vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32"))
+    if vres.count == 0:
+        z = torch.zeros((0, 3), dtype=torch.float32, device=dl.device)
+        return z, 0, origin_dev
+    raw = vres.f32
+    _, cen_dev, _, _, mask, _ = tw._ground_filter_percentile(raw, want_mask=True, zcol=vres.z32)
+    if origin_dev is None:
+        origin_dev = cen_dev.clone()
+    cand, g, _, _ = dv.compact_points(raw, None, 0.0, origin_dev, keep_mask=mask)
+    return cand, vres.count, origin_dev
+
+
+def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float = 0.1, chunk_size: int = 500000,
+                       eps: float = 8.0, min_points: int = 80, keep: bool = False, clusterer=None,
+                       **tower_kw) -> TiledResult:
+    """This rank's consecutive corridor tiles -> candidates per tile -> ONE DBSCAN over the tiles of all ranks
+    (halo exchange with the neighbouring ranks, tiles.tile_dbscan) -> towers from the all-reduced per-cluster
+    table (box = AABB rule of test/008.py:302-319).  Equals `dbscan_chunked(chunk=G)` on the concatenation of
+    all ranks' candidates, label for label."""
+    from . import tiles as tl
+    dv._require_cuda()
+    device = tiles[0].device if tiles else torch.device("cuda", torch.cuda.current_device())
+    # common frame: the centroid of rank 0's first tile
+    first = None
+    origin_dev = None
+    cands, n_vox, n_pts = [], 0, 0
+    if comm.rank == 0 and tiles:
+        first = tile_candidates(tiles[0], None, voxel_size, chunk_size)
+        origin_dev = first[2]
+    mine = origin_dev.cpu().numpy().astype(np.float32) if origin_dev is not None else np.zeros(0, np.float32)
+    got = comm.all_gather_np(mine)
+    if len(got[0]) != 3:
+        raise ValueError("rank 0 holds no points: no common frame")
+    origin = got[0].astype(np.float32)
+    origin_dev = torch.from_numpy(origin.copy()).to(device)
+    for i, dl in enumerate(tiles):
+        if i == 0 and first is not None:
+            c, m = first[0], first[1]
+        else:
+            c, m, _ = tile_candidates(dl, origin_dev, voxel_size, chunk_size)
+        cands.append(c)
+        n_vox += m
+        n_pts += dl.n
+    P_own = torch.cat(cands).contiguous() if len(cands) > 1 else (cands[0] if cands else
+                                                                  torch.zeros((0, 3), dtype=torch.float32, device=device))
+    res = tl.tile_dbscan(P_own, axis, eps, min_points, comm, clusterer)
+    stages = tw.TowerStages(None, origin, np.float32("nan"), 3.0, P_own, res.labels, res.n_clusters, res.stats)
+    towers = tw.select_towers(stages, box="aabb", want_points=False, **tower_kw)
+    halo = {"received": res.halo, "sent": res.sent, "p2p_bytes": 16 * sum(res.sent), "counts": res.counts}
+    return TiledResult(n_pts, n_vox, int(P_own.shape[0]), res.n_clusters, towers, res.labels if keep else None,
+                       P_own if keep else None, origin, halo)

@@ -1,0 +1,389 @@
+"""Whole-corridor clustering over spatial tiles with a halo exchange (DBSCAN row;
+BASELINE.json configs[3]/[4]).
+
+Parity definition: the un-chunked variant of the reference (test/zzzzz.py:79-84, ONE DBSCAN over the whole
+filtered cloud) applied to the concatenation of all tiles' candidate points.  N ranks, each holding one
+tile (its candidates in one common frame), must produce the labels that a single GPU produces on the
+concatenated array — not merely up to a permutation: clusters are numbered by their smallest core index
+in the concatenation, like scikit-learn does.
+
+Protocol (one process per GPU; `Comm` hides torch.distributed, so the same code runs on NCCL, on gloo and
+in-process over threads for a rank that holds several tiles):
+  1. all-gather per rank: candidate count and the extent [smin, smax] of the candidates along the
+     corridor axis  (24 B per rank).
+  2. halo: every rank SENDS its candidates within 2*eps of a neighbour's extent to that neighbour
+     (point-to-point, NCCL send/recv over NVLink: 16 B per halo point).  2*eps, not eps: a halo point within
+     eps of the cut needs ITS whole eps-neighbourhood to have an exact core flag.
+  3. local phase 1 (pch_dbscan_cores) on [left halo | own | right halo]: core flags + local cluster ids of
+     the core points.  A point flagged core locally IS core globally (a truncated neighbourhood can only
+     under-count), own points and halo points within eps of the cut are exact.
+  4. all-gather: (global point id, local cluster id) of every shared point that is core on the rank that
+     reports it, and per local cluster the smallest global id of its OWN core points.  Two local clusters
+     that contain the same core point are the same global cluster: union-find on every rank (identical
+     input -> identical result), global ids = rank of the component's smallest core point.
+  5. local phase 2 (pch_dbscan_finish): core labels rewritten with global ids, border points take the
+     smallest GLOBAL id among adjacent clusters, per-cluster count / AABB / sums over own points only.
+  6. all-reduce of the per-cluster table (count, sums: sum; AABB: min / max): K x 56 B.
+Every true core-core edge is seen by the rank that owns one endpoint (the other endpoint is in its halo
+and exact there), so the union of the local components is exactly the global clustering.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+I64_MAX = np.iinfo(np.int64).max
+STATS_DTYPE = np.dtype([("count", "<i8"), ("min", "<f4", 3), ("max", "<f4", 3), ("sum", "<f8", 3)])
+
+
+# -------------------------------------------------------------------------------------------------
+# communication: the three patterns the protocol needs
+# -------------------------------------------------------------------------------------------------
+class Comm:
+    rank: int = 0
+    world: int = 1
+
+    def all_gather_np(self, arr: np.ndarray) -> List[np.ndarray]:
+        """Every rank's 1-D array (sizes may differ), in rank order, on every rank."""
+        raise NotImplementedError
+
+    def neighbour_exchange(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor]):
+        """Send (k,4) float32 payloads to rank-1 / rank+1, receive theirs: (from_left, from_right)."""
+        raise NotImplementedError
+
+    def all_reduce_stats(self, stats: np.ndarray) -> np.ndarray:
+        out = stats.copy()
+        parts = self.all_gather_np(stats.view(np.uint8).reshape(-1))
+        rows = [p.view(STATS_DTYPE) for p in parts]
+        out["count"] = np.sum([p["count"] for p in rows], axis=0)
+        out["sum"] = np.sum([p["sum"] for p in rows], axis=0)          # rank order: the same bits on every rank
+        out["min"] = np.min([p["min"] for p in rows], axis=0)
+        out["max"] = np.max([p["max"] for p in rows], axis=0)
+        return out
+
+
+class SoloComm(Comm):
+    def all_gather_np(self, arr):
+        return [np.asarray(arr)]
+
+    def neighbour_exchange(self, to_left, to_right):
+        return None, None
+
+
+class TorchComm(Comm):
+    """torch.distributed: NCCL with device tensors (halo payloads travel GPU to GPU), gloo with host tensors."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.nccl = dist.get_backend() == "nccl"
+        self.device = torch.device(device if device is not None else
+                                   (f"cuda:{torch.cuda.current_device()}" if self.nccl else "cpu"))
+        self.bytes_p2p = 0
+        self.bytes_gather = 0
+
+    def _gather_fixed(self, t: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        try:
+            self.dist.all_gather_into_tensor(out, t)
+        except (RuntimeError, NotImplementedError, AttributeError):
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            self.dist.all_gather(parts, t)
+            out = torch.stack(parts)
+        return out
+
+    def all_gather_np(self, arr):
+        a = np.ascontiguousarray(arr)
+        raw = a.view(np.uint8).reshape(-1)
+        sizes = self._gather_fixed(torch.tensor([raw.size], dtype=torch.int64, device=self.device)).cpu().numpy().reshape(-1)
+        mx = int(sizes.max())
+        pad = np.zeros(max(mx, 1), dtype=np.uint8)
+        pad[: raw.size] = raw
+        got = self._gather_fixed(torch.from_numpy(pad).to(self.device)).cpu().numpy()
+        self.bytes_gather += int(sizes.sum())
+        return [got[r, : int(sizes[r])].copy().view(a.dtype) for r in range(self.world)]
+
+    def neighbour_exchange(self, to_left, to_right):
+        dist = self.dist
+        dev = self.device
+        kl = 0 if to_left is None else int(to_left.shape[0])
+        kr = 0 if to_right is None else int(to_right.shape[0])
+        sizes = self._gather_fixed(torch.tensor([kl, kr], dtype=torch.int64, device=dev)).cpu().numpy()
+        ops, from_left, from_right = [], None, None
+        r, W = self.rank, self.world
+        if r > 0 and int(sizes[r - 1, 1]) > 0:
+            from_left = torch.empty((int(sizes[r - 1, 1]), 4), dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, from_left, r - 1))
+        if r + 1 < W and int(sizes[r + 1, 0]) > 0:
+            from_right = torch.empty((int(sizes[r + 1, 0]), 4), dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, from_right, r + 1))
+        if r > 0 and kl > 0:
+            ops.append(dist.P2POp(dist.isend, to_left.to(dev).contiguous(), r - 1))
+        if r + 1 < W and kr > 0:
+            ops.append(dist.P2POp(dist.isend, to_right.to(dev).contiguous(), r + 1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.bytes_p2p += 16 * (kl + kr)
+        return from_left, from_right
+
+
+class ThreadComm(Comm):
+    """W ranks as threads of one process (a GPU that holds several tiles; the CPU tests): the collectives are
+    rendezvous on a barrier.  Kernels of different ranks never wait on each other — only host threads do."""
+
+    class Group:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, group: "ThreadComm.Group", rank: int):
+        self.g, self.rank, self.world = group, rank, group.world
+
+    def _exchange(self, value):
+        g = self.g
+        g.slots[self.rank] = value
+        g.barrier.wait()
+        got = list(g.slots)
+        g.barrier.wait()
+        return got
+
+    def all_gather_np(self, arr):
+        return [np.asarray(a).copy() for a in self._exchange(np.ascontiguousarray(arr))]
+
+    def neighbour_exchange(self, to_left, to_right):
+        got = self._exchange((to_left, to_right))
+        r = self.rank
+        from_left = got[r - 1][1] if r > 0 else None
+        from_right = got[r + 1][0] if r + 1 < self.world else None
+        fix = lambda t: None if t is None or t.shape[0] == 0 else t.clone()
+        return fix(from_left), fix(from_right)
+
+
+# -------------------------------------------------------------------------------------------------
+# the per-rank kernels behind an interface (the CPU tests plug in an oracle-backed one)
+# -------------------------------------------------------------------------------------------------
+class DeviceClusterer:
+    """libpch_b200 kernels on the current CUDA device."""
+
+    def __init__(self):
+        from . import _native, device as dv
+        self.dv, self.lib, self.check = dv, _native.lib(), _native.check
+        dv._require_cuda()
+        self._ws = None
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def extent(self, P: torch.Tensor, axis) -> Tuple[float, float]:
+        if P.shape[0] == 0:
+            return math.inf, -math.inf
+        mm = torch.empty(2, dtype=torch.float64, device=P.device)
+        self.check(self.lib.pch_axis_extent(P.data_ptr(), P.shape[0], float(axis[0]), float(axis[1]), mm.data_ptr(),
+                                            self._stream()), "pch_axis_extent")
+        lo, hi = mm.cpu().numpy()
+        return float(lo), float(hi)
+
+    def band_indices(self, P: torch.Tensor, axis, lo: float, hi: float) -> torch.Tensor:
+        """Indices (int32, ascending) of the points with lo <= s <= hi."""
+        n = P.shape[0]
+        if n == 0:
+            return torch.zeros(0, dtype=torch.int32, device=P.device)
+        mask = torch.empty(n + 16, dtype=torch.uint8, device=P.device)[:n]
+        self.check(self.lib.pch_axis_band_mask(P.data_ptr(), n, float(axis[0]), float(axis[1]), float(lo), float(hi), None,
+                                               mask.data_ptr(), self._stream()), "pch_axis_band_mask")
+        _, k, src, _ = self.dv.compact_points(P, None, 0.0, None, keep_mask=mask, want_src=True)
+        return src
+
+    def cores(self, P: torch.Tensor, eps: float, min_samples: int):
+        G = P.shape[0]
+        dev = P.device
+        labels = torch.empty(G, dtype=torch.int32, device=dev)
+        cap = max(4096, G // 256)
+        wsb = self.lib.pch_dbscan_fused_workspace_bytes(G, G, cap)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        self.check(self.lib.pch_dbscan_cores(P.data_ptr(), G, G, float(eps), int(min_samples), labels.data_ptr(), cap,
+                                             ws.data_ptr(), wsb, self._stream()), "pch_dbscan_cores")
+        sc = ws[:256].cpu().numpy()
+        if int(sc[208 + 24: 208 + 28].view(np.int32)[0]) != 0:
+            raise ValueError("DBSCAN cell grid does not fit the packed key")
+        if int(sc[:4].view(np.int32)[0]):
+            raise RuntimeError("device look-back spin limit hit in dbscan")
+        k = int(sc[136:144].view(np.int64)[0])
+        self._ws = (P, G, float(eps), int(min_samples), cap, ws, wsb)
+        return labels, k
+
+    def min_index(self, labels: torch.Tensor, lo: int, hi: int, base: int, k: int) -> np.ndarray:
+        table = torch.full((max(k, 1),), I64_MAX, dtype=torch.int64, device=labels.device)
+        self.check(self.lib.pch_label_min_index(labels.data_ptr(), lo, hi, int(base), k, table.data_ptr(), self._stream()),
+                   "pch_label_min_index")
+        return table[:k].cpu().numpy()
+
+    def labels_at(self, labels: torch.Tensor, idx: torch.Tensor) -> np.ndarray:
+        return labels[idx.long()].cpu().numpy() if idx.numel() else np.zeros(0, dtype=np.int32)
+
+    def finish(self, label_map: np.ndarray, n_global: int, own_lo: int, own_hi: int):
+        P, G, eps, min_samples, cap, ws, wsb = self._ws
+        dev = P.device
+        m = torch.from_numpy(np.ascontiguousarray(label_map, dtype=np.int32)).to(dev) if len(label_map) else \
+            torch.zeros(1, dtype=torch.int32, device=dev)
+        labels = torch.empty(G, dtype=torch.int32, device=dev)
+        item = STATS_DTYPE.itemsize
+        stats = torch.zeros(max(n_global, 1) * item, dtype=torch.uint8, device=dev)
+        acc = torch.empty(self.lib.pch_dbscan_acc_bytes(n_global), dtype=torch.uint8, device=dev)
+        self.check(self.lib.pch_dbscan_finish(P.data_ptr(), G, G, eps, min_samples, m.data_ptr(), int(n_global), int(own_lo),
+                                              int(own_hi), labels.data_ptr(), stats.data_ptr(), acc.data_ptr(), cap,
+                                              ws.data_ptr(), wsb, self._stream()), "pch_dbscan_finish")
+        host = stats[: n_global * item].cpu().numpy().view(STATS_DTYPE).copy()
+        self._ws = None
+        return labels, host
+
+
+# -------------------------------------------------------------------------------------------------
+# host logic shared by every rank: which local clusters are the same global cluster
+# -------------------------------------------------------------------------------------------------
+def merge_local_clusters(entries: Sequence[np.ndarray], tables: Sequence[np.ndarray]):
+    """entries[r]: int64 (k_r, 2) rows (global point id, local cluster id on rank r) of shared core points;
+    tables[r]: int64 [K_r] smallest global id of rank r's OWN core points per local cluster (I64_MAX = none).
+    Returns (maps, n_global): maps[r][local id] = global id (-1: a cluster without any own core point anywhere,
+    i.e. seen only in the outer halo band).  Global ids rank the clusters by their smallest core point, the
+    order scikit-learn numbers them in on the concatenated cloud."""
+    W = len(tables)
+    node_off = np.concatenate([[0], np.cumsum([len(t) for t in tables])]).astype(np.int64)
+    n_nodes = int(node_off[-1])
+    key = np.concatenate([np.asarray(t, dtype=np.int64) for t in tables]) if n_nodes else np.zeros(0, np.int64)
+    parent = np.arange(n_nodes, dtype=np.int64)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    rows = [np.stack([np.asarray(e, dtype=np.int64).reshape(-1, 2)[:, 0],
+                      np.asarray(e, dtype=np.int64).reshape(-1, 2)[:, 1] + node_off[r]], axis=1)
+            for r, e in enumerate(entries) if len(e)]
+    if rows:
+        allr = np.concatenate(rows)
+        allr = allr[np.argsort(allr[:, 0], kind="stable")]
+        same = allr[1:, 0] == allr[:-1, 0]
+        pairs = np.stack([allr[:-1, 1][same], allr[1:, 1][same]], axis=1)
+        pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+        if len(pairs):
+            pairs = np.unique(np.sort(pairs, axis=1), axis=0)
+        for a, b in pairs:
+            ra, rb = find(int(a)), find(int(b))
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+    roots = np.array([find(i) for i in range(n_nodes)], dtype=np.int64)
+    comp_key = np.full(n_nodes, I64_MAX, dtype=np.int64)
+    np.minimum.at(comp_key, roots, key)
+    live = np.nonzero((roots == np.arange(n_nodes)) & (comp_key < I64_MAX))[0]
+    order = live[np.argsort(comp_key[live], kind="stable")]
+    gid_of_root = np.full(n_nodes, -1, dtype=np.int64)
+    gid_of_root[order] = np.arange(len(order))
+    node_gid = gid_of_root[roots] if n_nodes else np.zeros(0, np.int64)
+    maps = [node_gid[node_off[r]: node_off[r + 1]].astype(np.int32) for r in range(W)]
+    return maps, int(len(order))
+
+
+@dataclasses.dataclass
+class TileDbscanResult:
+    labels: torch.Tensor          # int32 [G_own]: global cluster ids of this rank's candidates
+    n_clusters: int               # K, the same on every rank
+    stats: np.ndarray             # STATS_DTYPE [K], reduced over all ranks
+    offset: int                   # global id of this rank's first candidate
+    counts: List[int]             # candidates per rank
+    halo: Tuple[int, int]         # halo points received from the left / right neighbour
+    sent: Tuple[int, int]         # halo points sent to the left / right neighbour
+
+
+def halo_widths(eps: float) -> Tuple[float, float]:
+    """(zone in which a neighbour's points can be within eps of mine, halo width) with a little slack for the
+    rounding of the projection: supersets are harmless, a missed point is not."""
+    e1 = float(eps) * (1.0 + 1e-6) + 1e-6
+    return e1, 2.0 * e1
+
+
+def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samples: int, comm: Comm,
+                clusterer=None) -> TileDbscanResult:
+    """One whole-corridor DBSCAN over the tiles of all ranks; see the module docstring."""
+    clu = clusterer if clusterer is not None else DeviceClusterer()
+    r, W = comm.rank, comm.world
+    ax = np.asarray(axis, dtype=np.float64)
+    ax = ax / np.linalg.norm(ax)
+    G = int(P_own.shape[0])
+    smin, smax = clu.extent(P_own, ax)
+    meta = comm.all_gather_np(np.array([G, smin, smax], dtype=np.float64))
+    counts = [int(m[0]) for m in meta]
+    lo_s = [float(m[1]) for m in meta]
+    hi_s = [float(m[2]) for m in meta]
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    _, e2 = halo_widths(eps)
+    for i in range(W):
+        for j in range(i + 2, W):
+            if counts[i] and counts[j] and not (hi_s[i] + e2 < lo_s[j] or hi_s[j] + e2 < lo_s[i]):
+                raise ValueError(f"tiles {i} and {j} are closer than 2*eps along the axis: only neighbouring tiles may touch")
+    dev = P_own.device
+    empty_idx = torch.zeros(0, dtype=torch.int32, device=dev)
+    idx_l = clu.band_indices(P_own, ax, -math.inf, hi_s[r - 1] + e2) if (r > 0 and counts[r - 1] and G) else empty_idx
+    idx_r = clu.band_indices(P_own, ax, lo_s[r + 1] - e2, math.inf) if (r + 1 < W and counts[r + 1] and G) else empty_idx
+
+    def payload(idx):
+        if idx.numel() == 0:
+            return None
+        rows = P_own.index_select(0, idx.long())
+        return torch.cat([rows, idx.to(torch.int32).view(torch.float32).unsqueeze(1)], dim=1).contiguous()
+
+    from_left, from_right = comm.neighbour_exchange(payload(idx_l), payload(idx_r))
+    parts, gid_halo = [], []
+    nL = 0 if from_left is None else int(from_left.shape[0])
+    nR = 0 if from_right is None else int(from_right.shape[0])
+    if nL:
+        fl = from_left.to(dev)
+        parts.append(fl[:, :3])
+        gid_halo.append(offs[r - 1] + fl[:, 3].contiguous().view(torch.int32).cpu().numpy().astype(np.int64))
+    parts.append(P_own)
+    if nR:
+        fr = from_right.to(dev)
+        parts.append(fr[:, :3])
+        gid_halo.append(offs[r + 1] + fr[:, 3].contiguous().view(torch.int32).cpu().numpy().astype(np.int64))
+    n_local = nL + G + nR
+    if n_local == 0:
+        labels_core, k_local = torch.zeros(0, dtype=torch.int32, device=dev), 0
+    else:
+        P_local = torch.cat(parts).contiguous() if len(parts) > 1 else P_own.contiguous()
+        labels_core, k_local = clu.cores(P_local, eps, min_samples)
+    # shared core points: the halo I received, and the own points I sent
+    halo_pos = torch.cat([torch.arange(0, nL, device=dev), torch.arange(nL + G, n_local, device=dev)]).to(torch.int32)
+    sent_idx = torch.unique(torch.cat([idx_l, idx_r]).long()).to(torch.int32) if (idx_l.numel() + idx_r.numel()) else empty_idx
+    lab_halo = clu.labels_at(labels_core, halo_pos) if n_local else np.zeros(0, np.int32)
+    lab_sent = clu.labels_at(labels_core, (sent_idx.long() + nL).to(torch.int32)) if n_local else np.zeros(0, np.int32)
+    gid_h = np.concatenate(gid_halo) if gid_halo else np.zeros(0, np.int64)
+    gid_s = offs[r] + sent_idx.cpu().numpy().astype(np.int64)
+    ent = np.concatenate([np.stack([gid_h, lab_halo.astype(np.int64)], axis=1)[lab_halo >= 0],
+                          np.stack([gid_s, lab_sent.astype(np.int64)], axis=1)[lab_sent >= 0]]).astype(np.int64)
+    table = clu.min_index(labels_core, nL, nL + G, int(offs[r]), k_local) if (n_local and k_local) else np.zeros(0, np.int64)
+    entries = [e.reshape(-1, 2) for e in comm.all_gather_np(ent.reshape(-1))]
+    tables = comm.all_gather_np(table)
+    maps, n_global = merge_local_clusters(entries, tables)
+    if n_local:
+        labels_all, stats_own = clu.finish(maps[r], n_global, nL, nL + G)
+        labels = labels_all[nL: nL + G]
+    else:
+        labels = torch.zeros(0, dtype=torch.int32, device=dev)
+        stats_own = np.zeros(n_global, dtype=STATS_DTYPE)
+    if len(stats_own) != n_global:
+        stats_own = np.zeros(n_global, dtype=STATS_DTYPE)
+    empty = stats_own["count"] == 0
+    stats_own["min"][empty] = np.inf
+    stats_own["max"][empty] = -np.inf
+    stats = comm.all_reduce_stats(stats_own)
+    return TileDbscanResult(labels, n_global, stats, int(offs[r]), counts, (nL, nR), (int(idx_l.numel()), int(idx_r.numel())))

@@ -1,0 +1,139 @@
+"""CPU: the halo-exchange protocol of tiles.tile_dbscan (DBSCAN row) — host logic, communication
+patterns and the two-phase split — with an oracle-backed clusterer in place of the CUDA kernels.  Parity
+definition: N tiles + halo == scikit-learn DBSCAN on the concatenated cloud (test/zzzzz.py:79-84), label for label."""
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+EPS, MINPTS = 8.0, 20
+
+
+def _reference(tiles):
+    from sklearn.cluster import DBSCAN
+    allp = np.concatenate(tiles)
+    return DBSCAN(eps=EPS, min_samples=MINPTS, algorithm="ball_tree").fit(allp).labels_.astype(np.int32)
+
+
+def test_merge_local_clusters_joins_by_shared_points_and_orders_by_first_core():
+    from pointcloudhookup_b200 import tiles as tl
+    BIG = tl.I64_MAX
+    # rank 0: clusters 0 (cores from gid 5), 1 (from gid 40); rank 1: clusters 0 (halo only, = rank 0's 1), 1 (own, gid 120),
+    # 2 (own from gid 100 AND shares a point with rank 0's cluster 0), 3 (outer-band halo only: dropped)
+    tables = [np.array([5, 40]), np.array([BIG, 120, 100, BIG])]
+    entries = [np.array([[90, 1], [100, 0]]),            # rank 0 reports its own point 90 (in 1) and halo point 100 (in 0)
+               np.array([[90, 0], [100, 2], [95, 3]])]   # rank 1 reports halo 90 (in 0), own 100 (in 2), halo 95 (in 3)
+    maps, k = tl.merge_local_clusters(entries, tables)
+    assert k == 3
+    assert maps[0].tolist() == [0, 1]                   # {r0c0, r1c2} first core 5 -> 0; {r0c1, r1c0} first core 40 -> 1
+    assert maps[1].tolist() == [1, 2, 0, -1]            # r1c1 first core 120 -> 2; r1c3 has no own core anywhere -> -1
+    maps, k = tl.merge_local_clusters([np.zeros((0, 2), np.int64)], [np.zeros(0, np.int64)])
+    assert k == 0 and maps[0].tolist() == []
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_tile_dbscan_threads_equal_sklearn_on_the_concatenation(world):
+    import halo_oracle as ho
+    from pointcloudhookup_b200 import tiles as tl
+    tiles = ho.corridor_candidates(7, world)
+    ref = _reference(tiles)
+    group = tl.ThreadComm.Group(world)
+    out, errs = [None] * world, []
+
+    def run(r):
+        try:
+            out[r] = tl.tile_dbscan(torch.from_numpy(tiles[r]), (1.0, 0.0), EPS, MINPTS, tl.ThreadComm(group, r), ho.OracleClusterer())
+        except BaseException as e:      # a failing rank must not leave the others at the barrier
+            errs.append(e)
+            group.barrier.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    got = np.concatenate([o.labels.numpy() for o in out])
+    assert np.array_equal(got, ref)                      # identical labels, not only the same partition
+    k = int(ref.max()) + 1
+    assert all(o.n_clusters == k for o in out)
+    if world > 1:
+        assert sum(sum(o.sent) for o in out) > 0 and any(len(set(ref[ref >= 0])) for o in out)
+        # at least one cluster spans a cut (the conductor line / the blobs on the cuts)
+        offs = np.concatenate([[0], np.cumsum([len(t) for t in tiles])])
+        spans = [len({int(np.searchsorted(offs, i, side="right")) for i in np.nonzero(ref == c)[0]}) for c in range(k)]
+        assert max(spans) >= 2
+    # per-cluster table: all-reduced, identical on every rank, equal to the table of the concatenation
+    allp = np.concatenate(tiles)
+    for c in range(k):
+        m = ref == c
+        assert out[0].stats["count"][c] == m.sum()
+        assert np.array_equal(out[0].stats["min"][c], allp[m].min(0)) and np.array_equal(out[0].stats["max"][c], allp[m].max(0))
+        assert np.allclose(out[0].stats["sum"][c], allp[m].astype(np.float64).sum(0), rtol=1e-12)
+    for o in out[1:]:
+        assert o.stats.tobytes() == out[0].stats.tobytes()
+
+
+def test_tiles_closer_than_two_eps_are_refused():
+    import halo_oracle as ho
+    from pointcloudhookup_b200 import tiles as tl
+    tiles = ho.corridor_candidates(3, 3, per_tile=600, tile_len=10.0)     # tile 0 and tile 2 are 10 m apart
+    group = tl.ThreadComm.Group(3)
+    errs = []
+
+    def run(r):
+        try:
+            tl.tile_dbscan(torch.from_numpy(tiles[r]), (1.0, 0.0), EPS, MINPTS, tl.ThreadComm(group, r), ho.OracleClusterer())
+        except ValueError as e:
+            errs.append(str(e))
+    th = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert len(errs) == 3 and all("2*eps" in e for e in errs)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    import halo_oracle as ho
+    from pointcloudhookup_b200 import tiles as tl
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tiles = ho.corridor_candidates(11, world)
+    comm = tl.TorchComm()
+    res = tl.tile_dbscan(torch.from_numpy(tiles[rank]), (1.0, 0.0), EPS, MINPTS, comm, ho.OracleClusterer())
+    q.put((rank, res.labels.numpy(), res.n_clusters, res.stats.tobytes(), res.sent, res.halo, comm.bytes_p2p))
+    dist.destroy_process_group()
+
+
+def test_tile_dbscan_world2_gloo():
+    """Two processes over gloo: point-to-point halo send/recv, all-gathers of equivalences, all-reduced table."""
+    import halo_oracle as ho
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=180) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    tiles = ho.corridor_candidates(11, 2)
+    ref = _reference(tiles)
+    assert np.array_equal(np.concatenate([out[0][1], out[1][1]]), ref)
+    assert out[0][2] == out[1][2] == int(ref.max()) + 1
+    assert out[0][3] == out[1][3]
+    assert out[0][4][1] == out[1][5][0] > 0 and out[1][4][0] == out[0][5][1] > 0     # sent right == received from left, and back
+    assert out[0][6] == 16 * sum(out[0][4])

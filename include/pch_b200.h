@@ -213,8 +213,24 @@ int pch_compact_points(const float* xyz_dev, const float* zs_dev, const uint8_t*
                        uint8_t* out_mask_dev, int64_t* count_dev, void* workspace_dev,
                        size_t workspace_bytes, pch_stream_t stream);
 
-/* north_star extension (no reference code): ground = min z per XY cell, keep = z - ground > hag.
- * cell index = floor((xy - min_xy)/cell) in float32; cell_min_dev: nx*ny uint32 scratch. */
+/* Grid min-z ground model (north_star subsystem 2; the reference has no such code, cf. its percentile and
+ * RANSAC variants test/main_ground.py:8-131): p = xyz - centroid (float32), cell (i,j) = floor((p.xy - min_xy) /
+ * cell) in float32, ground = min p.z per cell, keep = p.z - ground > hag.  oracle/ground.py::grid_min_keep_mask.
+ *   pch_grid_min            : cell_min_dev[nx*ny] (uint32, order-preserving encoding of the float32 minimum).
+ *                             The centroid shift is applied on the fly (centroid3_dev nullable = no shift); tiles
+ *                             are staged in shared memory, lanes of a warp that fall into the same cell reduce
+ *                             with one warp-shuffle minimum, a per-CTA cell table in shared memory absorbs the
+ *                             rest: one global atomicMin per (tile, cell).
+ *   pch_compact_points_grid : pch_compact_points whose keep flag is the height-above-ground test, derived from
+ *                             the cloud and the cell table inside the compaction (no mask, no shifted cloud).
+ *   pch_grid_min_ground     : the two steps with explicit outputs (keep mask, ground z per point) on an
+ *                             already shifted cloud. */
+int pch_grid_min(const float* xyz_dev, int64_t m, const float* centroid3_dev, float min_x, float min_y, float cell,
+                 int32_t nx, int32_t ny, uint32_t* cell_min_dev, pch_stream_t stream);
+int pch_compact_points_grid(const float* xyz_dev, int64_t m, const float* centroid3_dev, float min_x, float min_y,
+                            float cell, int32_t nx, int32_t ny, float hag, const uint32_t* cell_min_dev,
+                            float* out_xyz_dev, int32_t* out_src_dev, uint8_t* out_mask_dev, int64_t* count_dev,
+                            void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 int pch_grid_min_ground(const float* xyz_dev, int64_t m, float min_x, float min_y, float cell, int32_t nx,
                         int32_t ny, float hag, uint32_t* cell_min_dev, uint8_t* keep_dev,
                         float* ground_z_dev, pch_stream_t stream);

@@ -72,6 +72,9 @@ SIGNATURES.update({
     "pch_select_f32": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "pch_compact_workspace_bytes": (_sz, [_i64]),
     "pch_compact_points": (C.c_int, [_p, _p, _p, _i64, _p, C.c_float, _p, _p, _p, _p, _p, _sz, _p]),
+    "pch_grid_min": (C.c_int, [_p, _i64, _p, C.c_float, C.c_float, C.c_float, _i32, _i32, _p, _p]),
+    "pch_compact_points_grid": (C.c_int, [_p, _i64, _p, C.c_float, C.c_float, C.c_float, _i32, _i32, C.c_float, _p, _p, _p, _p, _p,
+                                          _p, _sz, _p]),
     "pch_grid_min_ground": (C.c_int, [_p, _i64, C.c_float, C.c_float, C.c_float, _i32, _i32, C.c_float, _p, _p, _p, _p]),
     "pch_f32_minmax": (C.c_int, [_p, _i64, _p, _p]),
     "pch_label_words": (C.c_int, [_p, _i64, _p, _p]),

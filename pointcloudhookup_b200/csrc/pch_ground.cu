@@ -762,6 +762,29 @@ extern "C" int pch_select_f32(const float* v, int64_t n, int64_t rank0, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// grid min-z ground model, shared pieces (north_star subsystem 2; no reference implementation exists):
+//   p = raw - centroid (float32), cell (i, j) = floor((p.xy - min_xy) / cell) in float32 arithmetic,
+//   ground_z(cell) = min p.z of the cell, keep = (p.z - ground_z) > hag.   oracle/ground.py::grid_min_keep_mask
+// ------------------------------------------------------------------------------------------------
+struct GridTest {
+    const uint32_t* cell_min;   // [nx*ny] order-preserving encoding of the float32 minima; NULL = no grid test
+    float minx, miny, cell, hag;
+    int32_t ny;
+    long long n_cells;
+};
+__device__ __forceinline__ long long grid_cell_of(float sx, float sy, const GridTest& gt) {
+    const long long ix = (long long)floorf(__fdiv_rn(__fsub_rn(sx, gt.minx), gt.cell));
+    const long long iy = (long long)floorf(__fdiv_rn(__fsub_rn(sy, gt.miny), gt.cell));
+    const long long cid = ix * gt.ny + iy;
+    return (ix < 0 || iy < 0 || iy >= gt.ny || cid >= gt.n_cells) ? -1 : cid;
+}
+__device__ __forceinline__ bool grid_keep(float sx, float sy, float sz, const GridTest& gt) {
+    const long long cid = grid_cell_of(sx, sy, gt);
+    const float g = cid >= 0 ? pch_ordered_to_f32(__ldg(gt.cell_min + cid)) : sz;
+    return __fsub_rn(sz, g) > gt.hag;
+}
+
+// ------------------------------------------------------------------------------------------------
 // order-preserving compaction of points with z_shifted > thr
 // ------------------------------------------------------------------------------------------------
 #define CP_THREADS 256
@@ -773,7 +796,7 @@ extern "C" size_t pch_compact_workspace_bytes(int64_t m) { return 256 + (size_t)
 // keep[i] = zs[i] > thr  (mode 0)   or   keep_mask[i] != 0 (mode 1, zs == nullptr)   or
 // float32(z[i] - centroid.z) > thr from the cloud itself (mode 2, zs == keep_mask == nullptr)
 __global__ void __launch_bounds__(CP_THREADS)
-k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask,
+k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask, GridTest gt,
           int64_t m, const float* __restrict__ centroid, float thr, float* __restrict__ out_xyz,
           int32_t* __restrict__ out_src, uint8_t* __restrict__ out_mask, long long* __restrict__ count_out,
           uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
@@ -791,11 +814,15 @@ k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uin
     uint32_t rank[CP_ROWS];
     uint32_t keep_bits = 0, wtotal = 0;
     const float cz_keep = (!zs && !keep_mask && centroid) ? centroid[2] : 0.f;
+    const float cx_keep = (gt.cell_min && centroid) ? centroid[0] : 0.f, cy_keep = (gt.cell_min && centroid) ? centroid[1] : 0.f;
 #pragma unroll
     for (int j = 0; j < CP_ROWS; ++j) {
         int64_t i = start + wbase + j * 32 + lane;
         bool keep = false;
-        if (i < m) keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(xyz[i * 3 + 2], cz_keep) > thr));
+        if (i < m) {
+            if (gt.cell_min) keep = grid_keep(__fsub_rn(xyz[i * 3 + 0], cx_keep), __fsub_rn(xyz[i * 3 + 1], cy_keep), __fsub_rn(xyz[i * 3 + 2], cz_keep), gt);
+            else keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(xyz[i * 3 + 2], cz_keep) > thr));
+        }
         if (out_mask && i < m) out_mask[i] = keep ? 1 : 0;
         uint32_t b = __ballot_sync(0xffffffffu, keep);
         rank[j] = wtotal + __popc(b & ((1u << lane) - 1u));
@@ -854,7 +881,7 @@ k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uin
 // rows in registers), and the packed span leaves with fully coalesced stores — instead of 4-byte accesses at
 // a 12-byte stride on both sides.  Same flags, same order, same outputs as k_compact.
 __global__ void __launch_bounds__(CP_THREADS)
-k_compact_xyz(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask,
+k_compact_xyz(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask, GridTest gt,
               int64_t m, const float* __restrict__ centroid, float thr, float* __restrict__ out_xyz,
               int32_t* __restrict__ out_src, uint8_t* __restrict__ out_mask, long long* __restrict__ count_out,
               uint64_t* __restrict__ status, uint32_t* __restrict__ counter, int* __restrict__ err) {
@@ -888,7 +915,10 @@ k_compact_xyz(const float* __restrict__ xyz, const float* __restrict__ zs, const
         const int li = wbase + j * 32 + lane;
         const int64_t i = start + li;
         bool keep = false;
-        if (li < cnt) keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(s_row[li * 3 + 2], cz) > thr));
+        if (li < cnt) {
+            if (gt.cell_min) keep = grid_keep(__fsub_rn(s_row[li * 3 + 0], cx), __fsub_rn(s_row[li * 3 + 1], cy), __fsub_rn(s_row[li * 3 + 2], cz), gt);
+            else keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(s_row[li * 3 + 2], cz) > thr));
+        }
         if (out_mask && li < cnt) out_mask[i] = keep ? 1 : 0;
         uint32_t b = __ballot_sync(0xffffffffu, keep);
         rank[j] = wtotal + __popc(b & ((1u << lane) - 1u));
@@ -1031,10 +1061,10 @@ k_compact_flags(const uint8_t* __restrict__ mask, int64_t m, int32_t* __restrict
     }
 }
 
-extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8_t* keep_mask, int64_t m,
-                                  const float* centroid3, float thr, float* out_xyz, int32_t* out_src,
-                                  uint8_t* out_mask, int64_t* count_dev, void* workspace, size_t workspace_bytes,
-                                  pch_stream_t stream) {
+static int compact_impl(const float* xyz, const float* zs, const uint8_t* keep_mask, GridTest gt, int64_t m,
+                        const float* centroid3, float thr, float* out_xyz, int32_t* out_src,
+                        uint8_t* out_mask, int64_t* count_dev, void* workspace, size_t workspace_bytes,
+                        pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PCH_CHECK_ARG(m >= 0, "m must be >= 0");
     PCH_CHECK_ARG(count_dev && workspace, "null pointer");
@@ -1052,69 +1082,169 @@ extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8
     uint32_t* counter = (uint32_t*)((uint8_t*)workspace + 64);
     uint64_t* status = (uint64_t*)((uint8_t*)workspace + 256);
     int64_t tiles = pch_ceil_div(m, CP_TILE);
-    if (keep_mask && !zs && !out_xyz && !out_mask && (reinterpret_cast<uintptr_t>(keep_mask) & 15) == 0) {
+    if (keep_mask && !gt.cell_min && !zs && !out_xyz && !out_mask && (reinterpret_cast<uintptr_t>(keep_mask) & 15) == 0) {
         // flags -> index list only (needs CF_TILE/CP_TILE times fewer status words than were zeroed above)
         PCH_LAUNCH(st, "k_compact_flags", k_compact_flags<<<(unsigned)pch_ceil_div(m, CF_TILE), CP_THREADS, 0, st>>>(
                                               keep_mask, m, out_src, (long long*)count_dev, status, counter, err));
     } else if (out_xyz && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
-        PCH_LAUNCH(st, "k_compact_xyz", k_compact_xyz<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src,
+        PCH_LAUNCH(st, "k_compact_xyz", k_compact_xyz<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src,
                                                               out_mask, (long long*)count_dev, status, counter, err));
     } else {
-        PCH_LAUNCH(st, "k_compact", k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, m, centroid3, thr, out_xyz, out_src, out_mask,
+        PCH_LAUNCH(st, "k_compact", k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src, out_mask,
                                                           (long long*)count_dev, status, counter, err));
     }
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }
 
+extern "C" int pch_compact_points(const float* xyz, const float* zs, const uint8_t* keep_mask, int64_t m,
+                                  const float* centroid3, float thr, float* out_xyz, int32_t* out_src,
+                                  uint8_t* out_mask, int64_t* count_dev, void* workspace, size_t workspace_bytes,
+                                  pch_stream_t stream) {
+    GridTest gt;
+    memset(&gt, 0, sizeof(gt));
+    return compact_impl(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src, out_mask, count_dev, workspace,
+                        workspace_bytes, stream);
+}
+
 // ------------------------------------------------------------------------------------------------
-// grid min-z ground model (north_star extension; no reference implementation exists)
-//   cell = floor((xy - min_xy)/cell) in float32; ground_z = min z of the cell; keep = z-ground_z > hag
+// grid min-z pass.  The cloud arrives in voxel order (x-major per chunk), so the 2048 points of a tile fall
+// into a few dozen XY cells.  The tile's rows are staged in shared memory with 16-byte loads; each warp row
+// groups its lanes by cell (match_any), takes the minimum of every group with ONE redux (warp-shuffle minimum)
+// and its leader folds it into a per-CTA cell table in shared memory; per tile and cell, one global
+// atomicMin leaves the CTA.  The centroid shift is applied on the fly: no shifted cloud is materialised.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_grid_min(const float* __restrict__ xyz, int64_t m, float minx, float miny, float cell, int ny,
-                           int64_t n_cells, uint32_t* __restrict__ cell_min) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < m; i += stride) {
-        float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
-        long long ix = (long long)floorf(__fdiv_rn(__fsub_rn(x, minx), cell));
-        long long iy = (long long)floorf(__fdiv_rn(__fsub_rn(y, miny), cell));
-        long long cid = ix * ny + iy;
-        if (cid < 0 || cid >= n_cells) continue;
-        atomicMin(&cell_min[cid], pch_f32_to_ordered(z));
+#define GM_THREADS 256
+#define GM_ROWS 8
+#define GM_TILE (GM_THREADS * GM_ROWS)
+#define GM_SLOTS 1024
+#define GM_PROBES 12
+
+__global__ void __launch_bounds__(GM_THREADS)
+k_grid_min(const float* __restrict__ xyz, int64_t m, const float* __restrict__ centroid, GridTest gt,
+           uint32_t* __restrict__ cell_min) {
+    __shared__ __align__(16) float s_row[GM_TILE * 3];
+    __shared__ int s_key[GM_SLOTS];
+    __shared__ uint32_t s_val[GM_SLOTS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float cx = centroid ? centroid[0] : 0.f, cy = centroid ? centroid[1] : 0.f, cz = centroid ? centroid[2] : 0.f;
+    const int64_t n_tiles = (m + GM_TILE - 1) / GM_TILE;
+    const bool aligned = (reinterpret_cast<uintptr_t>(xyz) & 15) == 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t start = tile * GM_TILE;
+        const int cnt = (int)min((int64_t)GM_TILE, m - start);
+        if (cnt == GM_TILE && aligned) {
+            const float4* src = reinterpret_cast<const float4*>(xyz + start * 3);   // 24 576-byte tiles of a 16-byte aligned base
+            float4* dst = reinterpret_cast<float4*>(s_row);
+#pragma unroll
+            for (int k = 0; k < GM_TILE * 3 / 4 / GM_THREADS; ++k) dst[tid + k * GM_THREADS] = __ldg(src + tid + k * GM_THREADS);
+        } else {
+            for (int w = tid; w < cnt * 3; w += GM_THREADS) s_row[w] = xyz[start * 3 + w];
+        }
+        for (int k = tid; k < GM_SLOTS; k += GM_THREADS) { s_key[k] = -1; s_val[k] = 0xffffffffu; }
+        __syncthreads();
+        const int wbase = warp * (32 * GM_ROWS);
+#pragma unroll
+        for (int j = 0; j < GM_ROWS; ++j) {
+            const int li = wbase + j * 32 + lane;
+            int key = -1;
+            uint32_t zo = 0xffffffffu;
+            if (li < cnt) {
+                const float sx = __fsub_rn(s_row[li * 3 + 0], cx), sy = __fsub_rn(s_row[li * 3 + 1], cy);
+                key = (int)grid_cell_of(sx, sy, gt);
+                zo = pch_f32_to_ordered(__fsub_rn(s_row[li * 3 + 2], cz));
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            const uint32_t mn = __reduce_min_sync(peers, zo);                 // warp-shuffle minimum of the lanes in my cell
+            if (key >= 0 && (peers & ((1u << lane) - 1u)) == 0) {             // the group's first lane owns the update
+                uint32_t slot = ((uint32_t)key * 2654435761u) >> 22;          // GM_SLOTS = 2^10
+                bool done = false;
+#pragma unroll 1
+                for (int pr = 0; pr < GM_PROBES && !done; ++pr) {
+                    const int prev = atomicCAS(&s_key[slot], -1, key);
+                    if (prev == -1 || prev == key) {
+                        atomicMin(&s_val[slot], mn);
+                        done = true;
+                    }
+                    slot = (slot + 1) & (GM_SLOTS - 1);
+                }
+                if (!done) atomicMin(&cell_min[key], mn);                     // table full (an unordered cloud): straight to global
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < GM_SLOTS; k += GM_THREADS) {
+            const int key = s_key[k];
+            if (key >= 0) atomicMin(&cell_min[key], s_val[k]);
+        }
+        __syncthreads();
     }
 }
 
-__global__ void k_grid_label(const float* __restrict__ xyz, int64_t m, float minx, float miny, float cell, int ny,
-                             int64_t n_cells, const uint32_t* __restrict__ cell_min, float hag,
+__global__ void k_grid_label(const float* __restrict__ xyz, int64_t m, const float* __restrict__ centroid, GridTest gt,
                              uint8_t* __restrict__ keep, float* __restrict__ ground_z) {
+    const float cx = centroid ? centroid[0] : 0.f, cy = centroid ? centroid[1] : 0.f, cz = centroid ? centroid[2] : 0.f;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < m; i += stride) {
-        float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
-        long long ix = (long long)floorf(__fdiv_rn(__fsub_rn(x, minx), cell));
-        long long iy = (long long)floorf(__fdiv_rn(__fsub_rn(y, miny), cell));
-        long long cid = ix * ny + iy;
-        float g = z;
-        if (cid >= 0 && cid < n_cells) g = pch_ordered_to_f32(cell_min[cid]);
+        const float x = __fsub_rn(xyz[i * 3 + 0], cx), y = __fsub_rn(xyz[i * 3 + 1], cy), z = __fsub_rn(xyz[i * 3 + 2], cz);
+        const long long cid = grid_cell_of(x, y, gt);
+        const float g = cid >= 0 ? pch_ordered_to_f32(gt.cell_min[cid]) : z;
         if (ground_z) ground_z[i] = g;
-        keep[i] = (__fsub_rn(z, g) > hag) ? 1 : 0;
+        keep[i] = (__fsub_rn(z, g) > gt.hag) ? 1 : 0;
     }
+}
+
+static int grid_args(int64_t m, float cell, int32_t nx, int32_t ny, GridTest& gt, float minx, float miny, float hag,
+                     const uint32_t* cell_min) {
+    PCH_CHECK_ARG(m >= 0 && nx >= 1 && ny >= 1 && cell > 0.f, "bad grid");
+    PCH_CHECK_ARG((int64_t)nx * ny <= 2147483647ll, "grid of %d x %d cells does not fit 31 bits", nx, ny);
+    gt.cell_min = cell_min;
+    gt.minx = minx; gt.miny = miny; gt.cell = cell; gt.hag = hag;
+    gt.ny = ny;
+    gt.n_cells = (long long)nx * ny;
+    return PCH_OK;
+}
+
+extern "C" int pch_grid_min(const float* xyz, int64_t m, const float* centroid3, float minx, float miny, float cell,
+                            int32_t nx, int32_t ny, uint32_t* cell_min, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    GridTest gt;
+    int rc = grid_args(m, cell, nx, ny, gt, minx, miny, 0.f, cell_min);
+    if (rc) return rc;
+    PCH_CHECK_ARG(cell_min && (m == 0 || xyz), "null pointer");
+    PCH_CUDA(cudaMemsetAsync(cell_min, 0xff, (size_t)gt.n_cells * 4, st));
+    if (m == 0) return PCH_OK;
+    int64_t tiles = pch_ceil_div(m, GM_TILE);
+    int64_t grid = (int64_t)pch_sm_count() * 6;
+    if (grid > tiles) grid = tiles;
+    PCH_LAUNCH(st, "k_grid_min", k_grid_min<<<(unsigned)grid, GM_THREADS, 0, st>>>(xyz, m, centroid3, gt, cell_min));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+extern "C" int pch_compact_points_grid(const float* xyz, int64_t m, const float* centroid3, float minx, float miny,
+                                       float cell, int32_t nx, int32_t ny, float hag, const uint32_t* cell_min,
+                                       float* out_xyz, int32_t* out_src, uint8_t* out_mask, int64_t* count_dev,
+                                       void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    GridTest gt;
+    int rc = grid_args(m, cell, nx, ny, gt, minx, miny, hag, cell_min);
+    if (rc) return rc;
+    PCH_CHECK_ARG(cell_min, "null cell table");
+    return compact_impl(xyz, nullptr, nullptr, gt, m, centroid3, 0.f, out_xyz, out_src, out_mask, count_dev, workspace,
+                        workspace_bytes, stream);
 }
 
 extern "C" int pch_grid_min_ground(const float* xyz, int64_t m, float minx, float miny, float cell, int32_t nx,
                                    int32_t ny, float hag, uint32_t* cell_min, uint8_t* keep, float* ground_z,
                                    pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    PCH_CHECK_ARG(m >= 0 && nx >= 1 && ny >= 1 && cell > 0.f, "bad grid");
     if (m == 0) return PCH_OK;
     PCH_CHECK_ARG(xyz && cell_min && keep, "null pointer");
-    int64_t n_cells = (int64_t)nx * ny;
-    PCH_CUDA(cudaMemsetAsync(cell_min, 0xff, (size_t)n_cells * 4, st));
-    unsigned grid = grid_for(m, 256, 8);
-    PCH_LAUNCH(st, "k_grid_min", k_grid_min<<<grid, 256, 0, st>>>(xyz, m, minx, miny, cell, ny, n_cells, cell_min));
-    PCH_LAUNCH_CHECK();
-    PCH_LAUNCH(st, "k_grid_label", k_grid_label<<<grid, 256, 0, st>>>(xyz, m, minx, miny, cell, ny, n_cells, cell_min, hag, keep, ground_z));
+    int rc = pch_grid_min(xyz, m, nullptr, minx, miny, cell, nx, ny, cell_min, stream);
+    if (rc) return rc;
+    GridTest gt;
+    if ((rc = grid_args(m, cell, nx, ny, gt, minx, miny, hag, cell_min))) return rc;
+    PCH_LAUNCH(st, "k_grid_label", k_grid_label<<<grid_for(m, 256, 8), 256, 0, st>>>(xyz, m, nullptr, gt, keep, ground_z));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

@@ -234,6 +234,7 @@ class VoxelResult:
     plan: Optional[dict] = None
     sorted_keys: Optional[torch.Tensor] = None
     z32: Optional[torch.Tensor] = None      # (M,) the z column of f32 as a dense array
+    chunk_minmax: Optional[torch.Tensor] = None   # (n_chunks,6) int32 lattice extrema of the INPUT points per chunk
 
 
 class VoxelSink:
@@ -311,7 +312,7 @@ def voxel_downsample(dl: DeviceLas, voxel_size: float, chunk_size: int,
                        f32[:m] if f32 is not None else None,
                        plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_},
                        sorted_keys=skeys,
-                       z32=z32[:m] if z32 is not None else None)
+                       z32=z32[:m] if z32 is not None else None, chunk_minmax=mm)
 
 
 def _voxel_downsample_wide(dl: DeviceLas, voxel_size: float, cs: int, want, sink) -> VoxelResult:
@@ -419,8 +420,31 @@ def f32_minmax(xyz: torch.Tensor) -> np.ndarray:
     return out.cpu().numpy()
 
 
+GRID_MAX_CELLS_PER_POINT = 64     # a cell table beyond max(this * m, 2^22) cells means an outlier blew the extent up
+
+
+def grid_shape(mn_xy, mx_xy, cell: float, m: int):
+    """(nx, ny) of the grid over [mn, mx] (float32 arithmetic, like the kernels); ValueError when the table would
+    be out of proportion to the cloud (one far outlier) or overflow the int32 cell index of the C ABI."""
+    c = np.float32(cell)
+    if not (c > 0):
+        raise ValueError("cell must be > 0")
+    mn = np.asarray(mn_xy, dtype=np.float32)
+    mx = np.asarray(mx_xy, dtype=np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        ext = np.floor((mx - mn) / c).astype(np.float64)
+    if not np.all(np.isfinite(ext)):
+        raise ValueError("grid extent is not finite")
+    nx, ny = int(ext[0]) + 1, int(ext[1]) + 1
+    cap = max(GRID_MAX_CELLS_PER_POINT * max(int(m), 1), 1 << 22)
+    if nx * ny > min(cap, 2 ** 31 - 1):
+        raise ValueError(f"grid of {nx} x {ny} cells for {m} points: extent out of proportion (outlier?) — crop the cloud "
+                         f"or use a larger cell")
+    return nx, ny
+
+
 def grid_min_ground(xyz: torch.Tensor, cell: float = 2.0, hag: float = 3.0):
-    """north_star grid min-z ground model: (keep mask uint8 (m), ground_z float32 (m))."""
+    """north_star grid min-z ground model on an already shifted cloud: (keep mask uint8 (m), ground_z float32 (m))."""
     assert xyz.dtype == torch.float32 and xyz.is_contiguous()
     m = xyz.shape[0]
     dev = xyz.device
@@ -428,8 +452,7 @@ def grid_min_ground(xyz: torch.Tensor, cell: float = 2.0, hag: float = 3.0):
         return torch.zeros(0, dtype=torch.uint8, device=dev), torch.zeros(0, dtype=torch.float32, device=dev)
     mm = f32_minmax(xyz)
     c = np.float32(cell)
-    nx = int(np.floor((mm[3] - mm[0]) / c)) + 1
-    ny = int(np.floor((mm[4] - mm[1]) / c)) + 1
+    nx, ny = grid_shape(mm[0:2], mm[3:5], cell, m)
     cell_min = torch.empty(nx * ny, dtype=torch.int32, device=dev)
     keep = torch.empty(m, dtype=torch.uint8, device=dev)
     gz = torch.empty(m, dtype=torch.float32, device=dev)
@@ -437,6 +460,38 @@ def grid_min_ground(xyz: torch.Tensor, cell: float = 2.0, hag: float = 3.0):
                                             float(np.float32(hag)), cell_min.data_ptr(), keep.data_ptr(),
                                             gz.data_ptr(), _stream()), "pch_grid_min_ground")
     return keep, gz
+
+
+def f32_minmax_dev(xyz: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(6, dtype=torch.float32, device=xyz.device)
+    check(_native.lib().pch_f32_minmax(xyz.data_ptr(), xyz.shape[0], out.data_ptr(), _stream()), "pch_f32_minmax")
+    return out
+
+
+def compact_points_grid(raw: torch.Tensor, centroid: torch.Tensor, mn_xy, nx: int, ny: int, cell: float, hag: float,
+                        want_mask: bool = False):
+    """Grid min-z filter of the RAW cloud with the centroid shift applied on the fly: (filtered (G,3) float32 =
+    (raw - centroid)[keep], G, mask or None).  Two kernels: the cell minima, then the compaction whose keep flag is
+    the height-above-ground test."""
+    assert raw.dtype == torch.float32 and raw.is_contiguous()
+    lib = _native.lib()
+    m = raw.shape[0]
+    dev = raw.device
+    st = _stream()
+    c = float(np.float32(cell))
+    cell_min = torch.empty(nx * ny, dtype=torch.int32, device=dev)
+    check(lib.pch_grid_min(raw.data_ptr(), m, centroid.data_ptr(), float(mn_xy[0]), float(mn_xy[1]), c, nx, ny,
+                           cell_min.data_ptr(), st), "pch_grid_min")
+    out = torch.empty((m, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty(m, dtype=torch.uint8, device=dev) if want_mask else None
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    wsb = lib.pch_compact_workspace_bytes(m)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(lib.pch_compact_points_grid(raw.data_ptr(), m, centroid.data_ptr(), float(mn_xy[0]), float(mn_xy[1]), c, nx, ny,
+                                      float(np.float32(hag)), cell_min.data_ptr(), out.data_ptr(), None, _ptr(mask),
+                                      cnt.data_ptr(), ws.data_ptr(), wsb, st), "pch_compact_points_grid")
+    g = int(cnt.item())
+    return out[:g], g, mask
 
 
 @dataclasses.dataclass

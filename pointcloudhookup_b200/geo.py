@@ -181,13 +181,18 @@ def grid_window(grid: DeviceGrid, lat_min, lat_max, lon_min, lon_max, max_bytes=
 
 
 def las_to_geodetic(dl: dv.DeviceLas, grid: DeviceGrid, multiplier: float = -1.0, tm: Optional[TmParams] = EPSG4547,
-                    window="auto") -> torch.Tensor:
-    """(n,3) float64 [lon, lat, h + multiplier*N] for every LAS point, one fused kernel."""
+                    window="auto", chunk_minmax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(n,3) float64 [lon, lat, h + multiplier*N] for every LAS point, one fused kernel.  `chunk_minmax`: the
+    (n_chunks,6) lattice extrema a voxel stage already computed for these records (VoxelResult.chunk_minmax); the
+    grid window is then derived from it instead of from another pass over the records."""
     out = torch.empty((dl.n, 3), dtype=torch.float64, device=dl.device)
     if dl.n == 0:
         return out
     if window == "auto":
-        mm = dv.chunk_minmax(dl, dl.n).cpu().numpy()[0].astype(np.float64)
+        if chunk_minmax is not None:
+            mm = torch.cat([chunk_minmax[:, :3].amin(0), chunk_minmax[:, 3:].amax(0)]).cpu().numpy().astype(np.float64)
+        else:
+            mm = dv.chunk_minmax(dl, dl.n).cpu().numpy()[0].astype(np.float64)
         xs = mm[[0, 3]] * dl.scales[0] + dl.offsets[0]
         ys = mm[[1, 4]] * dl.scales[1] + dl.offsets[1]
         cx = np.array([xs[0], xs[0], xs[1], xs[1], xs.mean(), xs.mean(), xs[0], xs[1]])

@@ -131,11 +131,23 @@ def ground_filter_grid(raw: torch.Tensor, cell: float = 2.0, hag: float = 3.0, w
 
 
 def _ground_filter_grid(raw: torch.Tensor, cell: float = 2.0, hag: float = 3.0, want_mask: bool = False):
+    """Centroid (main stream) and the raw cloud's bounding box (side stream) are read back together; the grid origin
+    is the shifted minimum float32(min_raw - c) (x -> float32(x - c) is monotone, so it equals the minimum of the
+    shifted cloud the oracle takes), and both grid kernels shift on the fly: no shifted copy of the cloud exists."""
+    main = torch.cuda.current_stream(raw.device)
+    side = _side_stream(raw.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        mm_dev = dv.f32_minmax_dev(raw)
     cen_dev, _ = dv.f32_centroid(raw)
-    _, shifted = dv.f32_shift(raw, cen_dev, want_z=False, want_xyz=True)
-    keep, _ = dv.grid_min_ground(shifted, cell, hag)
-    filtered, g, _, _ = dv.compact_points(shifted, None, 0.0, None, keep_mask=keep)
-    return filtered, cen_dev, np.float32("nan"), hag, (keep if want_mask else None), cen_dev.cpu().numpy()
+    main.wait_stream(side)
+    host = torch.cat([cen_dev, mm_dev]).cpu().numpy()          # one D2H: centroid + raw bounding box
+    cen = host[:3].copy()
+    mn = host[3:5] - cen[:2]                                    # float32 - float32, like the kernels' __fsub_rn
+    mx = host[6:8] - cen[:2]
+    nx, ny = dv.grid_shape(mn, mx, cell, raw.shape[0])
+    filtered, g, mask = dv.compact_points_grid(raw, cen_dev, mn, nx, ny, cell, hag, want_mask=want_mask)
+    return filtered, cen_dev, np.float32("nan"), hag, mask, cen
 
 
 def run_stages(raw: torch.Tensor, eps: float = 8.0, min_points: int = 80, ground: str = "percentile",

@@ -318,3 +318,20 @@ def test_slice_plan_of_the_host_entries():
     assert pipeline.slice_plan(0, 34, 500_000, 10, "none", 0, True)[1] == []
     with pytest.raises(ValueError):
         pipeline.slice_plan(10, 34, 5, 1, "zip", 0, True)
+
+
+def test_grid_shape_caps_the_cell_table():
+    """device.grid_shape: the grid-min cell table must stay in proportion to the cloud (one far outlier would
+    otherwise ask for gigabytes) and inside the int32 cell index of the C ABI."""
+    import pytest
+    from pointcloudhookup_b200 import device as dvm
+    assert dvm.grid_shape([0.0, 0.0], [299.9, 59.9], 2.0, 200000) == (150, 30)
+    assert dvm.grid_shape([-5.0, 1.0], [-5.0, 1.0], 2.0, 1) == (1, 1)
+    with pytest.raises(ValueError, match="out of proportion"):
+        dvm.grid_shape([0.0, 0.0], [1.0e7, 1.0e7], 2.0, 1000)
+    with pytest.raises(ValueError):
+        dvm.grid_shape([0.0, 0.0], [np.inf, 1.0], 2.0, 1000)
+    with pytest.raises(ValueError):
+        dvm.grid_shape([0.0, 0.0], [1.0, 1.0], 0.0, 1000)
+    # a long corridor is fine: 17.5 km x 5.5 km bounding box at 2 m cells for 78 M points
+    assert dvm.grid_shape([0.0, 0.0], [5500.0, 17500.0], 2.0, 78_000_000) == (2751, 8751)

@@ -145,3 +145,23 @@ def test_fullsize_sampled_chunks_match_oracle(corridor):
     assert g == stages.filtered.shape[0] and g > 1000
     checked = sp.check_dbscan_chunks(stages.filtered, stages.labels, 8.0, 80, 50_000, n_samples=5, seed=n % 997)
     assert len(checked) >= 5
+
+
+def test_fullsize_grid_ground_matches_oracle(corridor):
+    """The north_star grid min-z ground mode at the BASELINE sizes against oracle.ground.grid_min_keep_mask on the
+    WHOLE cloud (keep mask and filtered rows bit-equal).  Only the 20 M configuration: numpy's minimum.at needs
+    ~10 s per 10^7 points."""
+    from pointcloudhookup_b200 import device as dv, towers as tw
+    from oracle import ground as og
+    n, dl = corridor
+    if n > 20_000_000:
+        pytest.skip("oracle too slow at this size; covered at 20 M")
+    raw = dv.voxel_downsample(dl, 0.1, 500_000, want=("f32",)).f32
+    filtered, cen_dev, _, _, mask = tw.ground_filter_grid(raw, 2.0, 3.0, want_mask=True)
+    rawh = raw.cpu().numpy()
+    cen = np.mean(rawh, axis=0)
+    assert np.array_equal(cen, cen_dev.cpu().numpy())
+    shifted = rawh - cen
+    keep, _ = og.grid_min_keep_mask(shifted, 2.0, 3.0)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), keep)
+    assert np.array_equal(filtered.cpu().numpy(), shifted[keep])

@@ -306,6 +306,24 @@ int pch_axis_extent(const float* xyz_dev, int64_t n, double ux, double uy, doubl
 int pch_axis_band_mask(const float* xyz_dev, int64_t n, double ux, double uy, double lo, double hi,
                        const int32_t* labels_dev /* nullable */, uint8_t* mask_dev, pch_stream_t stream);
 
+/* trimesh.PointCloud(cluster_points).bounding_box_oriented (utils/tower_extraction.py:137-139) for a batch of
+ * clusters, on the device: convex hull by gift wrapping (after an exact interior cull), then for EVERY hull-face
+ * normal the minimum-area rectangle aligned with an edge of the projected hull; the smallest volume wins.  (trimesh
+ * thins the normals on a 0.1 rad grid in Qhull's facet order first; every box it can return is among the candidates
+ * here, so this box is never larger.)  points_dev: (L,3) float32 rows; ranges_dev: int64 [n_clusters][2] = first row,
+ * end row of each cluster; one CTA per cluster.  status: 0 ok, 1 fewer than 4 points / no extent, 2 degenerate (flat
+ * or collinear), 3 capacity (hull with more than 16384 faces): the caller falls back to its host path for those. */
+typedef struct pch_obb_result {
+    double extents[3];   /* rectangle long side, rectangle short side, thickness along the face normal */
+    double center[3];    /* box centre in the frame of the points */
+    double rotation[9];  /* row-major 3x3, columns = box axes (long, short, normal) in the frame of the points */
+    double volume;
+    int32_t n_faces, n_vertices, n_candidates, status;
+} pch_obb_result;
+size_t pch_obb_workspace_bytes(int32_t n_clusters);
+int pch_obb_batch(const float* points_dev, const int64_t* ranges_dev, int32_t n_clusters, pch_obb_result* out_dev,
+                  void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
+
 /* `cluster_points = filtered_points[all_labels == label]` for every label at once
  * (utils/tower_extraction.py:133-134): pch_label_words builds (label << 32 | index) words (noise sorts
  * last), pch_sort_u64_segmented orders them by label (stable), pch_gather_rows_f32 gathers the rows of

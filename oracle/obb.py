@@ -114,3 +114,70 @@ def bounding_box_oriented(points, ordered=False):
     """(transform box->world 4x4, extents) — the two attributes the reference reads."""
     to_origin, ext = oriented_bounds(points, ordered=ordered)
     return np.linalg.inv(to_origin), ext
+
+
+# ------------------------------------------------------------------------------------------------
+# Exhaustive variant: trimesh's search without its 0.1 rad thinning of the face normals.
+# The thinning keeps, per bin of rounded spherical angles, the FIRST normal in Qhull's facet order; that order is an
+# implementation detail of Qhull that no other hull construction reproduces, so the product (pch_obb.cu, gift
+# wrapping on the device) evaluates every face normal instead.  Every box trimesh can return is among these
+# candidates, hence  volume(faces) <= volume(trimesh-like).  This function is the CHECKER of the device kernel and
+# is written independently of it: Qhull for the 3-D hull, Qhull again for the 2-D hull of every projection (the
+# kernel never builds a 2-D hull: it takes the silhouette edges of the 3-D hull), plain numpy for the rectangles.
+# ------------------------------------------------------------------------------------------------
+def canonical_axes(ax0, ax2):
+    """Sign convention shared (by specification, not by code) with the product: the long axis and the normal point
+    into the half-space of positive x / z (first non-zero of x, y, z resp. z, y, x); axis 1 completes a right-handed
+    frame."""
+    def pos(v, order):
+        for k in order:
+            if abs(v[k]) > 1e-12:
+                return v if v[k] > 0 else -v
+        return v
+    a0 = pos(np.asarray(ax0, dtype=np.float64), (0, 1, 2))
+    a2 = pos(np.asarray(ax2, dtype=np.float64), (2, 1, 0))
+    return a0, np.cross(a2, a0), a2
+
+
+def min_volume_box_all_faces(points):
+    """(transform box->world 4x4, extents (long, short, along-normal), volume) over ALL hull-face normals."""
+    pts = np.asarray(points, dtype=np.float64)
+    hull = ConvexHull(pts, qhull_options="QbB Pp Qt")
+    verts = pts[hull.vertices]
+    normals = hull.equations[:, :3]
+    _, first = np.unique(np.round(normals, 9), axis=0, return_index=True)
+    best = None
+    for i in np.sort(first):
+        n = normals[i] / np.linalg.norm(normals[i])
+        helper = np.eye(3)[int(np.argmin(np.abs(n)))]
+        u0 = np.cross(n, helper)
+        u0 /= np.linalg.norm(u0)
+        v0 = np.cross(n, u0)
+        xy = np.column_stack((verts @ u0, verts @ v0))
+        thick = np.ptp(verts @ n)
+        h2 = ConvexHull(xy)
+        ring = xy[h2.vertices]
+        edges = np.roll(ring, -1, axis=0) - ring
+        ln = np.linalg.norm(edges, axis=1)
+        for e in edges[ln > 1e-10] / ln[ln > 1e-10][:, None]:
+            p = np.array([-e[1], e[0]])
+            a, b = ring @ e, ring @ p
+            w, h = np.ptp(a), np.ptp(b)
+            vol = w * h * thick
+            if best is None or vol < best[0]:
+                ax_u = e[0] * u0 + e[1] * v0
+                best = (vol, n, ax_u)
+    vol, n, ax_u = best
+    ax_v = np.cross(n, ax_u)
+    ext = np.array([np.ptp(verts @ ax_u), np.ptp(verts @ ax_v), np.ptp(verts @ n)])
+    if ext[0] < ext[1]:
+        ax_u, ax_v = ax_v, -ax_u
+        ext[[0, 1]] = ext[[1, 0]]
+    a0, a1, a2 = canonical_axes(ax_u, n)
+    R = np.column_stack((a0, a1, a2))
+    loc = verts @ R
+    centre = R @ (loc.min(axis=0) + 0.5 * np.ptp(loc, axis=0))
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = centre
+    return T, ext, vol

@@ -6,8 +6,9 @@ Stage C  :96-122   DBSCAN on consecutive 50 000-point chunks, labels offset per 
 Stage D  :125-147  per label in ``set(all_labels) - {-1}`` ORDER: box, size filter
 Stage E  :150-218  centre, duplicate check against accepted centres, north angle
 The real numpy and the real scikit-learn DBSCAN are called (they are the reference's own
-dependencies).  The box is the restated trimesh OBB (oracle.obb, PARITY UNPINNED) or, with
-``box="aabb"``, the axis-aligned variant of test/008.py:302-319 (exactly restatable).
+dependencies).  The box is trimesh's hull-face search over every face normal (``box="obb"``,
+oracle.obb.min_volume_box_all_faces), its literal thinned form (``box="obb_trimesh"``; both PARITY UNPINNED) or,
+with ``box="aabb"``, the axis-aligned variant of test/008.py:302-319 (exactly restatable).
 """
 import numpy as np
 from sklearn.cluster import DBSCAN
@@ -55,6 +56,10 @@ def cluster_box(cluster_points, box):
         mn = np.min(cluster_points, axis=0)
         mx = np.max(cluster_points, axis=0)
         return (mx - mn).astype(np.float64), ((mn + mx) / 2).astype(np.float64), np.eye(3)
+    if box == "obb":      # every hull-face normal (what the device kernel evaluates)
+        tr, ext, _ = obb.min_volume_box_all_faces(cluster_points)
+        return ext, tr[:3, 3], tr[:3, :3]
+    # "obb_trimesh" / "obb_ordered": trimesh's own thinned search, literally
     tr, ext = obb.bounding_box_oriented(cluster_points, ordered=(box == "obb_ordered"))
     return ext, tr[:3, 3], tr[:3, :3]
 

@@ -1450,11 +1450,20 @@ extern "C" int pch_dbscan_finish(const float* P, int64_t G, int64_t chunk, doubl
 // table_dev[k], which the caller initialises): "smallest core index of a cluster" in a numbering that spans ranks
 __global__ void k_label_min_index(const int32_t* __restrict__ labels, int64_t lo, int64_t hi, long long base, int64_t K,
                                   long long* __restrict__ table) {
-    int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // lanes of a warp hold consecutive points, and clusters are long runs of equal labels: the lanes that share a
+    // label elect their lowest lane (= their smallest index) and only that one issues the atomic
+    const int lane = threadIdx.x & 31;
+    int64_t i0 = lo + (blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < hi; i += stride) {
-        const int32_t l = labels[i];
-        if (l >= 0 && l < K) atomicMin(&table[l], base + (long long)(i - lo));
+    for (; i0 < hi; i0 += stride) {
+        const int64_t i = i0 + lane;
+        int32_t l = -1;
+        if (i < hi) {
+            l = labels[i];
+            if (l >= K) l = -1;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, l);
+        if (l >= 0 && (peers & ((1u << lane) - 1u)) == 0) atomicMin(&table[l], base + (long long)(i - lo));
     }
 }
 

@@ -1,0 +1,574 @@
+// Minimum-volume oriented bounding box of every candidate cluster, on the device.
+// Reference call site: utils/tower_extraction.py:137-139, `trimesh.PointCloud(cluster_points).bounding_box_oriented`
+// -> `extents`, `transform`.  trimesh's search (convex hull; for every hull-face normal the minimum-area
+// edge-aligned rectangle of the projected hull; smallest volume wins) is evaluated here for EVERY face normal —
+// trimesh itself de-duplicates normals on a 0.1 rad grid and keeps the first one in Qhull's facet order, which no
+// independent hull can reproduce and which only ever makes its box larger.
+//
+// One CTA per cluster, three steps, all in float64 on the float32 points:
+//   1. hull candidates: S = the extreme points of 256 fixed directions; H1 = hull(S) by gift wrapping; every point
+//      clearly inside H1 is interior to the hull and dropped (float32 plane tests with a safety margin), the rest
+//      (typically 1-3 % of the cluster) + S are the candidates C.
+//   2. hull(C) by gift wrapping: a stack of open directed edges, a hash set of the directed edges already owned by
+//      a face, and per edge one block-wide scan for the point all others lie behind (orientation predicate;
+//      coplanar ties go to the point farthest from the edge).  Faces (a,b,c) are counter-clockwise seen from outside.
+//   3. box search: one warp per face normal n: thickness along n; every hull edge whose two faces look to opposite
+//      sides of n is an edge of the projected hull: rectangle aligned with it, area * thickness -> block minimum.
+#include "pch_common.cuh"
+
+#define OBB_THREADS 256
+#define OBB_WARPS (OBB_THREADS / 32)
+#define OBB_DIRS 256
+#define OBB_MAXF 16384
+#define OBB_MAXC 32768
+#define OBB_HASH 65536
+#define OBB_STACK (3 * OBB_MAXF)
+
+struct ObbWs {
+    int32_t* cand;      // [OBB_MAXC]
+    int32_t* faces;     // [OBB_MAXF*3]
+    double* planes;     // [OBB_MAXF*4] unit outward normal, offset (n.x = d on the plane)
+    unsigned long long* eset;  // [OBB_HASH] directed edges (a << 32 | b) + 1, 0 = empty
+    int32_t* face_of;   // [OBB_HASH] face that owns the directed edge of the same slot
+    int4* stack;        // [OBB_STACK] open directed edges: a, b, vertex opposite to the edge in the face that is known
+    int32_t* verts;     // [OBB_MAXC] hull vertices (indices into the cluster rows)
+    uint32_t* mark;     // [OBB_MAXC/32+1] scratch bitmap
+    int32_t* twin;      // [OBB_MAXF*3] face across directed edge j of face g
+};
+static const size_t OBB_WS_BYTES = pch_align_up((size_t)OBB_MAXC * 4, 256) + pch_align_up((size_t)OBB_MAXF * 12, 256) +
+                                   pch_align_up((size_t)OBB_MAXF * 32, 256) + pch_align_up((size_t)OBB_HASH * 8, 256) +
+                                   pch_align_up((size_t)OBB_HASH * 4, 256) + pch_align_up((size_t)OBB_STACK * 16, 256) +
+                                   pch_align_up((size_t)OBB_MAXC * 4, 256) + pch_align_up((size_t)(OBB_MAXC / 32 + 1) * 4, 256) +
+                                   pch_align_up((size_t)OBB_MAXF * 12, 256);
+
+__host__ __device__ static inline ObbWs obb_ws(uint8_t* base) {
+    ObbWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t* p = base + off; off += (bytes + 255) / 256 * 256; return p; };
+    w.cand = (int32_t*)take((size_t)OBB_MAXC * 4);
+    w.faces = (int32_t*)take((size_t)OBB_MAXF * 12);
+    w.planes = (double*)take((size_t)OBB_MAXF * 32);
+    w.eset = (unsigned long long*)take((size_t)OBB_HASH * 8);
+    w.face_of = (int32_t*)take((size_t)OBB_HASH * 4);
+    w.stack = (int4*)take((size_t)OBB_STACK * 16);
+    w.verts = (int32_t*)take((size_t)OBB_MAXC * 4);
+    w.mark = (uint32_t*)take((size_t)(OBB_MAXC / 32 + 1) * 4);
+    w.twin = (int32_t*)take((size_t)OBB_MAXF * 12);
+    return w;
+}
+
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ D3 ld3(const float* __restrict__ P, int i) { return D3{(double)P[i * 3 + 0], (double)P[i * 3 + 1], (double)P[i * 3 + 2]}; }
+__device__ __forceinline__ D3 sub3(D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 cross3(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double dot3(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// block-wide "best index" reduction with a caller-supplied comparator better(i, j): true when j beats i.
+// -1 = no candidate.  All threads get the winner.
+template <class BETTER>
+__device__ __forceinline__ int block_best(int mine, BETTER better, int* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, mine, o);
+        // both lanes of a pair must agree on the winner: order the pair so the comparison is evaluated identically
+        const int lo = (lane & o) ? other : mine, hi = (lane & o) ? mine : other;
+        int win;
+        if (lo < 0) win = hi;
+        else if (hi < 0) win = lo;
+        else win = better(lo, hi) ? hi : lo;
+        mine = win;
+    }
+    __syncthreads();
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    int best = s_red[0];
+    for (int w = 1; w < OBB_WARPS; ++w) {
+        const int c = s_red[w];
+        if (best < 0) best = c;
+        else if (c >= 0 && better(best, c)) best = c;
+    }
+    __syncthreads();
+    return best;
+}
+
+struct WrapCtx {
+    const float* P;      // cluster rows
+    const int32_t* idx;  // candidate list (NULL = all rows 0..n)
+    int n;
+    double tol3;         // coplanarity threshold on 6*volume
+    double tol2;         // collinearity threshold on |cross|^2
+};
+__device__ __forceinline__ int cand_at(const WrapCtx& c, int k) { return c.idx ? c.idx[k] : k; }
+
+// The next face around the directed hull edge a->b: the point d with the largest rotation angle about the edge,
+// measured from the half-plane of the face that is already known (O = a vector from a into that half-plane; for the
+// very first edge a direction pointing out of the hull).  All points lie within half a turn of that half-plane, so
+// "j is further round than i" is the sign of the triple product (e, I, J): a total order, evaluated pairwise.
+// Coplanar ties: same half-plane -> the point farther from the edge line; opposite half-planes (angle 0 against half
+// a turn) -> the one on the far side from O.
+__device__ int wrap_edge(const WrapCtx& c, int a, int b, D3 O, int* s_red) {
+    const D3 A = ld3(c.P, a), B = ld3(c.P, b);
+    const D3 e = sub3(B, A);
+    const double e2 = dot3(e, e);
+    const D3 nO = cross3(e, O);
+    auto better = [&](int i, int j) -> bool {   // does j beat i?
+        const D3 I = sub3(ld3(c.P, i), A), J = sub3(ld3(c.P, j), A);
+        const D3 nI = cross3(e, I);
+        const double v = dot3(nI, J);                       // > 0: j is further round than i
+        if (v > c.tol3) return true;
+        if (v < -c.tol3) return false;
+        const D3 nJ = cross3(e, J);
+        if (dot3(nI, nJ) > 0.0) return dot3(nJ, nJ) > dot3(nI, nI);
+        return dot3(nJ, nO) < dot3(nI, nO);
+    };
+    int mine = -1;
+    for (int k = threadIdx.x; k < c.n; k += OBB_THREADS) {
+        const int q = cand_at(c, k);
+        if (q == a || q == b) continue;
+        const D3 Q = sub3(ld3(c.P, q), A);
+        const D3 nq = cross3(e, Q);
+        if (dot3(nq, nq) <= c.tol2 * e2) continue;          // on the edge line: cannot span a face with it
+        if (mine < 0 || better(mine, q)) mine = q;
+    }
+    return block_best(mine, better, s_red);
+}
+
+__device__ __forceinline__ uint32_t edge_slot(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 48) & (OBB_HASH - 1); }
+__device__ bool eset_has(const ObbWs& w, int a, int b) {
+    const unsigned long long key = (((unsigned long long)(uint32_t)a << 32) | (uint32_t)b) + 1ull;
+    uint32_t s = edge_slot(key);
+    for (int p = 0; p < OBB_HASH; ++p) {
+        const unsigned long long v = w.eset[s];
+        if (v == 0) return false;
+        if (v == key) return true;
+        s = (s + 1) & (OBB_HASH - 1);
+    }
+    return false;
+}
+__device__ void eset_add(const ObbWs& w, int a, int b, int face) {
+    const unsigned long long key = (((unsigned long long)(uint32_t)a << 32) | (uint32_t)b) + 1ull;
+    uint32_t s = edge_slot(key);
+    for (int p = 0; p < OBB_HASH; ++p) {
+        const unsigned long long v = w.eset[s];
+        if (v == 0 || v == key) { w.eset[s] = key; w.face_of[s] = face; return; }
+        s = (s + 1) & (OBB_HASH - 1);
+    }
+}
+__device__ int eset_face(const ObbWs& w, int a, int b) {
+    const unsigned long long key = (((unsigned long long)(uint32_t)a << 32) | (uint32_t)b) + 1ull;
+    uint32_t s = edge_slot(key);
+    for (int p = 0; p < OBB_HASH; ++p) {
+        const unsigned long long v = w.eset[s];
+        if (v == 0) return -1;
+        if (v == key) return w.face_of[s];
+        s = (s + 1) & (OBB_HASH - 1);
+    }
+    return -1;
+}
+
+// Gift wrapping of the candidate set.  Returns the number of faces (0 = degenerate input, -1 = capacity).
+__device__ int gift_wrap(const WrapCtx& c, const ObbWs& w, int max_faces, int* s_red, int* s_ctl) {
+    const int tid = threadIdx.x;
+    for (int k = tid; k < OBB_HASH; k += OBB_THREADS) w.eset[k] = 0ull;
+    // lowest point (x, then y, then z) and its neighbour on the silhouette of the xy projection
+    auto lower = [&](int i, int j) -> bool {
+        const float* a = c.P + (size_t)i * 3; const float* b = c.P + (size_t)j * 3;
+        if (b[0] != a[0]) return b[0] < a[0];
+        if (b[1] != a[1]) return b[1] < a[1];
+        if (b[2] != a[2]) return b[2] < a[2];
+        return j < i;
+    };
+    int mine = -1;
+    for (int k = tid; k < c.n; k += OBB_THREADS) {
+        const int q = cand_at(c, k);
+        if (mine < 0 || lower(mine, q)) mine = q;
+    }
+    const int p0 = block_best(mine, lower, s_red);
+    if (p0 < 0) return 0;
+    const D3 A = ld3(c.P, p0);
+    auto right_of = [&](int i, int j) -> bool {   // j beats i when it lies to the right of p0->i in the xy projection
+        const D3 I = sub3(ld3(c.P, i), A), J = sub3(ld3(c.P, j), A);
+        const double cr = I.x * J.y - I.y * J.x;
+        const double sc = sqrt((I.x * I.x + I.y * I.y) * (J.x * J.x + J.y * J.y));
+        if (cr < -1e-12 * sc) return true;
+        if (cr > 1e-12 * sc) return false;
+        return (J.x * J.x + J.y * J.y) > (I.x * I.x + I.y * I.y);   // same direction: the farther one
+    };
+    mine = -1;
+    for (int k = tid; k < c.n; k += OBB_THREADS) {
+        const int q = cand_at(c, k);
+        if (q == p0) continue;
+        const D3 Q = sub3(ld3(c.P, q), A);
+        if (Q.x * Q.x + Q.y * Q.y <= c.tol2) continue;      // straight above / below p0
+        if (mine < 0 || right_of(mine, q)) mine = q;
+    }
+    const int p1 = block_best(mine, right_of, s_red);
+    if (p1 < 0) return 0;
+    int n_faces = 0, sp = 0;
+    if (tid == 0) {
+        w.stack[0] = make_int4(p0, p1, -1, 0);     // -1: no face known yet; reference direction = out of the hull
+        s_ctl[0] = 1;
+    }
+    __syncthreads();
+    sp = 1;
+    while (sp > 0) {
+        // pop until an edge without a face turns up (thread 0 decides, everyone follows)
+        if (tid == 0) {
+            int a = -1, b = -1, op = -1, s = sp;
+            while (s > 0) {
+                const int4 e = w.stack[--s];
+                if (!eset_has(w, e.x, e.y)) { a = e.x; b = e.y; op = e.z; break; }
+            }
+            s_ctl[0] = s; s_ctl[1] = a; s_ctl[2] = b; s_ctl[3] = op;
+        }
+        __syncthreads();
+        sp = s_ctl[0];
+        const int a = s_ctl[1], b = s_ctl[2], op = s_ctl[3];
+        __syncthreads();
+        if (a < 0) break;
+        D3 O;
+        if (op >= 0) O = sub3(ld3(c.P, op), ld3(c.P, a));
+        else {
+            // first edge: every point is to the left of a->b in the xy projection, so the right-hand side is outside
+            const D3 e = sub3(ld3(c.P, b), ld3(c.P, a));
+            O = D3{e.y, -e.x, 0.0};
+        }
+        const int d = wrap_edge(c, a, b, O, s_red);
+        if (d < 0) {                       // everything collinear with this edge: degenerate
+            if (n_faces == 0) return 0;
+            if (tid == 0) eset_add(w, a, b, -1);
+            __syncthreads();
+            continue;
+        }
+        if (n_faces >= max_faces || sp + 3 >= OBB_STACK) return -1;
+        if (tid == 0) {
+            const int f = n_faces;
+            w.faces[f * 3 + 0] = a; w.faces[f * 3 + 1] = b; w.faces[f * 3 + 2] = d;
+            const D3 PA = ld3(c.P, a), PB = ld3(c.P, b), PD = ld3(c.P, d);
+            D3 n = cross3(sub3(PB, PA), sub3(PD, PA));
+            const double l = sqrt(dot3(n, n));
+            if (l > 0.0) { n.x /= l; n.y /= l; n.z /= l; }
+            w.planes[f * 4 + 0] = n.x; w.planes[f * 4 + 1] = n.y; w.planes[f * 4 + 2] = n.z;
+            w.planes[f * 4 + 3] = dot3(n, PA);
+            eset_add(w, a, b, f); eset_add(w, b, d, f); eset_add(w, d, a, f);
+            int s = sp;
+            if (!eset_has(w, b, a)) w.stack[s++] = make_int4(b, a, d, 0);
+            if (!eset_has(w, d, b)) w.stack[s++] = make_int4(d, b, a, 0);
+            if (!eset_has(w, a, d)) w.stack[s++] = make_int4(a, d, b, 0);
+            s_ctl[0] = s;
+        }
+        __syncthreads();
+        sp = s_ctl[0];
+        ++n_faces;
+        __syncthreads();
+    }
+    return n_faces;
+}
+
+struct ObbOut {   // mirrors pch_obb_result
+    double extents[3];
+    double center[3];
+    double rot[9];      // columns = box axes in world coordinates (box -> world rotation, row-major)
+    double volume;
+    int32_t n_faces, n_verts, n_candidates, status;
+};
+
+__global__ void __launch_bounds__(OBB_THREADS)
+k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, int n_clusters, uint8_t* __restrict__ ws_base,
+      size_t ws_stride, ObbOut* __restrict__ out) {
+    __shared__ int s_red[OBB_WARPS];
+    __shared__ int s_ctl[4];
+    __shared__ float s_dirmax[OBB_DIRS];
+    __shared__ int s_dirarg[OBB_DIRS];
+    __shared__ float4 s_plane[1024];
+    __shared__ double s_best[OBB_WARPS];
+    __shared__ int s_bestf[OBB_WARPS], s_beste[OBB_WARPS];
+    __shared__ int s_count;
+    const int k = blockIdx.x;
+    if (k >= n_clusters) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long r0 = ranges[2 * k];
+    const int n = (int)min((long long)INT_MAX / 4, ranges[2 * k + 1] - r0);
+    const float* P = points + r0 * 3;
+    ObbWs w = obb_ws(ws_base + (size_t)k * ws_stride);
+    ObbOut* o = out + k;
+    auto fail = [&](int status) {
+        if (tid == 0) { o->status = status; o->n_faces = 0; o->n_verts = 0; o->n_candidates = 0; o->volume = 0.0; }
+    };
+    if (n < 4) { fail(1); return; }
+
+    // ---- extent -> tolerances
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < n; i += OBB_THREADS)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = P[i * 3 + a]; mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v); }
+    __shared__ uint32_t s_mm[6];
+    if (tid < 6) s_mm[tid] = tid < 3 ? 0xffffffffu : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, pch_f32_to_ordered(mn[a]));
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, pch_f32_to_ordered(mx[a]));
+        if (lane == 0) { atomicMin(&s_mm[a], lo); atomicMax(&s_mm[3 + a], hi); }
+    }
+    __syncthreads();
+    const double L = fmax(fmax((double)pch_ordered_to_f32(s_mm[3]) - (double)pch_ordered_to_f32(s_mm[0]),
+                               (double)pch_ordered_to_f32(s_mm[4]) - (double)pch_ordered_to_f32(s_mm[1])),
+                          (double)pch_ordered_to_f32(s_mm[5]) - (double)pch_ordered_to_f32(s_mm[2]));
+    if (!(L > 0.0)) { fail(1); return; }
+    WrapCtx c;
+    c.P = P;
+    c.tol3 = 1e-11 * L * L * L;
+    c.tol2 = 1e-18 * L * L;
+
+    // ---- step 1: extreme points of OBB_DIRS directions (Fibonacci sphere), hull of those, interior cull
+    for (int d = tid; d < OBB_DIRS; d += OBB_THREADS) { s_dirmax[d] = -INFINITY; s_dirarg[d] = -1; }
+    __syncthreads();
+    for (int d0 = 0; d0 < OBB_DIRS; d0 += OBB_WARPS) {
+        const int d = d0 + warp;
+        const float zz = 1.0f - 2.0f * ((float)d + 0.5f) / (float)OBB_DIRS;
+        const float rr = sqrtf(fmaxf(0.f, 1.0f - zz * zz));
+        const float ph = 2.399963229728653f * (float)d;
+        const float dx = rr * cosf(ph), dy = rr * sinf(ph), dz = zz;
+        float best = -INFINITY;
+        int arg = -1;
+        for (int i = lane; i < n; i += 32) {
+            const float v = P[i * 3 + 0] * dx + P[i * 3 + 1] * dy + P[i * 3 + 2] * dz;
+            if (v > best) { best = v; arg = i; }
+        }
+#pragma unroll
+        for (int s = 16; s; s >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, s);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, s);
+            if (ob > best || (ob == best && oa >= 0 && (arg < 0 || oa < arg))) { best = ob; arg = oa; }
+        }
+        if (lane == 0) { s_dirmax[d] = best; s_dirarg[d] = arg; }
+    }
+    __syncthreads();
+    // S = distinct extreme points, in w.cand
+    if (tid == 0) {
+        int m = 0;
+        for (int d = 0; d < OBB_DIRS; ++d) {
+            const int a = s_dirarg[d];
+            bool dup = a < 0;
+            for (int j = 0; j < m && !dup; ++j) dup = w.cand[j] == a;
+            if (!dup) w.cand[m++] = a;
+        }
+        s_count = m;
+    }
+    __syncthreads();
+    int n_s = s_count;
+    c.idx = w.cand;
+    c.n = n_s;
+    int f1 = gift_wrap(c, w, 1024, s_red, s_ctl);
+    __syncthreads();
+    int n_c = n_s;
+    if (f1 > 0) {
+        // planes of H1 in shared memory (float32 with a margin), cull
+        const float margin = (float)(1e-4 * L) + 1e-4f;
+        for (int f = tid; f < f1; f += OBB_THREADS)
+            s_plane[f] = make_float4((float)w.planes[f * 4 + 0], (float)w.planes[f * 4 + 1], (float)w.planes[f * 4 + 2],
+                                     (float)w.planes[f * 4 + 3] - margin);
+        for (int i = tid; i < OBB_MAXC / 32 + 1; i += OBB_THREADS) w.mark[i] = 0u;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += OBB_THREADS) {
+            const int i = i0 + tid;
+            bool keep = false;
+            if (i < n) {
+                const float x = P[i * 3 + 0], y = P[i * 3 + 1], z = P[i * 3 + 2];
+                for (int f = 0; f < f1 && !keep; ++f) {
+                    const float4 pl = s_plane[f];
+                    keep = (pl.x * x + pl.y * y + pl.z * z) > pl.w;      // not clearly inside this face
+                }
+                if (keep)
+                    for (int j = 0; j < n_s && keep; ++j) keep = w.cand[j] != i;   // S is already in the list
+            }
+            // append kept points (order inside the list does not matter)
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_count, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                if (pos < OBB_MAXC) w.cand[pos] = i;
+            }
+        }
+        __syncthreads();
+        n_c = s_count;
+        if (n_c > OBB_MAXC) { fail(3); return; }
+    } else {
+        // S is degenerate (flat / thin cluster): wrap all points
+        c.idx = nullptr;
+        n_c = n;
+    }
+    __syncthreads();
+
+    // ---- step 2: hull of the candidates
+    c.n = n_c;
+    const int F = gift_wrap(c, w, OBB_MAXF, s_red, s_ctl);
+    __syncthreads();
+    if (F <= 0) { fail(F == 0 ? 2 : 3); return; }
+    // hull vertices
+    if (tid == 0) s_count = 0;
+    for (int i = tid; i < OBB_MAXC / 32 + 1; i += OBB_THREADS) w.mark[i] = 0u;
+    __syncthreads();
+    // vertex indices can be any row of the cluster (up to n): dedupe through the edge set instead of a bitmap:
+    // a vertex v is recorded by the face that owns a directed edge starting at v with the smallest slot: simpler,
+    // thread 0 walks the faces and keeps a small open-addressing set in w.stack (free now)
+    if (tid == 0) {
+        int m = 0;
+        int* set = (int*)w.stack;                    // OBB_STACK*4 ints, all free after the wrap
+        const int cap = 65536;                       // < OBB_STACK*4
+        for (int i = 0; i < cap; ++i) set[i] = -1;
+        for (int f = 0; f < F; ++f)
+            for (int j = 0; j < 3; ++j) {
+                const int v = w.faces[f * 3 + j];
+                uint32_t s = ((uint32_t)v * 2654435761u) >> 16;
+                bool found = false;
+                while (set[s] >= 0) { if (set[s] == v) { found = true; break; } s = (s + 1) & (cap - 1); }
+                if (!found) { set[s] = v; if (m < OBB_MAXC) w.verts[m] = v; ++m; }
+            }
+        s_count = m;
+    }
+    __syncthreads();
+    const int V = s_count;
+    if (V > OBB_MAXC) { fail(3); return; }
+
+    // ---- step 3: box search.  One warp per face normal.
+    for (int i = tid; i < 3 * F; i += OBB_THREADS) {
+        const int g = i / 3, j = i - 3 * g;
+        w.twin[i] = eset_face(w, w.faces[g * 3 + (j + 1) % 3], w.faces[g * 3 + j]);
+    }
+    __syncthreads();
+    double best_vol = INFINITY;
+    int best_f = -1, best_e = -1;
+    for (int f = warp; f < F; f += OBB_WARPS) {
+        const D3 nrm{w.planes[f * 4 + 0], w.planes[f * 4 + 1], w.planes[f * 4 + 2]};
+        if (!(dot3(nrm, nrm) > 0.5)) continue;                       // degenerate triangle
+        double lo = INFINITY, hi = -INFINITY;
+        for (int v = lane; v < V; v += 32) {
+            const double t = dot3(nrm, ld3(P, w.verts[v]));
+            lo = fmin(lo, t); hi = fmax(hi, t);
+        }
+#pragma unroll
+        for (int s = 16; s; s >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, s)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, s)); }
+        const double thick = hi - lo;
+        // silhouette edges: a directed edge of a face that looks along n (n.n_g >= 0) whose twin's face looks away.
+        // Lanes test 32 edges at a time; each hit is then evaluated by the whole warp.
+        for (int i0 = 0; i0 < 3 * F; i0 += 32) {
+            const int i = i0 + lane;
+            bool sil = false;
+            if (i < 3 * F) {
+                const int g = i / 3, tf = w.twin[i];
+                if (tf >= 0) {
+                    const double sg = nrm.x * w.planes[g * 4 + 0] + nrm.y * w.planes[g * 4 + 1] + nrm.z * w.planes[g * 4 + 2];
+                    const double st = nrm.x * w.planes[tf * 4 + 0] + nrm.y * w.planes[tf * 4 + 1] + nrm.z * w.planes[tf * 4 + 2];
+                    sil = sg >= 0.0 && st < 0.0;
+                }
+            }
+            uint32_t hits = __ballot_sync(0xffffffffu, sil);
+            while (hits) {
+                const int bit = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int ei = i0 + bit, g = ei / 3, j = ei - 3 * g;
+                const int a = w.faces[g * 3 + j], b = w.faces[g * 3 + (j + 1) % 3];
+                const D3 e = sub3(ld3(P, b), ld3(P, a));
+                const double en = dot3(e, nrm);
+                D3 u{e.x - en * nrm.x, e.y - en * nrm.y, e.z - en * nrm.z};
+                const double ul = sqrt(dot3(u, u));
+                if (!(ul > 1e-10)) continue;
+                u.x /= ul; u.y /= ul; u.z /= ul;
+                const D3 vv = cross3(nrm, u);
+                double ulo = INFINITY, uhi = -INFINITY, vlo = INFINITY, vhi = -INFINITY;
+                for (int v = lane; v < V; v += 32) {
+                    const D3 p = ld3(P, w.verts[v]);
+                    const double pu = dot3(u, p), pv = dot3(vv, p);
+                    ulo = fmin(ulo, pu); uhi = fmax(uhi, pu); vlo = fmin(vlo, pv); vhi = fmax(vhi, pv);
+                }
+#pragma unroll
+                for (int s = 16; s; s >>= 1) {
+                    ulo = fmin(ulo, __shfl_xor_sync(0xffffffffu, ulo, s)); uhi = fmax(uhi, __shfl_xor_sync(0xffffffffu, uhi, s));
+                    vlo = fmin(vlo, __shfl_xor_sync(0xffffffffu, vlo, s)); vhi = fmax(vhi, __shfl_xor_sync(0xffffffffu, vhi, s));
+                }
+                const double vol = (uhi - ulo) * (vhi - vlo) * thick;
+                if (vol < best_vol || (vol == best_vol && (f < best_f || (f == best_f && ei < best_e)))) {
+                    best_vol = vol; best_f = f; best_e = ei;
+                }
+            }
+        }
+    }
+    if (lane == 0) { s_best[warp] = best_vol; s_bestf[warp] = best_f; s_beste[warp] = best_e; }
+    __syncthreads();
+    if (warp == 0) {
+        double bv = INFINITY; int bf = -1, be = -1;
+        for (int q = 0; q < OBB_WARPS; ++q)
+            if (s_bestf[q] >= 0 && (s_best[q] < bv || (s_best[q] == bv && (s_bestf[q] < bf || (s_bestf[q] == bf && s_beste[q] < be))))) {
+                bv = s_best[q]; bf = s_bestf[q]; be = s_beste[q];
+            }
+        // no candidate frame, or a box without volume (all points in one plane: Qhull / trimesh raise for such input)
+        if (bf < 0 || !(bv > 1e-12 * L * L * L)) { if (lane == 0) { o->status = 2; o->n_faces = F; o->n_verts = V; o->n_candidates = n_c; o->volume = 0.0; } return; }
+        // rebuild the winning frame and write the result
+        const D3 nrm{w.planes[bf * 4 + 0], w.planes[bf * 4 + 1], w.planes[bf * 4 + 2]};
+        const int g = be / 3, j = be % 3;
+        const int a = w.faces[g * 3 + j], b = w.faces[g * 3 + (j + 1) % 3];
+        const D3 e = sub3(ld3(P, b), ld3(P, a));
+        const double en = dot3(e, nrm);
+        D3 u{e.x - en * nrm.x, e.y - en * nrm.y, e.z - en * nrm.z};
+        const double ul = sqrt(dot3(u, u));
+        u.x /= ul; u.y /= ul; u.z /= ul;
+        const D3 vv = cross3(nrm, u);
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int v = lane; v < V; v += 32) {
+            const D3 p = ld3(P, w.verts[v]);
+            const double t[3] = {dot3(u, p), dot3(vv, p), dot3(nrm, p)};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { lo[q] = fmin(lo[q], t[q]); hi[q] = fmax(hi[q], t[q]); }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int s = 16; s; s >>= 1) { lo[q] = fmin(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], s)); hi[q] = fmax(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], s)); }
+        if (lane == 0) {
+            // trimesh convention: extents = (rect long, rect short, along-normal); box axes = (long, short, normal)
+            double ex[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+            double ce[3] = {0.5 * (hi[0] + lo[0]), 0.5 * (hi[1] + lo[1]), 0.5 * (hi[2] + lo[2])};
+            D3 ax0 = u, ax1 = vv;
+            if (ex[0] < ex[1]) {      // rotate the rectangle by 90 degrees about the normal: (u, v) -> (v, -u)
+                const double t = ex[0]; ex[0] = ex[1]; ex[1] = t;
+                const double tc = ce[0]; ce[0] = ce[1]; ce[1] = -tc;
+                ax0 = vv; ax1 = D3{-u.x, -u.y, -u.z};
+            }
+            o->extents[0] = ex[0]; o->extents[1] = ex[1]; o->extents[2] = ex[2];
+            o->center[0] = ce[0] * ax0.x + ce[1] * ax1.x + ce[2] * nrm.x;
+            o->center[1] = ce[0] * ax0.y + ce[1] * ax1.y + ce[2] * nrm.y;
+            o->center[2] = ce[0] * ax0.z + ce[1] * ax1.z + ce[2] * nrm.z;
+            o->rot[0] = ax0.x; o->rot[1] = ax1.x; o->rot[2] = nrm.x;
+            o->rot[3] = ax0.y; o->rot[4] = ax1.y; o->rot[5] = nrm.y;
+            o->rot[6] = ax0.z; o->rot[7] = ax1.z; o->rot[8] = nrm.z;
+            o->volume = bv;
+            o->n_faces = F; o->n_verts = V; o->n_candidates = n_c; o->status = 0;
+        }
+    }
+}
+
+extern "C" size_t pch_obb_workspace_bytes(int32_t n_clusters) { return (size_t)(n_clusters > 0 ? n_clusters : 1) * OBB_WS_BYTES; }
+
+extern "C" int pch_obb_batch(const float* points_dev, const int64_t* ranges_dev, int32_t n_clusters, pch_obb_result* out_dev,
+                             void* workspace, size_t workspace_bytes, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    static_assert(sizeof(ObbOut) == sizeof(pch_obb_result), "pch_obb_result layout");
+    PCH_CHECK_ARG(n_clusters >= 0, "n_clusters must be >= 0");
+    if (n_clusters == 0) return PCH_OK;
+    PCH_CHECK_ARG(points_dev && ranges_dev && out_dev && workspace, "null pointer");
+    if (workspace_bytes < pch_obb_workspace_bytes(n_clusters)) {
+        pch_set_error("obb workspace too small: %zu < %zu", workspace_bytes, pch_obb_workspace_bytes(n_clusters));
+        return PCH_ERR_WORKSPACE;
+    }
+    PCH_LAUNCH(st, "k_obb", k_obb<<<(unsigned)n_clusters, OBB_THREADS, 0, st>>>(points_dev, (const long long*)ranges_dev, n_clusters,
+                                                                                   (uint8_t*)workspace, OBB_WS_BYTES, (ObbOut*)out_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}

@@ -605,6 +605,35 @@ def voxel_downsample_points(xyz: torch.Tensor, voxel_size: float, chunk_size: Op
     return VoxelResult(m, counts, mean[:m], plan={k: getattr(plan, k) for k, _ in VoxelPlan._fields_})
 
 
+class ObbResult(C.Structure):
+    _fields_ = [("extents", C.c_double * 3), ("center", C.c_double * 3), ("rotation", C.c_double * 9), ("volume", C.c_double),
+                ("n_faces", C.c_int32), ("n_vertices", C.c_int32), ("n_candidates", C.c_int32), ("status", C.c_int32)]
+
+
+OBB_DTYPE = np.dtype([("extents", "<f8", 3), ("center", "<f8", 3), ("rotation", "<f8", (3, 3)), ("volume", "<f8"),
+                      ("n_faces", "<i4"), ("n_vertices", "<i4"), ("n_candidates", "<i4"), ("status", "<i4")])
+assert OBB_DTYPE.itemsize == C.sizeof(ObbResult) == 144
+
+
+def obb_batch(rows: torch.Tensor, ranges: np.ndarray) -> np.ndarray:
+    """Minimum-volume oriented boxes of a batch of clusters on the device (pch_obb_batch): `rows` (L,3) float32,
+    `ranges` int64 (K,2) = first / end row of each cluster.  -> structured host array [K] (OBB_DTYPE)."""
+    _require_cuda()
+    assert rows.dtype == torch.float32 and rows.is_contiguous()
+    rg = np.ascontiguousarray(ranges, dtype=np.int64).reshape(-1, 2)
+    K = rg.shape[0]
+    if K == 0:
+        return np.zeros(0, dtype=OBB_DTYPE)
+    lib = _native.lib()
+    dev = rows.device
+    rg_dev = torch.from_numpy(rg).to(dev)
+    out = torch.empty(K * OBB_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    wsb = lib.pch_obb_workspace_bytes(K)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(lib.pch_obb_batch(rows.data_ptr(), rg_dev.data_ptr(), K, out.data_ptr(), ws.data_ptr(), wsb, _stream()), "pch_obb_batch")
+    return out.cpu().numpy().view(OBB_DTYPE).copy()
+
+
 def cluster_major_points(points: torch.Tensor, labels: torch.Tensor, counts: np.ndarray):
     """All `points[labels == k]` at once: ((L,3) float32 rows grouped by label in ascending label order, each
     group in original order; int64 offsets [K+1]).  L = number of labelled points."""

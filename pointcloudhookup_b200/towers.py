@@ -166,6 +166,21 @@ def run_stages(raw: torch.Tensor, eps: float = 8.0, min_points: int = 80, ground
 # ---------------------------------------------------------------------------------------------
 # host epilogue: O(#clusters)
 # ---------------------------------------------------------------------------------------------
+def canonical_box_axes(ax0, ax2):
+    """Sign convention of the device boxes: the long axis points into x >= 0 (first non-zero of x, y, z), the face
+    normal into z >= 0 (first non-zero of z, y, x), axis 1 completes a right-handed frame.  (The box itself does not
+    depend on the signs; the reference's north angle, read from the first column, does.)"""
+    def positive(v, order):
+        v = np.asarray(v, dtype=np.float64)
+        for k in order:
+            if abs(v[k]) > 1e-12:
+                return v if v[k] > 0 else -v
+        return v
+    a0 = positive(ax0, (0, 1, 2))
+    a2 = positive(ax2, (2, 1, 0))
+    return a0, np.cross(a2, a0), a2
+
+
 def north_angle_of(rotation: np.ndarray) -> float:
     x_axis = rotation[:, 0]
     h = np.array([x_axis[0], x_axis[1], 0])
@@ -304,14 +319,28 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
     towers, centres = [], []
     grouped = None   # cluster-major copy of the labelled points, built on the device on first use (O(G), not O(G*K))
 
-    def cluster_points(label):
+    def cluster_rows():
         nonlocal grouped
         if grouped is None:
             grouped = dv.cluster_major_points(stages.filtered, stages.labels, orig_counts)
-        rows, off = grouped
+        return grouped
+
+    def cluster_points(label):
+        rows, off = cluster_rows()
         if members is None:
             return rows[int(off[label]): int(off[label + 1])].cpu().numpy()
         return np.concatenate([rows[int(off[m]): int(off[m + 1])].cpu().numpy() for m in members[label]])
+
+    # box="obb": every cluster whose diameter could pass the size filter gets its oriented box ON THE DEVICE, all of
+    # them in one launch (one CTA per cluster, pch_obb.cu); nothing but the 144-byte results crosses PCIe
+    device_boxes = {}
+    if box == "obb" and K and members is None:
+        diag = np.linalg.norm((stats["max"][:K] - stats["min"][:K]).astype(np.float64), axis=1)
+        cand = [l for l in order if diag[l] > min_height and stats["count"][l] >= 4]
+        if cand:
+            rows, off = cluster_rows()
+            res = dv.obb_batch(rows, np.array([[off[l], off[l + 1]] for l in cand], dtype=np.int64))
+            device_boxes = {l: r for l, r in zip(cand, res)}
 
     for li, label in enumerate(order):
         try:
@@ -331,9 +360,19 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
                 diag = float(np.linalg.norm((st["max"] - st["min"]).astype(np.float64)))
                 if diag <= min_height:
                     continue
-                cp = cluster_points(label)
-                tr, ext = _obb.bounding_box_oriented(cp, ordered=(box == "obb_ordered"))
-                ctr, rot = tr[:3, 3], tr[:3, :3]
+                cp = None
+                r = device_boxes.get(label)
+                if r is not None and int(r["status"]) == 0:
+                    a0, a1, a2 = canonical_box_axes(r["rotation"][:, 0], r["rotation"][:, 2])
+                    rot = np.column_stack((a0, a1, a2))
+                    ext = np.array(r["extents"], dtype=np.float64)
+                    ctr = np.array(r["center"], dtype=np.float64)
+                else:
+                    # "obb_trimesh" / "obb_ordered" (trimesh's own thinned search, host Qhull) and the clusters the
+                    # device kernel turned away (degenerate: the host raises like trimesh does; capacity)
+                    cp = cluster_points(label)
+                    tr, ext = _obb.bounding_box_oriented(cp, ordered=(box == "obb_ordered"))
+                    ctr, rot = tr[:3, 3], tr[:3, :3]
                 height, width = ext[2], max(ext[0], ext[1])
             aspect = height / width
             if not (height > min_height and min_width < width < max_width and aspect > aspect_ratio_threshold):

@@ -134,7 +134,10 @@ def install_shims(geoid_grid=None):
 
         @property
         def bounding_box_oriented(self):
-            return _Box(*o_obb.bounding_box_oriented(self.vertices, ordered=False))
+            # trimesh's hull-face search without its 0.1 rad thinning in Qhull's facet order (which no other hull
+            # construction can reproduce): every face normal is a candidate.  oracle/obb.py explains.
+            t, ext, _ = o_obb.min_volume_box_all_faces(self.vertices)
+            return _Box(t, ext)
     trimesh.PointCloud = TPointCloud
 
     pyproj = types.ModuleType("pyproj")

@@ -231,3 +231,25 @@ def test_geoid_nodata_corners_are_reweighted_like_proj():
     assert np.isnan(geoid.geoid_height(grid2, [10.5], [101.5])[0])
     full = dict(grid, grid=np.array([[1, 2, 3], [3, 4, 5], [5, 6, 7]], dtype=np.float32))
     assert geoid.geoid_height(full, [10.5], [100.25])[0] == (0.375 * 1 + 0.125 * 2 + 0.375 * 3 + 0.125 * 4)
+
+
+def test_oracle_all_faces_box_is_never_larger_than_the_thinned_search():
+    """oracle.obb.min_volume_box_all_faces evaluates every hull-face normal; trimesh's thinned search (one normal per
+    0.1 rad bin, first in Qhull's facet order) can only pick among the same candidates."""
+    from oracle import obb
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        n = int(rng.integers(200, 4000))
+        p = (rng.uniform(-1, 1, (n, 3)) * rng.uniform(2, 25, 3)) @ q.T + rng.uniform(-50, 50, 3)
+        if trial % 2:
+            p = np.concatenate([p, rng.normal(0, 3, (n // 3, 3)) + p.mean(0)])
+        p = p.astype(np.float32)
+        t_all, ext_all, vol_all = obb.min_volume_box_all_faces(p)
+        t_tm, ext_tm = obb.bounding_box_oriented(p)
+        assert vol_all <= np.prod(ext_tm) * (1 + 1e-12)
+        assert abs(np.prod(ext_all) - vol_all) <= 1e-9 * vol_all
+        # the box contains every point
+        loc = (p.astype(np.float64) - t_all[:3, 3]) @ t_all[:3, :3]
+        assert np.all(np.abs(loc) <= ext_all / 2 + 1e-6)
+        assert abs(np.linalg.det(t_all[:3, :3]) - 1.0) < 1e-9

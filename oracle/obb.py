@@ -37,6 +37,21 @@ def _spherical_matrix_inv(theta, phi):
     return m
 
 
+def hull_face_normals(pts, hull):
+    """Outward unit normals of the hull triangles, computed from the triangle vertices in the ORIGINAL frame (what
+    trimesh's ``face_normals`` are).  ``hull.equations`` must not be used with the "QbB" option trimesh passes to
+    Qhull: QbB scales every axis of the input to a unit cube, and the equations are those of the scaled points."""
+    tri = pts[hull.simplices]
+    n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    ln = np.linalg.norm(n, axis=1)
+    ok = ln > 0
+    n = n[ok] / ln[ok][:, None]
+    inside = pts[hull.vertices].mean(axis=0)
+    flip = np.einsum("ij,ij->i", n, tri[ok][:, 0] - inside) < 0
+    n[flip] *= -1.0
+    return n
+
+
 def oriented_bounds_2d(points):
     hull = ConvexHull(points, qhull_options="QbB")
     hull_edges = hull.points[hull.simplices]
@@ -76,7 +91,7 @@ def oriented_bounds(points, angle_digits=1, ordered=False):
     pts = np.asarray(points, dtype=np.float64)
     hull = ConvexHull(pts, qhull_options="QbB Pp Qt")
     vertices = pts[hull.vertices]
-    normals = hull.equations[:, :3]
+    normals = hull_face_normals(pts, hull)
     hemi = _vector_hemisphere(normals)
     sph = np.column_stack((np.arctan2(hemi[:, 1], hemi[:, 0]), np.arccos(np.clip(hemi[:, 2], -1.0, 1.0))))
     hashed = np.round(sph * 10 ** angle_digits).astype(np.int64)
@@ -144,7 +159,7 @@ def min_volume_box_all_faces(points):
     pts = np.asarray(points, dtype=np.float64)
     hull = ConvexHull(pts, qhull_options="QbB Pp Qt")
     verts = pts[hull.vertices]
-    normals = hull.equations[:, :3]
+    normals = hull_face_normals(pts, hull)
     _, first = np.unique(np.round(normals, 9), axis=0, return_index=True)
     best = None
     for i in np.sort(first):

@@ -73,7 +73,14 @@ def oriented_bounds(points: np.ndarray, angle_digits: int = 1, ordered: bool = F
     pts = np.asarray(points, dtype=np.float64)
     hull = ConvexHull(pts, qhull_options="QbB Pp Qt")
     verts = pts[hull.vertices]
-    hemi = _fold_to_hemisphere(hull.equations[:, :3])
+    # face normals from the triangles in the original frame: with "QbB" Qhull's `equations` describe the points
+    # scaled to a unit cube (every axis by a different factor), not the input
+    tri = pts[hull.simplices]
+    fn = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    area2 = np.linalg.norm(fn, axis=1)
+    tri, fn = tri[area2 > 0], fn[area2 > 0] / area2[area2 > 0][:, None]
+    fn[np.einsum("ij,ij->i", fn, tri[:, 0] - verts.mean(axis=0)) < 0] *= -1.0
+    hemi = _fold_to_hemisphere(fn)
     angles = np.column_stack((np.arctan2(hemi[:, 1], hemi[:, 0]), np.arccos(np.clip(hemi[:, 2], -1.0, 1.0))))
     _, first = np.unique(np.round(angles * 10 ** angle_digits).astype(np.int64), axis=0, return_index=True)
     best_volume, best = np.inf, None

@@ -335,3 +335,39 @@ def test_grid_shape_caps_the_cell_table():
         dvm.grid_shape([0.0, 0.0], [1.0, 1.0], 0.0, 1000)
     # a long corridor is fine: 17.5 km x 5.5 km bounding box at 2 m cells for 78 M points
     assert dvm.grid_shape([0.0, 0.0], [5500.0, 17500.0], 2.0, 78_000_000) == (2751, 8751)
+
+
+def test_integration_stub_matches_the_abi():
+    """INTEGRATION.md §2 is executable documentation: every lib.pch_* call in the stub must pass as many arguments as
+    the ABI takes (round 1 shipped a call that was one short), and every argtypes list must equal _native's."""
+    import ast
+    import ctypes as C
+    import re
+    from pointcloudhookup_b200 import _native
+    text = open(os.path.join(ROOT, "INTEGRATION.md"), encoding="utf-8").read()
+    sec = text[text.index("## 2. Binding the C ABI directly"):text.index("## 3. Entry point")]
+    code = re.search(r"```python\n(.*?)```", sec, re.S).group(1)
+    tree = ast.parse(code)
+    calls, argtypes = {}, {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name) \
+                and node.func.value.id == "lib" and node.func.attr.startswith("pch_"):
+            calls.setdefault(node.func.attr, []).append(len(node.args))
+        if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Attribute) and node.targets[0].attr == "argtypes":
+            argtypes[node.targets[0].value.attr] = len(node.value.elts)
+    assert "pch_voxel_downsample_las" in calls and "pch_las_chunk_minmax" in calls
+    for name, counts in calls.items():
+        assert name in _native.SIGNATURES, name
+        for c in counts:
+            assert c == len(_native.SIGNATURES[name][1]), f"{name}: the stub passes {c} arguments, the ABI takes {len(_native.SIGNATURES[name][1])}"
+    for name, c in argtypes.items():
+        assert c == len(_native.SIGNATURES[name][1]), name
+    # every function the stub CALLS with pointers has argtypes set (else 64-bit pointers are truncated to c_int)
+    assert {"pch_voxel_downsample_las", "pch_las_chunk_minmax"} <= set(argtypes)
+    # the argtypes section runs against the real library
+    head = code[:code.index("def check")].replace('C.CDLL("pointcloudhookup_b200/libpch_b200.so")', f'C.CDLL({_native.LIB_PATH!r})')
+    head = head.replace("import ctypes as C, torch, numpy as np", "import ctypes as C")
+    ns = {}
+    exec(head, ns)
+    sig = _native.SIGNATURES["pch_voxel_downsample_las"][1]
+    assert [C.sizeof(t) for t in ns["lib"].pch_voxel_downsample_las.argtypes] == [C.sizeof(t) for t in sig]

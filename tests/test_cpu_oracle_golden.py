@@ -124,7 +124,9 @@ def test_oracle_obb_properties():
     local = (pts - tr[:3, 3]) @ tr[:3, :3]
     assert np.all(np.abs(local) <= ext / 2 + 1e-6)
     assert np.prod(ext) <= np.prod(np.ptp(pts, axis=0)) + 1e-9
-    assert np.allclose(sorted(ext), [6, 20, 40], rtol=0.04)
+    assert np.allclose(sorted(ext), [6, 20, 40], rtol=0.06)      # one normal per 0.1 rad bin: a few percent off the true box
+    _, ext_all, _ = obb.min_volume_box_all_faces(pts)
+    assert np.allclose(sorted(ext_all), [6, 20, 40], rtol=0.02) and np.prod(ext_all) <= np.prod(ext) * (1 + 1e-12)
 
 
 def test_oracle_match_towers_matches_reference_run():

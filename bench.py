@@ -528,12 +528,15 @@ def run_tiled(args):
     axis = pipeline.corridor_axis(synth.AZIMUTH_DEG)
 
     t0 = time.time()
-    pinned = []
-    for t in mine:
-        buf = torch.empty(n * 34, dtype=torch.uint8, pin_memory=True)
+    pinned = [torch.empty(n * 34, dtype=torch.uint8, pin_memory=True) for _ in mine]
+
+    def gen(i):
+        t = mine[i]
         synth.corridor_records(n, cfg["towers"], cfg["terrain"], cfg["seed"] * 100 + t,
-                               s_origin=t * cfg["towers"] * synth.SPAN, out=buf.numpy())
-        pinned.append(buf)
+                               s_origin=t * cfg["towers"] * synth.SPAN, out=pinned[i].numpy())
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(mine), (os.cpu_count() or 4) // max(1, world) // 2 or 1))) as ex:
+        list(ex.map(gen, range(len(mine))))         # workload generation only (numpy releases the GIL in its big loops)
     gen_s = time.time() - t0
     grid = None
     if cfg["geo"]:

@@ -174,6 +174,8 @@ int pch_voxel_downsample_las(const uint8_t* rec_dev, int64_t n, int32_t rec_len,
  * mismatches_dev[0] (int64) = number of a_dev[i] for which it does not (expected: 0).  Returns
  * PCH_ERR_INVALID for divisors the kernels themselves would route to the true divide. */
 int pch_selftest_fastdiv(const double* a_dev, int64_t n, double b, int64_t* mismatches_dev, pch_stream_t stream);
+/* the float32 twin (the cell index of the grid min-z kernels, `(p - min) / cell`) */
+int pch_selftest_fastdiv_f32(const float* a_dev, int64_t n, float b, int64_t* mismatches_dev, pch_stream_t stream);
 
 /* ---------------------------------------------------------------- tower extraction, stages A/B */
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "pch_voxel_index3_f64": (C.c_int, [_p, _i64, _i64, _f64, _p, _p, _p]),
     "pch_voxel_wide_words": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p]),
     "pch_selftest_fastdiv": (C.c_int, [_p, _i64, _f64, _p, _p]),
+    "pch_selftest_fastdiv_f32": (C.c_int, [_p, _i64, C.c_float, _p, _p]),
 }
 
 class ClusterStats(C.Structure):

@@ -769,14 +769,38 @@ extern "C" int pch_select_f32(const float* v, int64_t n, int64_t rank0, int64_t 
 struct GridTest {
     const uint32_t* cell_min;   // [nx*ny] order-preserving encoding of the float32 minima; NULL = no grid test
     float minx, miny, cell, hag;
+    float rcell;                // RN(1/cell) for the reciprocal division
+    int32_t fast;               // cell passed grid_recip_ok: (d / cell) may be evaluated as products + FMA corrections
     int32_t ny;
     long long n_cells;
 };
+// Correctly rounded float32 d / c from y = RN(1/c): the float32 twin of pch_div_by (Markstein: with a faithful
+// quotient, an exact FMA residual and the correctly rounded reciprocal, the last correction returns RN(d/c) unless
+// c's significand is all ones or something under/overflows).  Operands outside a comfortable range take the true
+// divide.  Checked against __fdiv_rn on the device by pch_selftest_fastdiv_f32.
+__device__ __forceinline__ float grid_div(float d, const GridTest& gt) {
+    const float m = fabsf(d);
+    if (!(gt.fast && m > 1e-30f && m < 1e30f)) return __fdiv_rn(d, gt.cell);
+    float q = __fmul_rn(d, gt.rcell);
+    float r = __fmaf_rn(-gt.cell, q, d);
+    q = __fmaf_rn(r, gt.rcell, q);
+    r = __fmaf_rn(-gt.cell, q, d);
+    return __fmaf_rn(r, gt.rcell, q);
+}
+static inline bool grid_recip_ok(float c) {
+    if (!(c == c) || c == 0.f) return false;
+    const float m = c < 0 ? -c : c;
+    if (!(m > 1e-15f && m < 1e15f)) return false;
+    uint32_t u;
+    memcpy(&u, &c, 4);
+    return (u & 0x7FFFFFu) != 0x7FFFFFu;
+}
 __device__ __forceinline__ long long grid_cell_of(float sx, float sy, const GridTest& gt) {
-    const long long ix = (long long)floorf(__fdiv_rn(__fsub_rn(sx, gt.minx), gt.cell));
-    const long long iy = (long long)floorf(__fdiv_rn(__fsub_rn(sy, gt.miny), gt.cell));
-    const long long cid = ix * gt.ny + iy;
-    return (ix < 0 || iy < 0 || iy >= gt.ny || cid >= gt.n_cells) ? -1 : cid;
+    const float qx = floorf(grid_div(__fsub_rn(sx, gt.minx), gt)), qy = floorf(grid_div(__fsub_rn(sy, gt.miny), gt));
+    // one range test on the floats (NaN fails it), then 32-bit conversions: the cell count fits 31 bits
+    if (!(qx >= 0.f && qy >= 0.f && qy < (float)gt.ny && qx < 2147483520.f)) return -1;
+    const long long cid = (long long)__float2int_rz(qx) * gt.ny + __float2int_rz(qy);
+    return cid >= gt.n_cells ? -1 : cid;
 }
 __device__ __forceinline__ bool grid_keep(float sx, float sy, float sz, const GridTest& gt) {
     const long long cid = grid_cell_of(sx, sy, gt);
@@ -1200,6 +1224,8 @@ static int grid_args(int64_t m, float cell, int32_t nx, int32_t ny, GridTest& gt
     PCH_CHECK_ARG((int64_t)nx * ny <= 2147483647ll, "grid of %d x %d cells does not fit 31 bits", nx, ny);
     gt.cell_min = cell_min;
     gt.minx = minx; gt.miny = miny; gt.cell = cell; gt.hag = hag;
+    gt.rcell = 1.0f / cell;
+    gt.fast = grid_recip_ok(cell) ? 1 : 0;
     gt.ny = ny;
     gt.n_cells = (long long)nx * ny;
     return PCH_OK;
@@ -1249,12 +1275,49 @@ extern "C" int pch_grid_min_ground(const float* xyz, int64_t m, float minx, floa
     return PCH_OK;
 }
 
-// componentwise float32 min/max of an (m,3) array -> out6 (minx,miny,minz,maxx,maxy,maxz)
-__global__ void k_minmax_f32(const float* __restrict__ xyz, int64_t m, uint32_t* __restrict__ out6) {
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+// self-test of the float32 reciprocal division used by the grid kernels: mismatches against __fdiv_rn
+__global__ void k_selftest_fastdiv_f32(const float* __restrict__ a, int64_t n, GridTest gt, unsigned long long* __restrict__ bad) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < m; i += stride) {
+    unsigned long long mine = 0;
+    for (; i < n; i += stride) mine += __float_as_uint(grid_div(a[i], gt)) != __float_as_uint(__fdiv_rn(a[i], gt.cell));
+    if (mine) atomicAdd(bad, mine);
+}
+extern "C" int pch_selftest_fastdiv_f32(const float* a_dev, int64_t n, float b, int64_t* mismatches_dev, pch_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PCH_CHECK_ARG(n >= 0 && mismatches_dev && (n == 0 || a_dev), "bad arguments");
+    PCH_CHECK_ARG(grid_recip_ok(b), "divisor %g is not eligible for the reciprocal path", (double)b);
+    PCH_CUDA(cudaMemsetAsync(mismatches_dev, 0, sizeof(int64_t), st));
+    if (n == 0) return PCH_OK;
+    GridTest gt;
+    memset(&gt, 0, sizeof(gt));
+    gt.cell = b; gt.rcell = 1.0f / b; gt.fast = 1;
+    PCH_LAUNCH(st, "k_selftest_fastdiv_f32", k_selftest_fastdiv_f32<<<grid_for(n, 256, 8), 256, 0, st>>>(a_dev, n, gt, (unsigned long long*)mismatches_dev));
+    PCH_LAUNCH_CHECK();
+    return PCH_OK;
+}
+
+// componentwise float32 min/max of an (m,3) array -> out6 (minx,miny,minz,maxx,maxy,maxz).  The flat array is read
+// with 16-byte loads (three float4 = four rows per thread and step), so the pass runs at the streaming rate.
+__global__ void k_minmax_f32(const float* __restrict__ xyz, int64_t m, uint32_t* __restrict__ out6) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int64_t n_quads = m / 4;
+    const bool aligned = (reinterpret_cast<uintptr_t>(xyz) & 15) == 0;
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (aligned) {
+        const float4* src = reinterpret_cast<const float4*>(xyz);
+        for (; q < n_quads; q += stride) {
+            const float4 a = __ldg(src + q * 3), b = __ldg(src + q * 3 + 1), c = __ldg(src + q * 3 + 2);
+            const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int k = 0; k < 12; ++k) { mn[k % 3] = fminf(mn[k % 3], v[k]); mx[k % 3] = fmaxf(mx[k % 3], v[k]); }
+        }
+        q = n_quads * 4 + (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+    } else {
+        q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    }
+    for (int64_t i = q; i < m; i += stride) {      // the tail (or everything, for an unaligned base)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float v = xyz[i * 3 + c];

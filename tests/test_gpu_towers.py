@@ -232,3 +232,28 @@ def test_ground_filter_variants_of_the_reference_scripts(cuda_device):
         assert base == b and used == off, (pct, float(base), float(b))
         assert np.array_equal(mask.cpu().numpy().astype(bool), keep), pct
         assert np.array_equal(filt.cpu().numpy(), pts[keep]), pct
+
+
+def test_grid_float32_reciprocal_division_equals_ieee_divide(cuda_device):
+    """The grid min-z kernels evaluate (p - min) / cell as a reciprocal product + FMA corrections (float32); on the
+    device that must equal __fdiv_rn bit for bit for shifted coordinates, random mantissas and the values the range
+    guard turns away."""
+    import ctypes
+    import torch
+    from pointcloudhookup_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(77)
+    n = 4_000_000
+    cases = [rng.uniform(0, 2e4, n).astype(np.float32),
+             (rng.uniform(437000, 438000, n).astype(np.float32) - np.float32(437000.0)),
+             (rng.integers(0, 2**24, n) * np.float32(0.5)).astype(np.float32),
+             np.ldexp(rng.uniform(1, 2, n), rng.integers(-30, 30, n)).astype(np.float32) * rng.choice([-1.0, 1.0], n).astype(np.float32),
+             np.array([0.0, -0.0, 1e-45, 1e-39, -1e-32, 1e32, np.inf, -np.inf, np.nan] * 1000, dtype=np.float32)]
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    for b in [2.0, 0.5, 1.0, 3.0, 0.1, 0.25, 1.5, 0.3, 2.5, 5.0, 10.0, 0.7, 1 / 3, 7.3]:
+        for a in cases:
+            d = torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+            rc = lib.pch_selftest_fastdiv_f32(d.data_ptr(), d.numel(), ctypes.c_float(b), bad.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, lib.pch_last_error()
+            assert int(bad.item()) == 0, (b, a[:4])

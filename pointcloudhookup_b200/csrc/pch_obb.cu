@@ -348,18 +348,32 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         if (lane == 0) { s_dirmax[d] = best; s_dirarg[d] = arg; }
     }
     __syncthreads();
-    // S = distinct extreme points, in w.cand
-    if (tid == 0) {
-        int m = 0;
-        for (int d = 0; d < OBB_DIRS; ++d) {
-            const int a = s_dirarg[d];
-            bool dup = a < 0;
-            for (int j = 0; j < m && !dup; ++j) dup = w.cand[j] == a;
-            if (!dup) w.cand[m++] = a;
+    // S = distinct extreme points, in w.cand (direction order): every direction looks for an earlier direction
+    // with the same extreme point in shared memory, the survivors are packed with ballots
+    {
+        __shared__ int s_wn[OBB_WARPS + 1];
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for (int d0 = 0; d0 < OBB_DIRS; d0 += OBB_THREADS) {
+            const int d = d0 + tid;
+            bool keep = false;
+            int a = -1;
+            if (d < OBB_DIRS) {
+                a = s_dirarg[d];
+                keep = a >= 0;
+                for (int j = 0; j < d && keep; ++j) keep = s_dirarg[j] != a;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_wn[warp] = __popc(bal);
+            __syncthreads();
+            int base = s_count;
+            for (int q = 0; q < warp; ++q) base += s_wn[q];
+            if (keep) w.cand[base + __popc(bal & ((1u << lane) - 1u))] = a;
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int q = 0; q < OBB_WARPS; ++q) t += s_wn[q]; s_count += t; }
+            __syncthreads();
         }
-        s_count = m;
     }
-    __syncthreads();
     int n_s = s_count;
     c.idx = w.cand;
     c.n = n_s;

@@ -469,7 +469,7 @@ def f32_minmax_dev(xyz: torch.Tensor) -> torch.Tensor:
 
 
 def compact_points_grid(raw: torch.Tensor, centroid: torch.Tensor, mn_xy, nx: int, ny: int, cell: float, hag: float,
-                        want_mask: bool = False):
+                        want_mask: bool = False, sync: bool = True):
     """Grid min-z filter of the RAW cloud with the centroid shift applied on the fly: (filtered (G,3) float32 =
     (raw - centroid)[keep], G, mask or None).  Two kernels: the cell minima, then the compaction whose keep flag is
     the height-above-ground test."""
@@ -490,6 +490,8 @@ def compact_points_grid(raw: torch.Tensor, centroid: torch.Tensor, mn_xy, nx: in
     check(lib.pch_compact_points_grid(raw.data_ptr(), m, centroid.data_ptr(), float(mn_xy[0]), float(mn_xy[1]), c, nx, ny,
                                       float(np.float32(hag)), cell_min.data_ptr(), out.data_ptr(), None, _ptr(mask),
                                       cnt.data_ptr(), ws.data_ptr(), wsb, st), "pch_compact_points_grid")
+    if not sync:
+        return out, cnt, mask            # the caller reads the count (with others) and slices out[:count]
     g = int(cnt.item())
     return out[:g], g, mask
 

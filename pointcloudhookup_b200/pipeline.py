@@ -348,31 +348,55 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
     from . import tiles as tl
     dv._require_cuda()
     device = tiles[0].device if tiles else torch.device("cuda", torch.cuda.current_device())
-    # common frame: the centroid of rank 0's first tile
-    first = None
-    origin_dev = None
-    cands, n_vox, n_pts = [], 0, 0
-    if comm.rank == 0 and tiles:
-        first = tile_candidates(tiles[0], None, voxel_size, chunk_size, ground, cell, hag)
-        origin_dev = first[2]
-    mine = origin_dev.cpu().numpy().astype(np.float32) if origin_dev is not None else np.zeros(0, np.float32)
-    got = comm.all_gather_np(mine)
-    if len(got[0]) != 3:
-        raise ValueError("rank 0 holds no points: no common frame")
-    origin = got[0].astype(np.float32)
-    origin_dev = torch.from_numpy(origin.copy()).to(device)
-    for i, dl in enumerate(tiles):
-        if i == 0 and first is not None:
-            c, vres = first[0], first[1]
-        else:
-            c, vres, _ = tile_candidates(dl, origin_dev, voxel_size, chunk_size, ground, cell, hag)
+    if ground not in ("percentile", "grid"):
+        raise ValueError(f"unknown ground mode {ground!r}")
+    # phase A — every rank, every tile, no dependency between ranks: voxel stage, and what defines the tile's frame
+    stage, n_vox, n_pts = [], 0, 0
+    for dl in tiles:
+        vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
         if per_tile is not None:
             per_tile(dl, vres)
-        cands.append(c)
         n_vox += vres.count
         n_pts += dl.n
-    P_own = torch.cat(cands).contiguous() if len(cands) > 1 else (cands[0] if cands else
-                                                                  torch.zeros((0, 3), dtype=torch.float32, device=device))
+        if vres.count == 0:
+            continue
+        raw = vres.f32
+        if ground == "grid":
+            stage.append({"raw": raw, "mm": dv.f32_minmax_dev(raw)})           # bounding box: no read-back yet
+        else:
+            _, cen_dev, _, _, mask, _ = tw._ground_filter_percentile(raw, want_mask=True, zcol=vres.z32)
+            stage.append({"raw": raw, "mask": mask, "cen": cen_dev})
+    # the common frame: the centre of the bounding box (grid) / the centroid (percentile) of rank 0's first tile
+    mm_all = None
+    if stage and ground == "grid":
+        mm_all = torch.stack([t["mm"] for t in stage]).cpu().numpy()           # ONE read-back for all tiles of this rank
+        mine = ((mm_all[0, :3] + mm_all[0, 3:]) * np.float32(0.5)).astype(np.float32)
+    elif stage:
+        mine = stage[0]["cen"].cpu().numpy().astype(np.float32)
+    else:
+        mine = np.full(3, np.nan, dtype=np.float32)
+    origin = comm.all_gather_fixed(mine)[0].astype(np.float32)
+    if not np.all(np.isfinite(origin)):
+        raise ValueError("rank 0 holds no points: no common frame")
+    origin_dev = torch.from_numpy(origin.copy()).to(device)
+    # phase B — ground removal relative to the common frame; the counts of all tiles are read back together
+    outs, cnts = [], []
+    for i, t in enumerate(stage):
+        raw = t["raw"]
+        if ground == "grid":
+            mn, mx = mm_all[i, 0:2] - origin[:2], mm_all[i, 3:5] - origin[:2]   # float32, like the kernels' shift
+            nx, ny = dv.grid_shape(mn, mx, cell, raw.shape[0])
+            out, cnt, _ = dv.compact_points_grid(raw, origin_dev, mn, nx, ny, cell, hag, sync=False)
+            outs.append(out)
+            cnts.append(cnt)
+        else:
+            cand, g, _, _ = dv.compact_points(raw, None, 0.0, origin_dev, keep_mask=t["mask"])
+            outs.append(cand)
+    if cnts:
+        got = torch.cat(cnts).cpu().numpy()
+        outs = [o[: int(c)] for o, c in zip(outs, got)]
+    P_own = torch.cat(outs).contiguous() if len(outs) > 1 else (outs[0].contiguous() if outs else
+                                                                torch.zeros((0, 3), dtype=torch.float32, device=device))
     res = tl.tile_dbscan(P_own, axis, eps, min_points, comm, clusterer)
     stages = tw.TowerStages(None, origin, np.float32("nan"), 3.0, P_own, res.labels, res.n_clusters, res.stats)
     towers = tw.select_towers(stages, box="aabb", want_points=False, **tower_kw)

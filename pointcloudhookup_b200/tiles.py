@@ -52,13 +52,17 @@ class Comm:
         """Every rank's 1-D array (sizes may differ), in rank order, on every rank."""
         raise NotImplementedError
 
+    def all_gather_fixed(self, arr: np.ndarray) -> List[np.ndarray]:
+        """The same for arrays whose size is the same on every rank (one collective instead of two)."""
+        return self.all_gather_np(arr)
+
     def neighbour_exchange(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor]):
         """Send (k,4) float32 payloads to rank-1 / rank+1, receive theirs: (from_left, from_right)."""
         raise NotImplementedError
 
     def all_reduce_stats(self, stats: np.ndarray) -> np.ndarray:
         out = stats.copy()
-        parts = self.all_gather_np(stats.view(np.uint8).reshape(-1))
+        parts = self.all_gather_fixed(stats.view(np.uint8).reshape(-1))
         rows = [p.view(STATS_DTYPE) for p in parts]
         out["count"] = np.sum([p["count"] for p in rows], axis=0)
         out["sum"] = np.sum([p["sum"] for p in rows], axis=0)          # rank order: the same bits on every rank
@@ -108,6 +112,15 @@ class TorchComm(Comm):
         got = self._gather_fixed(torch.from_numpy(pad).to(self.device)).cpu().numpy()
         self.bytes_gather += int(sizes.sum())
         return [got[r, : int(sizes[r])].copy().view(a.dtype) for r in range(self.world)]
+
+    def all_gather_fixed(self, arr):
+        a = np.ascontiguousarray(arr)
+        raw = a.view(np.uint8).reshape(-1)
+        if raw.size == 0:
+            return [a.copy() for _ in range(self.world)]
+        got = self._gather_fixed(torch.from_numpy(raw.copy()).to(self.device)).cpu().numpy()
+        self.bytes_gather += int(raw.size) * self.world
+        return [got[r].copy().view(a.dtype) for r in range(self.world)]
 
     def neighbour_exchange(self, to_left, to_right):
         dist = self.dist
@@ -191,16 +204,32 @@ class DeviceClusterer:
         lo, hi = mm.cpu().numpy()
         return float(lo), float(hi)
 
-    def band_indices(self, P: torch.Tensor, axis, lo: float, hi: float) -> torch.Tensor:
-        """Indices (int32, ascending) of the points with lo <= s <= hi."""
+    def band_pair(self, P: torch.Tensor, axis, hi_left: Optional[float], lo_right: Optional[float]):
+        """(indices with s <= hi_left, indices with s >= lo_right), int32 ascending; None = no neighbour on that side.
+        Both selections are launched before the ONE device->host read of their two counts."""
         n = P.shape[0]
-        if n == 0:
-            return torch.zeros(0, dtype=torch.int32, device=P.device)
-        mask = torch.empty(n + 16, dtype=torch.uint8, device=P.device)[:n]
-        self.check(self.lib.pch_axis_band_mask(P.data_ptr(), n, float(axis[0]), float(axis[1]), float(lo), float(hi), None,
-                                               mask.data_ptr(), self._stream()), "pch_axis_band_mask")
-        _, k, src, _ = self.dv.compact_points(P, None, 0.0, None, keep_mask=mask, want_src=True)
-        return src
+        dev = P.device
+        empty = torch.zeros(0, dtype=torch.int32, device=dev)
+        if n == 0 or (hi_left is None and lo_right is None):
+            return empty, empty
+        st = self._stream()
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        outs = [None, None]
+        for k, (lo, hi) in enumerate(((-math.inf, hi_left), (lo_right, math.inf))):
+            if (k == 0 and hi_left is None) or (k == 1 and lo_right is None):
+                continue
+            mask = torch.empty(n + 16, dtype=torch.uint8, device=dev)[:n]
+            self.check(self.lib.pch_axis_band_mask(P.data_ptr(), n, float(axis[0]), float(axis[1]), float(lo), float(hi), None,
+                                                   mask.data_ptr(), st), "pch_axis_band_mask")
+            src = torch.empty(n, dtype=torch.int32, device=dev)
+            wsb = self.lib.pch_compact_workspace_bytes(n)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            self.check(self.lib.pch_compact_points(P.data_ptr(), None, mask.data_ptr(), n, None, 0.0, None, src.data_ptr(), None,
+                                                   cnt[k:].data_ptr(), ws.data_ptr(), wsb, st), "pch_compact_points")
+            outs[k] = src
+        c = cnt.cpu().numpy()
+        return (outs[0][: int(c[0])] if outs[0] is not None else empty,
+                outs[1][: int(c[1])] if outs[1] is not None else empty)
 
     def cores(self, P: torch.Tensor, eps: float, min_samples: int):
         G = P.shape[0]
@@ -220,14 +249,18 @@ class DeviceClusterer:
         self._ws = (P, G, float(eps), int(min_samples), cap, ws, wsb)
         return labels, k
 
-    def min_index(self, labels: torch.Tensor, lo: int, hi: int, base: int, k: int) -> np.ndarray:
-        table = torch.full((max(k, 1),), I64_MAX, dtype=torch.int64, device=labels.device)
-        self.check(self.lib.pch_label_min_index(labels.data_ptr(), lo, hi, int(base), k, table.data_ptr(), self._stream()),
-                   "pch_label_min_index")
-        return table[:k].cpu().numpy()
-
-    def labels_at(self, labels: torch.Tensor, idx: torch.Tensor) -> np.ndarray:
-        return labels[idx.long()].cpu().numpy() if idx.numel() else np.zeros(0, dtype=np.int32)
+    def shared_report(self, labels: torch.Tensor, pos: torch.Tensor, extra: torch.Tensor, lo: int, hi: int, base: int, k: int):
+        """ONE device->host read for everything the exchange needs from phase 1: the labels at the local positions
+        `pos` (int32), the int32 payload `extra` (the senders' indices of the halo I received), and the table of the
+        smallest OWN core index (base + i - lo over i in [lo, hi)) per local cluster."""
+        dev = labels.device
+        table = torch.full((max(k, 1),), I64_MAX, dtype=torch.int64, device=dev)
+        if k and hi > lo:
+            self.check(self.lib.pch_label_min_index(labels.data_ptr(), lo, hi, int(base), k, table.data_ptr(), self._stream()),
+                       "pch_label_min_index")
+        lab = labels[pos.long()].to(torch.int64) if pos.numel() else torch.zeros(0, dtype=torch.int64, device=dev)
+        both = torch.cat([table[:k], lab, extra.to(torch.int64)]).cpu().numpy()
+        return both[k: k + pos.numel()].astype(np.int32), both[k + pos.numel():], both[:k].copy()
 
     def finish(self, label_map: np.ndarray, n_global: int, own_lo: int, own_hi: int):
         P, G, eps, min_samples, cap, ws, wsb = self._ws
@@ -321,7 +354,7 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
     ax = ax / np.linalg.norm(ax)
     G = int(P_own.shape[0])
     smin, smax = clu.extent(P_own, ax)
-    meta = comm.all_gather_np(np.array([G, smin, smax], dtype=np.float64))
+    meta = comm.all_gather_fixed(np.array([G, smin, smax], dtype=np.float64))
     counts = [int(m[0]) for m in meta]
     lo_s = [float(m[1]) for m in meta]
     hi_s = [float(m[2]) for m in meta]
@@ -332,9 +365,9 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
             if counts[i] and counts[j] and not (hi_s[i] + e2 < lo_s[j] or hi_s[j] + e2 < lo_s[i]):
                 raise ValueError(f"tiles {i} and {j} are closer than 2*eps along the axis: only neighbouring tiles may touch")
     dev = P_own.device
-    empty_idx = torch.zeros(0, dtype=torch.int32, device=dev)
-    idx_l = clu.band_indices(P_own, ax, -math.inf, hi_s[r - 1] + e2) if (r > 0 and counts[r - 1] and G) else empty_idx
-    idx_r = clu.band_indices(P_own, ax, lo_s[r + 1] - e2, math.inf) if (r + 1 < W and counts[r + 1] and G) else empty_idx
+    left = r > 0 and counts[r - 1] > 0 and G > 0
+    right = r + 1 < W and counts[r + 1] > 0 and G > 0
+    idx_l, idx_r = clu.band_pair(P_own, ax, hi_s[r - 1] + e2 if left else None, lo_s[r + 1] - e2 if right else None)
 
     def payload(idx):
         if idx.numel() == 0:
@@ -343,36 +376,42 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
         return torch.cat([rows, idx.to(torch.int32).view(torch.float32).unsqueeze(1)], dim=1).contiguous()
 
     from_left, from_right = comm.neighbour_exchange(payload(idx_l), payload(idx_r))
-    parts, gid_halo = [], []
     nL = 0 if from_left is None else int(from_left.shape[0])
     nR = 0 if from_right is None else int(from_right.shape[0])
+    parts, sender_idx = [], []
     if nL:
         fl = from_left.to(dev)
         parts.append(fl[:, :3])
-        gid_halo.append(offs[r - 1] + fl[:, 3].contiguous().view(torch.int32).cpu().numpy().astype(np.int64))
+        sender_idx.append(fl[:, 3].contiguous().view(torch.int32))
     parts.append(P_own)
     if nR:
         fr = from_right.to(dev)
         parts.append(fr[:, :3])
-        gid_halo.append(offs[r + 1] + fr[:, 3].contiguous().view(torch.int32).cpu().numpy().astype(np.int64))
+        sender_idx.append(fr[:, 3].contiguous().view(torch.int32))
     n_local = nL + G + nR
+    empty_i = torch.zeros(0, dtype=torch.int32, device=dev)
     if n_local == 0:
-        labels_core, k_local = torch.zeros(0, dtype=torch.int32, device=dev), 0
+        ent, table = np.zeros((0, 2), np.int64), np.zeros(0, np.int64)
     else:
         P_local = torch.cat(parts).contiguous() if len(parts) > 1 else P_own.contiguous()
         labels_core, k_local = clu.cores(P_local, eps, min_samples)
-    # shared core points: the halo I received, and the own points I sent
-    halo_pos = torch.cat([torch.arange(0, nL, device=dev), torch.arange(nL + G, n_local, device=dev)]).to(torch.int32)
-    sent_idx = torch.unique(torch.cat([idx_l, idx_r]).long()).to(torch.int32) if (idx_l.numel() + idx_r.numel()) else empty_idx
-    lab_halo = clu.labels_at(labels_core, halo_pos) if n_local else np.zeros(0, np.int32)
-    lab_sent = clu.labels_at(labels_core, (sent_idx.long() + nL).to(torch.int32)) if n_local else np.zeros(0, np.int32)
-    gid_h = np.concatenate(gid_halo) if gid_halo else np.zeros(0, np.int64)
-    gid_s = offs[r] + sent_idx.cpu().numpy().astype(np.int64)
-    ent = np.concatenate([np.stack([gid_h, lab_halo.astype(np.int64)], axis=1)[lab_halo >= 0],
-                          np.stack([gid_s, lab_sent.astype(np.int64)], axis=1)[lab_sent >= 0]]).astype(np.int64)
-    table = clu.min_index(labels_core, nL, nL + G, int(offs[r]), k_local) if (n_local and k_local) else np.zeros(0, np.int64)
-    entries = [e.reshape(-1, 2) for e in comm.all_gather_np(ent.reshape(-1))]
-    tables = comm.all_gather_np(table)
+        # shared core points: the halo I received, and the own points I sent
+        sent_idx = torch.unique(torch.cat([idx_l, idx_r]).long()).to(torch.int32) if (idx_l.numel() + idx_r.numel()) else empty_i
+        pos = torch.cat([torch.arange(0, nL, device=dev, dtype=torch.int32),
+                         torch.arange(nL + G, n_local, device=dev, dtype=torch.int32), sent_idx + nL])
+        extra = torch.cat(sender_idx + [sent_idx]) if (sender_idx or sent_idx.numel()) else empty_i
+        lab_at, extra_h, table = clu.shared_report(labels_core, pos, extra, nL, nL + G, int(offs[r]), k_local)
+        gid = extra_h.astype(np.int64)
+        gid[:nL] += offs[r - 1] if nL else 0
+        gid[nL: nL + nR] += offs[r + 1] if nR else 0
+        gid[nL + nR:] += offs[r]
+        ok = lab_at >= 0
+        ent = np.stack([gid[ok], lab_at[ok].astype(np.int64)], axis=1)
+    # one variable-size all-gather carries both the shared-point entries and the per-cluster tables
+    packed = np.concatenate([[len(ent), len(table)], ent.reshape(-1), table]).astype(np.int64)
+    got = comm.all_gather_np(packed)
+    entries = [g[2: 2 + 2 * int(g[0])].reshape(-1, 2) for g in got]
+    tables = [g[2 + 2 * int(g[0]): 2 + 2 * int(g[0]) + int(g[1])] for g in got]
     maps, n_global = merge_local_clusters(entries, tables)
     if n_local:
         labels_all, stats_own = clu.finish(maps[r], n_global, nL, nL + G)

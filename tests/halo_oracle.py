@@ -21,10 +21,13 @@ class OracleClusterer:
         s = p[:, 0] * axis[0] + p[:, 1] * axis[1]
         return float(s.min()), float(s.max())
 
-    def band_indices(self, P, axis, lo, hi):
+    def band_pair(self, P, axis, hi_left, lo_right):
         p = P.numpy().astype(np.float64)
         s = p[:, 0] * axis[0] + p[:, 1] * axis[1]
-        return torch.from_numpy(np.nonzero((s >= lo) & (s <= hi))[0].astype(np.int32))
+        sel = lambda m: torch.from_numpy(np.nonzero(m)[0].astype(np.int32))
+        empty = torch.zeros(0, dtype=torch.int32)
+        return (sel(s <= hi_left) if hi_left is not None and len(p) else empty,
+                sel(s >= lo_right) if lo_right is not None and len(p) else empty)
 
     def cores(self, P, eps, min_samples):
         pts = P.numpy()
@@ -35,15 +38,14 @@ class OracleClusterer:
         self._state = (pts, float(eps), core, lab)
         return torch.from_numpy(lab), int(db.labels_.max()) + 1 if len(pts) else 0
 
-    def min_index(self, labels, lo, hi, base, k):
+    def shared_report(self, labels, pos, extra, lo, hi, base, k):
         t = np.full(k, I64_MAX, dtype=np.int64)
-        lab = labels.numpy()[lo:hi]
-        ok = lab >= 0
-        np.minimum.at(t, lab[ok], base + np.nonzero(ok)[0].astype(np.int64))
-        return t
-
-    def labels_at(self, labels, idx):
-        return labels.numpy()[idx.numpy().astype(np.int64)] if idx.numel() else np.zeros(0, np.int32)
+        lab = labels.numpy()
+        own = lab[lo:hi]
+        ok = own >= 0
+        np.minimum.at(t, own[ok], base + np.nonzero(ok)[0].astype(np.int64))
+        at = lab[pos.numpy().astype(np.int64)] if pos.numel() else np.zeros(0, np.int32)
+        return at.astype(np.int32), extra.numpy().astype(np.int64), t
 
     def finish(self, label_map, n_global, own_lo, own_hi):
         pts, eps, core, lab = self._state

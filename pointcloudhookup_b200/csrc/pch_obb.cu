@@ -412,7 +412,10 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         }
         __syncthreads();
         n_c = s_count;
-        if (n_c > OBB_MAXC) { fail(3); return; }
+        if (n_c > OBB_MAXC) {     // the cull did not thin this cluster (a thin curved sheet): wrap all of its points
+            c.idx = nullptr;
+            n_c = n;
+        }
     } else {
         // S is degenerate (flat / thin cluster): wrap all points
         c.idx = nullptr;

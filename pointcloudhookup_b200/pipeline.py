@@ -350,6 +350,7 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
     device = tiles[0].device if tiles else torch.device("cuda", torch.cuda.current_device())
     if ground not in ("percentile", "grid"):
         raise ValueError(f"unknown ground mode {ground!r}")
+    tr = tl._Trace(comm.rank)
     # phase A — every rank, every tile, no dependency between ranks: voxel stage, and what defines the tile's frame
     stage, n_vox, n_pts = [], 0, 0
     for dl in tiles:
@@ -375,7 +376,9 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
         mine = stage[0]["cen"].cpu().numpy().astype(np.float32)
     else:
         mine = np.full(3, np.nan, dtype=np.float32)
+    tr.mark("voxel stage of all tiles")
     origin = comm.all_gather_fixed(mine)[0].astype(np.float32)
+    tr.mark("gather frame")
     if not np.all(np.isfinite(origin)):
         raise ValueError("rank 0 holds no points: no common frame")
     origin_dev = torch.from_numpy(origin.copy()).to(device)
@@ -397,9 +400,13 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
         outs = [o[: int(c)] for o, c in zip(outs, got)]
     P_own = torch.cat(outs).contiguous() if len(outs) > 1 else (outs[0].contiguous() if outs else
                                                                 torch.zeros((0, 3), dtype=torch.float32, device=device))
+    tr.mark("ground + compaction")
     res = tl.tile_dbscan(P_own, axis, eps, min_points, comm, clusterer)
+    tr.mark("tile_dbscan")
     stages = tw.TowerStages(None, origin, np.float32("nan"), 3.0, P_own, res.labels, res.n_clusters, res.stats)
     towers = tw.select_towers(stages, box="aabb", want_points=False, **tower_kw)
+    tr.mark("towers")
+    tr.done(f"run_pipeline_tiled tiles={len(tiles)}")
     halo = {"received": res.halo, "sent": res.sent, "p2p_bytes": 16 * sum(res.sent), "counts": res.counts}
     return TiledResult(n_pts, n_vox, int(P_own.shape[0]), res.n_clusters, towers, res.labels if keep else None,
                        P_own if keep else None, origin, halo)

@@ -345,16 +345,44 @@ def halo_widths(eps: float) -> Tuple[float, float]:
     return e1, 2.0 * e1
 
 
+class _Trace:
+    """PCH_TRACE_TILES=1: wall time of every step of the protocol on rank 0 (synchronising the device at each mark)."""
+
+    def __init__(self, rank):
+        import os
+        import time
+        self.on = bool(os.environ.get("PCH_TRACE_TILES")) and rank == 0
+        self.time = time
+        self.t = time.perf_counter()
+        self.rows = []
+
+    def mark(self, name):
+        if not self.on:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        now = self.time.perf_counter()
+        self.rows.append(f"{name} {1e3 * (now - self.t):.2f}")
+        self.t = now
+
+    def done(self, head):
+        if self.on:
+            print(f"[pch tiles] {head}: " + " | ".join(self.rows) + " ms", flush=True)
+
+
 def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samples: int, comm: Comm,
                 clusterer=None) -> TileDbscanResult:
     """One whole-corridor DBSCAN over the tiles of all ranks; see the module docstring."""
     clu = clusterer if clusterer is not None else DeviceClusterer()
+    tr = _Trace(comm.rank)
     r, W = comm.rank, comm.world
     ax = np.asarray(axis, dtype=np.float64)
     ax = ax / np.linalg.norm(ax)
     G = int(P_own.shape[0])
     smin, smax = clu.extent(P_own, ax)
+    tr.mark("extent")
     meta = comm.all_gather_fixed(np.array([G, smin, smax], dtype=np.float64))
+    tr.mark("gather meta")
     counts = [int(m[0]) for m in meta]
     lo_s = [float(m[1]) for m in meta]
     hi_s = [float(m[2]) for m in meta]
@@ -375,7 +403,9 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
         rows = P_own.index_select(0, idx.long())
         return torch.cat([rows, idx.to(torch.int32).view(torch.float32).unsqueeze(1)], dim=1).contiguous()
 
+    tr.mark("bands")
     from_left, from_right = comm.neighbour_exchange(payload(idx_l), payload(idx_r))
+    tr.mark("halo p2p")
     nL = 0 if from_left is None else int(from_left.shape[0])
     nR = 0 if from_right is None else int(from_right.shape[0])
     parts, sender_idx = [], []
@@ -395,6 +425,7 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
     else:
         P_local = torch.cat(parts).contiguous() if len(parts) > 1 else P_own.contiguous()
         labels_core, k_local = clu.cores(P_local, eps, min_samples)
+        tr.mark("cores")
         # shared core points: the halo I received, and the own points I sent
         sent_idx = torch.unique(torch.cat([idx_l, idx_r]).long()).to(torch.int32) if (idx_l.numel() + idx_r.numel()) else empty_i
         pos = torch.cat([torch.arange(0, nL, device=dev, dtype=torch.int32),
@@ -408,11 +439,14 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
         ok = lab_at >= 0
         ent = np.stack([gid[ok], lab_at[ok].astype(np.int64)], axis=1)
     # one variable-size all-gather carries both the shared-point entries and the per-cluster tables
+    tr.mark("report")
     packed = np.concatenate([[len(ent), len(table)], ent.reshape(-1), table]).astype(np.int64)
     got = comm.all_gather_np(packed)
+    tr.mark("gather entries")
     entries = [g[2: 2 + 2 * int(g[0])].reshape(-1, 2) for g in got]
     tables = [g[2 + 2 * int(g[0]): 2 + 2 * int(g[0]) + int(g[1])] for g in got]
     maps, n_global = merge_local_clusters(entries, tables)
+    tr.mark("merge")
     if n_local:
         labels_all, stats_own = clu.finish(maps[r], n_global, nL, nL + G)
         labels = labels_all[nL: nL + G]
@@ -424,5 +458,8 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
     empty = stats_own["count"] == 0
     stats_own["min"][empty] = np.inf
     stats_own["max"][empty] = -np.inf
+    tr.mark("finish")
     stats = comm.all_reduce_stats(stats_own)
+    tr.mark("reduce stats")
+    tr.done(f"tile_dbscan G={G} halo={nL}+{nR} K={n_global}")
     return TileDbscanResult(labels, n_global, stats, int(offs[r]), counts, (nL, nR), (int(idx_l.numel()), int(idx_r.numel())))

@@ -32,14 +32,31 @@ class PipelineResult:
     db_plan: Optional[dict] = None
 
 
+class nvtx_range:
+    """NVTX range around a pipeline stage (shows up in Nsight Systems / ncu --nvtx; free when no tool is attached)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def run_pipeline(dl: dv.DeviceLas, voxel_size: float = 0.1, chunk_size: int = 500000, eps: float = 8.0,
                  min_points: int = 80, ground: str = "percentile", box: str = "aabb", want_points: bool = False,
                  keep_stages: bool = False, **tower_kw) -> PipelineResult:
-    vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
+    with nvtx_range("pch.voxel_downsample"):
+        vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
     if vres.count == 0:
         return PipelineResult(dl.n, 0, 0, 0, [])
-    stages = tw.run_stages(vres.f32, eps, min_points, ground, zcol=vres.z32)
-    towers = tw.select_towers(stages, box=box, want_points=want_points, **tower_kw)
+    with nvtx_range("pch.ground+dbscan"):
+        stages = tw.run_stages(vres.f32, eps, min_points, ground, zcol=vres.z32)
+    with nvtx_range("pch.towers"):
+        towers = tw.select_towers(stages, box=box, want_points=want_points, **tower_kw)
     return PipelineResult(dl.n, vres.count, int(stages.filtered.shape[0]), stages.n_clusters, towers,
                           stages if keep_stages else None, vres.plan, stages.db_plan)
 
@@ -354,9 +371,11 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
     # phase A — every rank, every tile, no dependency between ranks: voxel stage, and what defines the tile's frame
     stage, n_vox, n_pts = [], 0, 0
     for dl in tiles:
-        vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
+        with nvtx_range("pch.tile.voxel_downsample"):
+            vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
         if per_tile is not None:
-            per_tile(dl, vres)
+            with nvtx_range("pch.tile.per_tile"):
+                per_tile(dl, vres)
         n_vox += vres.count
         n_pts += dl.n
         if vres.count == 0:
@@ -401,7 +420,8 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
     P_own = torch.cat(outs).contiguous() if len(outs) > 1 else (outs[0].contiguous() if outs else
                                                                 torch.zeros((0, 3), dtype=torch.float32, device=device))
     tr.mark("ground + compaction")
-    res = tl.tile_dbscan(P_own, axis, eps, min_points, comm, clusterer)
+    with nvtx_range("pch.tile_dbscan(halo)"):
+        res = tl.tile_dbscan(P_own, axis, eps, min_points, comm, clusterer)
     tr.mark("tile_dbscan")
     stages = tw.TowerStages(None, origin, np.float32("nan"), 3.0, P_own, res.labels, res.n_clusters, res.stats)
     towers = tw.select_towers(stages, box="aabb", want_points=False, **tower_kw)

@@ -305,14 +305,14 @@ def merge_local_clusters(entries: Sequence[np.ndarray], tables: Sequence[np.ndar
             for r, e in enumerate(entries) if len(e)]
     if rows:
         allr = np.concatenate(rows)
-        allr = allr[np.argsort(allr[:, 0], kind="stable")]
+        allr = allr[np.argsort(allr[:, 0])]           # equal point ids become neighbours (a point has at most 3 reports)
         same = allr[1:, 0] == allr[:-1, 0]
-        pairs = np.stack([allr[:-1, 1][same], allr[1:, 1][same]], axis=1)
-        pairs = pairs[pairs[:, 0] != pairs[:, 1]]
-        if len(pairs):
-            pairs = np.unique(np.sort(pairs, axis=1), axis=0)
-        for a, b in pairs:
-            ra, rb = find(int(a)), find(int(b))
+        a, b = allr[:-1, 1][same], allr[1:, 1][same]
+        differ = a != b
+        # thousands of shared points, a handful of distinct (cluster, cluster) pairs: reduce to those before the union-find
+        pair_keys = np.unique(np.minimum(a, b)[differ] * n_nodes + np.maximum(a, b)[differ])
+        for key_ab in pair_keys.tolist():
+            ra, rb = find(key_ab // n_nodes), find(key_ab % n_nodes)
             if ra != rb:
                 parent[max(ra, rb)] = min(ra, rb)
     roots = np.array([find(i) for i in range(n_nodes)], dtype=np.int64)

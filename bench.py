@@ -557,7 +557,8 @@ def run_tiled(args):
 
     def step(dls):
         geo_sums.clear()
-        res = pipeline.run_pipeline_tiled(dls, comm, axis, cfg["voxel"], cfg["chunk"], ground="grid", per_tile=per_tile)
+        res = pipeline.run_pipeline_tiled(dls, comm, axis, cfg["voxel"], cfg["chunk"], ground="grid", per_tile=per_tile,
+                                          origin=frame)
         if geo_sums:
             info["geo_checksum"] = float(torch.stack(geo_sums).sum().item())                     # the converted heights leave the device as a checksum
         info.update(M=res.n_voxels, G=res.n_candidates, K=res.n_clusters, towers=len(res.towers), halo=res.halo)

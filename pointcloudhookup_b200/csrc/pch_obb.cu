@@ -324,12 +324,15 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     c.tol3 = 1e-11 * L * L * L;
     c.tol2 = 1e-18 * L * L;
 
-    // ---- step 1: extreme points of OBB_DIRS directions (Fibonacci sphere), hull of those, interior cull
+    // ---- step 1: extreme points of n_dirs directions (Fibonacci sphere), hull of those, interior cull.  The hull of
+    // the extreme points costs one serial wrap step per face, so small clusters use fewer directions (a coarser cull
+    // is enough for them) and tiny ones skip the cull
+    const int n_dirs = n <= 512 ? 0 : (n < 4096 ? 64 : (n < 16384 ? 128 : OBB_DIRS));
     for (int d = tid; d < OBB_DIRS; d += OBB_THREADS) { s_dirmax[d] = -INFINITY; s_dirarg[d] = -1; }
     __syncthreads();
-    for (int d0 = 0; d0 < OBB_DIRS; d0 += OBB_WARPS) {
+    for (int d0 = 0; d0 < n_dirs; d0 += OBB_WARPS) {
         const int d = d0 + warp;
-        const float zz = 1.0f - 2.0f * ((float)d + 0.5f) / (float)OBB_DIRS;
+        const float zz = 1.0f - 2.0f * ((float)d + 0.5f) / (float)n_dirs;
         const float rr = sqrtf(fmaxf(0.f, 1.0f - zz * zz));
         const float ph = 2.399963229728653f * (float)d;
         const float dx = rr * cosf(ph), dy = rr * sinf(ph), dz = zz;
@@ -354,11 +357,11 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         __shared__ int s_wn[OBB_WARPS + 1];
         if (tid == 0) s_count = 0;
         __syncthreads();
-        for (int d0 = 0; d0 < OBB_DIRS; d0 += OBB_THREADS) {
+        for (int d0 = 0; d0 < n_dirs; d0 += OBB_THREADS) {
             const int d = d0 + tid;
             bool keep = false;
             int a = -1;
-            if (d < OBB_DIRS) {
+            if (d < n_dirs) {
                 a = s_dirarg[d];
                 keep = a >= 0;
                 for (int j = 0; j < d && keep; ++j) keep = s_dirarg[j] != a;
@@ -377,7 +380,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     int n_s = s_count;
     c.idx = w.cand;
     c.n = n_s;
-    int f1 = gift_wrap(c, w, 1024, s_red, s_ctl);
+    int f1 = n_s >= 4 ? gift_wrap(c, w, 1024, s_red, s_ctl) : 0;
     __syncthreads();
     int n_c = n_s;
     if (f1 > 0) {

@@ -355,13 +355,14 @@ def tile_candidates(dl: dv.DeviceLas, origin_dev: Optional[torch.Tensor], voxel_
 
 def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float = 0.1, chunk_size: int = 500000,
                        eps: float = 8.0, min_points: int = 80, keep: bool = False, clusterer=None,
-                       ground: str = "percentile", cell: float = 2.0, hag: float = 3.0, per_tile=None,
+                       ground: str = "percentile", cell: float = 2.0, hag: float = 3.0, per_tile=None, origin=None,
                        **tower_kw) -> TiledResult:
     """This rank's consecutive corridor tiles -> candidates per tile -> ONE DBSCAN over the tiles of all ranks
     (halo exchange with the neighbouring ranks, tiles.tile_dbscan) -> towers from the all-reduced per-cluster
     table (box = AABB rule of test/008.py:302-319).  Equals `dbscan_chunked(chunk=G)` on the concatenation of
     all ranks' candidates, label for label.  `per_tile(dl, voxel_result)` is called after each tile's voxel stage
-    (the geoid / CRS conversion of configs[4] hooks in here)."""
+    (the geoid / CRS conversion of configs[4] hooks in here).  `origin` (float32[3]): a frame every rank already knows
+    (e.g. the project's LAS header offset plus a nominal height) saves the collective that otherwise agrees on one."""
     from . import tiles as tl
     dv._require_cuda()
     device = tiles[0].device if tiles else torch.device("cuda", torch.cuda.current_device())
@@ -396,7 +397,10 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
     else:
         mine = np.full(3, np.nan, dtype=np.float32)
     tr.mark("voxel stage of all tiles")
-    origin = comm.all_gather_fixed(mine)[0].astype(np.float32)
+    if origin is None:
+        origin = comm.all_gather_fixed(mine)[0].astype(np.float32)
+    else:
+        origin = np.asarray(origin, dtype=np.float32).reshape(3)
     tr.mark("gather frame")
     if not np.all(np.isfinite(origin)):
         raise ValueError("rank 0 holds no points: no common frame")

@@ -17,10 +17,11 @@ in-process over threads for a rank that holds several tiles):
   3. local phase 1 (pch_dbscan_cores) on [left halo | own | right halo]: core flags + local cluster ids of
      the core points.  A point flagged core locally IS core globally (a truncated neighbourhood can only
      under-count), own points and halo points within eps of the cut are exact.
-  4. all-gather: (global point id, local cluster id) of every shared point that is core on the rank that
-     reports it, and per local cluster the smallest global id of its OWN core points.  Two local clusters
-     that contain the same core point are the same global cluster: union-find on every rank (identical
-     input -> identical result), global ids = rank of the component's smallest core point.
+  4. the way back (NCCL send/recv, 4 B per halo point): every rank returns its local cluster ids of the halo points
+     to their owners.  A point that is core on both sides joins the two local clusters; each rank reduces its
+     thousands of shared points to the handful of distinct (my cluster, neighbour's cluster) pairs.  all-gather:
+     those pairs and, per local cluster, the smallest global id of its OWN core points.  Union-find on every rank
+     (identical input -> identical result), global ids = rank of the component's smallest core point.
   5. local phase 2 (pch_dbscan_finish): core labels rewritten with global ids, border points take the
      smallest GLOBAL id among adjacent clusters, per-cluster count / AABB / sums over own points only.
   6. all-reduce of the per-cluster table (count, sums: sum; AABB: min / max): K x 56 B.
@@ -60,6 +61,11 @@ class Comm:
         """Send (k,4) float32 payloads to rank-1 / rank+1, receive theirs: (from_left, from_right)."""
         raise NotImplementedError
 
+    def neighbour_echo(self, back_left: Optional[torch.Tensor], back_right: Optional[torch.Tensor], n_left: int, n_right: int):
+        """The way back: int32 tensors for the points I RECEIVED go to the neighbour they came from; I get the
+        neighbours' tensors for the n_left / n_right points I sent them (sizes are known on both sides)."""
+        raise NotImplementedError
+
     def all_reduce_stats(self, stats: np.ndarray) -> np.ndarray:
         out = stats.copy()
         parts = self.all_gather_fixed(stats.view(np.uint8).reshape(-1))
@@ -76,6 +82,9 @@ class SoloComm(Comm):
         return [np.asarray(arr)]
 
     def neighbour_exchange(self, to_left, to_right):
+        return None, None
+
+    def neighbour_echo(self, back_left, back_right, n_left, n_right):
         return None, None
 
 
@@ -146,6 +155,27 @@ class TorchComm(Comm):
         self.bytes_p2p += 16 * (kl + kr)
         return from_left, from_right
 
+    def neighbour_echo(self, back_left, back_right, n_left, n_right):
+        dist, dev = self.dist, self.device
+        r, W = self.rank, self.world
+        ops, got_left, got_right = [], None, None
+        if r > 0 and n_left > 0:
+            got_left = torch.empty(n_left, dtype=torch.int32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, got_left, r - 1))
+        if r + 1 < W and n_right > 0:
+            got_right = torch.empty(n_right, dtype=torch.int32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, got_right, r + 1))
+        if r > 0 and back_left is not None and back_left.numel():
+            ops.append(dist.P2POp(dist.isend, back_left.to(dev).contiguous(), r - 1))
+            self.bytes_p2p += 4 * back_left.numel()
+        if r + 1 < W and back_right is not None and back_right.numel():
+            ops.append(dist.P2POp(dist.isend, back_right.to(dev).contiguous(), r + 1))
+            self.bytes_p2p += 4 * back_right.numel()
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return got_left, got_right
+
 
 class ThreadComm(Comm):
     """W ranks as threads of one process (a GPU that holds several tiles; the CPU tests): the collectives are
@@ -177,6 +207,14 @@ class ThreadComm(Comm):
         from_left = got[r - 1][1] if r > 0 else None
         from_right = got[r + 1][0] if r + 1 < self.world else None
         fix = lambda t: None if t is None or t.shape[0] == 0 else t.clone()
+        return fix(from_left), fix(from_right)
+
+    def neighbour_echo(self, back_left, back_right, n_left, n_right):
+        got = self._exchange((back_left, back_right))
+        r = self.rank
+        from_left = got[r - 1][1] if (r > 0 and n_left) else None          # the left neighbour's labels for what I sent it
+        from_right = got[r + 1][0] if (r + 1 < self.world and n_right) else None
+        fix = lambda t: None if t is None else t.clone()
         return fix(from_left), fix(from_right)
 
 
@@ -282,17 +320,17 @@ class DeviceClusterer:
 # -------------------------------------------------------------------------------------------------
 # host logic shared by every rank: which local clusters are the same global cluster
 # -------------------------------------------------------------------------------------------------
-def merge_local_clusters(entries: Sequence[np.ndarray], tables: Sequence[np.ndarray]):
-    """entries[r]: int64 (k_r, 2) rows (global point id, local cluster id on rank r) of shared core points;
-    tables[r]: int64 [K_r] smallest global id of rank r's OWN core points per local cluster (I64_MAX = none).
-    Returns (maps, n_global): maps[r][local id] = global id (-1: a cluster without any own core point anywhere,
-    i.e. seen only in the outer halo band).  Global ids rank the clusters by their smallest core point, the
-    order scikit-learn numbers them in on the concatenated cloud."""
+def merge_local_clusters(pairs: Sequence[np.ndarray], tables: Sequence[np.ndarray]):
+    """pairs[r]: int64 (p_r, 3) rows (neighbour rank q, local cluster id on rank r, local cluster id on rank q): the two
+    clusters contain the same core point;  tables[r]: int64 [K_r] smallest global id of rank r's OWN core points per
+    local cluster (I64_MAX = none).  Returns (maps, n_global): maps[r][local id] = global id (-1: a cluster without
+    any own core point anywhere, i.e. seen only in the outer halo band).  Global ids rank the clusters by their
+    smallest core point, the order scikit-learn numbers them in on the concatenated cloud."""
     W = len(tables)
     node_off = np.concatenate([[0], np.cumsum([len(t) for t in tables])]).astype(np.int64)
     n_nodes = int(node_off[-1])
     key = np.concatenate([np.asarray(t, dtype=np.int64) for t in tables]) if n_nodes else np.zeros(0, np.int64)
-    parent = np.arange(n_nodes, dtype=np.int64)
+    parent = list(range(n_nodes))
 
     def find(x):
         while parent[x] != x:
@@ -300,19 +338,9 @@ def merge_local_clusters(entries: Sequence[np.ndarray], tables: Sequence[np.ndar
             x = parent[x]
         return x
 
-    rows = [np.stack([np.asarray(e, dtype=np.int64).reshape(-1, 2)[:, 0],
-                      np.asarray(e, dtype=np.int64).reshape(-1, 2)[:, 1] + node_off[r]], axis=1)
-            for r, e in enumerate(entries) if len(e)]
-    if rows:
-        allr = np.concatenate(rows)
-        allr = allr[np.argsort(allr[:, 0])]           # equal point ids become neighbours (a point has at most 3 reports)
-        same = allr[1:, 0] == allr[:-1, 0]
-        a, b = allr[:-1, 1][same], allr[1:, 1][same]
-        differ = a != b
-        # thousands of shared points, a handful of distinct (cluster, cluster) pairs: reduce to those before the union-find
-        pair_keys = np.unique(np.minimum(a, b)[differ] * n_nodes + np.maximum(a, b)[differ])
-        for key_ab in pair_keys.tolist():
-            ra, rb = find(key_ab // n_nodes), find(key_ab % n_nodes)
+    for r, pr in enumerate(pairs):
+        for q, a, b in np.asarray(pr, dtype=np.int64).reshape(-1, 3).tolist():
+            ra, rb = find(int(node_off[r]) + a), find(int(node_off[q]) + b)
             if ra != rb:
                 parent[max(ra, rb)] = min(ra, rb)
     roots = np.array([find(i) for i in range(n_nodes)], dtype=np.int64)
@@ -408,43 +436,47 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
     tr.mark("halo p2p")
     nL = 0 if from_left is None else int(from_left.shape[0])
     nR = 0 if from_right is None else int(from_right.shape[0])
-    parts, sender_idx = [], []
+    parts = []
     if nL:
-        fl = from_left.to(dev)
-        parts.append(fl[:, :3])
-        sender_idx.append(fl[:, 3].contiguous().view(torch.int32))
+        parts.append(from_left.to(dev)[:, :3])
     parts.append(P_own)
     if nR:
-        fr = from_right.to(dev)
-        parts.append(fr[:, :3])
-        sender_idx.append(fr[:, 3].contiguous().view(torch.int32))
+        parts.append(from_right.to(dev)[:, :3])
     n_local = nL + G + nR
     empty_i = torch.zeros(0, dtype=torch.int32, device=dev)
-    if n_local == 0:
-        ent, table = np.zeros((0, 2), np.int64), np.zeros(0, np.int64)
-    else:
+    pair_rows, table = np.zeros((0, 3), np.int64), np.zeros(0, np.int64)
+    labels_core, k_local = None, 0
+    if n_local:
         P_local = torch.cat(parts).contiguous() if len(parts) > 1 else P_own.contiguous()
         labels_core, k_local = clu.cores(P_local, eps, min_samples)
         tr.mark("cores")
-        # shared core points: the halo I received, and the own points I sent
-        sent_idx = torch.unique(torch.cat([idx_l, idx_r]).long()).to(torch.int32) if (idx_l.numel() + idx_r.numel()) else empty_i
-        pos = torch.cat([torch.arange(0, nL, device=dev, dtype=torch.int32),
-                         torch.arange(nL + G, n_local, device=dev, dtype=torch.int32), sent_idx + nL])
-        extra = torch.cat(sender_idx + [sent_idx]) if (sender_idx or sent_idx.numel()) else empty_i
-        lab_at, extra_h, table = clu.shared_report(labels_core, pos, extra, nL, nL + G, int(offs[r]), k_local)
-        gid = extra_h.astype(np.int64)
-        gid[:nL] += offs[r - 1] if nL else 0
-        gid[nL: nL + nR] += offs[r + 1] if nR else 0
-        gid[nL + nR:] += offs[r]
-        ok = lab_at >= 0
-        ent = np.stack([gid[ok], lab_at[ok].astype(np.int64)], axis=1)
-    # one variable-size all-gather carries both the shared-point entries and the per-cluster tables
+    # the way back: what I think of the halo points goes to their owners, device to device; I learn what the
+    # neighbours think of the points I sent them.  A point that is core on both sides joins the two local clusters.
+    echo_l, echo_r = comm.neighbour_echo(labels_core[:nL].contiguous() if nL else None,
+                                         labels_core[nL + G:].contiguous() if nR else None,
+                                         int(idx_l.numel()), int(idx_r.numel()))
+    tr.mark("echo p2p")
+    if n_local:
+        n_sl, n_sr = (0 if echo_l is None else int(echo_l.numel())), (0 if echo_r is None else int(echo_r.numel()))
+        pos = torch.cat([idx_l[:n_sl] + nL, idx_r[:n_sr] + nL]) if (n_sl + n_sr) else empty_i
+        extra = torch.cat([t.to(dev) for t in (echo_l, echo_r) if t is not None]) if (n_sl + n_sr) else empty_i
+        mine, theirs, table = clu.shared_report(labels_core, pos, extra, nL, nL + G, int(offs[r]), k_local)
+        rows = []
+        for side, lo_, hi_ in ((r - 1, 0, n_sl), (r + 1, n_sl, n_sl + n_sr)):
+            a, b = mine[lo_:hi_].astype(np.int64), theirs[lo_:hi_].astype(np.int64)
+            ok = (a >= 0) & (b >= 0)
+            if ok.any():
+                u = np.unique(a[ok] * (1 << 32) + b[ok])        # thousands of shared points, a handful of cluster pairs
+                rows.append(np.stack([np.full(len(u), side, np.int64), u >> 32, u & 0xffffffff], axis=1))
+        if rows:
+            pair_rows = np.concatenate(rows)
     tr.mark("report")
-    packed = np.concatenate([[len(ent), len(table)], ent.reshape(-1), table]).astype(np.int64)
+    # one variable-size all-gather carries both the cluster pairs and the per-cluster tables
+    packed = np.concatenate([[len(pair_rows), len(table)], pair_rows.reshape(-1), table]).astype(np.int64)
     got = comm.all_gather_np(packed)
-    tr.mark("gather entries")
-    entries = [g[2: 2 + 2 * int(g[0])].reshape(-1, 2) for g in got]
-    tables = [g[2 + 2 * int(g[0]): 2 + 2 * int(g[0]) + int(g[1])] for g in got]
+    tr.mark("gather pairs")
+    entries = [g[2: 2 + 3 * int(g[0])].reshape(-1, 3) for g in got]
+    tables = [g[2 + 3 * int(g[0]): 2 + 3 * int(g[0]) + int(g[1])] for g in got]
     maps, n_global = merge_local_clusters(entries, tables)
     tr.mark("merge")
     if n_local:

@@ -25,13 +25,13 @@ def test_merge_local_clusters_joins_by_shared_points_and_orders_by_first_core():
     # rank 0: clusters 0 (cores from gid 5), 1 (from gid 40); rank 1: clusters 0 (halo only, = rank 0's 1), 1 (own, gid 120),
     # 2 (own from gid 100 AND shares a point with rank 0's cluster 0), 3 (outer-band halo only: dropped)
     tables = [np.array([5, 40]), np.array([BIG, 120, 100, BIG])]
-    entries = [np.array([[90, 1], [100, 0]]),            # rank 0 reports its own point 90 (in 1) and halo point 100 (in 0)
-               np.array([[90, 0], [100, 2], [95, 3]])]   # rank 1 reports halo 90 (in 0), own 100 (in 2), halo 95 (in 3)
-    maps, k = tl.merge_local_clusters(entries, tables)
+    pairs = [np.array([[1, 1, 0]]),                      # rank 0: my cluster 1 is rank 1's cluster 0 (a point I sent)
+             np.array([[0, 2, 0]])]                      # rank 1: my cluster 2 is rank 0's cluster 0 (a point I sent)
+    maps, k = tl.merge_local_clusters(pairs, tables)
     assert k == 3
     assert maps[0].tolist() == [0, 1]                   # {r0c0, r1c2} first core 5 -> 0; {r0c1, r1c0} first core 40 -> 1
     assert maps[1].tolist() == [1, 2, 0, -1]            # r1c1 first core 120 -> 2; r1c3 has no own core anywhere -> -1
-    maps, k = tl.merge_local_clusters([np.zeros((0, 2), np.int64)], [np.zeros(0, np.int64)])
+    maps, k = tl.merge_local_clusters([np.zeros((0, 3), np.int64)], [np.zeros(0, np.int64)])
     assert k == 0 and maps[0].tolist() == []
 
 
@@ -136,4 +136,4 @@ def test_tile_dbscan_world2_gloo():
     assert out[0][2] == out[1][2] == int(ref.max()) + 1
     assert out[0][3] == out[1][3]
     assert out[0][4][1] == out[1][5][0] > 0 and out[1][4][0] == out[0][5][1] > 0     # sent right == received from left, and back
-    assert out[0][6] == 16 * sum(out[0][4])
+    assert out[0][6] == 16 * sum(out[0][4]) + 4 * sum(out[0][5])          # halo out (16 B / point) + labels echoed back (4 B / point)

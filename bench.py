@@ -456,7 +456,9 @@ def run_b200(args):
         alg = model.get(name) or 0
         achieved = alg / (per_launch_ms / 1e3) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic_100M.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic_100M.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic_100M.json")
         if args.workload == "pipeline" and n == 100_000_000 and os.path.exists(tpath):
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
             # capture of this same configuration (profiles/r1_ncu_summary.md)

@@ -432,26 +432,16 @@ k_db_core2(DbGeom g, const float4* __restrict__ spts, const int32_t* __restrict_
         const float mn[3] = {pch_ordered_to_f32(bounds[ch * 6 + 0]), pch_ordered_to_f32(bounds[ch * 6 + 1]),
                              pch_ordered_to_f32(bounds[ch * 6 + 2])};
         int count = 0;
-        // the 25 column descriptors are fetched by 25 lanes at once (nearest columns first), and the cell table of a
-        // column by up to 6 lanes: the chain of dependent table look-ups becomes one round trip per level
-        int nc_l = 0;
-        int32_t f_l = 0;
-        if (lane < 25) {
-            const int col = c_db_order[lane];
-            nc_l = nbr_cnt[(int64_t)u * 25 + col];
-            f_l = nc_l ? nbr_first[(int64_t)u * 25 + col] : 0;
-        }
         for (int oi = 0; oi < 25 && count < g.min_pts; ++oi) {
-            const int nc = __shfl_sync(0xffffffffu, nc_l, oi);
+            const int col = c_db_order[oi];
+            const int nc = nbr_cnt[(int64_t)u * 25 + col];
             if (nc == 0) continue;
-            const int32_t f = __shfl_sync(0xffffffffu, f_l, oi);
-            const int32_t cs_l = lane <= nc ? cell_start[f + lane] : 0;
-            const uint64_t key_l = lane < nc ? cell_key[f + lane] : 0ull;
+            const int32_t f = nbr_first[(int64_t)u * 25 + col];
             for (int kc = 0; kc < nc && count < g.min_pts; ++kc) {
                 const int32_t v = f + kc;
-                const int32_t b = __shfl_sync(0xffffffffu, cs_l, kc), e = __shfl_sync(0xffffffffu, cs_l, kc + 1);
-                const uint64_t key = __shfl_sync(0xffffffffu, key_l, kc);
+                const int32_t b = cell_start[v], e = cell_start[v + 1];
                 if (v != u) {
+                    const uint64_t key = cell_key[v];
                     double dmin2, dmax2;
                     db_cell_bounds(p, mn, g.cell, (long long)(key >> bxy), (long long)((key >> g.bits_z) & my),
                                    (long long)(key & mz), dmin2, dmax2);
@@ -1001,19 +991,11 @@ k_db_labels_border(DbGeom g, const float4* __restrict__ spts, const int32_t* __r
         const int32_t u = pt_cell[pos];
         const float4 p = spts[pos];
         int32_t best = INT_MAX;
-        int nc_l = 0;
-        int32_t b_l = 0, e_l = 0;
-        if (lane < 25) {     // 25 lanes fetch the 25 column descriptors and their point ranges at once
-            nc_l = nbr_cnt[(int64_t)u * 25 + lane];
-            if (nc_l) {
-                const int32_t f = nbr_first[(int64_t)u * 25 + lane];
-                b_l = cell_start[f]; e_l = cell_start[f + nc_l];
-            }
-        }
         for (int col = 0; col < 25; ++col) {
-            const int nc = __shfl_sync(0xffffffffu, nc_l, col);
+            const int nc = nbr_cnt[(int64_t)u * 25 + col];
             if (nc == 0) continue;
-            const int32_t b = __shfl_sync(0xffffffffu, b_l, col), e = __shfl_sync(0xffffffffu, e_l, col);
+            const int32_t f = nbr_first[(int64_t)u * 25 + col];
+            const int32_t b = cell_start[f], e = cell_start[f + nc];
             for (int32_t q0 = b; q0 < e; q0 += 32) {
                 const int32_t q = q0 + lane;
                 if (q < e && core[q]) {

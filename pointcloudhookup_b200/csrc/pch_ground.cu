@@ -904,6 +904,7 @@ k_compact(const float* __restrict__ xyz, const float* __restrict__ zs, const uin
 // with coalesced 16-byte loads into shared memory, the kept rows are packed there (after every warp has its
 // rows in registers), and the packed span leaves with fully coalesced stores — instead of 4-byte accesses at
 // a 12-byte stride on both sides.  Same flags, same order, same outputs as k_compact.
+template <bool GRID>
 __global__ void __launch_bounds__(CP_THREADS)
 k_compact_xyz(const float* __restrict__ xyz, const float* __restrict__ zs, const uint8_t* __restrict__ keep_mask, GridTest gt,
               int64_t m, const float* __restrict__ centroid, float thr, float* __restrict__ out_xyz,
@@ -940,7 +941,7 @@ k_compact_xyz(const float* __restrict__ xyz, const float* __restrict__ zs, const
         const int64_t i = start + li;
         bool keep = false;
         if (li < cnt) {
-            if (gt.cell_min) keep = grid_keep(__fsub_rn(s_row[li * 3 + 0], cx), __fsub_rn(s_row[li * 3 + 1], cy), __fsub_rn(s_row[li * 3 + 2], cz), gt);
+            if (GRID) keep = grid_keep(__fsub_rn(s_row[li * 3 + 0], cx), __fsub_rn(s_row[li * 3 + 1], cy), __fsub_rn(s_row[li * 3 + 2], cz), gt);
             else keep = zs ? (zs[i] > thr) : (keep_mask ? (keep_mask[i] != 0) : (__fsub_rn(s_row[li * 3 + 2], cz) > thr));
         }
         if (out_mask && li < cnt) out_mask[i] = keep ? 1 : 0;
@@ -1111,8 +1112,12 @@ static int compact_impl(const float* xyz, const float* zs, const uint8_t* keep_m
         PCH_LAUNCH(st, "k_compact_flags", k_compact_flags<<<(unsigned)pch_ceil_div(m, CF_TILE), CP_THREADS, 0, st>>>(
                                               keep_mask, m, out_src, (long long*)count_dev, status, counter, err));
     } else if (out_xyz && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0) {
-        PCH_LAUNCH(st, "k_compact_xyz", k_compact_xyz<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src,
-                                                              out_mask, (long long*)count_dev, status, counter, err));
+        if (gt.cell_min)
+            PCH_LAUNCH(st, "k_compact_xyz", k_compact_xyz<true><<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src,
+                                                                  out_mask, (long long*)count_dev, status, counter, err));
+        else
+            PCH_LAUNCH(st, "k_compact_xyz", k_compact_xyz<false><<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src,
+                                                                  out_mask, (long long*)count_dev, status, counter, err));
     } else {
         PCH_LAUNCH(st, "k_compact", k_compact<<<(unsigned)tiles, CP_THREADS, 0, st>>>(xyz, zs, keep_mask, gt, m, centroid3, thr, out_xyz, out_src, out_mask,
                                                           (long long*)count_dev, status, counter, err));

@@ -11,3 +11,7 @@ $CMDG > gpurun_out/r2_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_grid_min|k_compact_xyz|k_minmax_f32' -s 3 -c 3 -o gpurun_out/r2_prof_grid $CMDG > gpurun_out/r2_ncu3.log 2>&1
 tail -2 gpurun_out/r2_ncu2.log gpurun_out/r2_ncu3.log
 ls -la gpurun_out/r2_prof*.ncu-rep gpurun_out/r2_launches.csv
+CMDO="python tools/prof_obb.py 50e6"
+$CMDO > gpurun_out/r2_plain4.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_obb' -c 1 -o gpurun_out/r2_prof_obb $CMDO > gpurun_out/r2_ncu4.log 2>&1
+tail -2 gpurun_out/r2_ncu4.log

@@ -771,7 +771,7 @@ struct GridTest {
     float minx, miny, cell, hag;
     float rcell;                // RN(1/cell) for the reciprocal division
     int32_t fast;               // cell passed grid_recip_ok: (d / cell) may be evaluated as products + FMA corrections
-    int32_t ny;
+    int32_t nx, ny;
     long long n_cells;
 };
 // Correctly rounded float32 d / c from y = RN(1/c): the float32 twin of pch_div_by (Markstein: with a faithful
@@ -787,6 +787,19 @@ __device__ __forceinline__ float grid_div(float d, const GridTest& gt) {
     r = __fmaf_rn(-gt.cell, q, d);
     return __fmaf_rn(r, gt.rcell, q);
 }
+// floor(d / cell) for the cell index, without the range guard of grid_div: the guard only protects quotients that
+// cannot be a valid cell anyway.  d == 0 gives exactly 0; 0 < d < 1e-30 gives a quotient below 1 whatever its last
+// bit, i.e. floor 0 like the true divide; |d| >= 1e30, inf and nan give a quotient that fails the range test of
+// grid_cell_of exactly like the true divide's would; a negative d cannot occur for a point inside the bounding box
+// the grid origin was taken from (and floors to a negative, rejected index if it does).
+__device__ __forceinline__ float grid_floor_div(float d, const GridTest& gt) {
+    if (!gt.fast) return floorf(__fdiv_rn(d, gt.cell));
+    float q = __fmul_rn(d, gt.rcell);
+    float r = __fmaf_rn(-gt.cell, q, d);
+    q = __fmaf_rn(r, gt.rcell, q);
+    r = __fmaf_rn(-gt.cell, q, d);
+    return floorf(__fmaf_rn(r, gt.rcell, q));
+}
 static inline bool grid_recip_ok(float c) {
     if (!(c == c) || c == 0.f) return false;
     const float m = c < 0 ? -c : c;
@@ -795,15 +808,15 @@ static inline bool grid_recip_ok(float c) {
     memcpy(&u, &c, 4);
     return (u & 0x7FFFFFu) != 0x7FFFFFu;
 }
-__device__ __forceinline__ long long grid_cell_of(float sx, float sy, const GridTest& gt) {
-    const float qx = floorf(grid_div(__fsub_rn(sx, gt.minx), gt)), qy = floorf(grid_div(__fsub_rn(sy, gt.miny), gt));
-    // one range test on the floats (NaN fails it), then 32-bit conversions: the cell count fits 31 bits
-    if (!(qx >= 0.f && qy >= 0.f && qy < (float)gt.ny && qx < 2147483520.f)) return -1;
-    const long long cid = (long long)__float2int_rz(qx) * gt.ny + __float2int_rz(qy);
-    return cid >= gt.n_cells ? -1 : cid;
+__device__ __forceinline__ int grid_cell_of(float sx, float sy, const GridTest& gt) {
+    const float qx = grid_floor_div(__fsub_rn(sx, gt.minx), gt), qy = grid_floor_div(__fsub_rn(sy, gt.miny), gt);
+    // one range test on the floats (NaN fails it), then 32-bit arithmetic: nx * ny fits 31 bits (checked on the host)
+    if (!(qx >= 0.f && qy >= 0.f && qy < (float)gt.ny && qx < (float)gt.nx)) return -1;
+    const uint32_t cid = (uint32_t)__float2int_rz(qx) * (uint32_t)gt.ny + (uint32_t)__float2int_rz(qy);
+    return cid < (uint32_t)gt.n_cells ? (int)cid : -1;      // (float)nx may round up for grids wider than 2^24 cells
 }
 __device__ __forceinline__ bool grid_keep(float sx, float sy, float sz, const GridTest& gt) {
-    const long long cid = grid_cell_of(sx, sy, gt);
+    const int cid = grid_cell_of(sx, sy, gt);
     const float g = cid >= 0 ? pch_ordered_to_f32(__ldg(gt.cell_min + cid)) : sz;
     return __fsub_rn(sz, g) > gt.hag;
 }
@@ -1180,7 +1193,7 @@ k_grid_min(const float* __restrict__ xyz, int64_t m, const float* __restrict__ c
             uint32_t zo = 0xffffffffu;
             if (li < cnt) {
                 const float sx = __fsub_rn(s_row[li * 3 + 0], cx), sy = __fsub_rn(s_row[li * 3 + 1], cy);
-                key = (int)grid_cell_of(sx, sy, gt);
+                key = grid_cell_of(sx, sy, gt);
                 zo = pch_f32_to_ordered(__fsub_rn(s_row[li * 3 + 2], cz));
             }
             const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -1216,7 +1229,7 @@ __global__ void k_grid_label(const float* __restrict__ xyz, int64_t m, const flo
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < m; i += stride) {
         const float x = __fsub_rn(xyz[i * 3 + 0], cx), y = __fsub_rn(xyz[i * 3 + 1], cy), z = __fsub_rn(xyz[i * 3 + 2], cz);
-        const long long cid = grid_cell_of(x, y, gt);
+        const int cid = grid_cell_of(x, y, gt);
         const float g = cid >= 0 ? pch_ordered_to_f32(gt.cell_min[cid]) : z;
         if (ground_z) ground_z[i] = g;
         keep[i] = (__fsub_rn(z, g) > gt.hag) ? 1 : 0;
@@ -1231,7 +1244,7 @@ static int grid_args(int64_t m, float cell, int32_t nx, int32_t ny, GridTest& gt
     gt.minx = minx; gt.miny = miny; gt.cell = cell; gt.hag = hag;
     gt.rcell = 1.0f / cell;
     gt.fast = grid_recip_ok(cell) ? 1 : 0;
-    gt.ny = ny;
+    gt.nx = nx; gt.ny = ny;
     gt.n_cells = (long long)nx * ny;
     return PCH_OK;
 }

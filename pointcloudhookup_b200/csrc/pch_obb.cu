@@ -94,14 +94,34 @@ __device__ __forceinline__ int block_best(int mine, BETTER better, int* s_red) {
     return best;
 }
 
+#define OBB_SPTS 2048   // candidate coordinates staged in shared memory when they fit (the usual case)
+
+// The wrap works on LOCAL ids 0..n-1 (positions in the candidate list); row ids only come back at the end.
 struct WrapCtx {
     const float* P;      // cluster rows
-    const int32_t* idx;  // candidate list (NULL = all rows 0..n)
+    const int32_t* idx;  // candidate list: local id -> row (NULL = identity, all rows)
+    const float* S;      // coordinates of the candidates in shared memory, by local id (NULL = read the rows)
     int n;
     double tol3;         // coplanarity threshold on 6*volume
     double tol2;         // collinearity threshold on |cross|^2
 };
-__device__ __forceinline__ int cand_at(const WrapCtx& c, int k) { return c.idx ? c.idx[k] : k; }
+__device__ __forceinline__ int row_of(const WrapCtx& c, int k) { return c.idx ? c.idx[k] : k; }
+__device__ __forceinline__ D3 cpt(const WrapCtx& c, int k) {
+    if (c.S) return D3{(double)c.S[k * 3 + 0], (double)c.S[k * 3 + 1], (double)c.S[k * 3 + 2]};
+    return ld3(c.P, row_of(c, k));
+}
+// all threads: stage the candidates' coordinates when they fit
+__device__ __forceinline__ void stage_candidates(WrapCtx& c, float* s_pts) {
+    c.S = nullptr;
+    if (c.n <= OBB_SPTS) {
+        for (int k = threadIdx.x; k < c.n; k += OBB_THREADS) {
+            const int r = row_of(c, k);
+            s_pts[k * 3 + 0] = c.P[r * 3 + 0]; s_pts[k * 3 + 1] = c.P[r * 3 + 1]; s_pts[k * 3 + 2] = c.P[r * 3 + 2];
+        }
+        c.S = s_pts;
+    }
+    __syncthreads();
+}
 
 // The next face around the directed hull edge a->b: the point d with the largest rotation angle about the edge,
 // measured from the half-plane of the face that is already known (O = a vector from a into that half-plane; for the
@@ -110,12 +130,12 @@ __device__ __forceinline__ int cand_at(const WrapCtx& c, int k) { return c.idx ?
 // Coplanar ties: same half-plane -> the point farther from the edge line; opposite half-planes (angle 0 against half
 // a turn) -> the one on the far side from O.
 __device__ int wrap_edge(const WrapCtx& c, int a, int b, D3 O, int* s_red) {
-    const D3 A = ld3(c.P, a), B = ld3(c.P, b);
+    const D3 A = cpt(c, a), B = cpt(c, b);
     const D3 e = sub3(B, A);
     const double e2 = dot3(e, e);
     const D3 nO = cross3(e, O);
     auto better = [&](int i, int j) -> bool {   // does j beat i?
-        const D3 I = sub3(ld3(c.P, i), A), J = sub3(ld3(c.P, j), A);
+        const D3 I = sub3(cpt(c, i), A), J = sub3(cpt(c, j), A);
         const D3 nI = cross3(e, I);
         const double v = dot3(nI, J);                       // > 0: j is further round than i
         if (v > c.tol3) return true;
@@ -125,10 +145,9 @@ __device__ int wrap_edge(const WrapCtx& c, int a, int b, D3 O, int* s_red) {
         return dot3(nJ, nO) < dot3(nI, nO);
     };
     int mine = -1;
-    for (int k = threadIdx.x; k < c.n; k += OBB_THREADS) {
-        const int q = cand_at(c, k);
+    for (int q = threadIdx.x; q < c.n; q += OBB_THREADS) {
         if (q == a || q == b) continue;
-        const D3 Q = sub3(ld3(c.P, q), A);
+        const D3 Q = sub3(cpt(c, q), A);
         const D3 nq = cross3(e, Q);
         if (dot3(nq, nq) <= c.tol2 * e2) continue;          // on the edge line: cannot span a face with it
         if (mine < 0 || better(mine, q)) mine = q;
@@ -175,22 +194,20 @@ __device__ int gift_wrap(const WrapCtx& c, const ObbWs& w, int max_faces, int* s
     for (int k = tid; k < OBB_HASH; k += OBB_THREADS) w.eset[k] = 0ull;
     // lowest point (x, then y, then z) and its neighbour on the silhouette of the xy projection
     auto lower = [&](int i, int j) -> bool {
-        const float* a = c.P + (size_t)i * 3; const float* b = c.P + (size_t)j * 3;
-        if (b[0] != a[0]) return b[0] < a[0];
-        if (b[1] != a[1]) return b[1] < a[1];
-        if (b[2] != a[2]) return b[2] < a[2];
-        return j < i;
+        const D3 a = cpt(c, i), b = cpt(c, j);
+        if (b.x != a.x) return b.x < a.x;
+        if (b.y != a.y) return b.y < a.y;
+        if (b.z != a.z) return b.z < a.z;
+        return row_of(c, j) < row_of(c, i);
     };
     int mine = -1;
-    for (int k = tid; k < c.n; k += OBB_THREADS) {
-        const int q = cand_at(c, k);
+    for (int q = tid; q < c.n; q += OBB_THREADS)
         if (mine < 0 || lower(mine, q)) mine = q;
-    }
     const int p0 = block_best(mine, lower, s_red);
     if (p0 < 0) return 0;
-    const D3 A = ld3(c.P, p0);
+    const D3 A = cpt(c, p0);
     auto right_of = [&](int i, int j) -> bool {   // j beats i when it lies to the right of p0->i in the xy projection
-        const D3 I = sub3(ld3(c.P, i), A), J = sub3(ld3(c.P, j), A);
+        const D3 I = sub3(cpt(c, i), A), J = sub3(cpt(c, j), A);
         const double cr = I.x * J.y - I.y * J.x;
         const double sc = sqrt((I.x * I.x + I.y * I.y) * (J.x * J.x + J.y * J.y));
         if (cr < -1e-12 * sc) return true;
@@ -198,10 +215,9 @@ __device__ int gift_wrap(const WrapCtx& c, const ObbWs& w, int max_faces, int* s
         return (J.x * J.x + J.y * J.y) > (I.x * I.x + I.y * I.y);   // same direction: the farther one
     };
     mine = -1;
-    for (int k = tid; k < c.n; k += OBB_THREADS) {
-        const int q = cand_at(c, k);
+    for (int q = tid; q < c.n; q += OBB_THREADS) {
         if (q == p0) continue;
-        const D3 Q = sub3(ld3(c.P, q), A);
+        const D3 Q = sub3(cpt(c, q), A);
         if (Q.x * Q.x + Q.y * Q.y <= c.tol2) continue;      // straight above / below p0
         if (mine < 0 || right_of(mine, q)) mine = q;
     }
@@ -230,10 +246,10 @@ __device__ int gift_wrap(const WrapCtx& c, const ObbWs& w, int max_faces, int* s
         __syncthreads();
         if (a < 0) break;
         D3 O;
-        if (op >= 0) O = sub3(ld3(c.P, op), ld3(c.P, a));
+        if (op >= 0) O = sub3(cpt(c, op), cpt(c, a));
         else {
             // first edge: every point is to the left of a->b in the xy projection, so the right-hand side is outside
-            const D3 e = sub3(ld3(c.P, b), ld3(c.P, a));
+            const D3 e = sub3(cpt(c, b), cpt(c, a));
             O = D3{e.y, -e.x, 0.0};
         }
         const int d = wrap_edge(c, a, b, O, s_red);
@@ -247,7 +263,7 @@ __device__ int gift_wrap(const WrapCtx& c, const ObbWs& w, int max_faces, int* s
         if (tid == 0) {
             const int f = n_faces;
             w.faces[f * 3 + 0] = a; w.faces[f * 3 + 1] = b; w.faces[f * 3 + 2] = d;
-            const D3 PA = ld3(c.P, a), PB = ld3(c.P, b), PD = ld3(c.P, d);
+            const D3 PA = cpt(c, a), PB = cpt(c, b), PD = cpt(c, d);
             D3 n = cross3(sub3(PB, PA), sub3(PD, PA));
             const double l = sqrt(dot3(n, n));
             if (l > 0.0) { n.x /= l; n.y /= l; n.z /= l; }
@@ -284,6 +300,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     __shared__ float s_dirmax[OBB_DIRS];
     __shared__ int s_dirarg[OBB_DIRS];
     __shared__ float4 s_plane[1024];
+    __shared__ float s_pts[OBB_SPTS * 3];
     __shared__ double s_best[OBB_WARPS];
     __shared__ int s_bestf[OBB_WARPS], s_beste[OBB_WARPS];
     __shared__ int s_count;
@@ -321,6 +338,8 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     if (!(L > 0.0)) { fail(1); return; }
     WrapCtx c;
     c.P = P;
+    c.S = nullptr;
+    c.idx = nullptr;
     c.tol3 = 1e-11 * L * L * L;
     c.tol2 = 1e-18 * L * L;
 
@@ -380,6 +399,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     int n_s = s_count;
     c.idx = w.cand;
     c.n = n_s;
+    stage_candidates(c, s_pts);
     int f1 = n_s >= 4 ? gift_wrap(c, w, 1024, s_red, s_ctl) : 0;
     __syncthreads();
     int n_c = n_s;
@@ -401,7 +421,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
                     keep = (pl.x * x + pl.y * y + pl.z * z) > pl.w;      // not clearly inside this face
                 }
                 if (keep)
-                    for (int j = 0; j < n_s && keep; ++j) keep = w.cand[j] != i;   // S is already in the list
+                    for (int d = 0; d < n_dirs && keep; ++d) keep = s_dirarg[d] != i;   // S is already in the list
             }
             // append kept points (order inside the list does not matter)
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
@@ -428,9 +448,19 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
 
     // ---- step 2: hull of the candidates
     c.n = n_c;
+    stage_candidates(c, s_pts);
     const int F = gift_wrap(c, w, OBB_MAXF, s_red, s_ctl);
     __syncthreads();
     if (F <= 0) { fail(F == 0 ? 2 : 3); return; }
+    // faces across every directed edge (the edge set speaks local ids), then the faces go back to row ids
+    for (int i = tid; i < 3 * F; i += OBB_THREADS) {
+        const int g = i / 3, j = i - 3 * g;
+        w.twin[i] = eset_face(w, w.faces[g * 3 + (j + 1) % 3], w.faces[g * 3 + j]);
+    }
+    __syncthreads();
+    if (c.idx)
+        for (int i = tid; i < 3 * F; i += OBB_THREADS) w.faces[i] = c.idx[w.faces[i]];
+    __syncthreads();
     // hull vertices
     if (tid == 0) s_count = 0;
     for (int i = tid; i < OBB_MAXC / 32 + 1; i += OBB_THREADS) w.mark[i] = 0u;
@@ -458,11 +488,6 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     if (V > OBB_MAXC) { fail(3); return; }
 
     // ---- step 3: box search.  One warp per face normal.
-    for (int i = tid; i < 3 * F; i += OBB_THREADS) {
-        const int g = i / 3, j = i - 3 * g;
-        w.twin[i] = eset_face(w, w.faces[g * 3 + (j + 1) % 3], w.faces[g * 3 + j]);
-    }
-    __syncthreads();
     double best_vol = INFINITY;
     int best_f = -1, best_e = -1;
     for (int f = warp; f < F; f += OBB_WARPS) {

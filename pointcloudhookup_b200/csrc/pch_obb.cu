@@ -15,6 +15,7 @@
 //   3. box search: one warp per face normal n: thickness along n; every hull edge whose two faces look to opposite
 //      sides of n is an edge of the projected hull: rectangle aligned with it, area * thickness -> block minimum.
 #include "pch_common.cuh"
+#include <stdlib.h>
 
 #define OBB_THREADS 256
 #define OBB_WARPS (OBB_THREADS / 32)
@@ -94,6 +95,8 @@ __device__ __forceinline__ int block_best(int mine, BETTER better, int* s_red) {
     return best;
 }
 
+#define OBB_SMAX 512    // seed points of the cull (their hull has < 1024 faces)
+#define OBB_ROUNDS 4
 #define OBB_SPTS 2048   // candidate coordinates staged in shared memory when they fit (the usual case)
 
 // The wrap works on LOCAL ids 0..n-1 (positions in the candidate list); row ids only come back at the end.
@@ -294,13 +297,16 @@ struct ObbOut {   // mirrors pch_obb_result
 
 __global__ void __launch_bounds__(OBB_THREADS)
 k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, int n_clusters, uint8_t* __restrict__ ws_base,
-      size_t ws_stride, ObbOut* __restrict__ out) {
+      size_t ws_stride, ObbOut* __restrict__ out, int max_cand) {
     __shared__ int s_red[OBB_WARPS];
     __shared__ int s_ctl[4];
     __shared__ float s_dirmax[OBB_DIRS];
     __shared__ int s_dirarg[OBB_DIRS];
-    __shared__ float4 s_plane[1024];
-    __shared__ float s_pts[OBB_SPTS * 3];
+    // one buffer, two lives: the staged candidate coordinates during a wrap, the planes of the seed hull during a cull
+    __shared__ __align__(16) unsigned char s_buf[OBB_SPTS * 12];
+    float* s_pts = reinterpret_cast<float*>(s_buf);
+    float4* s_plane = reinterpret_cast<float4*>(s_buf);
+    __shared__ unsigned long long s_far[1024];
     __shared__ double s_best[OBB_WARPS];
     __shared__ int s_bestf[OBB_WARPS], s_beste[OBB_WARPS];
     __shared__ int s_count;
@@ -396,57 +402,103 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
             __syncthreads();
         }
     }
+    // The seed S (<= OBB_SMAX points) lives in w.cand[0..n_s); survivors ping-pong between listA / listB.
+    // Rounds (quickhull in batches): H = hull(S); every point clearly inside H is interior and dropped; per face of H
+    // the farthest point outside it joins S.  A thin sheet, which the first coarse H cannot thin at all, is down to its
+    // hull neighbourhood after two or three rounds.
     int n_s = s_count;
-    c.idx = w.cand;
-    c.n = n_s;
-    stage_candidates(c, s_pts);
-    int f1 = n_s >= 4 ? gift_wrap(c, w, 1024, s_red, s_ctl) : 0;
-    __syncthreads();
-    int n_c = n_s;
-    if (f1 > 0) {
-        // planes of H1 in shared memory (float32 with a margin), cull
-        const float margin = (float)(1e-4 * L) + 1e-4f;
-        for (int f = tid; f < f1; f += OBB_THREADS)
-            s_plane[f] = make_float4((float)w.planes[f * 4 + 0], (float)w.planes[f * 4 + 1], (float)w.planes[f * 4 + 2],
-                                     (float)w.planes[f * 4 + 3] - margin);
-        for (int i = tid; i < OBB_MAXC / 32 + 1; i += OBB_THREADS) w.mark[i] = 0u;
+    int32_t* listA = w.cand + OBB_SMAX;
+    int32_t* listB = w.verts;                  // free until the hull vertices are collected
+    const int list_cap = OBB_MAXC - OBB_SMAX;
+    const int32_t* src = nullptr;              // nullptr = all rows
+    int n_src = n, n_c = n;
+    bool have_list = false;
+    const float margin = (float)(1e-4 * L) + 1e-4f;
+    for (int round = 0; round < OBB_ROUNDS && n_s >= 4; ++round) {
+        c.idx = w.cand;
+        c.n = n_s;
+        stage_candidates(c, s_pts);
+        const int f1 = gift_wrap(c, w, 1024, s_red, s_ctl);
         __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += OBB_THREADS) {
-            const int i = i0 + tid;
+        if (f1 <= 0) break;                    // degenerate seed (flat / collinear cluster): no cull
+        for (int f = tid; f < f1; f += OBB_THREADS) {
+            s_plane[f] = make_float4((float)w.planes[f * 4 + 0], (float)w.planes[f * 4 + 1], (float)w.planes[f * 4 + 2],
+                                     (float)w.planes[f * 4 + 3]);
+            s_far[f] = 0ull;
+        }
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        int32_t* dst = (src == listA) ? listB : listA;
+        for (int k0 = 0; k0 < n_src; k0 += OBB_THREADS) {
+            const int k = k0 + tid;
             bool keep = false;
-            if (i < n) {
+            int i = -1;
+            if (k < n_src) {
+                i = src ? src[k] : k;
                 const float x = P[i * 3 + 0], y = P[i * 3 + 1], z = P[i * 3 + 2];
-                for (int f = 0; f < f1 && !keep; ++f) {
+                float dmax = -INFINITY;
+                int fmax = 0;
+                for (int f = 0; f < f1; ++f) {
                     const float4 pl = s_plane[f];
-                    keep = (pl.x * x + pl.y * y + pl.z * z) > pl.w;      // not clearly inside this face
+                    const float d = pl.x * x + pl.y * y + pl.z * z - pl.w;
+                    if (d > dmax) { dmax = d; fmax = f; }
                 }
-                if (keep)
-                    for (int d = 0; d < n_dirs && keep; ++d) keep = s_dirarg[d] != i;   // S is already in the list
+                keep = dmax > -margin;                           // not clearly inside every face
+                if (dmax > margin)                               // clearly outside: candidate for the next seed
+                    atomicMax(&s_far[fmax], ((unsigned long long)__float_as_uint(dmax) << 32) | (uint32_t)i);
             }
-            // append kept points (order inside the list does not matter)
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
             int base = 0;
             if (lane == 0 && bal) base = atomicAdd(&s_count, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (keep) {
                 const int pos = base + __popc(bal & ((1u << lane) - 1u));
-                if (pos < OBB_MAXC) w.cand[pos] = i;
+                if (pos < list_cap) dst[pos] = i;
             }
         }
         __syncthreads();
-        n_c = s_count;
-        if (n_c > OBB_MAXC) {     // the cull did not thin this cluster (a thin curved sheet): wrap all of its points
-            c.idx = nullptr;
-            n_c = n;
+        const int kept = s_count;
+        __syncthreads();
+        if (kept <= list_cap) { src = dst; n_src = kept; n_c = kept; have_list = true; }
+        // grow the seed by the farthest point of every face that still has something outside (thread 0: <= 1024 faces)
+        if (tid == 0) {
+            int m = n_s;
+            for (int f = 0; f < f1 && m < OBB_SMAX; ++f) {
+                const unsigned long long v = s_far[f];
+                if (!v) continue;
+                const int i = (int)(uint32_t)v;
+                bool dup = false;
+                for (int j = n_s; j < m && !dup; ++j) dup = w.cand[j] == i;   // the same point can be farthest for several faces
+                if (!dup) w.cand[m++] = i;
+            }
+            s_ctl[0] = m;
         }
-    } else {
-        // S is degenerate (flat / thin cluster): wrap all points
+        __syncthreads();
+        const int grown = s_ctl[0];
+        __syncthreads();
+        const bool done = grown == n_s || (have_list && n_c <= OBB_SPTS);
+        n_s = grown;
+        if (done) break;
+    }
+    if (have_list) {
+        if (src == listB) {       // w.verts is needed for the hull vertices later: move the survivors to the other list
+            for (int k = tid; k < n_c; k += OBB_THREADS) listA[k] = listB[k];
+            __syncthreads();
+            src = listA;
+        }
+        c.idx = src;
+    } else {      // no usable cull (degenerate seed, or more survivors than the lists hold): wrap all points
         c.idx = nullptr;
         n_c = n;
     }
     __syncthreads();
 
-    // ---- step 2: hull of the candidates
+    // ---- step 2: hull of the candidates.  Gift wrapping costs (candidates x faces); a cluster the cull cannot thin (a
+    // thin convex sheet: every point is a hull vertex) is cheaper in Qhull on the host than here
+    if (n_c > max_cand) {
+        if (tid == 0) { o->status = 3; o->n_faces = 0; o->n_verts = 0; o->n_candidates = n_c; o->volume = 0.0; }
+        return;
+    }
     c.n = n_c;
     stage_candidates(c, s_pts);
     const int F = gift_wrap(c, w, OBB_MAXF, s_red, s_ctl);
@@ -601,6 +653,12 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
 
 extern "C" size_t pch_obb_workspace_bytes(int32_t n_clusters) { return (size_t)(n_clusters > 0 ? n_clusters : 1) * OBB_WS_BYTES; }
 
+static int obb_max_candidates() {      // PCH_OBB_MAX_CAND: tuning knob (clusters with more hull candidates go to the host)
+    const char* e = getenv("PCH_OBB_MAX_CAND");
+    int v = e ? atoi(e) : OBB_MAXC;
+    return v < 16 ? 16 : v;
+}
+
 extern "C" int pch_obb_batch(const float* points_dev, const int64_t* ranges_dev, int32_t n_clusters, pch_obb_result* out_dev,
                              void* workspace, size_t workspace_bytes, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -613,7 +671,8 @@ extern "C" int pch_obb_batch(const float* points_dev, const int64_t* ranges_dev,
         return PCH_ERR_WORKSPACE;
     }
     PCH_LAUNCH(st, "k_obb", k_obb<<<(unsigned)n_clusters, OBB_THREADS, 0, st>>>(points_dev, (const long long*)ranges_dev, n_clusters,
-                                                                                   (uint8_t*)workspace, OBB_WS_BYTES, (ObbOut*)out_dev));
+                                                                                   (uint8_t*)workspace, OBB_WS_BYTES, (ObbOut*)out_dev,
+                                                                                   obb_max_candidates()));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

@@ -114,3 +114,41 @@ def bounding_box_oriented(points: np.ndarray, ordered: bool = False):
     reference reads (utils/tower_extraction.py:139,151,165)."""
     to_origin, ext = oriented_bounds(points, ordered=ordered)
     return np.linalg.inv(to_origin), ext
+
+
+def min_volume_box_faces(points: np.ndarray):
+    """Host stand-in for the device kernel (pch_obb.cu) on the clusters it hands back (hulls beyond its capacity): the
+    SAME search — every hull-face normal, every hull edge as rectangle direction — so that a tower list does not depend
+    on where a box was computed.  Brute force over (normal x edge), vectorised; Qhull raises for flat input like trimesh.
+    -> (transform box->world 4x4, extents (long, short, along-normal))."""
+    pts = np.asarray(points, dtype=np.float64)
+    hull = ConvexHull(pts, qhull_options="Pp Qt")
+    verts = pts[hull.vertices]
+    tri = pts[hull.simplices]
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    ln = np.linalg.norm(nrm, axis=1)
+    nrm = nrm[ln > 0] / ln[ln > 0][:, None]
+    edges = np.concatenate([tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 1], tri[:, 0] - tri[:, 2]])
+    best = (np.inf, None, None)
+    for n in nrm:
+        u = edges - np.outer(edges @ n, n)
+        ul = np.linalg.norm(u, axis=1)
+        u = u[ul > 1e-10] / ul[ul > 1e-10][:, None]
+        v = np.cross(n, u)
+        pu, pv = verts @ u.T, verts @ v.T
+        vol = np.ptp(pu, axis=0) * np.ptp(pv, axis=0) * np.ptp(verts @ n)
+        k = int(np.argmin(vol))
+        if vol[k] < best[0]:
+            best = (float(vol[k]), n, u[k])
+    _, n, u = best
+    v = np.cross(n, u)
+    ext = np.array([np.ptp(verts @ u), np.ptp(verts @ v), np.ptp(verts @ n)])
+    if ext[0] < ext[1]:
+        u, v = v, -u
+        ext[[0, 1]] = ext[[1, 0]]
+    rot = np.column_stack((u, v, n))
+    loc = verts @ rot
+    t = np.eye(4)
+    t[:3, :3] = rot
+    t[:3, 3] = rot @ (loc.min(axis=0) + 0.5 * np.ptp(loc, axis=0))
+    return t, ext

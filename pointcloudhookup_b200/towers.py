@@ -371,7 +371,12 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
                     # "obb_trimesh" / "obb_ordered" (trimesh's own thinned search, host Qhull) and the clusters the
                     # device kernel turned away (degenerate: the host raises like trimesh does; capacity)
                     cp = cluster_points(label)
-                    tr, ext = _obb.bounding_box_oriented(cp, ordered=(box == "obb_ordered"))
+                    if box == "obb":      # a cluster the kernel handed back: the same exhaustive search on the host
+                        tr, ext = _obb.min_volume_box_faces(cp)
+                        a0, a1, a2 = canonical_box_axes(tr[:3, 0], tr[:3, 2])
+                        tr[:3, :3] = np.column_stack((a0, a1, a2))
+                    else:
+                        tr, ext = _obb.bounding_box_oriented(cp, ordered=(box == "obb_ordered"))
                     ctr, rot = tr[:3, 3], tr[:3, :3]
                 height, width = ext[2], max(ext[0], ext[1])
             aspect = height / width

@@ -32,3 +32,16 @@ torch.cuda.synchronize(); t1 = time.perf_counter()
 print(f"obb_batch: {len(cand)} clusters in {1e3*(t1-t0):.1f} ms; status counts {np.bincount(res['status'], minlength=4).tolist()}; "
       f"faces median {int(np.median(res['n_faces']))} max {int(res['n_faces'].max())}; candidates median {int(np.median(res['n_candidates']))} "
       f"max {int(res['n_candidates'].max())}; points median {int(np.median(st['count'][cand]))}", flush=True)
+nc = res["n_candidates"]
+print("candidate quantiles 50/90/99/max:", np.percentile(nc, [50, 90, 99, 100]).astype(int).tolist(),
+      " >2048:", int((nc > 2048).sum()), " >8192:", int((nc > 8192).sum()), " faces 50/90/99/max:", np.percentile(res["n_faces"], [50, 90, 99, 100]).astype(int).tolist())
+from pointcloudhookup_b200 import obb as hobb
+bad = [l for l, r in zip(cand, res) if r["status"] != 0]
+t0 = time.perf_counter()
+for l in bad:
+    pts = rows[int(off[l]): int(off[l + 1])].cpu().numpy()
+    try:
+        hobb.bounding_box_oriented(pts)
+    except Exception as e:
+        pass
+print(f"host fallback for {len(bad)} clusters: {1e3*(time.perf_counter()-t0):.1f} ms", flush=True)

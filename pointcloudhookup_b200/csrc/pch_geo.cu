@@ -8,6 +8,8 @@
 #include "pch_common.cuh"
 #include "pch_tiles.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #define PCH_GEOID_NODATA (-88.8888f)
 
@@ -172,10 +174,11 @@ struct GeoAffine {
 template <int ALIGN, bool STAGED>
 __global__ void __launch_bounds__(PCH_TILE_THREADS, 1)
 k_las_geodetic(const uint8_t* __restrict__ rec, PchTileGeom tg, GeoAffine a, pch_tm_params tm, const float* __restrict__ grid,
-               pch_geoid_grid g, GeoWindow w, double mult, int use_crs, double* __restrict__ out /*(n,3)*/) {
+               pch_geoid_grid g, GeoWindow w, double mult, int use_crs, double* __restrict__ out /*(n,3)*/,
+               const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const size_t tile_bytes = 128 + (size_t)PCH_STAGES * tg.stage_bytes;
-    float* s_win = reinterpret_cast<float*>(smem + tile_bytes + 16);
+    float* s_win = reinterpret_cast<float*>(smem + tile_bytes + 128);      // 128-byte aligned: a tensor-map destination
     uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
     if (STAGED) {
         if (threadIdx.x == 0) {
@@ -183,8 +186,16 @@ k_las_geodetic(const uint8_t* __restrict__ rec, PchTileGeom tg, GeoAffine a, pch
             pch_fence_mbar_init();
             const uint32_t row_bytes = (uint32_t)w.cols * 4u;
             pch_mbar_arrive_expect_tx(wbar, row_bytes * (uint32_t)w.rows);
-            for (int r = 0; r < w.rows; ++r)
-                pch_tma_load_1d(s_win + (size_t)r * w.cols, grid + (size_t)(w.row0 + r) * g.pitch + w.col0, row_bytes, wbar);
+            if (use_tmap) {
+                // the whole window of the geoid grid in ONE 2-D tensor-map copy (cp.async.bulk.tensor.2d -> SASS UTMALDG):
+                // box = (cols, rows) at coordinate (col0, row0) of the (pitch x rows) float32 grid
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(pch_smem_u32(s_win)), "l"(&tmap), "r"(w.col0), "r"(w.row0), "r"(pch_smem_u32(wbar))
+                             : "memory");
+            } else {
+                for (int r = 0; r < w.rows; ++r)
+                    pch_tma_load_1d(s_win + (size_t)r * w.cols, grid + (size_t)(w.row0 + r) * g.pitch + w.col0, row_bytes, wbar);
+            }
         }
         __syncthreads();
         pch_mbar_wait(wbar, 0);
@@ -245,13 +256,38 @@ extern "C" int pch_las_geodetic(const uint8_t* rec, int64_t n, int32_t rec_len, 
                       "geoid window larger than 64 KiB");
     }
     PchTileGeom tg = pch_tile_geom(n, rec_len, n);
-    size_t smem = pch_tile_smem_bytes(tg) + 16 + (staged ? (size_t)win_rows * win_cols * 4 : 0);
+    size_t smem = pch_tile_smem_bytes(tg) + 128 + (staged ? (size_t)win_rows * win_cols * 4 : 0);
+    // 2-D tensor map of the grid, box = the window (each box side <= 256 elements); without it (older driver, larger
+    // window) the window is staged row by row with 1-D bulk copies
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tmap = 0;
+    if (staged && win_rows <= 256 && win_cols <= 256 && !getenv("PCH_GEO_NO_TENSORMAP")) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)g->pitch, (cuuint64_t)g->rows};
+            const cuuint64_t gstride[1] = {(cuuint64_t)g->pitch * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)win_cols, (cuuint32_t)win_rows};
+            const cuuint32_t estr[2] = {1, 1};
+            if (((encode_fn)fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)grid, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                use_tmap = 1;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     int grid_dim = pch_tile_grid(tg, smem * 2 <= 220 * 1024 ? 2 : 1);
     int al = pch_rec_align(rec_len);
 #define LAUNCH_GEO(A, S)                                                                                         \
     do {                                                                                                         \
         PCH_CUDA(cudaFuncSetAttribute(k_las_geodetic<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        PCH_LAUNCH(st, "k_las_geodetic", k_las_geodetic<A, S><<<grid_dim, PCH_TILE_THREADS, smem, st>>>(rec, tg, a, tmv, grid, *g, w, multiplier, use_crs, out)); \
+        PCH_LAUNCH(st, "k_las_geodetic", k_las_geodetic<A, S><<<grid_dim, PCH_TILE_THREADS, smem, st>>>(rec, tg, a, tmv, grid, *g, w, multiplier, use_crs, out, tmap, use_tmap)); \
     } while (0)
     if (staged) {
         if (al == 4) LAUNCH_GEO(4, true); else if (al == 2) LAUNCH_GEO(2, true); else LAUNCH_GEO(1, true);

@@ -420,7 +420,13 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         stage_candidates(c, s_pts);
         const int f1 = gift_wrap(c, w, 1024, s_red, s_ctl);
         __syncthreads();
-        if (f1 <= 0) break;                    // degenerate seed (flat / collinear cluster): no cull
+        if (f1 <= 0) {
+            // The hull of the extreme points did not close: the cluster is flat within the tolerances (f1 == 0), or so
+            // nearly flat that the coplanar tie-breaks kept producing faces (f1 < 0).  Wrapping all points would only
+            // repeat that at full cost: hand the cluster to the host, where Qhull decides (it raises for flat input).
+            if (round == 0) { fail(f1 == 0 ? 2 : 3); return; }
+            break;
+        }
         for (int f = tid; f < f1; f += OBB_THREADS) {
             s_plane[f] = make_float4((float)w.planes[f * 4 + 0], (float)w.planes[f * 4 + 1], (float)w.planes[f * 4 + 2],
                                      (float)w.planes[f * 4 + 3]);

@@ -493,7 +493,9 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
             src = listA;
         }
         c.idx = src;
-    } else {      // no usable cull (degenerate seed, or more survivors than the lists hold): wrap all points
+    } else {      // no cull: a small cluster (no seed rounds) is wrapped whole; a big one whose survivors never fitted the
+                  // lists (tens of thousands of points all near the hull) costs Qhull far less than gift wrapping
+        if (n > 4096) { fail(3); return; }
         c.idx = nullptr;
         n_c = n;
     }

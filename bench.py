@@ -548,7 +548,8 @@ def run_tiled(args):
         grid = geo.load_grid(path, dev)
 
     info = {}
-
+    # the common float32 frame of the candidates: known to every rank from the LAS header (its offsets) — no collective
+    frame = np.array([synth.OFFSETS[0], synth.OFFSETS[1], 100.0], dtype=np.float32)
     geo_sums = []
 
     def per_tile(dl, vres):

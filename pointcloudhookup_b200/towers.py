@@ -340,7 +340,16 @@ def select_towers(stages: TowerStages, aspect_ratio_threshold=0.8, min_height=15
         if cand:
             rows, off = cluster_rows()
             res = dv.obb_batch(rows, np.array([[off[l], off[l + 1]] for l in cand], dtype=np.int64))
-            device_boxes = {l: r for l, r in zip(cand, res)}
+            # the size filter for all device boxes at once (same comparisons as the per-label code below); only the
+            # boxes that pass, and the clusters the kernel handed back, reach the python loop — in the same set() order
+            ext_d = res["extents"]
+            h_d, w_d = ext_d[:, 2], np.maximum(ext_d[:, 0], ext_d[:, 1])
+            with np.errstate(divide="ignore", invalid="ignore"):
+                passes = (h_d > min_height) & (min_width < w_d) & (w_d < max_width) & (h_d / w_d > aspect_ratio_threshold)
+            go = passes | (res["status"] != 0)
+            device_boxes = {l: r for l, r, g in zip(cand, res, go) if g}
+            alive = set(device_boxes)
+            order = [l for l in order if l in alive]
 
     for li, label in enumerate(order):
         try:

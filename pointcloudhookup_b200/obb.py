@@ -118,22 +118,35 @@ def bounding_box_oriented(points: np.ndarray, ordered: bool = False):
 
 def min_volume_box_faces(points: np.ndarray):
     """Host stand-in for the device kernel (pch_obb.cu) on the clusters it hands back (hulls beyond its capacity): the
-    SAME search — every hull-face normal, every hull edge as rectangle direction — so that a tower list does not depend
-    on where a box was computed.  Brute force over (normal x edge), vectorised; Qhull raises for flat input like trimesh.
+    SAME search — every hull-face normal; for each, every SILHOUETTE edge of the hull (the two faces that share it look to
+    opposite sides of the normal = an edge of the projected hull) as rectangle direction — so that a tower list does not
+    depend on where a box was computed.  Qhull raises for flat input like trimesh.
     -> (transform box->world 4x4, extents (long, short, along-normal))."""
     pts = np.asarray(points, dtype=np.float64)
     hull = ConvexHull(pts, qhull_options="Pp Qt")
     verts = pts[hull.vertices]
-    tri = pts[hull.simplices]
+    simp, nb = hull.simplices, hull.neighbors
+    tri = pts[simp]
     nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
     ln = np.linalg.norm(nrm, axis=1)
-    nrm = nrm[ln > 0] / ln[ln > 0][:, None]
-    edges = np.concatenate([tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 1], tri[:, 0] - tri[:, 2]])
+    ok = ln > 0
+    nrm[ok] /= ln[ok][:, None]
+    nrm[np.einsum("ij,ij->i", nrm, tri[:, 0] - verts.mean(axis=0)) < 0] *= -1.0
+    # edge k of simplex i is opposite vertex k; its neighbour facet is neighbors[i][k]
+    f_of = np.repeat(np.arange(len(simp)), 3)
+    g_of = nb.reshape(-1)
+    ev = np.stack([pts[simp[:, [1, 2, 0]].reshape(-1)], pts[simp[:, [2, 0, 1]].reshape(-1)]], axis=1)
+    evec = ev[:, 1] - ev[:, 0]
+    uniq = np.unique(np.round(nrm[ok], 12), axis=0, return_index=True)[1]
     best = (np.inf, None, None)
-    for n in nrm:
-        u = edges - np.outer(edges @ n, n)
+    for n in nrm[ok][np.sort(uniq)]:
+        side = nrm @ n
+        sil = (side[f_of] >= 0) & (side[g_of] < 0)
+        u = evec[sil] - np.outer(evec[sil] @ n, n)
         ul = np.linalg.norm(u, axis=1)
         u = u[ul > 1e-10] / ul[ul > 1e-10][:, None]
+        if len(u) == 0:
+            continue
         v = np.cross(n, u)
         pu, pv = verts @ u.T, verts @ v.T
         vol = np.ptp(pu, axis=0) * np.ptp(pv, axis=0) * np.ptp(verts @ n)

@@ -95,7 +95,7 @@ __device__ __forceinline__ int block_best(int mine, BETTER better, int* s_red) {
     return best;
 }
 
-#define OBB_SMAX 512    // seed points of the cull (their hull has < 1024 faces)
+#define OBB_SMAX 256    // seed points of the cull (their hull has about 500 faces; every face is one serial wrap step)
 #define OBB_ROUNDS 4
 #define OBB_SPTS 2048   // candidate coordinates staged in shared memory when they fit (the usual case)
 
@@ -466,19 +466,32 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         const int kept = s_count;
         __syncthreads();
         if (kept <= list_cap) { src = dst; n_src = kept; n_c = kept; have_list = true; }
-        // grow the seed by the farthest point of every face that still has something outside (thread 0: <= 1024 faces)
-        if (tid == 0) {
-            int m = n_s;
-            for (int f = 0; f < f1 && m < OBB_SMAX; ++f) {
-                const unsigned long long v = s_far[f];
-                if (!v) continue;
-                const int i = (int)(uint32_t)v;
-                bool dup = false;
-                for (int j = n_s; j < m && !dup; ++j) dup = w.cand[j] == i;   // the same point can be farthest for several faces
-                if (!dup) w.cand[m++] = i;
+        // grow the seed by the farthest point of every face that still has something outside.  The same point can be the
+        // farthest for several faces: every face looks for an earlier face with the same point in shared memory, the
+        // distinct ones are appended with ballots (a serial version of this loop, reading the list from global memory,
+        // was most of the kernel's time)
+        if (tid == 0) s_ctl[0] = n_s;
+        __syncthreads();
+        for (int f0 = 0; f0 < f1; f0 += OBB_THREADS) {
+            const int f = f0 + tid;
+            bool add = false;
+            int i = -1;
+            if (f < f1 && s_far[f]) {
+                i = (int)(uint32_t)s_far[f];
+                add = true;
+                for (int g = 0; g < f && add; ++g) add = (int)(uint32_t)s_far[g] != i || !s_far[g];
             }
-            s_ctl[0] = m;
+            const uint32_t bal = __ballot_sync(0xffffffffu, add);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_ctl[0], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (add) {
+                const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                if (pos < OBB_SMAX) w.cand[pos] = i;
+            }
         }
+        __syncthreads();
+        if (tid == 0 && s_ctl[0] > OBB_SMAX) s_ctl[0] = OBB_SMAX;
         __syncthreads();
         const int grown = s_ctl[0];
         __syncthreads();

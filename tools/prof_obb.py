@@ -45,3 +45,19 @@ for l in bad:
     except Exception as e:
         pass
 print(f"host fallback for {len(bad)} clusters: {1e3*(time.perf_counter()-t0):.1f} ms", flush=True)
+# kernel-only time of the batch (library events) against the wall time of the call
+import ctypes
+from pointcloudhookup_b200 import _native
+lib = _native.lib()
+rgs = np.array([[off[l], off[l + 1]] for l in cand], dtype=np.int64)
+for rep in range(3):
+    lib.pch_profile_enable(1)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = dv.obb_batch(rows, rgs)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    lib.pch_profile_enable(0)
+    buf = ctypes.create_string_buffer(65536); lib.pch_profile_report(buf, 65536)
+    print(f"obb_batch rep {rep}: wall {1e3*(t1-t0):.1f} ms; kernels: {buf.value.decode().strip()}", flush=True)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+ws = torch.empty(lib.pch_obb_workspace_bytes(len(cand)), dtype=torch.uint8, device=rows.device)
+torch.cuda.synchronize(); print(f"workspace alloc {ws.numel()/1e9:.2f} GB: {1e3*(time.perf_counter()-t0):.1f} ms", flush=True)

@@ -98,6 +98,7 @@ __device__ __forceinline__ int block_best(int mine, BETTER better, int* s_red) {
 #define OBB_SMAX 256    // seed points of the cull (their hull has about 500 faces; every face is one serial wrap step)
 #define OBB_ROUNDS 4
 #define OBB_SPTS 2048   // candidate coordinates staged in shared memory when they fit (the usual case)
+#define OBB_BIG_SPTS 16384   // second launch, one CTA per SM with 192 KB of dynamic shared memory: the few clusters that keep more
 
 // The wrap works on LOCAL ids 0..n-1 (positions in the candidate list); row ids only come back at the end.
 struct WrapCtx {
@@ -114,9 +115,9 @@ __device__ __forceinline__ D3 cpt(const WrapCtx& c, int k) {
     return ld3(c.P, row_of(c, k));
 }
 // all threads: stage the candidates' coordinates when they fit
-__device__ __forceinline__ void stage_candidates(WrapCtx& c, float* s_pts) {
+__device__ __forceinline__ void stage_candidates(WrapCtx& c, float* s_pts, int spts) {
     c.S = nullptr;
-    if (c.n <= OBB_SPTS) {
+    if (c.n <= spts) {
         for (int k = threadIdx.x; k < c.n; k += OBB_THREADS) {
             const int r = row_of(c, k);
             s_pts[k * 3 + 0] = c.P[r * 3 + 0]; s_pts[k * 3 + 1] = c.P[r * 3 + 1]; s_pts[k * 3 + 2] = c.P[r * 3 + 2];
@@ -297,13 +298,14 @@ struct ObbOut {   // mirrors pch_obb_result
 
 __global__ void __launch_bounds__(OBB_THREADS)
 k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, int n_clusters, uint8_t* __restrict__ ws_base,
-      size_t ws_stride, ObbOut* __restrict__ out, int max_cand) {
+      size_t ws_stride, ObbOut* __restrict__ out, int max_cand, int spts, int pass) {
     __shared__ int s_red[OBB_WARPS];
     __shared__ int s_ctl[4];
     __shared__ float s_dirmax[OBB_DIRS];
     __shared__ int s_dirarg[OBB_DIRS];
-    // one buffer, two lives: the staged candidate coordinates during a wrap, the planes of the seed hull during a cull
-    __shared__ __align__(16) unsigned char s_buf[OBB_SPTS * 12];
+    // one buffer (dynamic: spts * 12 bytes), two lives: the staged candidate coordinates during a wrap, the planes of
+    // the seed hull during a cull
+    extern __shared__ __align__(16) unsigned char s_buf[];
     float* s_pts = reinterpret_cast<float*>(s_buf);
     float4* s_plane = reinterpret_cast<float4*>(s_buf);
     __shared__ unsigned long long s_far[1024];
@@ -318,6 +320,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     const float* P = points + r0 * 3;
     ObbWs w = obb_ws(ws_base + (size_t)k * ws_stride);
     ObbOut* o = out + k;
+    if (pass == 1 && o->status != 4) return;      // the second launch only takes the clusters the first one deferred
     auto fail = [&](int status) {
         if (tid == 0) { o->status = status; o->n_faces = 0; o->n_verts = 0; o->n_candidates = 0; o->volume = 0.0; }
     };
@@ -417,7 +420,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
     for (int round = 0; round < OBB_ROUNDS && n_s >= 4; ++round) {
         c.idx = w.cand;
         c.n = n_s;
-        stage_candidates(c, s_pts);
+        stage_candidates(c, s_pts, spts);
         const int f1 = gift_wrap(c, w, 1024, s_red, s_ctl);
         __syncthreads();
         if (f1 <= 0) {
@@ -495,7 +498,7 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         __syncthreads();
         const int grown = s_ctl[0];
         __syncthreads();
-        const bool done = grown == n_s || (have_list && n_c <= OBB_SPTS);
+        const bool done = grown == n_s || (have_list && n_c <= OBB_SPTS);     // small enough for the fast path of either launch
         n_s = grown;
         if (done) break;
     }
@@ -520,8 +523,14 @@ k_obb(const float* __restrict__ points, const long long* __restrict__ ranges, in
         if (tid == 0) { o->status = 3; o->n_faces = 0; o->n_verts = 0; o->n_candidates = n_c; o->volume = 0.0; }
         return;
     }
+    if (pass == 0 && n_c > spts && n_c <= OBB_BIG_SPTS) {
+        // more candidates than this launch can stage: wrapping them from global memory costs tens of milliseconds per
+        // cluster; the second launch (large shared memory, one CTA per SM) takes it
+        if (tid == 0) o->status = 4;
+        return;
+    }
     c.n = n_c;
-    stage_candidates(c, s_pts);
+    stage_candidates(c, s_pts, spts);
     const int F = gift_wrap(c, w, OBB_MAXF, s_red, s_ctl);
     __syncthreads();
     if (F <= 0) { fail(F == 0 ? 2 : 3); return; }
@@ -691,9 +700,16 @@ extern "C" int pch_obb_batch(const float* points_dev, const int64_t* ranges_dev,
         pch_set_error("obb workspace too small: %zu < %zu", workspace_bytes, pch_obb_workspace_bytes(n_clusters));
         return PCH_ERR_WORKSPACE;
     }
-    PCH_LAUNCH(st, "k_obb", k_obb<<<(unsigned)n_clusters, OBB_THREADS, 0, st>>>(points_dev, (const long long*)ranges_dev, n_clusters,
-                                                                                   (uint8_t*)workspace, OBB_WS_BYTES, (ObbOut*)out_dev,
-                                                                                   obb_max_candidates()));
+    const int max_cand = obb_max_candidates();
+    PCH_LAUNCH(st, "k_obb", k_obb<<<(unsigned)n_clusters, OBB_THREADS, (size_t)OBB_SPTS * 12, st>>>(
+                                points_dev, (const long long*)ranges_dev, n_clusters, (uint8_t*)workspace, OBB_WS_BYTES,
+                                (ObbOut*)out_dev, max_cand, OBB_SPTS, 0));
+    PCH_LAUNCH_CHECK();
+    // second launch for the clusters the first one deferred (status 4): same kernel, 192 KB of dynamic shared memory
+    PCH_CUDA(cudaFuncSetAttribute(k_obb, cudaFuncAttributeMaxDynamicSharedMemorySize, OBB_BIG_SPTS * 12));
+    PCH_LAUNCH(st, "k_obb_big", k_obb<<<(unsigned)n_clusters, OBB_THREADS, (size_t)OBB_BIG_SPTS * 12, st>>>(
+                                    points_dev, (const long long*)ranges_dev, n_clusters, (uint8_t*)workspace, OBB_WS_BYTES,
+                                    (ObbOut*)out_dev, max_cand, OBB_BIG_SPTS, 1));
     PCH_LAUNCH_CHECK();
     return PCH_OK;
 }

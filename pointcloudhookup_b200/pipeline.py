@@ -318,41 +318,6 @@ def corridor_axis(azimuth_deg: float):
     return float(np.sin(a)), float(np.cos(a))
 
 
-def tile_candidates(dl: dv.DeviceLas, origin_dev: Optional[torch.Tensor], voxel_size: float, chunk_size: int,
-                    ground: str = "percentile", cell: float = 2.0, hag: float = 3.0):
-    """Voxel downsample + ground removal on ONE tile; the kept points are expressed relative to `origin_dev`
-    (float32[3], common to all tiles), so that every rank computes distances on identical coordinates.
-      ground="percentile": the reference's height filter with the tile's OWN centroid and percentile, i.e. the
-                           reference run on that tile's LAS (utils/tower_extraction.py:57-93).
-      ground="grid":       north_star's grid min-z / height-above-ground model of the tile, in the common frame
-                           (cells from the tile's own minimum; no centroid, so no exact-sum kernels).
-    origin_dev None: this tile defines the frame (its centroid, resp. the centre of its bounding box).
-    -> (candidates (G,3) float32, voxel result, origin_dev)."""
-    vres = dv.voxel_downsample(dl, voxel_size, chunk_size, want=("f32", "z32") if ground == "percentile" else ("f32",))
-    if vres.count == 0:
-        z = torch.zeros((0, 3), dtype=torch.float32, device=dl.device)
-        return z, vres, origin_dev
-    raw = vres.f32
-    if ground == "percentile":
-        _, cen_dev, _, _, mask, _ = tw._ground_filter_percentile(raw, want_mask=True, zcol=vres.z32)
-        if origin_dev is None:
-            origin_dev = cen_dev.clone()
-        cand, g, _, _ = dv.compact_points(raw, None, 0.0, origin_dev, keep_mask=mask)
-    elif ground == "grid":
-        mm = dv.f32_minmax_dev(raw).cpu().numpy()
-        if origin_dev is None:
-            origin = ((mm[:3] + mm[3:]) * np.float32(0.5)).astype(np.float32)
-            origin_dev = torch.from_numpy(origin).to(raw.device)
-        else:
-            origin = origin_dev.cpu().numpy()
-        mn, mx = mm[0:2] - origin[:2], mm[3:5] - origin[:2]          # float32, like the kernels' shift
-        nx, ny = dv.grid_shape(mn, mx, cell, raw.shape[0])
-        cand, g, _ = dv.compact_points_grid(raw, origin_dev, mn, nx, ny, cell, hag)
-    else:
-        raise ValueError(f"unknown ground mode {ground!r}")
-    return cand, vres, origin_dev
-
-
 def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float = 0.1, chunk_size: int = 500000,
                        eps: float = 8.0, min_points: int = 80, keep: bool = False, clusterer=None,
                        ground: str = "percentile", cell: float = 2.0, hag: float = 3.0, per_tile=None, origin=None,

@@ -325,7 +325,12 @@ def run_pipeline_tiled(tiles: List[dv.DeviceLas], comm, axis, voxel_size: float 
     """This rank's consecutive corridor tiles -> candidates per tile -> ONE DBSCAN over the tiles of all ranks
     (halo exchange with the neighbouring ranks, tiles.tile_dbscan) -> towers from the all-reduced per-cluster
     table (box = AABB rule of test/008.py:302-319).  Equals `dbscan_chunked(chunk=G)` on the concatenation of
-    all ranks' candidates, label for label.  `per_tile(dl, voxel_result)` is called after each tile's voxel stage
+    all ranks' candidates, label for label.
+    Ground removal stays per tile: ground="percentile" is the reference's height filter with the tile's OWN centroid and
+    percentile, i.e. the reference run on that tile's LAS (utils/tower_extraction.py:57-93); ground="grid" is north_star's
+    grid min-z / height-above-ground model of the tile (cells from the tile's own minimum).  The kept points of every
+    tile are then expressed in ONE float32 frame, so that all ranks compute distances on identical coordinates.
+    `per_tile(dl, voxel_result)` is called after each tile's voxel stage
     (the geoid / CRS conversion of configs[4] hooks in here).  `origin` (float32[3]): a frame every rank already knows
     (e.g. the project's LAS header offset plus a nominal height) saves the collective that otherwise agrees on one."""
     from . import tiles as tl

@@ -445,10 +445,16 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
     n_local = nL + G + nR
     empty_i = torch.zeros(0, dtype=torch.int32, device=dev)
     pair_rows, table = np.zeros((0, 3), np.int64), np.zeros(0, np.int64)
-    labels_core, k_local = None, 0
+    labels_core, k_local, failure = None, 0, None
     if n_local:
         P_local = torch.cat(parts).contiguous() if len(parts) > 1 else P_own.contiguous()
-        labels_core, k_local = clu.cores(P_local, eps, min_samples)
+        try:
+            labels_core, k_local = clu.cores(P_local, eps, min_samples)
+        except (ValueError, RuntimeError) as e:
+            # a rank that stopped here would leave its neighbours waiting in the echo: it keeps to the protocol with
+            # "no cluster anywhere" and reports the failure in the gather below, where EVERY rank raises
+            failure = e
+            labels_core, k_local = torch.full((n_local,), -1, dtype=torch.int32, device=dev), 0
         tr.mark("cores")
     # the way back: what I think of the halo points goes to their owners, device to device; I learn what the
     # neighbours think of the points I sent them.  A point that is core on both sides joins the two local clusters.
@@ -456,7 +462,7 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
                                          labels_core[nL + G:].contiguous() if nR else None,
                                          int(idx_l.numel()), int(idx_r.numel()))
     tr.mark("echo p2p")
-    if n_local:
+    if n_local and failure is None:
         n_sl, n_sr = (0 if echo_l is None else int(echo_l.numel())), (0 if echo_r is None else int(echo_r.numel()))
         pos = torch.cat([idx_l[:n_sl] + nL, idx_r[:n_sr] + nL]) if (n_sl + n_sr) else empty_i
         extra = torch.cat([t.to(dev) for t in (echo_l, echo_r) if t is not None]) if (n_sl + n_sr) else empty_i
@@ -472,11 +478,16 @@ def tile_dbscan(P_own: torch.Tensor, axis: Sequence[float], eps: float, min_samp
             pair_rows = np.concatenate(rows)
     tr.mark("report")
     # one variable-size all-gather carries both the cluster pairs and the per-cluster tables
-    packed = np.concatenate([[len(pair_rows), len(table)], pair_rows.reshape(-1), table]).astype(np.int64)
+    packed = np.concatenate([[len(pair_rows), len(table), int(failure is not None)], pair_rows.reshape(-1), table]).astype(np.int64)
     got = comm.all_gather_np(packed)
     tr.mark("gather pairs")
-    entries = [g[2: 2 + 3 * int(g[0])].reshape(-1, 3) for g in got]
-    tables = [g[2 + 3 * int(g[0]): 2 + 3 * int(g[0]) + int(g[1])] for g in got]
+    failed = [q for q, g in enumerate(got) if int(g[2])]
+    if failure is not None:
+        raise failure
+    if failed:
+        raise RuntimeError(f"whole-corridor DBSCAN: phase 1 failed on rank(s) {failed}")
+    entries = [g[3: 3 + 3 * int(g[0])].reshape(-1, 3) for g in got]
+    tables = [g[3 + 3 * int(g[0]): 3 + 3 * int(g[0]) + int(g[1])] for g in got]
     maps, n_global = merge_local_clusters(entries, tables)
     tr.mark("merge")
     if n_local:

@@ -93,6 +93,33 @@ def test_tiles_closer_than_two_eps_are_refused():
     assert len(errs) == 3 and all("2*eps" in e for e in errs)
 
 
+def test_a_failure_in_phase_one_on_one_rank_raises_on_every_rank():
+    """The rank whose local clustering fails keeps to the exchange protocol, so its neighbours are not left waiting
+    for labels that never come; the failure travels with the pair gather and every rank raises."""
+    import halo_oracle as ho
+    from pointcloudhookup_b200 import tiles as tl
+    tiles = ho.corridor_candidates(5, 3, per_tile=600)
+
+    class Failing(ho.OracleClusterer):
+        def cores(self, P, eps, min_samples):
+            raise ValueError("DBSCAN cell grid does not fit the packed key")
+    group = tl.ThreadComm.Group(3)
+    errs = [None] * 3
+
+    def run(r):
+        try:
+            tl.tile_dbscan(torch.from_numpy(tiles[r]), (1.0, 0.0), EPS, MINPTS, tl.ThreadComm(group, r),
+                           Failing() if r == 1 else ho.OracleClusterer())
+        except (ValueError, RuntimeError) as e:
+            errs[r] = e
+    th = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(3)]
+    [t.start() for t in th]
+    [t.join(timeout=60) for t in th]
+    assert not any(t.is_alive() for t in th), "a rank is still waiting for its failed neighbour"
+    assert isinstance(errs[1], ValueError) and "packed key" in str(errs[1])
+    assert all(isinstance(errs[r], RuntimeError) and "[1]" in str(errs[r]) for r in (0, 2))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

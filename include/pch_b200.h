@@ -326,6 +326,52 @@ size_t pch_obb_workspace_bytes(int32_t n_clusters);
 int pch_obb_batch(const float* points_dev, const int64_t* ranges_dev, int32_t n_clusters, pch_obb_result* out_dev,
                   void* workspace_dev, size_t workspace_bytes, pch_stream_t stream);
 
+/* ---------------------------------------------------------------- tiled RANSAC ground
+ *
+ * remove_ground_tiled_ransac(points, tile_size, distance_threshold, max_iterations) of test/main_ground.py:77-115:
+ * squares of tile_size metres between np.arange edges (:84-91), and in every square with >= 10 points (:101) a
+ * scikit-learn RANSACRegressor plane z = f(x, y) (:8-32): inliers are ground, outliers non-ground, both stacked
+ * tile by tile (:110-113).  Points beyond the last edge and squares with < 10 points appear in NEITHER output,
+ * as in the reference.
+ *
+ * pch_xy_minmax_f64: out4_dev = min x, min y, max x, max y of (n,3) float64 rows (np.min / np.max, :84-85);
+ *   scratch32_dev: 32 bytes of device scratch.
+ * pch_ransac_tile_words: word = tile << 32 | index with tile = i * (n_y_edges-1) + j, the order of the reference's two
+ *   loops; points outside every tile get tile = (n_x_edges-1)*(n_y_edges-1).  *_edges3 (HOST pointers) = edges[0],
+ *   edges[1], edges[1]-edges[0] of np.arange(min, max, tile_size): np.arange fills edges[i] = edges[0] + i*delta,
+ *   and the kernel evaluates exactly that, so `(x >= e[i]) & (x < e[i+1])` selects the same points.
+ *   Sorting the words (pch_sort_u64_segmented) and pch_word_bounds give each tile's slice; pch_gather_rows_f64
+ *   gathers rows[word & 0xffffffff] of the first m words = `points[tile_mask]` for every tile, concatenated.
+ * pch_ransac_tiles: RANSACRegressor.fit per tile, one CTA each (scikit-learn 1.x _ransac.py: min_samples 3,
+ *   residual = |z - prediction| <= distance_threshold, more inliers wins, equal inliers -> R^2 on the inliers decides,
+ *   max_trials shrinks by _dynamic_max_trials(stop_probability, 0.99 in the reference)).  The three sample rows of
+ *   trial k (1-based) of tile t come from triples_dev[(t*max_trials + k-1)*3 ..] when given (a test replays the
+ *   draws of scikit-learn's own generator this way), else from splitmix64 streams keyed by (seed, t, k).  The plane
+ *   through the three samples is solved in closed form (LinearRegression on 3 points is that plane; samples
+ *   collinear in xy, where LinearRegression returns a minimum-norm fit, are skipped as a trial).
+ *   flags_dev[row] = 1 ground (inlier), 0 non-ground, 2 in neither output.  status: 0 ok, 1 fewer than
+ *   min_tile_points rows, 2 no valid consensus set (scikit-learn raises ValueError).
+ * pch_ransac_split: ordered compaction of the gathered rows into the two outputs; *_off_dev[t] = first output row
+ *   of tile t (exclusive sums of n_inliers / n_points - n_inliers over the tiles with status 0). */
+typedef struct pch_ransac_tile {
+    int32_t n_points, n_trials, n_inliers, status;
+    double anchor[3];   /* first sample of the winning trial */
+    double slope[2];    /* z - anchor_z = slope[0]*(x - anchor_x) + slope[1]*(y - anchor_y) */
+    double score;       /* R^2 of the winning trial on its inliers */
+} pch_ransac_tile;
+int pch_xy_minmax_f64(const double* points_dev, int64_t n, double* out4_dev, void* scratch32_dev, pch_stream_t stream);
+int pch_ransac_tile_words(const double* points_dev, int64_t n, const double* x_edges3, int32_t n_x_edges,
+                          const double* y_edges3, int32_t n_y_edges, uint64_t* words_dev, pch_stream_t stream);
+int pch_gather_rows_f64(const double* points_dev, const uint64_t* words_dev, int64_t m, double* out_dev,
+                        pch_stream_t stream);
+int pch_ransac_tiles(const double* tile_points_dev, const int64_t* bounds_dev, int32_t n_tiles,
+                     double distance_threshold, int32_t max_trials, double stop_probability, uint64_t seed,
+                     const int32_t* triples_dev /* nullable */, int32_t min_tile_points, uint8_t* flags_dev,
+                     pch_ransac_tile* tiles_out_dev, pch_stream_t stream);
+int pch_ransac_split(const double* tile_points_dev, const uint8_t* flags_dev, const int64_t* bounds_dev, int32_t n_tiles,
+                     const int64_t* ground_off_dev, const int64_t* other_off_dev, double* ground_out_dev,
+                     double* other_out_dev, pch_stream_t stream);
+
 /* `cluster_points = filtered_points[all_labels == label]` for every label at once
  * (utils/tower_extraction.py:133-134): pch_label_words builds (label << 32 | index) words (noise sorts
  * last), pch_sort_u64_segmented orders them by label (stable), pch_gather_rows_f32 gathers the rows of

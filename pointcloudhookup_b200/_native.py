@@ -90,6 +90,11 @@ SIGNATURES.update({
     "pch_label_min_index": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p]),
     "pch_axis_extent": (C.c_int, [_p, _i64, _f64, _f64, _p, _p]),
     "pch_axis_band_mask": (C.c_int, [_p, _i64, _f64, _f64, _f64, _f64, _p, _p, _p]),
+    "pch_xy_minmax_f64": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "pch_ransac_tile_words": (C.c_int, [_p, _i64, C.POINTER(C.c_double), _i32, C.POINTER(C.c_double), _i32, _p, _p]),
+    "pch_gather_rows_f64": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "pch_ransac_tiles": (C.c_int, [_p, _p, _i32, _f64, _i32, _f64, C.c_uint64, _p, _i32, _p, _p, _p]),
+    "pch_ransac_split": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p]),
     "pch_obb_workspace_bytes": (_sz, [_i32]),
     "pch_obb_batch": (C.c_int, [_p, _p, _i32, _p, _p, _sz, _p]),
     "pch_dbscan_run": (C.c_int, [_p, _i64, _i64, _f64, _i32, _p, C.POINTER(VoxelPlan), _p, _p, _p, _i64, _p, _sz, _p]),

@@ -371,3 +371,23 @@ def test_integration_stub_matches_the_abi():
     exec(head, ns)
     sig = _native.SIGNATURES["pch_voxel_downsample_las"][1]
     assert [C.sizeof(t) for t in ns["lib"].pch_voxel_downsample_las.argtypes] == [C.sizeof(t) for t in sig]
+
+
+def test_arange_edges3_reproduces_numpy_arange():
+    """pch_ransac_tile_words rebuilds the tile edges as e[0] + i*(e[1]-e[0]) with e[1] taken as given: that is
+    np.arange's fill rule, bit for bit, also where (start + step) - start != step."""
+    from pointcloudhookup_b200 import ground_ransac as gr
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        lo = float(rng.choice([rng.uniform(-1, 1), rng.uniform(4e5, 6e5), rng.uniform(-3e6, 3e6)]))
+        step = float(rng.choice([10.0, 20.0, 0.1, 7.3]))
+        hi = lo + float(rng.uniform(0, 40)) * step
+        e = np.arange(lo, hi, step)
+        n, e3 = gr.arange_edges3(lo, hi, step)
+        assert n == len(e)
+        if n < 2:
+            assert e3 is None
+            continue
+        assert e3[0] == e[0] and e3[1] == e[1]
+        rebuilt = [e3[0] if i == 0 else e3[1] if i == 1 else e3[0] + i * e3[2] for i in range(n)]
+        assert np.array_equal(np.array(rebuilt), e)

@@ -255,3 +255,40 @@ def test_oracle_all_faces_box_is_never_larger_than_the_thinned_search():
         loc = (p.astype(np.float64) - t_all[:3, 3]) @ t_all[:3, :3]
         assert np.all(np.abs(loc) <= ext_all / 2 + 1e-6)
         assert abs(np.linalg.det(t_all[:3, :3]) - 1.0) < 1e-9
+
+
+def test_ransac_oracle_replaying_sklearns_draws_equals_sklearn():
+    """oracle.ransac restates RANSACRegressor's trial loop with a closed-form 3-point plane; with the subsets
+    scikit-learn's own generator draws for random_state=seed it must return scikit-learn's inlier mask and stop after
+    the same number of trials — on single tiles, and through the reference's tile loops (test/main_ground.py:77-115)."""
+    from sklearn.linear_model import RANSACRegressor
+    from oracle import ransac as orz
+    import ransac_cases as rc
+    for seed in range(12):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(12, 1200))
+        xy = rng.uniform(0, 10, (n, 2)) + np.array([500000.0, 3.2e6])
+        z = 100 + 0.05 * (xy[:, 0] - 500000) - 0.02 * (xy[:, 1] - 3.2e6) + rng.normal(0, 0.03, n)
+        z[: int([0.1, 0.4, 0.7][seed % 3] * n)] += rng.uniform(0.5, 25, int([0.1, 0.4, 0.7][seed % 3] * n))
+        pts = np.column_stack([xy, z])
+        T = 150
+        tri = orz.sklearn_triples(n, T, seed)
+        mask, info = orz.ransac_inlier_mask(pts, 0.1, T, lambda k: tuple(int(v) for v in tri[k - 1]))
+        sk = RANSACRegressor(residual_threshold=0.1, max_trials=T, random_state=seed).fit(pts[:, :2], pts[:, 2])
+        assert np.array_equal(mask, sk.inlier_mask_) and info["n_trials"] == sk.n_trials_
+    pts = rc.terrain_cloud(5, nx_m=38.0, ny_m=27.0)
+    seed_of_tile = lambda t: 1000 + t
+    exp_ng, exp_g, sizes, n_tiles = rc.literal_reference(pts, 10.0, 0.1, 120, seed_of_tile)
+    tri = rc.replay_triples(sizes, n_tiles, 120, seed_of_tile)
+    ng, g, _ = orz.remove_ground_tiled_ransac(pts, 10.0, 0.1, 120, triples={t: tri[t] for t in range(n_tiles)})
+    assert np.array_equal(ng, exp_ng) and np.array_equal(g, exp_g)
+    assert min(sizes.values()) < 10 and len(g) + len(ng) < len(pts)       # a skipped tile and the strip beyond the last edge
+
+
+def test_ransac_counter_generator_draws_three_distinct_rows():
+    from oracle import ransac as orz
+    for n in (3, 4, 10, 1000):
+        for k in range(1, 40):
+            t = orz.counter_triple(9, 5, k, n)
+            assert len(set(t)) == 3 and all(0 <= v < n for v in t)
+    assert orz.counter_triple(9, 5, 1, 1000) != orz.counter_triple(9, 6, 1, 1000) != orz.counter_triple(10, 5, 1, 1000)

@@ -32,10 +32,6 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _empty(n, dtype, device):
-    return torch.empty(int(n), dtype=dtype, device=device)
-
-
 @dataclasses.dataclass
 class DeviceLas:
     """Raw LAS point records resident in HBM (record i at byte i*rec_len, buffer padded to 16 B)."""

@@ -104,6 +104,11 @@ def test_no_cpu_fallback_without_cuda():
     from pointcloudhookup_b200.ui import import_PC
     with pytest.raises(Exception):
         import_PC.process_chunk(np.zeros((4, 3)), 0.1)
+    from pointcloudhookup_b200 import ground_ransac, tiles
+    with pytest.raises(_native.NativeError):
+        ground_ransac.remove_ground_tiled_ransac(np.zeros((100, 3)))
+    with pytest.raises(_native.NativeError):
+        tiles.DeviceClusterer()
 
 
 def test_product_does_not_import_oracle():

@@ -119,7 +119,8 @@ k_ransac_tile_words(const double* __restrict__ P, int64_t n, RzAxis ax, RzAxis a
 extern "C" int pch_ransac_tile_words(const double* points_dev, int64_t n, const double* x_edges3, int32_t n_x_edges,
                                      const double* y_edges3, int32_t n_y_edges, uint64_t* words_dev, pch_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    PCH_CHECK_ARG(n > 0 && n < (1ll << 31) && points_dev && words_dev && x_edges3 && y_edges3, "pch_ransac_tile_words: bad arguments");
+    PCH_CHECK_ARG(n > 0 && n < (1ll << 31) - 4096 && points_dev && words_dev && x_edges3 && y_edges3,
+                  "pch_ransac_tile_words: bad arguments (n must stay below 2^31 - 4096: 32-bit row numbers)");
     RzAxis ax = {x_edges3[0], x_edges3[1], x_edges3[2], n_x_edges}, ay = {y_edges3[0], y_edges3[1], y_edges3[2], n_y_edges};
     PCH_CHECK_ARG(n_x_edges >= 2 && n_y_edges >= 2 && ax.delta > 0 && ay.delta > 0, "pch_ransac_tile_words: no tiles");
     PCH_CHECK_ARG((int64_t)(n_x_edges - 1) * (n_y_edges - 1) < (1ll << 31) - 1, "pch_ransac_tile_words: too many tiles");

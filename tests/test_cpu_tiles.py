@@ -164,3 +164,63 @@ def test_tile_dbscan_world2_gloo():
     assert out[0][3] == out[1][3]
     assert out[0][4][1] == out[1][5][0] > 0 and out[1][4][0] == out[0][5][1] > 0     # sent right == received from left, and back
     assert out[0][6] == 16 * sum(out[0][4]) + 4 * sum(out[0][5])          # halo out (16 B / point) + labels echoed back (4 B / point)
+
+
+def test_merge_local_clusters_random_graphs_against_a_flood_fill():
+    """Random cluster tables and shared-point pairs over 2..5 ranks: the union-find result equals a flood fill, global ids
+    rank the components by their smallest own core index, components without any own core index get -1."""
+    from pointcloudhookup_b200 import tiles as tl
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        W = int(rng.integers(2, 6))
+        sizes = [int(rng.integers(0, 7)) for _ in range(W)]
+        keys = rng.permutation(10_000)[: sum(sizes)].astype(np.int64)
+        tables, k = [], 0
+        for s in sizes:
+            t = keys[k: k + s].copy()
+            k += s
+            t[rng.uniform(size=s) < 0.2] = tl.I64_MAX                       # clusters seen only in the halo
+            tables.append(t)
+        pairs = []
+        for r in range(W):
+            rows = []
+            for q in (r - 1, r + 1):
+                if 0 <= q < W and sizes[r] and sizes[q]:
+                    for _ in range(int(rng.integers(0, 4))):
+                        rows.append((q, int(rng.integers(sizes[r])), int(rng.integers(sizes[q]))))
+            pairs.append(np.array(rows, dtype=np.int64).reshape(-1, 3))
+        maps, n_global = tl.merge_local_clusters(pairs, tables)
+        # flood fill over (rank, local id) nodes
+        nodes = [(r, a) for r in range(W) for a in range(sizes[r])]
+        adj = {v: set() for v in nodes}
+        for r, pr in enumerate(pairs):
+            for q, a, b in pr.tolist():
+                adj[(r, a)].add((q, b))
+                adj[(q, b)].add((r, a))
+        comp, comps = {}, []
+        for v in nodes:
+            if v in comp:
+                continue
+            stack, members = [v], []
+            comp[v] = len(comps)
+            while stack:
+                u = stack.pop()
+                members.append(u)
+                for w in adj[u]:
+                    if w not in comp:
+                        comp[w] = len(comps)
+                        stack.append(w)
+            comps.append(members)
+        comp_key = [min(int(tables[r][a]) for r, a in m) for m in comps]
+        live = sorted((key, c) for c, key in enumerate(comp_key) if key < tl.I64_MAX)
+        gid = {c: g for g, (_, c) in enumerate(live)}
+        assert n_global == len(live)
+        for r, a in nodes:
+            assert maps[r][a] == gid.get(comp[(r, a)], -1)
+
+
+def test_halo_widths_cover_eps_with_slack():
+    from pointcloudhookup_b200 import tiles as tl
+    for eps in (0.5, 8.0, 30.0):
+        e1, e2 = tl.halo_widths(eps)
+        assert eps < e1 < eps * 1.001 + 1e-5 and e2 == 2 * e1

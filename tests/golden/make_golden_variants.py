@@ -7,6 +7,9 @@ stages that widen the hot path:
   test/kuangxuan.py:60-79   per-tower box + `tower_points = points[mask]`
   test/tttt.py:93-175       cluster post-processing: merge adjacent clusters (centres, KDTree radius query, union-find,
                             relabel)
+  test/main_ground.py:8-32, 77-115   remove_ground_ransac / remove_ground_tiled_ransac, with the REAL scikit-learn
+                            RANSACRegressor; the only intervention is random_state = 1000 + call number, so that the draws
+                            can be replayed (the reference passes none and is not reproducible run to run)
 
 Neither file can be imported (kuangxuan.py opens a Windows path and an open3d window at import; tttt.py lacks its
 own imports), so the line ranges are read from /root/reference at generation time, dedented and exec'd in a
@@ -22,7 +25,7 @@ import textwrap
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from variant_inputs import crop_inputs, digest, merge_inputs  # noqa: E402
+from variant_inputs import crop_inputs, digest, merge_inputs, terrain_cloud  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -74,6 +77,32 @@ def main():
                        "n_merged_clusters": int(len(set(merged.tolist()) - {-1})),
                        "iteration_order": [int(v) for v in ns["unique_labels"]]})
     out["merge"] = merges
+    # ---- tiled RANSAC ground: the reference's two functions, scikit-learn's estimator seeded per call
+    from sklearn.linear_model import RANSACRegressor as RealRansac
+    out["source"]["ransac"] = "test/main_ground.py:8-32,77-115"
+    code = ref_lines("test/main_ground.py", 8, 32) + "\n\n" + ref_lines("test/main_ground.py", 77, 115)
+    runs = []
+    for seed, kw, tile, iters in ((5, dict(nx_m=38.0, ny_m=27.0), 10.0, 120),
+                                  (6, dict(nx_m=31.0, ny_m=29.0, origin=(-14.2, -9.9)), 7.5, 80)):
+        points = terrain_cloud(seed, **kw)
+        sizes = []
+
+        class Recording(RealRansac):
+            def fit(self, X, y, **k):
+                sizes.append(int(len(X)))
+                return super().fit(X, y, **k)
+
+        def seeded(**k):
+            return Recording(random_state=1000 + len(sizes), **k)
+
+        ns = {"np": np, "RANSACRegressor": seeded}
+        exec(code, ns)
+        non_ground, ground = ns["remove_ground_tiled_ransac"](points, tile_size=tile, distance_threshold=0.1, max_iterations=iters)
+        runs.append({"seed": seed, "cloud": kw, "tile_size": tile, "distance_threshold": 0.1, "max_iterations": iters,
+                     "n": int(len(points)), "points_sha256": digest(points), "fit_sizes": sizes,
+                     "non_ground": {"rows": int(len(non_ground)), "sha256": digest(non_ground)},
+                     "ground": {"rows": int(len(ground)), "sha256": digest(ground)}})
+    out["ransac"] = runs
     with open(OUT, "w", encoding="utf-8") as f:
         json.dump(out, f, indent=1, ensure_ascii=False)
     print("wrote", OUT)

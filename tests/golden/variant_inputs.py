@@ -35,3 +35,19 @@ def merge_inputs(seed):
     pts, labs = np.concatenate(pts), np.concatenate(labs)
     perm = rng.permutation(len(labs))
     return pts[perm], labs[perm]
+
+
+def terrain_cloud(seed, nx_m=47.0, ny_m=33.0, per_m2=18.0, origin=(500000.0, 3.2e6), outliers=0.35, noise=0.03):
+    """A gently rolling surface sampled at random xy, vegetation / structure points above it, and a sparse corner
+    (a tile with fewer than 10 points).  Absolute projected coordinates like a LAS file's."""
+    rng = np.random.default_rng(seed)
+    n = int(nx_m * ny_m * per_m2)
+    xy = rng.uniform(0, 1, size=(n, 2)) * np.array([nx_m, ny_m])
+    z = 120.0 + 0.04 * xy[:, 0] - 0.03 * xy[:, 1] + 0.4 * np.sin(xy[:, 0] / 9.0) + rng.normal(0, noise, n)
+    k = int(outliers * n)
+    pick = rng.choice(n, size=k, replace=False)
+    z[pick] += rng.uniform(0.3, 30.0, k)
+    sparse = (xy[:, 0] < 10.0) & (xy[:, 1] < 10.0)            # thin the first tile down to a handful of points
+    keep = ~sparse | (rng.uniform(size=n) < 4.0 / max(1, int(sparse.sum())))
+    pts = np.column_stack([xy + np.asarray(origin), z])[keep]
+    return np.ascontiguousarray(pts)

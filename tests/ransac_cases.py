@@ -1,21 +1,11 @@
 """Synthetic clouds for the tiled-RANSAC ground tests (shared by the CPU oracle test and the GPU parity test)."""
+import os
+import sys
+
 import numpy as np
 
-
-def terrain_cloud(seed, nx_m=47.0, ny_m=33.0, per_m2=18.0, origin=(500000.0, 3.2e6), outliers=0.35, noise=0.03):
-    """A gently rolling surface sampled at random xy, vegetation / structure points above it, and a sparse corner
-    (a tile with fewer than 10 points).  Absolute projected coordinates like a LAS file's."""
-    rng = np.random.default_rng(seed)
-    n = int(nx_m * ny_m * per_m2)
-    xy = rng.uniform(0, 1, size=(n, 2)) * np.array([nx_m, ny_m])
-    z = 120.0 + 0.04 * xy[:, 0] - 0.03 * xy[:, 1] + 0.4 * np.sin(xy[:, 0] / 9.0) + rng.normal(0, noise, n)
-    k = int(outliers * n)
-    pick = rng.choice(n, size=k, replace=False)
-    z[pick] += rng.uniform(0.3, 30.0, k)
-    sparse = (xy[:, 0] < 10.0) & (xy[:, 1] < 10.0)            # thin the first tile down to a handful of points
-    keep = ~sparse | (rng.uniform(size=n) < 4.0 / max(1, int(sparse.sum())))
-    pts = np.column_stack([xy + np.asarray(origin), z])[keep]
-    return np.ascontiguousarray(pts)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from variant_inputs import terrain_cloud  # noqa: E402,F401  (the seeded cloud the golden run used)
 
 
 def literal_reference(points, tile_size, distance_threshold, max_iterations, seed_of_tile):
@@ -55,3 +45,28 @@ def replay_triples(sizes, n_tiles, max_iterations, seed_of_tile):
         if n >= 10:
             tri[t] = orz.sklearn_triples(n, max_iterations, seed_of_tile(t))
     return tri
+
+
+def tile_sizes(points, tile_size):
+    """{tile number: points in the tile}, number of tiles — the reference's edges and masks (test/main_ground.py:84-99)."""
+    min_xy = np.min(points[:, :2], axis=0)
+    max_xy = np.max(points[:, :2], axis=0)
+    x_edges = np.arange(min_xy[0], max_xy[0], tile_size)
+    y_edges = np.arange(min_xy[1], max_xy[1], tile_size)
+    sizes = {}
+    for i in range(len(x_edges) - 1):
+        for j in range(len(y_edges) - 1):
+            m = (points[:, 0] >= x_edges[i]) & (points[:, 0] < x_edges[i + 1]) & \
+                (points[:, 1] >= y_edges[j]) & (points[:, 1] < y_edges[j + 1])
+            sizes[i * (len(y_edges) - 1) + j] = int(m.sum())
+    return sizes, max(0, len(x_edges) - 1) * max(0, len(y_edges) - 1)
+
+
+def golden_run_triples(points, case):
+    """The draws of the golden run (tests/golden/make_golden_variants.py seeds scikit-learn's estimator with 1000 + call
+    number; calls happen for the tiles with >= 10 points in tile order) as a (n_tiles, max_iterations, 3) array."""
+    sizes, n_tiles = tile_sizes(points, case["tile_size"])
+    fitted = [t for t in sorted(sizes) if sizes[t] >= 10]
+    assert [sizes[t] for t in fitted] == case["fit_sizes"]
+    seed = {t: 1000 + c for c, t in enumerate(fitted)}
+    return replay_triples({t: sizes[t] for t in fitted}, n_tiles, case["max_iterations"], lambda t: seed[t])

@@ -292,3 +292,20 @@ def test_ransac_counter_generator_draws_three_distinct_rows():
             t = orz.counter_triple(9, 5, k, n)
             assert len(set(t)) == 3 and all(0 <= v < n for v in t)
     assert orz.counter_triple(9, 5, 1, 1000) != orz.counter_triple(9, 6, 1, 1000) != orz.counter_triple(10, 5, 1, 1000)
+
+
+def test_tiled_ransac_oracle_reproduces_the_reference_functions():
+    """variants_run.json["ransac"]: test/main_ground.py:8-32 and :77-115 exec'd by make_golden_variants.py around the REAL
+    scikit-learn RANSACRegressor (seeded per call).  The oracle, replaying the same draws, must stack the same rows."""
+    from oracle import ransac as orz
+    import ransac_cases as rc
+    gold, vi = _variants()
+    assert len(gold["ransac"]) >= 2
+    for case in gold["ransac"]:
+        pts = vi.terrain_cloud(case["seed"], **{k: tuple(v) if isinstance(v, list) else v for k, v in case["cloud"].items()})
+        assert len(pts) == case["n"] and vi.digest(pts) == case["points_sha256"]
+        tri = rc.golden_run_triples(pts, case)
+        ng, g, _ = orz.remove_ground_tiled_ransac(pts, case["tile_size"], case["distance_threshold"], case["max_iterations"],
+                                                  triples={t: tri[t] for t in range(len(tri))})
+        assert len(g) == case["ground"]["rows"] and vi.digest(g) == case["ground"]["sha256"]
+        assert len(ng) == case["non_ground"]["rows"] and vi.digest(ng) == case["non_ground"]["sha256"]

@@ -43,6 +43,25 @@ def test_tiled_ransac_replaying_sklearns_draws_equals_sklearn(cuda_device):
     assert len(g) > 1000 and len(ng) > 1000
 
 
+def test_tiled_ransac_reproduces_the_golden_run_of_the_reference_functions(cuda_device):
+    """tests/golden/variants_run.json["ransac"]: the reference's own two functions exec'd around the real estimator (see
+    make_golden_variants.py); nothing of /root/reference is read here."""
+    import json
+    import os
+    import ransac_cases as rc
+    from variant_inputs import digest, terrain_cloud
+    from pointcloudhookup_b200 import ground_ransac as gr
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "variants_run.json"), encoding="utf-8"))
+    for case in gold["ransac"]:
+        pts = terrain_cloud(case["seed"], **{k: tuple(v) if isinstance(v, list) else v for k, v in case["cloud"].items()})
+        assert digest(pts) == case["points_sha256"]
+        tri = rc.golden_run_triples(pts, case)
+        ng, g = gr.remove_ground_tiled_ransac(pts, tile_size=case["tile_size"], distance_threshold=case["distance_threshold"],
+                                              max_iterations=case["max_iterations"], triples=tri)
+        assert len(g) == case["ground"]["rows"] and digest(g) == case["ground"]["sha256"]
+        assert len(ng) == case["non_ground"]["rows"] and digest(ng) == case["non_ground"]["sha256"]
+
+
 def test_tiled_ransac_edge_cases(cuda_device):
     import torch
     from pointcloudhookup_b200 import ground_ransac as gr
